@@ -1,0 +1,232 @@
+// common.cuh -- device helpers shared by every kernel of the decoder-layer hot path (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/b200llm.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ error plumbing (host)
+void set_error(const char *fmt, ...);
+int cuda_status(const char *what);  // cudaGetLastError() -> B200_OK / B200_ERR_CUDA (+ message)
+int sm_count();
+
+#define B200_REQUIRE(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            ::b200::set_error(__VA_ARGS__);     \
+            return B200_ERR_INVALID_ARG;        \
+        }                                       \
+    } while (0)
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Library workspace (device memory, caller- or library-owned): [tickets | scratch].
+struct Workspace {
+    unsigned int *tickets;  // zero-initialised, self-resetting counters
+    size_t n_tickets;
+    char *scratch;
+    size_t scratch_bytes;
+};
+// Returns false (and sets the error) if no workspace is available.
+bool get_workspace(Workspace *ws);
+
+// Launch with the programmatic-dependent-launch attribute so that the prologue of kernel i+1
+// (weight prefetch, smem carve-up) overlaps the tail of kernel i.  Kernels call pdl_wait() before
+// touching anything the previous kernel wrote and pdl_launch_dependents() as early as they can.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ PDL (device)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ element traits
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int kDtype = B200_F32;
+    static constexpr int kVec = 4;  // elements per 16-byte vector
+    __device__ __forceinline__ static float to_f(float v) { return v; }
+    __device__ __forceinline__ static float from_f(float v) { return v; }
+};
+template <> struct Elem<__half> {
+    static constexpr int kDtype = B200_F16;
+    static constexpr int kVec = 8;
+    __device__ __forceinline__ static float to_f(__half v) { return __half2float(v); }
+    __device__ __forceinline__ static __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int kDtype = B200_BF16;
+    static constexpr int kVec = 8;
+    __device__ __forceinline__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ __forceinline__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 16-byte vector of T unpacked to fp32 lanes.
+template <typename T> struct Vec16 {
+    static constexpr int N = Elem<T>::kVec;
+};
+
+// streaming (read-once) 128-bit load: bypass L1 allocation
+__device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// plain coherent 128-bit load (data another kernel / CTA may have just written)
+__device__ __forceinline__ uint4 ld_v4(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void st_v4(void *p, const uint4 &v) { *reinterpret_cast<uint4 *>(p) = v; }
+
+__device__ __forceinline__ void bf16x2_to_f32(uint32_t u, float &lo, float &hi) {
+    lo = __uint_as_float(u << 16);
+    hi = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ void f16x2_to_f32(uint32_t u, float &lo, float &hi) {
+    __half2 h = *reinterpret_cast<__half2 *>(&u);
+    float2 f = __half22float2(h);
+    lo = f.x;
+    hi = f.y;
+}
+
+// unpack one 16-byte vector of T into Elem<T>::kVec floats
+template <typename T> __device__ __forceinline__ void unpack16(const uint4 &v, float *f);
+template <> __device__ __forceinline__ void unpack16<float>(const uint4 &v, float *f) {
+    f[0] = __uint_as_float(v.x);
+    f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z);
+    f[3] = __uint_as_float(v.w);
+}
+template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4 &v, float *f) {
+    bf16x2_to_f32(v.x, f[0], f[1]);
+    bf16x2_to_f32(v.y, f[2], f[3]);
+    bf16x2_to_f32(v.z, f[4], f[5]);
+    bf16x2_to_f32(v.w, f[6], f[7]);
+}
+template <> __device__ __forceinline__ void unpack16<__half>(const uint4 &v, float *f) {
+    f16x2_to_f32(v.x, f[0], f[1]);
+    f16x2_to_f32(v.y, f[2], f[3]);
+    f16x2_to_f32(v.z, f[4], f[5]);
+    f16x2_to_f32(v.w, f[6], f[7]);
+}
+
+// pack Elem<T>::kVec floats into one 16-byte vector of T (round-to-nearest-even)
+template <typename T> __device__ __forceinline__ uint4 pack16(const float *f);
+template <> __device__ __forceinline__ uint4 pack16<float>(const float *f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+}
+template <> __device__ __forceinline__ uint4 pack16<__nv_bfloat16>(const float *f) {
+    uint4 r;
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]);
+    __nv_bfloat162 d = __floats2bfloat162_rn(f[6], f[7]);
+    r.x = *reinterpret_cast<uint32_t *>(&a);
+    r.y = *reinterpret_cast<uint32_t *>(&b);
+    r.z = *reinterpret_cast<uint32_t *>(&c);
+    r.w = *reinterpret_cast<uint32_t *>(&d);
+    return r;
+}
+template <> __device__ __forceinline__ uint4 pack16<__half>(const float *f) {
+    uint4 r;
+    __half2 a = __floats2half2_rn(f[0], f[1]);
+    __half2 b = __floats2half2_rn(f[2], f[3]);
+    __half2 c = __floats2half2_rn(f[4], f[5]);
+    __half2 d = __floats2half2_rn(f[6], f[7]);
+    r.x = *reinterpret_cast<uint32_t *>(&a);
+    r.y = *reinterpret_cast<uint32_t *>(&b);
+    r.z = *reinterpret_cast<uint32_t *>(&c);
+    r.w = *reinterpret_cast<uint32_t *>(&d);
+    return r;
+}
+
+// ------------------------------------------------------------------ reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// Block-wide sum broadcast to every thread.  `red` = shared float[33].  All threads must call.
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nwarp ? red[lane] : 0.0f;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nwarp ? red[lane] : -INFINITY;
+        t = warp_max(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+#endif  // __CUDACC__
+
+// dtype dispatch on the host: calls f(T{}) with the element type
+#define B200_DISPATCH_DTYPE(dtype, ...)                                  \
+    switch (dtype) {                                                     \
+        case B200_F32: {                                                 \
+            using T = float;                                             \
+            __VA_ARGS__;                                                 \
+        } break;                                                         \
+        case B200_F16: {                                                 \
+            using T = __half;                                            \
+            __VA_ARGS__;                                                 \
+        } break;                                                         \
+        case B200_BF16: {                                                \
+            using T = __nv_bfloat16;                                     \
+            __VA_ARGS__;                                                 \
+        } break;                                                         \
+        default:                                                         \
+            ::b200::set_error("unknown dtype %d", (int)(dtype));         \
+            return B200_ERR_INVALID_ARG;                                 \
+    }
+
+}  // namespace b200
