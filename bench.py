@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s + fraction of HBM roofline for the Llama-2 decoder-layer hot path (BASELINE.json).
+
+A "step" is one decode step over one batch of synthetic input: embedding gather -> 32 fused decoder layers over the KV cache ->
+final RMSNorm + LM head -> top-k -> sampling.  Default workload (N=1): BASELINE.json configs[1], Llama-2-7B, 32 layers, bf16,
+batch 1, 1024-token context.  With --gpus N > 1 the same model runs tensor-parallel over N ranks (column-sharded QKV / gate-up,
+row-sharded O / down, head-sharded KV cache, one NCCL all-reduce per attention and per MLP block): total work is fixed, so
+"scaling" is "strong".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 7b|70b] [--batch B] [--ctx C]
+                  [--wformat bf16|fp8|int4]
+
+`value`  : device-resident decode tokens/s (inputs in HBM, CUDA-graph replay, timed with CUDA events, max over ranks).
+`e2e`    : the same through the C ABI with HOST buffers: token ids copied H2D from pinned memory and sampled ids copied D2H
+           inside the timed region, every step.
+`roofline`: the weight-streaming GEMV (the dominant kernel: >96 % of a step's bytes) timed live with CUDA events over one step's
+           worth of launches; algorithmic bytes = the packed weight bytes it must read.
+`cpu_baseline` / --impl reference: the CPU restatement of the reference's path (oracle/, "port": the reference has no CPU
+           inference path of its own) on the host cores, bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "7b": dict(name="Llama-2-7B", hidden=4096, head_num=32, kv_head_num=32, head_size=128, inter=11008, layers=32, vocab=32000),
+    "70b": dict(name="Llama-2-70B-shaped", hidden=8192, head_num=64, kv_head_num=8, head_size=128, inter=28672, layers=80, vocab=32000),
+}
+WBYTES = {"bf16": 2.0, "fp8": 1.0, "int4": 0.5}
+
+
+def algorithmic_bytes(cfg, batch, ctx, wformat, tp=1, group=128):
+    """Bytes one decode step must read from HBM on ONE rank: packed layer weights (+ quantisation
+    scales / zero points) + the KV rows of [0, ctx) + the bf16 LM head.  Activations, gammas, the appended KV row and the
+    embedding row (< 0.01 %) are excluded."""
+    h, H, Hkv, d, I, L, V = (cfg[k] for k in ("hidden", "head_num", "kv_head_num", "head_size", "inter", "layers", "vocab"))
+    params = h * (H + 2 * Hkv) * d + H * d * h + 3 * h * I
+    wb = params * WBYTES[wformat] / tp
+    if wformat == "fp8":
+        wb += 4 * ((H + 2 * Hkv) * d + h + 2 * I + h) / tp
+    if wformat == "int4":
+        wb += params / group * 3 / tp
+    kv = batch * 2 * (Hkv // tp if Hkv >= tp else 1) * d * ctx * 2
+    return L * (wb + kv) + V * h * 2, L * wb + V * h * 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_tokens_per_s(cfg, batch, ctx, threads, budget_s=20.0):
+    """Time the oracle (fp32 restatement of the reference's layer, OpenMP over output columns) on a bounded sample:
+    ONE decoder layer + the LM head, extrapolated to layers + head.  Returns (tokens/s, sample description, cores)."""
+    import numpy as np
+
+    from oracle import oracle
+
+    oracle.set_threads(threads)
+    rng = np.random.default_rng(0)
+    h, H, Hkv, d, I, V = (cfg[k] for k in ("hidden", "head_num", "kv_head_num", "head_size", "inter", "vocab"))
+    S = ctx + 8
+
+    def rnd(*shape, scale=1.0):
+        return (rng.random(shape, dtype=np.float32) - 0.5) * (2 * scale)
+
+    w = dict(g1=1 + rnd(h, scale=0.1), wqkv=rnd((H + 2 * Hkv) * d, h, scale=0.03), bqkv=None, wo=rnd(h, H * d, scale=0.03), bo=None,
+             g2=1 + rnd(h, scale=0.1), wgu=rnd(2 * I, h, scale=0.03), wd=rnd(h, I, scale=0.03))
+    kc, vc = rnd(1, batch, Hkv, S, d), rnd(1, batch, Hkv, S, d)
+    lm = rnd(V, h, scale=0.03)
+    ocfg = dict(head_num=H, kv_head_num=Hkv, head_size=d, inter=I, eps=1e-6, rot_dim=d, base=10000.0)
+    x = rnd(batch, h)
+    oracle.decoder_layer(x.copy(), w, kc, vc, ocfg, ctx, 0)  # warm caches / page in
+    reps, t_layer = 0, 0.0
+    t_end = time.perf_counter() + budget_s * 0.7
+    while reps < 3 or (time.perf_counter() < t_end and reps < 50):
+        xx = x.copy()
+        t0 = time.perf_counter()
+        oracle.decoder_layer(xx, w, kc, vc, ocfg, ctx, 0)
+        t_layer += time.perf_counter() - t0
+        reps += 1
+    t_layer /= reps
+    t0 = time.perf_counter()
+    for _ in range(2):
+        oracle.linear(x, lm, "nk")
+    t_lm = (time.perf_counter() - t0) / 2
+    t_step = cfg["layers"] * t_layer + t_lm
+    sample = (f"1 of {cfg['layers']} decoder layers ({reps} reps, {t_layer * 1e3:.1f} ms each) + LM head ({t_lm * 1e3:.1f} ms), fp32, "
+              f"batch {batch}, ctx {ctx}, extrapolated to {cfg['layers']} layers")
+    return batch / t_step, sample, threads
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    from oracle import oracle
+
+    threads = oracle.max_threads()
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        budget = max(4.0, 150.0 / (args.warmup + args.steps))
+        v, sample, cores = cpu_reference_tokens_per_s(cfg, args.batch, args.ctx, threads, budget_s=min(budget, 20.0))
+        if i >= args.warmup:
+            vals.append(v)
+        if time.perf_counter() - t_all > 200:
+            break
+    vals = vals or [v]
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, cfg),
+            "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference has no CPU inference path and its CUDA path is fp32/sm_86 single-GPU (SURVEY.md 8d); this arm times "
+                    "the CPU restatement of its decoder layer (oracle/llama_oracle.c) with OpenMP on all host cores"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg):
+    return {"workload": f"{cfg['name']} {cfg['layers']}-layer {args.wformat} decode, batch {args.batch}, {args.ctx}-token context",
+            "batch": args.batch, "context": args.ctx, "weights": args.wformat, "kv_cache": "bf16",
+            "parallelism": f"tp{args.gpus}" if args.gpus > 1 else "single-gpu",
+            "cache_policy": "inputs larger than L2 (13.7 GB of weights + KV per step vs 126 MB L2); no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="7b", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--ctx", type=int, default=1024)
+    ap.add_argument("--wformat", default="bf16", choices=list(WBYTES))
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only: makes the number INVALID)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = dict(CONFIGS[args.config])
+    if args.layers:
+        cfg["layers"] = args.layers
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    mod = importlib.import_module("llm-inference-engine_b200")
+    mod.lib()  # fails loudly if libb200llm.so is missing
+    tp = world
+    assert tp == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE {world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if tp > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h, H, Hkv, d, I, L, V = (cfg[k] for k in ("hidden", "head_num", "kv_head_num", "head_size", "inter", "layers", "vocab"))
+    assert H % tp == 0 and I % tp == 0 and (Hkv % tp == 0), "tensor-parallel degree must divide heads / kv heads / inter"
+    Hl, Hkvl, Il = H // tp, Hkv // tp, I // tp
+    B, ctx = args.batch, args.ctx
+    S = ((ctx + 64 + 127) // 128) * 128
+    step = ctx  # positions [0, ctx) are attended: ctx-1 cached rows + the token being appended
+    wfmt = {"bf16": mod.W_DENSE, "fp8": mod.W_FP8, "int4": mod.W_INT4}[args.wformat]
+    dt = torch.bfloat16
+
+    # ---------------- synthetic model (seeded; every rank generates its own shard from a rank-specific seed)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+
+    def randw(n, k):
+        w = torch.empty((n, k), dtype=dt, device=dev)
+        w.normal_(0.0, 0.02, generator=gen)
+        if wfmt == mod.W_FP8:
+            return mod.quantize_fp8(w)
+        if wfmt == mod.W_INT4:
+            return mod.quantize_int4(w, 128)
+        return w
+
+    dc = mod.DecoderConfig(h, Hl, Hkvl, d, Il, L, S, B, mod.BF16, wfmt, 128, 1e-5, d, 10000.0, tp, rank)
+    dec = mod.Decoder(dc, dev)
+    ggen = torch.Generator(device=dev)
+    ggen.manual_seed(99)  # replicated tensors: same seed on every rank
+    for l in range(L):
+        g1 = (1 + 0.1 * torch.randn(h, device=dev, generator=ggen)).to(dt)
+        g2 = (1 + 0.1 * torch.randn(h, device=dev, generator=ggen)).to(dt)
+        dec.set_layer(l, dict(g1=g1, qkv=randw((Hl + 2 * Hkvl) * d, h), o=randw(h, Hl * d), g2=g2, gate_up=randw(2 * Il, h), down=randw(h, Il)))
+    final_gamma = (1 + 0.1 * torch.randn(h, device=dev, generator=ggen)).to(dt)
+    lm_head = torch.empty((V, h), dtype=dt, device=dev).normal_(0.0, 0.02, generator=ggen)
+    emb = torch.empty((V, h), dtype=dt, device=dev).normal_(0.0, 1.0, generator=ggen)
+    kc = torch.empty((L, B, Hkvl, S, d), dtype=dt, device=dev).normal_(0.0, 0.5, generator=gen)
+    vc = torch.empty((L, B, Hkvl, S, d), dtype=dt, device=dev).normal_(0.0, 0.5, generator=gen)
+    K_TOP, END_ID = 5, 2
+    ids_dev = torch.randint(3, V, (B,), dtype=torch.int32, device=dev, generator=ggen)
+    hidden = torch.empty((B, h), dtype=dt, device=dev)
+    y_attn = torch.empty((B, h), dtype=dt, device=dev)
+    y_ffn = torch.empty((B, h), dtype=dt, device=dev)
+    bufs = dict(logits=torch.empty((B, V), dtype=torch.float32, device=dev), tmp_ids=torch.empty((B, 8, K_TOP), dtype=torch.int32, device=dev),
+                tmp_vals=torch.empty((B, 8, K_TOP), dtype=torch.float32, device=dev), topk_ids=torch.empty((B, K_TOP), dtype=torch.int32, device=dev),
+                topk_vals=torch.empty((B, K_TOP), dtype=torch.float32, device=dev), seq_len=torch.full((B,), ctx, dtype=torch.int32, device=dev),
+                finished=torch.zeros(B, dtype=torch.uint8, device=dev), output_id=torch.zeros(B, dtype=torch.int32, device=dev))
+    launches_per_step = 1 + L * 5 + 1 + (B + 3) // 4 + 2 + 1
+
+    def decode_step():
+        """embedding -> L layers -> fold -> final norm + LM head -> top-k -> sampling; all on the current stream."""
+        mod.check(mod.lib().b200_input_embedding(mod.ptr(ids_dev), mod.ptr(emb), mod.ptr(hidden), B, h, mod.BF16, mod.stream()))
+        if tp == 1:
+            dec.step(hidden, kc, vc, step)
+        else:
+            pending = None
+            for l in range(L):
+                dec.attn_block(l, hidden, pending, kc, vc, y_attn, step)
+                dist.all_reduce(y_attn)
+                dec.ffn_block(l, y_attn, y_ffn)
+                dist.all_reduce(y_ffn)
+                pending = y_ffn
+            dec.fold(hidden, pending)
+        dec.lm_head_topk_sample(hidden, final_gamma, lm_head, bufs, K_TOP, step, END_ID)
+
+    stream = torch.cuda.Stream(device=dev)
+    graph = None
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            decode_step()
+        stream.synchronize()
+        if not args.no_graph:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    decode_step()
+                graph.replay()
+                stream.synchronize()
+            except Exception as e:  # report, and measure the eager path instead
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+                graph = None
+                torch.cuda.synchronize()
+
+        def run_step():
+            if graph is not None:
+                graph.replay()
+            else:
+                decode_step()
+
+        def barrier():
+            if tp > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def max_over_ranks(ms):
+            if tp == 1:
+                return ms
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        # ---------------- value: device-resident, CUDA events, max over ranks
+        for _ in range(args.warmup):
+            run_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            e0.record(stream)
+            for _ in range(args.steps):
+                run_step()
+            e1.record(stream)
+            barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        ms_step = ms_total / args.steps
+        value = B * 1e3 / ms_step
+
+        # ---------------- e2e: host buffers through the C ABI, H2D + D2H inside the timed region every step
+        ids_host = torch.randint(3, V, (B,), dtype=torch.int32).pin_memory()
+        out_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+        for _ in range(3):
+            ids_dev.copy_(ids_host, non_blocking=True)
+            run_step()
+            out_host.copy_(bufs["output_id"], non_blocking=True)
+            stream.synchronize()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for _ in range(args.steps):
+            ids_dev.copy_(ids_host, non_blocking=True)
+            run_step()
+            out_host.copy_(bufs["output_id"], non_blocking=True)
+            stream.synchronize()  # the next token id is only known once this one is on the host
+            ids_host.copy_(out_host.clamp_(min=0))
+        e3.record(stream)
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
+        e2e_value = B * 1e3 / ms_e2e
+
+        # ---------------- roofline of the dominant kernel: every GEMV launch of one step, back to back, CUDA events
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        step_bytes, gemv_bytes = algorithmic_bytes(cfg, B, ctx, args.wformat, tp)
+        xin = torch.randn(B, h, device=dev).to(dt)
+        xin_i = torch.randn(B, Il, device=dev).to(dt)
+        xin_a = torch.randn(B, Hl * d, device=dev).to(dt)
+        outs = {n: torch.empty((B, n), dtype=dt, device=dev) for n in {(Hl + 2 * Hkvl) * d, h, 2 * Il, V}}
+
+        def lin(x, w, n):
+            if isinstance(w, (tuple, list)):
+                q, s, z = (list(w) + [None])[:3]
+                mod.linear(x, q, mod.LAYOUT_NK, wfmt, s, z, 128, N=n, out=outs[n])
+            else:
+                mod.linear(x, w, mod.LAYOUT_NK, N=n, out=outs[n])
+
+        def gemv_pass():
+            for l in range(L):
+                w = dec._keep[l]
+                lin(xin, w["qkv"], (Hl + 2 * Hkvl) * d)
+                lin(xin_a, w["o"], h)
+                lin(xin, w["gate_up"], 2 * Il)
+                lin(xin_i, w["down"], h)
+            lin(xin, lm_head, V)
+
+        n_gemv = 4 * L + 1
+        for _ in range(2):
+            gemv_pass()
+        stream.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        r0.record(stream)
+        for _ in range(reps):
+            gemv_pass()
+        r1.record(stream)
+        stream.synchronize()
+        gemv_ms = r0.elapsed_time(r1) / reps
+        achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        cpu = None
+        if tp == 1 and not args.no_cpu_baseline:
+            from oracle import oracle  # checker only: the CPU baseline leg
+
+            v, sample, cores = cpu_reference_tokens_per_s(cfg, B, ctx, oracle.max_threads(), budget_s=15.0)
+            cpu = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": "decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, cfg),
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4 * B, "ms_per_step": ms_e2e},
+            "gpu_launches": launches_per_step * args.steps,
+            "launch_mode": "cuda-graph replay" if graph is not None else "eager",
+            "roofline": {"bound": "hbm", "kernel": "gemv_nk_kernel (all %d weight-streaming linears of one step, back to back)" % n_gemv,
+                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_step_launches": gemv_bytes, "ms": gemv_ms,
+                         "whole_step": {"bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                                        "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak_gbs,
+                                        "frac_of_8000_nominal": step_bytes / (ms_step * 1e-3) / 1e9 / 8000.0}},
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if tp > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,7 +2,7 @@
  * b200llm.h -- C ABI of the B200-native (sm_100a) Llama-2 decoder-layer hot path.
  *
  * This is the drop-in boundary for chongchen1999/llm-inference-engine: one entry point per
- * `launch*` function of the reference's src/kernels/includes/*.cuh (cited per function below,
+ * `launch*` function of the reference's src/kernels/includes/ headers (cited per function below,
  * paths relative to the reference root), plus the fused decode engine that the reference's
  * src/layers classes map onto.  Plain pointers and sizes only: no C++ types, no torch types,
  * no exceptions across the boundary.
@@ -234,6 +234,10 @@ int b200_topk(const void *logits, int *tmp_ids, void *tmp_vals, int *final_ids, 
  * candidate 0; id %= vocab; ++seq_len unless finished; finished = (id == end_id). */
 int b200_sampling(const int *topk_id, void *topk_val, int *seq_len, uint8_t *finished, int *output_id,
                   int batch, int k, int step, int end_id, int vocab, int dtype, b200_stream_t stream);
+
+/* Test helper: out[b] = the first curand_uniform() of curand_init(seed, subsequence=b, offset=0) (XORWOW),
+ * i.e. the random number launchSampling draws for batch row b at step == seed. */
+int b200_xorwow_uniform(float *out, int n, unsigned long long seed, b200_stream_t stream);
 
 /* ======================================= fused decode engine ========================================
  * The reference's LlamaSelfDecoder<T>::forward (src/layers/self_decoder.cpp:24-122) + the sampling

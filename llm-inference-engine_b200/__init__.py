@@ -1,0 +1,415 @@
+"""llm-inference-engine_b200 -- Python plumbing over libb200llm.so (the C ABI of include/b200llm.h).
+
+The product is the shared library (hand-written sm_100a CUDA behind a C ABI) and the C++ shim in
+`shim/` that re-provides the reference's launch* / layer / weight classes.  This module only binds the
+C ABI with ctypes so that tests and bench.py can drive it with torch tensors as device memory.  There is
+no CPU or PyTorch fallback: if the library is missing or a call fails, an exception is raised.
+
+The directory name contains a hyphen; import it with
+    importlib.import_module("llm-inference-engine_b200")
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200llm.so")
+
+F32, F16, BF16 = 0, 1, 2
+W_DENSE, W_FP8, W_INT4 = 0, 1, 2
+LAYOUT_KN, LAYOUT_NK = 0, 1
+TOPK_BLOCKS, TOPK_MAX_K = 8, 8
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class DecoderConfig(C.Structure):
+    _fields_ = [(n, t) for n, t in [
+        ("hidden", C.c_int), ("head_num", C.c_int), ("kv_head_num", C.c_int), ("head_size", C.c_int),
+        ("inter_size", C.c_int), ("num_layers", C.c_int), ("max_seq_len", C.c_int), ("max_batch", C.c_int),
+        ("dtype", C.c_int), ("w_format", C.c_int), ("group", C.c_int), ("rmsnorm_eps", C.c_float),
+        ("rotary_dim", C.c_int), ("rotary_base", C.c_float), ("tp_world", C.c_int), ("tp_rank", C.c_int)]]
+
+
+class LinearWeight(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("scales", C.c_void_p), ("zeros", C.c_void_p)]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [("attn_norm_gamma", C.c_void_p), ("qkv", LinearWeight), ("qkv_bias", C.c_void_p), ("o", LinearWeight),
+                ("o_bias", C.c_void_p), ("ffn_norm_gamma", C.c_void_p), ("gate_up", LinearWeight), ("down", LinearWeight)]
+
+
+_P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+# name -> argtypes (restype int unless listed in _RESTYPES); must list every symbol of include/b200llm.h
+SIGNATURES = {
+    "b200_last_error_string": [],
+    "b200_abi_version": [],
+    "b200_sm_count": [],
+    "b200_workspace_default_bytes": [],
+    "b200_workspace_set": [_P, _SZ],
+    "b200_workspace_ensure": [_SZ],
+    "b200_rmsnorm": [_P, _P, _P, _F, _I, _I, _I, _P],
+    "b200_fused_add_bias_residual_rmsnorm": [_P, _P, _P, _P, _F, _I, _I, _I, _P],
+    "b200_add_residual": [_P, _P, _I, _I, _I, _P],
+    "b200_linear": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b200_batched_gemm": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_quantize_fp8": [_P, _P, _P, _I, _I, _I, _P],
+    "b200_quantize_int4": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_dequantize": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "b200_transpose2d": [_P, _P, _I, _I, _I, _P],
+    "b200_rope_decode": [_P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_decode_mha": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_qkv_bias_transpose_rope": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_concat_kv_cache": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b200_repeat_kv_cache": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b200_scale_mask_softmax": [_P, _P, _P, _F, _I, _I, _I, _I, _I, _P],
+    "b200_build_causal_masks": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_cal_padding_offset": [_P, _P, _P, _I, _I, _P],
+    "b200_transpose_remove_padding": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_context_attention": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_silu_and_mul": [_P, _P, _I, _I, _I, _P],
+    "b200_input_embedding": [_P, _P, _P, _I, _I, _I, _P],
+    "b200_topk": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_sampling": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_xorwow_uniform": [_P, _I, C.c_ulonglong, _P],
+    "b200_decoder_create": [C.POINTER(DecoderConfig)],
+    "b200_decoder_destroy": [_P],
+    "b200_decoder_set_layer": [_P, _I, C.POINTER(LayerWeights)],
+    "b200_decoder_scratch_bytes": [_P],
+    "b200_decoder_set_scratch": [_P, _P, _SZ],
+    "b200_decoder_step": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_decoder_attn_block": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P],
+    "b200_decoder_ffn_block": [_P, _I, _P, _P, _P, _I, _P],
+    "b200_decoder_fold": [_P, _P, _P, _I, _P],
+    "b200_lm_head_topk_sample": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+}
+_RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_workspace_default_bytes": _SZ, "b200_decoder_create": _P,
+             "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ}
+
+_lib = None
+
+
+def lib():
+    """The loaded libb200llm.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} is missing: build it with __graft_entry__.build() (make -C llm-inference-engine_b200/csrc)")
+        handle = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B200Error(f"b200 status {rc}: {lib().b200_last_error_string().decode()}")
+
+
+# ------------------------------------------------------------------ torch plumbing (device memory + streams only)
+def _torch():
+    import torch
+
+    return torch
+
+
+def dtype_code(t):
+    torch = _torch()
+    return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[t.dtype]
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device tensors must be contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+_ws_holder = {}
+
+
+def ensure_workspace(nbytes=None):
+    """Hand the library a torch-allocated workspace for the current device (once)."""
+    torch = _torch()
+    dev = torch.cuda.current_device()
+    nbytes = nbytes or lib().b200_workspace_default_bytes()
+    if dev not in _ws_holder or _ws_holder[dev].numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+        check(lib().b200_workspace_set(ptr(buf), nbytes))
+        _ws_holder[dev] = buf
+
+
+# thin op wrappers (same argument meaning as the reference launchers; see include/b200llm.h)
+def rmsnorm(x, residual, gamma, eps):
+    check(lib().b200_rmsnorm(ptr(x), ptr(residual), ptr(gamma), eps, x.shape[0], x.shape[1], dtype_code(x), stream()))
+
+
+def fused_add_bias_residual_rmsnorm(residual, out, bias, gamma, eps):
+    check(lib().b200_fused_add_bias_residual_rmsnorm(ptr(residual), ptr(out), ptr(bias), ptr(gamma), eps, out.shape[0], out.shape[1],
+                                                     dtype_code(out), stream()))
+
+
+def add_residual(residual, out):
+    check(lib().b200_add_residual(ptr(residual), ptr(out), out.shape[0], out.shape[1], dtype_code(out), stream()))
+
+
+def linear(x, w, layout=LAYOUT_NK, w_format=W_DENSE, scales=None, zeros=None, group=0, N=None, out=None):
+    torch = _torch()
+    M, K = x.shape
+    if N is None:
+        N = w.shape[0] if layout == LAYOUT_NK else w.shape[1]
+    y = out if out is not None else torch.empty((M, N), dtype=x.dtype, device=x.device)
+    if layout == LAYOUT_KN:
+        ensure_workspace()
+    check(lib().b200_linear(ptr(x), ptr(w), ptr(scales), ptr(zeros), ptr(y), M, K, N, dtype_code(x), w_format, layout, group, stream()))
+    return y
+
+
+def batched_gemm(a, b, trans_b):
+    torch = _torch()
+    batch, M, K = a.shape
+    N = b.shape[1] if trans_b else b.shape[2]
+    c = torch.empty((batch, M, N), dtype=a.dtype, device=a.device)
+    check(lib().b200_batched_gemm(ptr(a), ptr(b), ptr(c), batch, M, N, K, int(trans_b), dtype_code(a), stream()))
+    return c
+
+
+def quantize_fp8(w):
+    torch = _torch()
+    N, K = w.shape
+    q = torch.empty((N, K), dtype=torch.uint8, device=w.device)
+    sc = torch.empty(N, dtype=torch.float32, device=w.device)
+    check(lib().b200_quantize_fp8(ptr(w), ptr(q), ptr(sc), N, K, dtype_code(w), stream()))
+    return q, sc
+
+
+def quantize_int4(w, group):
+    torch = _torch()
+    N, K = w.shape
+    q = torch.empty((N, K // 2), dtype=torch.uint8, device=w.device)
+    sc = torch.empty((N, K // group), dtype=w.dtype, device=w.device)
+    z = torch.empty((N, K // group), dtype=torch.uint8, device=w.device)
+    check(lib().b200_quantize_int4(ptr(w), ptr(q), ptr(sc), ptr(z), N, K, group, dtype_code(w), stream()))
+    return q, sc, z
+
+
+def dequantize(q, scales, zeros, w_format, group, dtype, K):
+    torch = _torch()
+    N = q.shape[0]
+    dst = torch.empty((N, K), dtype=dtype, device=q.device)
+    check(lib().b200_dequantize(ptr(q), ptr(scales), ptr(zeros), ptr(dst), N, K, w_format, group, dtype_code(dst), stream()))
+    return dst
+
+
+def transpose2d(src):
+    torch = _torch()
+    rows, cols = src.shape
+    dst = torch.empty((cols, rows), dtype=src.dtype, device=src.device)
+    check(lib().b200_transpose2d(ptr(src), ptr(dst), rows, cols, dtype_code(src), stream()))
+    return dst
+
+
+def rope_decode(qkv, head_num, kv_head_num, step, rot_dim, base):
+    B, _, d = qkv.shape
+    check(lib().b200_rope_decode(ptr(qkv), B, head_num, kv_head_num, d, step, rot_dim, base, dtype_code(qkv), stream()))
+
+
+def decode_mha(qkv, bias, k_cache, v_cache, head_num, kv_head_num, step, layer, apply_rope=False, rot_dim=0, base=10000.0):
+    torch = _torch()
+    ensure_workspace()
+    B, _, d = qkv.shape
+    S = k_cache.shape[3]
+    out = torch.empty((B, head_num * d), dtype=qkv.dtype, device=qkv.device)
+    check(lib().b200_decode_mha(ptr(qkv), ptr(bias), ptr(k_cache), ptr(v_cache), ptr(out), None, B, head_num, kv_head_num, d, S, step,
+                                layer, int(apply_rope), rot_dim, base, dtype_code(qkv), stream()))
+    return out
+
+
+def silu_and_mul(x):
+    torch = _torch()
+    t, _, inter = x.shape
+    out = torch.empty((t, inter), dtype=x.dtype, device=x.device)
+    check(lib().b200_silu_and_mul(ptr(x), ptr(out), t, inter, dtype_code(x), stream()))
+    return out
+
+
+def input_embedding(ids, table):
+    torch = _torch()
+    out = torch.empty((ids.shape[0], table.shape[1]), dtype=table.dtype, device=table.device)
+    check(lib().b200_input_embedding(ptr(ids), ptr(table), ptr(out), ids.shape[0], table.shape[1], dtype_code(table), stream()))
+    return out
+
+
+def topk(logits, k):
+    torch = _torch()
+    rows, vocab = logits.shape
+    dev = logits.device
+    tmp_i = torch.empty((rows, TOPK_BLOCKS, k), dtype=torch.int32, device=dev)
+    tmp_v = torch.empty((rows, TOPK_BLOCKS, k), dtype=logits.dtype, device=dev)
+    ids = torch.empty((rows, k), dtype=torch.int32, device=dev)
+    vals = torch.empty((rows, k), dtype=logits.dtype, device=dev)
+    check(lib().b200_topk(ptr(logits), ptr(tmp_i), ptr(tmp_v), ptr(ids), ptr(vals), rows, vocab, k, dtype_code(logits), stream()))
+    return ids, vals
+
+
+def sampling(topk_id, topk_val, seq_len, finished, step, end_id, vocab):
+    torch = _torch()
+    B, k = topk_id.shape
+    out = torch.empty(B, dtype=torch.int32, device=topk_id.device)
+    check(lib().b200_sampling(ptr(topk_id), ptr(topk_val), ptr(seq_len), ptr(finished), ptr(out), B, k, step, end_id, vocab,
+                              dtype_code(topk_val), stream()))
+    return out
+
+
+def xorwow_uniform(n, seed, device):
+    torch = _torch()
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(lib().b200_xorwow_uniform(ptr(out), n, seed, stream()))
+    return out
+
+
+def cal_padding_offset(input_lengths, max_q_len, fill=0):
+    torch = _torch()
+    B = input_lengths.shape[0]
+    po = torch.full((B, max_q_len), fill, dtype=torch.int32, device=input_lengths.device)
+    cum = torch.empty(B + 1, dtype=torch.int32, device=input_lengths.device)
+    check(lib().b200_cal_padding_offset(ptr(po), ptr(cum), ptr(input_lengths), B, max_q_len, stream()))
+    return po, cum
+
+
+def build_causal_masks(q_lens, k_lens, max_q_len, max_k_len, dtype):
+    torch = _torch()
+    B = q_lens.shape[0]
+    mask = torch.empty((B, max_q_len, max_k_len), dtype=dtype, device=q_lens.device)
+    check(lib().b200_build_causal_masks(ptr(mask), ptr(q_lens), ptr(k_lens), B, max_q_len, max_k_len, dtype_code(mask), stream()))
+    return mask
+
+
+def qkv_bias_transpose_rope(qkv, padding_offset, history_len, input_len, batch, seq_len, head_num, kv_head_num, rot_dim, base):
+    torch = _torch()
+    T, _, d = qkv.shape
+    q = torch.zeros((batch, head_num, seq_len, d), dtype=qkv.dtype, device=qkv.device)
+    k = torch.zeros((batch, kv_head_num, seq_len, d), dtype=qkv.dtype, device=qkv.device)
+    v = torch.zeros((batch, kv_head_num, seq_len, d), dtype=qkv.dtype, device=qkv.device)
+    check(lib().b200_qkv_bias_transpose_rope(ptr(q), ptr(k), ptr(v), ptr(qkv), None, ptr(padding_offset), ptr(history_len), ptr(input_len),
+                                             batch, seq_len, T, head_num, kv_head_num, d, rot_dim, base, dtype_code(qkv), stream()))
+    return q, k, v
+
+
+def concat_kv_cache(k_src, v_src, k_cache, v_cache, cur_len, history_len, layer):
+    B, Hkv, mq, d = k_src.shape
+    S = k_cache.shape[3]
+    check(lib().b200_concat_kv_cache(ptr(k_src), ptr(v_src), ptr(k_cache), ptr(v_cache), ptr(cur_len), ptr(history_len), layer, B, Hkv, mq,
+                                     S, d, dtype_code(k_src), stream()))
+
+
+def repeat_kv_cache(k_cache, v_cache, context_len, layer, head_num, max_k_len):
+    torch = _torch()
+    _, B, Hkv, S, d = k_cache.shape
+    kd = torch.zeros((B, head_num, max_k_len, d), dtype=k_cache.dtype, device=k_cache.device)
+    vd = torch.zeros((B, head_num, max_k_len, d), dtype=k_cache.dtype, device=k_cache.device)
+    check(lib().b200_repeat_kv_cache(ptr(k_cache), ptr(v_cache), ptr(kd), ptr(vd), ptr(context_len), layer, B, head_num, Hkv, max_k_len, S,
+                                     d, dtype_code(k_cache), stream()))
+    return kd, vd
+
+
+def scale_mask_softmax(qk, mask, scale, out=None):
+    torch = _torch()
+    B, H, ql, kl = qk.shape
+    out = out if out is not None else torch.empty_like(qk)
+    check(lib().b200_scale_mask_softmax(ptr(qk), ptr(mask), ptr(out), scale, B, H, ql, kl, dtype_code(qk), stream()))
+    return out
+
+
+def transpose_remove_padding(src, padding_offset, num_tokens):
+    torch = _torch()
+    B, H, S, d = src.shape
+    dst = torch.empty((num_tokens, H, d), dtype=src.dtype, device=src.device)
+    check(lib().b200_transpose_remove_padding(ptr(src), ptr(padding_offset), ptr(dst), num_tokens, B, S, H, d, dtype_code(src), stream()))
+    return dst
+
+
+def context_attention(q, k_cache, v_cache, padding_offset, input_len, context_len, layer, num_tokens, scale):
+    torch = _torch()
+    ensure_workspace()
+    B, H, mq, d = q.shape
+    _, _, Hkv, S, _ = k_cache.shape
+    out = torch.empty((num_tokens, H, d), dtype=q.dtype, device=q.device)
+    check(lib().b200_context_attention(ptr(q), ptr(k_cache), ptr(v_cache), ptr(out), ptr(padding_offset), ptr(input_len), ptr(context_len),
+                                       layer, B, H, Hkv, mq, S, d, num_tokens, scale, dtype_code(q), stream()))
+    return out
+
+
+class Decoder:
+    """The fused decode engine (b200_decoder_*): weights are torch tensors in the packed [N,K] layout."""
+
+    def __init__(self, cfg: DecoderConfig, device):
+        torch = _torch()
+        self.cfg = cfg
+        self.device = device
+        self.handle = lib().b200_decoder_create(C.byref(cfg))
+        if not self.handle:
+            raise B200Error(lib().b200_last_error_string().decode())
+        nbytes = lib().b200_decoder_scratch_bytes(self.handle)
+        self.scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        base = (self.scratch.data_ptr() + 255) // 256 * 256
+        check(lib().b200_decoder_set_scratch(self.handle, C.c_void_p(base), nbytes))
+        self._keep = []
+
+    def set_layer(self, layer, w):
+        """w: dict with g1, qkv, o, g2, gate_up, down (each linear = tensor or (q, scales, zeros)), optional qkv_bias, o_bias."""
+        def lw(x):
+            if isinstance(x, (tuple, list)):
+                q, s, z = (list(x) + [None, None])[:3]
+                return LinearWeight(q.data_ptr(), s.data_ptr() if s is not None else None, z.data_ptr() if z is not None else None)
+            return LinearWeight(x.data_ptr(), None, None)
+
+        def p(x):
+            return x.data_ptr() if x is not None else None
+
+        s = LayerWeights(p(w["g1"]), lw(w["qkv"]), p(w.get("qkv_bias")), lw(w["o"]), p(w.get("o_bias")), p(w["g2"]), lw(w["gate_up"]),
+                         lw(w["down"]))
+        self._keep.append(w)
+        check(lib().b200_decoder_set_layer(self.handle, layer, C.byref(s)))
+
+    def step(self, hidden, k_cache, v_cache, step, layer_begin=0, layer_end=None):
+        layer_end = self.cfg.num_layers if layer_end is None else layer_end
+        check(lib().b200_decoder_step(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], step, layer_begin, layer_end,
+                                      stream()))
+
+    def attn_block(self, layer, hidden, pending, k_cache, v_cache, partial, step):
+        batch = partial.shape[0]
+        check(lib().b200_decoder_attn_block(self.handle, layer, ptr(hidden), ptr(pending), ptr(k_cache), ptr(v_cache), ptr(partial), batch,
+                                            step, stream()))
+
+    def ffn_block(self, layer, pending, partial):
+        check(lib().b200_decoder_ffn_block(self.handle, layer, None, ptr(pending), ptr(partial), partial.shape[0], stream()))
+
+    def fold(self, hidden, pending):
+        check(lib().b200_decoder_fold(self.handle, ptr(hidden), ptr(pending), hidden.shape[0], stream()))
+
+    def lm_head_topk_sample(self, hidden, final_gamma, lm_head, bufs, k, step, end_id):
+        """bufs: dict(logits[B,V] f32, tmp_ids, tmp_vals, topk_ids, topk_vals, seq_len, finished(uint8), output_id)."""
+        vocab = lm_head.shape[0]
+        g = bufs.get
+        check(lib().b200_lm_head_topk_sample(self.handle, ptr(hidden), ptr(final_gamma), ptr(lm_head), vocab, ptr(bufs["logits"]),
+                                             ptr(g("tmp_ids")), ptr(g("tmp_vals")), ptr(g("topk_ids")), ptr(g("topk_vals")),
+                                             ptr(g("seq_len")), ptr(g("finished")), ptr(g("output_id")), hidden.shape[0], k, step, end_id,
+                                             stream()))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().b200_decoder_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

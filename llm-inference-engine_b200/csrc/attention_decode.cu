@@ -1,0 +1,442 @@
+// attention_decode.cu -- decode-time RoPE and masked multi-head attention over the KV cache for sm_100a.
+//
+// Reference semantics: src/kernels/rope.cu:4-43 (+ rope_utils.cuh:6-19) and
+// src/kernels/decoder_self_attention.cu:56-188 (bias after RoPE, K/V appended at step-1, logits q.k*rsqrt(d),
+// softmax with +1e-6 in the denominator and the max-with-0 quirk when step < head_size, P.V).
+//
+// B200 design (HBM-bound: the K and V rows of [0, step) are read exactly once):
+//   * split-KV ("flash-decoding"): grid = (splits, Hkv, B) so that B*Hkv = 32 still fills 148 SMs; every CTA
+//     serves ALL q heads of its kv head (GQA: K/V rows are loaded once per group, not once per q head);
+//   * a K/V row of 128 elements is 16 lanes x 16 bytes (16-bit) or 32 lanes x 16 bytes (fp32): 128-bit coalesced
+//     loads, 4 rows in flight per lane, warp-shuffle dot products;
+//   * RoPE + bias + cache append of the new token are fused here (the new K/V row never round-trips through HBM
+//     before being used);
+//   * partial (max, sum, out) per split go to scratch; the last CTA of a (b, kv head) -- elected with a
+//     self-resetting ticket -- merges them in split order (deterministic) and applies the reference's final
+//     normalisation.
+#include "attention_decode.cuh"
+
+namespace b200 {
+
+// theta denominators exactly as the reference computes them on the host side of its unit tests:
+// powf(base, zid / rot_dim) with a correctly rounded result (the device powf may be 4 ulp off, which at
+// position ~1000 moves cos/sin by 1e-4).
+__device__ __forceinline__ float rope_denominator(float base, int zid, int rot_dim) {
+    const float e = (float)zid / (float)rot_dim;
+    return (float)pow((double)base, (double)e);
+}
+__device__ __forceinline__ void rope_rotate(float &x0, float &x1, float pos, float denom) {
+    const float th = pos / denom;
+    const float c = cosf(th), s = sinf(th);
+    const float a = x0, b = x1;
+    x0 = a * c - b * s;
+    x1 = b * c + a * s;
+}
+
+// ------------------------------------------------------------------ standalone decode RoPE (launchRope)
+template <typename T>
+__global__ void rope_decode_kernel(T *qkv, int head_num, int kv_head_num, int head_size, int step, int rot_dim, float base) {
+    const int b = blockIdx.y, h = blockIdx.x;  // h over q heads then k heads
+    T *p = qkv + ((size_t)b * (head_num + 2 * kv_head_num) + h) * head_size;
+    pdl_wait();
+    for (int i = threadIdx.x; i < rot_dim / 2; i += blockDim.x) {
+        float x0 = Elem<T>::to_f(p[i]), x1 = Elem<T>::to_f(p[i + head_size / 2]);
+        rope_rotate(x0, x1, (float)(step - 1), rope_denominator(base, 2 * i, rot_dim));
+        p[i] = Elem<T>::from_f(x0);
+        p[i + head_size / 2] = Elem<T>::from_f(x1);
+    }
+}
+
+// ------------------------------------------------------------------ fused split-KV decode attention, head_size 128
+constexpr int kAttnThreads = 128;
+constexpr int kAttnD = 128;
+
+template <typename T> __device__ __forceinline__ float round_t(float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); }
+
+// final normalisation shared by the single-split path and the merge: reference decoder_self_attention.cu:145-165
+__device__ __forceinline__ float final_max(float m, int step, int head_size) { return (step < head_size && m < 0.0f) ? 0.0f : m; }
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kAttnThreads)
+decode_attn_kernel(const DecodeAttnArgs a) {
+    constexpr int D = kAttnD;
+    constexpr int V = Elem<T>::kVec;          // elements per 16-byte vector
+    constexpr int LPR = D / V;                // lanes per K/V row: 16 (16-bit) or 32 (fp32)
+    constexpr int RG = kAttnThreads / LPR;    // row groups per CTA: 8 or 4
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *qs = reinterpret_cast<float *>(smem_raw);   // [G][D]
+    float *knew = qs + G * D;                          // [D]
+    float *vnew = knew + D;                            // [D]
+    float *ms = vnew + D;                              // [G] chunk max, [G] chunk sum
+    float *ls = ms + 2 * G;                            // [G][chunk]
+    float *red = ls + G * a.chunk;                     // [RG][G][D]
+    __shared__ bool is_last;
+
+    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int H = a.head_num, Hkv = a.kv_head_num;
+    const int qkv_heads = H + 2 * Hkv;
+    const int step = a.step;
+    const int p0 = split * a.chunk, p1 = min(step, p0 + a.chunk);
+    const bool has_new = p1 == step;  // this CTA owns position step-1 (the token being appended)
+    const T *qkv = reinterpret_cast<const T *>(a.qkv) + (size_t)b * qkv_heads * D;
+    const T *bias = reinterpret_cast<const T *>(a.bias);
+    T *kc = reinterpret_cast<T *>(a.k_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
+    T *vc = reinterpret_cast<T *>(a.v_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
+
+    pdl_wait();
+
+    // ---- q (all G heads of the group), and the new k / v row: RoPE at step-1, then bias (reference order)
+    for (int i = tid; i < (G + 1) * (D / 2); i += kAttnThreads) {
+        const int g = i / (D / 2), j = i % (D / 2);  // g == G: the k head
+        if (g == G && !has_new) continue;
+        const int head = g < G ? kvh * G + g : H + kvh;
+        float x0 = Elem<T>::to_f(qkv[(size_t)head * D + j]), x1 = Elem<T>::to_f(qkv[(size_t)head * D + j + D / 2]);
+        if (a.apply_rope && j < a.rot_dim / 2) {
+            rope_rotate(x0, x1, (float)(step - 1), rope_denominator(a.rot_base, 2 * j, a.rot_dim));
+            x0 = round_t<T>(x0), x1 = round_t<T>(x1);  // launchRope writes T back before the MHA kernel reads it
+        }
+        if (bias) {
+            x0 = round_t<T>(x0 + Elem<T>::to_f(bias[(size_t)head * D + j]));
+            x1 = round_t<T>(x1 + Elem<T>::to_f(bias[(size_t)head * D + j + D / 2]));
+        }
+        float *dst = g < G ? qs + g * D : knew;
+        dst[j] = x0;
+        dst[j + D / 2] = x1;
+    }
+    if (has_new) {
+        for (int j = tid; j < D; j += kAttnThreads) {
+            const int head = H + Hkv + kvh;
+            float v = Elem<T>::to_f(qkv[(size_t)head * D + j]);
+            if (bias) v = round_t<T>(v + Elem<T>::to_f(bias[(size_t)head * D + j]));
+            vnew[j] = v;
+        }
+    }
+    __syncthreads();
+    if (has_new) {  // cache append (decoder_self_attention.cu:126,172)
+        for (int j = tid; j < D; j += kAttnThreads) {
+            kc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(knew[j]);
+            vc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(vnew[j]);
+        }
+    }
+    pdl_launch_dependents();
+
+    const int rg = tid / LPR, l = tid % LPR;
+    // shuffles run among the LPR lanes of one row only: the two rows of a warp (16-bit types) may diverge at the chunk tail
+    const unsigned row_mask = LPR == 32 ? 0xffffffffu : (0xffffu << (tid & 16));
+    const float scale = rsqrtf((float)D);
+    // this lane's slice of every q head
+    float qf[G][V];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < V; ++e) qf[g][e] = qs[g * D + l * V + e];
+
+    // ---- logits for positions [p0, p1)
+    constexpr int U = 4;
+    for (int pb = p0 + rg; pb < p1; pb += RG * U) {
+        uint4 kv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * RG;
+            kv[u] = make_uint4(0, 0, 0, 0);
+            if (p < p1 && p != step - 1) kv[u] = ld_stream_v4(kc + (size_t)p * D + l * V);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * RG;
+            if (p < p1) {  // uniform across the LPR lanes of a row
+                float kf[V];
+                if (p == step - 1) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) kf[e] = knew[l * V + e];
+                } else {
+                    unpack16<T>(kv[u], kf);
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < V; ++e) s = fmaf(qf[g][e], kf[e], s);
+#pragma unroll
+                    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(row_mask, s, o);
+                    if (l == 0) ls[g * a.chunk + (p - p0)] = s * scale;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- chunk softmax statistics: one warp per q head
+    {
+        const int warp = tid >> 5, lane = tid & 31, n = p1 - p0;
+        for (int g = warp; g < G; g += kAttnThreads / 32) {
+            float m = -INFINITY;
+            for (int j = lane; j < n; j += 32) m = fmaxf(m, ls[g * a.chunk + j]);
+            m = warp_max(m);
+            float s = 0.0f;
+            for (int j = lane; j < n; j += 32) {
+                const float e = expf(ls[g * a.chunk + j] - m);
+                ls[g * a.chunk + j] = e;
+                s += e;
+            }
+            s = warp_sum(s);
+            if (lane == 0) ms[g] = m, ms[G + g] = s;
+        }
+    }
+    __syncthreads();
+
+    // ---- P.V over the chunk
+    float of[G][V];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < V; ++e) of[g][e] = 0.0f;
+    for (int pb = p0 + rg; pb < p1; pb += RG * U) {
+        uint4 vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * RG;
+            vv[u] = make_uint4(0, 0, 0, 0);
+            if (p < p1 && p != step - 1) vv[u] = ld_stream_v4(vc + (size_t)p * D + l * V);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * RG;
+            if (p < p1) {
+                float vf[V];
+                if (p == step - 1) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) vf[e] = vnew[l * V + e];
+                } else {
+                    unpack16<T>(vv[u], vf);
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float pw = ls[g * a.chunk + (p - p0)];
+#pragma unroll
+                    for (int e = 0; e < V; ++e) of[g][e] = fmaf(pw, vf[e], of[g][e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < V; ++e) red[((size_t)rg * G + g) * D + l * V + e] = of[g][e];
+    __syncthreads();
+
+    // ---- reduce the row groups; single split: finish here, else publish the partial
+    float *part = a.partials + (((size_t)b * Hkv + kvh) * a.nsplit + split) * (size_t)G * (D + 2);
+    T *out = reinterpret_cast<T *>(a.out) + ((size_t)b * H + (size_t)kvh * G) * D;
+    for (int i = tid; i < G * D; i += kAttnThreads) {
+        const int g = i / D, d = i % D;
+        float o = 0.0f;
+#pragma unroll
+        for (int r = 0; r < RG; ++r) o += red[((size_t)r * G + g) * D + d];
+        if (a.nsplit == 1) {
+            const float m = ms[g], mf = final_max(m, step, D), c = expf(m - mf);
+            out[(size_t)g * D + d] = Elem<T>::from_f(o * c / (ms[G + g] * c + 1e-6f));
+        } else {
+            part[(size_t)g * (D + 2) + d] = o;
+        }
+    }
+    if (a.nsplit == 1) return;
+    if (tid < G) {
+        part[(size_t)tid * (D + 2) + D] = ms[tid];
+        part[(size_t)tid * (D + 2) + D + 1] = ms[G + tid];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicInc(&a.tickets[b * Hkv + kvh], a.nsplit - 1) == (unsigned)(a.nsplit - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // ---- merge the splits in order (deterministic)
+    const float *pbase = a.partials + ((size_t)b * Hkv + kvh) * a.nsplit * (size_t)G * (D + 2);
+    for (int i = tid; i < G * D; i += kAttnThreads) {
+        const int g = i / D, d = i % D;
+        float m = -INFINITY;
+        for (int s = 0; s < a.nsplit; ++s) m = fmaxf(m, __ldcg(pbase + ((size_t)s * G + g) * (D + 2) + D));
+        m = final_max(m, step, D);
+        float sum = 0.0f, o = 0.0f;
+        for (int s = 0; s < a.nsplit; ++s) {
+            const float *ps = pbase + ((size_t)s * G + g) * (D + 2);
+            const float c = expf(__ldcg(ps + D) - m);
+            sum = fmaf(__ldcg(ps + D + 1), c, sum);
+            o = fmaf(__ldcg(ps + d), c, o);
+        }
+        out[(size_t)g * D + d] = Elem<T>::from_f(o / (sum + 1e-6f));
+    }
+}
+
+// ------------------------------------------------------------------ any head size (toy shapes of the reference's examples)
+template <typename T>
+__global__ void decode_attn_generic_kernel(const DecodeAttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.head_size;
+    float *q = reinterpret_cast<float *>(smem_raw);  // [D]
+    float *knew = q + D, *vnew = knew + D;           // [D] each
+    float *ls = vnew + D;                            // [step]
+    __shared__ float red[33];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int H = a.head_num, Hkv = a.kv_head_num, rep = H / Hkv, kvh = h / rep;
+    const int step = a.step;
+    const T *qkv = reinterpret_cast<const T *>(a.qkv) + (size_t)b * (H + 2 * Hkv) * D;
+    const T *bias = reinterpret_cast<const T *>(a.bias);
+    T *kc = reinterpret_cast<T *>(a.k_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
+    T *vc = reinterpret_cast<T *>(a.v_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
+    pdl_wait();
+    for (int j = tid; j < D; j += blockDim.x) {
+        const int half = D / 2;
+        const int qh = h, kh = H + kvh, vh = H + Hkv + kvh;
+        float qv = Elem<T>::to_f(qkv[(size_t)qh * D + j]), kv = Elem<T>::to_f(qkv[(size_t)kh * D + j]);
+        if (a.apply_rope && (j % half) < a.rot_dim / 2 && j < 2 * half) {
+            const int i = j % half;
+            const float den = rope_denominator(a.rot_base, 2 * i, a.rot_dim), pos = (float)(step - 1);
+            float q0 = Elem<T>::to_f(qkv[(size_t)qh * D + i]), q1 = Elem<T>::to_f(qkv[(size_t)qh * D + i + half]);
+            float k0 = Elem<T>::to_f(qkv[(size_t)kh * D + i]), k1 = Elem<T>::to_f(qkv[(size_t)kh * D + i + half]);
+            rope_rotate(q0, q1, pos, den);
+            rope_rotate(k0, k1, pos, den);
+            qv = round_t<T>(j < half ? q0 : q1);
+            kv = round_t<T>(j < half ? k0 : k1);
+        }
+        float vv = Elem<T>::to_f(qkv[(size_t)vh * D + j]);
+        if (bias) {
+            qv = round_t<T>(qv + Elem<T>::to_f(bias[(size_t)qh * D + j]));
+            kv = round_t<T>(kv + Elem<T>::to_f(bias[(size_t)kh * D + j]));
+            vv = round_t<T>(vv + Elem<T>::to_f(bias[(size_t)vh * D + j]));
+        }
+        q[j] = qv, knew[j] = kv, vnew[j] = vv;
+        if (h % rep == 0) {
+            kc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(kv);
+            vc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(vv);
+        }
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)D);
+    float m = -INFINITY;
+    for (int p = tid; p < step; p += blockDim.x) {
+        float s = 0.0f;
+        for (int j = 0; j < D; ++j) s = fmaf(q[j], p == step - 1 ? knew[j] : Elem<T>::to_f(kc[(size_t)p * D + j]), s);
+        s *= scale;
+        ls[p] = s;
+        m = fmaxf(m, s);
+    }
+    m = final_max(block_max(m, red), step, D);
+    float sum = 0.0f;
+    for (int p = tid; p < step; p += blockDim.x) {
+        const float e = expf(ls[p] - m);
+        ls[p] = e;
+        sum += e;
+    }
+    sum = block_sum(sum, red) + 1e-6f;
+    T *out = reinterpret_cast<T *>(a.out) + ((size_t)b * H + h) * D;
+    for (int j = tid; j < D; j += blockDim.x) {
+        float o = 0.0f;
+        for (int p = 0; p < step; ++p) o = fmaf(ls[p], p == step - 1 ? vnew[j] : Elem<T>::to_f(vc[(size_t)p * D + j]), o);
+        out[j] = Elem<T>::from_f(o / sum);
+    }
+}
+
+size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int head_size, int max_splits) {
+    return (size_t)batch * kv_head_num * max_splits * (head_num / kv_head_num) * (head_size + 2);
+}
+
+int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk) {
+    // enough CTAs for ~4 per SM, chunks of 32..256 positions
+    int want = (4 * sm_count() + batch * kv_head_num - 1) / (batch * kv_head_num);
+    int c = (step + want - 1) / want;
+    if (c < 32) c = 32;
+    if (c > 256) c = 256;
+    c = (c + 7) & ~7;
+    *chunk = c;
+    return (step + c - 1) / c;
+}
+
+template <typename T>
+static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
+    const int G = a.head_num / a.kv_head_num;
+    const bool fast = a.head_size == kAttnD && (G == 1 || G == 2 || G == 4 || G == 8) && aligned16(a.k_cache) && aligned16(a.v_cache);
+    if (fast) {
+        const int RG = kAttnThreads / (kAttnD / Elem<T>::kVec);
+        const size_t smem = sizeof(float) * ((size_t)G * kAttnD + 2 * kAttnD + 2 * G + (size_t)G * a.chunk + (size_t)RG * G * kAttnD);
+        dim3 grid(a.nsplit, a.kv_head_num, a.batch);
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_pdl(kern, grid, dim3(kAttnThreads), smem, st, true, a);
+        };
+        switch (G) {
+            case 1: go(decode_attn_kernel<T, 1>); break;
+            case 2: go(decode_attn_kernel<T, 2>); break;
+            case 4: go(decode_attn_kernel<T, 4>); break;
+            default: go(decode_attn_kernel<T, 8>); break;
+        }
+        return cuda_status("decode_attn launch");
+    }
+    const size_t smem = sizeof(float) * ((size_t)3 * a.head_size + a.step);
+    if (smem > 200 * 1024) {
+        set_error("decode_mha: step %d too long for the generic head-size path", a.step);
+        return B200_ERR_UNSUPPORTED;
+    }
+    cudaFuncSetAttribute(decode_attn_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_pdl(decode_attn_generic_kernel<T>, dim3(a.head_num, a.batch), dim3(128), smem, st, true, a);
+    return cuda_status("decode_attn_generic launch");
+}
+
+int launch_decode_attn(const DecodeAttnArgs &a, int dtype, cudaStream_t st) {
+    B200_DISPATCH_DTYPE(dtype, return launch_decode_attn_t<T>(a, st));
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_rope_decode(void *qkv, int batch, int head_num, int kv_head_num, int head_size, int step, int rotary_dim,
+                     float rotary_base, int dtype, b200_stream_t stream) {
+    B200_REQUIRE(qkv, "rope_decode: null qkv");
+    B200_REQUIRE(batch >= 0 && head_num > 0 && kv_head_num > 0 && head_size > 0 && step >= 1, "rope_decode: bad shape");
+    B200_REQUIRE(rotary_dim >= 0 && rotary_dim <= head_size && rotary_dim % 2 == 0, "rope_decode: bad rotary_dim %d", rotary_dim);
+    if (batch == 0 || rotary_dim == 0) return B200_OK;
+    dim3 grid(head_num + kv_head_num, batch);
+    B200_DISPATCH_DTYPE(dtype, launch_pdl(rope_decode_kernel<T>, grid, dim3(64), 0, as_stream(stream), true, (T *)qkv, head_num,
+                                          kv_head_num, head_size, step, rotary_dim, rotary_base));
+    return cuda_status("rope_decode launch");
+}
+
+int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const uint8_t *finished,
+                    int batch, int head_num, int kv_head_num, int head_size, int max_seq_len, int step, int layer,
+                    int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
+    (void)finished;  // unused by the reference kernel as well
+    B200_REQUIRE(qkv && k_cache && v_cache && out, "decode_mha: null pointer");
+    B200_REQUIRE(batch >= 0 && head_num > 0 && kv_head_num > 0 && head_size > 0, "decode_mha: bad shape");
+    B200_REQUIRE(head_num % kv_head_num == 0, "decode_mha: head_num %d not a multiple of kv_head_num %d", head_num, kv_head_num);
+    B200_REQUIRE(step >= 1 && step <= max_seq_len, "decode_mha: step %d outside [1, max_seq_len=%d]", step, max_seq_len);
+    B200_REQUIRE(layer >= 0, "decode_mha: negative layer");
+    B200_REQUIRE(!apply_rope || (rotary_dim >= 0 && rotary_dim <= head_size && rotary_dim % 2 == 0), "decode_mha: bad rotary_dim");
+    if (batch == 0) return B200_OK;
+    Workspace ws;
+    if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
+    const size_t eb = dtype == B200_F32 ? 4 : 2;
+    const size_t layer_off = (size_t)layer * batch * kv_head_num * max_seq_len * head_size * eb;
+    DecodeAttnArgs a = {};
+    a.qkv = qkv, a.bias = qkv_bias;
+    a.k_cache = (char *)k_cache + layer_off, a.v_cache = (char *)v_cache + layer_off;
+    a.out = out;
+    a.batch = batch, a.head_num = head_num, a.kv_head_num = kv_head_num, a.head_size = head_size;
+    a.max_seq_len = max_seq_len, a.step = step;
+    a.apply_rope = apply_rope, a.rot_dim = rotary_dim, a.rot_base = rotary_base;
+    a.nsplit = decode_attn_plan(batch, kv_head_num, step, &a.chunk);
+    a.partials = reinterpret_cast<float *>(ws.scratch);
+    a.tickets = ws.tickets;
+    B200_REQUIRE((size_t)batch * kv_head_num <= ws.n_tickets, "decode_mha: batch*kv_head_num exceeds the ticket pool");
+    B200_REQUIRE(decode_attn_partials_floats(batch, head_num, kv_head_num, head_size, a.nsplit) * 4 <= ws.scratch_bytes,
+                 "decode_mha: library workspace too small for %d splits", a.nsplit);
+    return launch_decode_attn(a, dtype, as_stream(stream));
+}
+
+}  // extern "C"

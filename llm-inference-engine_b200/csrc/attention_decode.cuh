@@ -1,0 +1,26 @@
+// attention_decode.cuh -- internal interface of the fused decode attention (used by the C ABI entry and the engine).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct DecodeAttnArgs {
+    const void *qkv;   // [B, H+2Hkv, d]
+    const void *bias;  // [(H+2Hkv)*d] or NULL
+    void *k_cache;     // layer base: [B, Hkv, S, d]
+    void *v_cache;
+    void *out;         // [B, H*d]
+    float *partials;   // [B*Hkv][nsplit][G][d+2]
+    unsigned int *tickets;  // [B*Hkv], zero-initialised, self-resetting
+    int batch, head_num, kv_head_num, head_size, max_seq_len, step;
+    int apply_rope, rot_dim;
+    float rot_base;
+    int nsplit, chunk;
+};
+
+// number of KV splits (and positions per split) for a decode step
+int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk);
+size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int head_size, int max_splits);
+int launch_decode_attn(const DecodeAttnArgs &a, int dtype, cudaStream_t st);
+
+}  // namespace b200

@@ -40,6 +40,11 @@ struct Workspace {
 // Returns false (and sets the error) if no workspace is available.
 bool get_workspace(Workspace *ws);
 
+// out = gamma * (o + bias) * rsqrt(mean((o+bias)^2)+eps), o = in (+ rin); rout <- o.  in == NULL: in place on out.
+// gamma == NULL: out = o + bias.  (norm.cu)
+int launch_norm_any(int dtype, const void *in, void *out, const void *rin, void *rout, const void *bias, const void *gamma,
+                    float eps, int tokens, int hidden, cudaStream_t st);
+
 // Launch with the programmatic-dependent-launch attribute so that the prologue of kernel i+1
 // (weight prefetch, smem carve-up) overlaps the tail of kernel i.  Kernels call pdl_wait() before
 // touching anything the previous kernel wrote and pdl_launch_dependents() as early as they can.

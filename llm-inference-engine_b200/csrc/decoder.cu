@@ -1,0 +1,317 @@
+// decoder.cu -- the fused decode engine: LlamaSelfDecoder<T>::forward (reference src/layers/self_decoder.cpp:24-122,
+// self_attention.cpp:63-151, ffn.cpp:76-144) and the sampling tail (src/models/llama/llama.cpp:247-311) as a
+// stream-ordered, allocation-free, sync-free, CUDA-graph-capturable launch sequence.
+//
+// Per layer (batch <= 4: five launches, all chained with programmatic dependent launch):
+//   1. gemv  Wqkv   prologue: fold the pending FFN output into the residual stream + RMSNorm(gamma1)
+//   2. attn         RoPE + qkv bias + KV append + split-KV attention + merge
+//   3. gemv  Wo
+//   4. gemv  Wgu    prologue: residual += attn out; (+ o bias); RMSNorm(gamma2);  epilogue: SwiGLU
+//   5. gemv  Wdown
+// For batch > 4 the same dataflow runs un-fused: norm kernel -> b200_linear (tensor-core GEMM) -> ...
+// The residual stream lives in two engine-owned ping-pong buffers so that no kernel writes a tensor another CTA of
+// the same kernel still reads.
+#include "attention_decode.cuh"
+#include "gemv.cuh"
+
+#include <new>
+#include <vector>
+
+struct b200_decoder {
+    b200_decoder_config_t cfg;
+    std::vector<b200_layer_weights_t> layers;
+    std::vector<char> layer_set;
+    // scratch carve-up
+    char *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *res[2] = {nullptr, nullptr};
+    void *xn = nullptr;      // normalised activations (un-fused path)
+    void *qkv = nullptr, *attn = nullptr, *y_attn = nullptr, *gu = nullptr, *act = nullptr, *y_ffn = nullptr;
+    float *partials = nullptr;
+    unsigned int *tickets = nullptr;
+    int max_splits = 0;
+    int cur = 0;  // which res[] holds the residual stream
+};
+
+namespace b200 {
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t esize(int dtype) { return dtype == B200_F32 ? 4 : 2; }
+
+struct Carve {
+    size_t res, xn, qkv, attn, y, gu, act, partials, tickets, total;
+};
+static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
+    Carve k;
+    const size_t e = esize(c.dtype), B = c.max_batch;
+    k.res = align_up(B * c.hidden * e);
+    k.xn = align_up(B * (size_t)(c.hidden > c.inter_size ? c.hidden : c.inter_size) * e);
+    k.qkv = align_up(B * (size_t)(c.head_num + 2 * c.kv_head_num) * c.head_size * e);
+    k.attn = align_up(B * (size_t)c.head_num * c.head_size * e);
+    k.y = align_up(B * c.hidden * e);
+    k.gu = align_up(B * (size_t)2 * c.inter_size * e);
+    k.act = align_up(B * (size_t)c.inter_size * e);
+    // worst case number of KV splits: chunk >= 32 positions
+    *max_splits = (c.max_seq_len + 31) / 32;
+    k.partials = align_up(decode_attn_partials_floats(c.max_batch, c.head_num, c.kv_head_num, c.head_size, *max_splits) * sizeof(float));
+    k.tickets = align_up((size_t)c.max_batch * c.kv_head_num * sizeof(unsigned int));
+    k.total = 2 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets;
+    return k;
+}
+
+// prologue (add residual / bias / RMSNorm) + linear (+ SwiGLU): fused GEMV for M <= 4, un-fused otherwise
+static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void *res_out, const void *bias, const void *gamma,
+                       const b200_linear_weight_t &w, int K, int N, bool swiglu, void *y, int M, cudaStream_t st) {
+    const b200_decoder_config_t &c = d->cfg;
+    if (M <= 4) {
+        GemvArgs a = {};
+        a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
+        a.x = x, a.y = y;
+        a.res_in = res_in, a.res_out = res_out, a.bias = bias, a.gamma = gamma, a.eps = c.rmsnorm_eps, a.norm = 1;
+        a.M = M, a.K = K, a.N = N, a.group = c.group, a.inter = swiglu ? N / 2 : 0;
+        const int rc = launch_gemv_nk(a, c.dtype, c.w_format, swiglu, st);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+    int rc = launch_norm_any(c.dtype, x, d->xn, res_in, res_out, bias, gamma, c.rmsnorm_eps, M, K, st);
+    if (rc != B200_OK) return rc;
+    if (!swiglu) return b200_linear(d->xn, w.w, w.scales, w.zeros, y, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
+    rc = b200_linear(d->xn, w.w, w.scales, w.zeros, d->gu, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
+    if (rc != B200_OK) return rc;
+    return b200_silu_and_mul(d->gu, y, M, N / 2, c.dtype, st);
+}
+
+static int plain_linear(b200_decoder *d, const void *x, const b200_linear_weight_t &w, int K, int N, void *y, int M, cudaStream_t st) {
+    const b200_decoder_config_t &c = d->cfg;
+    if (M <= 4) {
+        GemvArgs a = {};
+        a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
+        a.x = x, a.y = y;
+        a.M = M, a.K = K, a.N = N, a.group = c.group;
+        const int rc = launch_gemv_nk(a, c.dtype, c.w_format, false, st);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+    return b200_linear(x, w.w, w.scales, w.zeros, y, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
+}
+
+template <typename T>
+__global__ void fold_kernel(T *out, const T *a, const T *b, size_t n) {
+    pdl_wait();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = Elem<T>::from_f(Elem<T>::to_f(a[i]) + (b ? Elem<T>::to_f(b[i]) : 0.0f));
+}
+
+static int check_ready(const b200_decoder *d, int batch) {
+    if (!d) {
+        set_error("decoder: null handle");
+        return B200_ERR_INVALID_ARG;
+    }
+    if (!d->scratch) {
+        set_error("decoder: scratch not set (b200_decoder_set_scratch)");
+        return B200_ERR_STATE;
+    }
+    if (batch < 1 || batch > d->cfg.max_batch) {
+        set_error("decoder: batch %d outside [1, %d]", batch, d->cfg.max_batch);
+        return B200_ERR_INVALID_ARG;
+    }
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+b200_decoder_t *b200_decoder_create(const b200_decoder_config_t *cfg) {
+    if (!cfg) {
+        set_error("decoder_create: null config");
+        return nullptr;
+    }
+    const b200_decoder_config_t &c = *cfg;
+    if (c.hidden <= 0 || c.head_num <= 0 || c.kv_head_num <= 0 || c.head_size <= 0 || c.inter_size <= 0 || c.num_layers <= 0 ||
+        c.max_seq_len <= 0 || c.max_batch <= 0 || c.head_num % c.kv_head_num != 0) {
+        set_error("decoder_create: bad model shape");
+        return nullptr;
+    }
+    if (c.dtype != B200_F32 && c.dtype != B200_F16 && c.dtype != B200_BF16) {
+        set_error("decoder_create: unknown dtype %d", c.dtype);
+        return nullptr;
+    }
+    if (c.w_format < B200_W_DENSE || c.w_format > B200_W_INT4 || (c.w_format != B200_W_DENSE && c.dtype == B200_F32)) {
+        set_error("decoder_create: weight format %d not available for dtype %d", c.w_format, c.dtype);
+        return nullptr;
+    }
+    if (c.w_format == B200_W_INT4 && (c.group < 32 || c.group % 32 != 0 || c.hidden % c.group != 0 || c.inter_size % c.group != 0 ||
+                                     (c.head_num * c.head_size) % c.group != 0)) {
+        set_error("decoder_create: INT4 group %d must divide every K dimension", c.group);
+        return nullptr;
+    }
+    b200_decoder *d = new (std::nothrow) b200_decoder();
+    if (!d) return nullptr;
+    d->cfg = c;
+    d->layers.resize(c.num_layers);
+    d->layer_set.assign(c.num_layers, 0);
+    return d;
+}
+
+void b200_decoder_destroy(b200_decoder_t *dec) { delete dec; }
+
+int b200_decoder_set_layer(b200_decoder_t *dec, int layer, const b200_layer_weights_t *w) {
+    B200_REQUIRE(dec && w, "decoder_set_layer: null argument");
+    B200_REQUIRE(layer >= 0 && layer < dec->cfg.num_layers, "decoder_set_layer: layer %d out of range", layer);
+    B200_REQUIRE(w->attn_norm_gamma && w->ffn_norm_gamma && w->qkv.w && w->o.w && w->gate_up.w && w->down.w,
+                 "decoder_set_layer: missing weight pointer");
+    if (dec->cfg.w_format != B200_W_DENSE)
+        B200_REQUIRE(w->qkv.scales && w->o.scales && w->gate_up.scales && w->down.scales, "decoder_set_layer: missing scales");
+    if (dec->cfg.w_format == B200_W_INT4)
+        B200_REQUIRE(w->qkv.zeros && w->o.zeros && w->gate_up.zeros && w->down.zeros, "decoder_set_layer: missing zero points");
+    dec->layers[layer] = *w;
+    dec->layer_set[layer] = 1;
+    return B200_OK;
+}
+
+size_t b200_decoder_scratch_bytes(const b200_decoder_t *dec) {
+    if (!dec) return 0;
+    int ms;
+    return carve(dec->cfg, &ms).total;
+}
+
+int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
+    B200_REQUIRE(dec && ptr, "decoder_set_scratch: null argument");
+    B200_REQUIRE(aligned16(ptr) && ((uintptr_t)ptr & 255) == 0, "decoder_set_scratch: pointer must be 256-byte aligned");
+    int ms;
+    const Carve k = carve(dec->cfg, &ms);
+    B200_REQUIRE(bytes >= k.total, "decoder_set_scratch: need %zu bytes, got %zu", k.total, bytes);
+    char *p = (char *)ptr;
+    dec->scratch = p, dec->scratch_bytes = bytes, dec->max_splits = ms;
+    dec->res[0] = p, p += k.res;
+    dec->res[1] = p, p += k.res;
+    dec->xn = p, p += k.xn;
+    dec->qkv = p, p += k.qkv;
+    dec->attn = p, p += k.attn;
+    dec->y_attn = p, p += k.y;
+    dec->y_ffn = p, p += k.y;
+    dec->gu = p, p += k.gu;
+    dec->act = p, p += k.act;
+    dec->partials = (float *)p, p += k.partials;
+    dec->tickets = (unsigned int *)p;
+    if (cudaMemset(dec->tickets, 0, k.tickets) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
+    dec->cur = 0;
+    return B200_OK;
+}
+
+int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache,
+                            void *partial, int batch, int step, b200_stream_t stream) {
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    const b200_decoder_config_t &c = dec->cfg;
+    B200_REQUIRE(layer >= 0 && layer < c.num_layers && dec->layer_set[layer], "decoder: layer %d not set", layer);
+    B200_REQUIRE(k_cache && v_cache && partial, "decoder_attn_block: null pointer");
+    B200_REQUIRE(pending || hidden, "decoder_attn_block: need `hidden` (first block) or `pending`");
+    B200_REQUIRE(step >= 1 && step <= c.max_seq_len, "decoder: step %d outside [1, %d]", step, c.max_seq_len);
+    cudaStream_t st = as_stream(stream);
+    const b200_layer_weights_t &w = dec->layers[layer];
+    const int qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size;
+    // 1. residual fold + RMSNorm + QKV
+    void *res_out = dec->res[dec->cur ^ 1];
+    rc = norm_linear(dec, pending ? pending : hidden, pending ? dec->res[dec->cur] : nullptr, res_out, nullptr, w.attn_norm_gamma, w.qkv,
+                     c.hidden, qkv_n, false, dec->qkv, batch, st);
+    if (rc != B200_OK) return rc;
+    dec->cur ^= 1;
+    // 2. attention
+    DecodeAttnArgs a = {};
+    const size_t layer_off = (size_t)layer * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
+    a.qkv = dec->qkv, a.bias = w.qkv_bias;
+    a.k_cache = (char *)k_cache + layer_off, a.v_cache = (char *)v_cache + layer_off;
+    a.out = dec->attn;
+    a.batch = batch, a.head_num = c.head_num, a.kv_head_num = c.kv_head_num, a.head_size = c.head_size;
+    a.max_seq_len = c.max_seq_len, a.step = step;
+    a.apply_rope = c.rotary_dim > 0, a.rot_dim = c.rotary_dim, a.rot_base = c.rotary_base;
+    a.nsplit = decode_attn_plan(batch, c.kv_head_num, step, &a.chunk);
+    a.partials = dec->partials, a.tickets = dec->tickets;
+    rc = launch_decode_attn(a, c.dtype, st);
+    if (rc != B200_OK) return rc;
+    // 3. O projection (row-sharded under TP: `partial` is this rank's partial sum)
+    return plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, partial, batch, st);
+}
+
+int b200_decoder_ffn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *partial, int batch,
+                           b200_stream_t stream) {
+    (void)hidden;
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    const b200_decoder_config_t &c = dec->cfg;
+    B200_REQUIRE(layer >= 0 && layer < c.num_layers && dec->layer_set[layer], "decoder: layer %d not set", layer);
+    B200_REQUIRE(pending && partial, "decoder_ffn_block: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const b200_layer_weights_t &w = dec->layers[layer];
+    // 4. residual += attention output; + o bias (tp rank 0 semantics: bias is replicated, added after the reduce);
+    //    RMSNorm; gate/up; SwiGLU
+    rc = norm_linear(dec, pending, dec->res[dec->cur], dec->res[dec->cur ^ 1], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
+                     2 * c.inter_size, true, dec->act, batch, st);
+    if (rc != B200_OK) return rc;
+    dec->cur ^= 1;
+    // 5. down projection
+    return plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, partial, batch, st);
+}
+
+int b200_decoder_fold(b200_decoder_t *dec, void *hidden, const void *pending, int batch, b200_stream_t stream) {
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    B200_REQUIRE(hidden, "decoder_fold: null pointer");
+    const size_t n = (size_t)batch * dec->cfg.hidden;
+    const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    B200_DISPATCH_DTYPE(dec->cfg.dtype, launch_pdl(fold_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), true, (T *)hidden,
+                                                   (const T *)dec->res[dec->cur], (const T *)pending, n));
+    return cuda_status("decoder_fold launch");
+}
+
+int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin,
+                      int layer_end, b200_stream_t stream) {
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    B200_REQUIRE(dec->cfg.tp_world <= 1, "decoder_step: tensor-parallel engines drive attn_block / ffn_block themselves");
+    B200_REQUIRE(hidden && k_cache && v_cache, "decoder_step: null pointer");
+    B200_REQUIRE(layer_begin >= 0 && layer_end <= dec->cfg.num_layers && layer_begin < layer_end, "decoder_step: bad layer range");
+    const void *pending = nullptr;
+    for (int l = layer_begin; l < layer_end; ++l) {
+        rc = b200_decoder_attn_block(dec, l, hidden, pending, k_cache, v_cache, dec->y_attn, batch, step, stream);
+        if (rc != B200_OK) return rc;
+        rc = b200_decoder_ffn_block(dec, l, hidden, dec->y_attn, dec->y_ffn, batch, stream);
+        if (rc != B200_OK) return rc;
+        pending = dec->y_ffn;
+    }
+    return b200_decoder_fold(dec, hidden, pending, batch, stream);
+}
+
+int b200_lm_head_topk_sample(b200_decoder_t *dec, const void *hidden, const void *final_gamma, const void *lm_head, int vocab,
+                             float *logits, int *tmp_ids, float *tmp_vals, int *topk_ids, float *topk_vals, int *seq_len,
+                             uint8_t *finished, int *output_id, int batch, int k, int step, int end_id, b200_stream_t stream) {
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    B200_REQUIRE(hidden && final_gamma && lm_head && logits, "lm_head_topk_sample: null pointer");
+    B200_REQUIRE(vocab > 0, "lm_head_topk_sample: bad vocab");
+    const b200_decoder_config_t &c = dec->cfg;
+    cudaStream_t st = as_stream(stream);
+    // final RMSNorm (reference llama.cpp:247-253) fused into the LM-head GEMV; logits in fp32
+    for (int m0 = 0; m0 < batch; m0 += 4) {
+        GemvArgs a = {};
+        a.w = lm_head;
+        a.x = (const char *)hidden + (size_t)m0 * c.hidden * esize(c.dtype);
+        a.y = logits + (size_t)m0 * vocab;
+        a.y_f32 = 1;
+        a.gamma = final_gamma, a.eps = c.rmsnorm_eps, a.norm = 1;
+        a.M = batch - m0 < 4 ? batch - m0 : 4, a.K = c.hidden, a.N = vocab;
+        rc = launch_gemv_nk(a, c.dtype, WF_DENSE, false, st);
+        if (rc == B200_ERR_UNSUPPORTED) set_error("lm_head_topk_sample: hidden size %d not supported by the GEMV", c.hidden);
+        if (rc != B200_OK) return rc;
+    }
+    if (!topk_ids) return B200_OK;  // logits only
+    B200_REQUIRE(tmp_ids && tmp_vals && topk_vals, "lm_head_topk_sample: null top-k buffer");
+    rc = b200_topk(logits, tmp_ids, tmp_vals, topk_ids, topk_vals, batch, vocab, k, B200_F32, stream);
+    if (rc != B200_OK || !output_id) return rc;
+    B200_REQUIRE(seq_len && finished, "lm_head_topk_sample: null sampling buffer");
+    return b200_sampling(topk_ids, topk_vals, seq_len, finished, output_id, batch, k, step, end_id, vocab, B200_F32, stream);
+}
+
+}  // extern "C"

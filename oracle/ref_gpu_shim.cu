@@ -32,7 +32,11 @@ template <typename T> TensorWrapper<T> *gpu(std::vector<int> shape, const T *dat
     return view<T>(Device::GPU, shape, const_cast<T *>(data));
 }
 TensorWrapper<int> *host_int(int v) { return view<int>(Device::CPU, {1}, new int(v)); }
-int sync_status() { return (int)cudaDeviceSynchronize(); }
+int sync_status() {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();  // launch-configuration failures do not show up in the sync
+    return (int)e;
+}
 }  // namespace
 
 #define REF_TRY(...)                        \

@@ -1,0 +1,217 @@
+"""Parity of the fused decode engine (b200_decoder_*) against the CPU oracle's decoder_layer composition
+(reference src/layers/self_decoder.cpp:69-119) on identical seeded inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from util import assert_close, b200, rounded, to_dev, to_np, torch_dtype
+
+
+def make_model(cfg, seed=0, bias=True):
+    """fp32 master weights in the packed [N,K] layout."""
+    rng = np.random.default_rng(seed)
+    h, H, Hkv, d, I, L = cfg["hidden"], cfg["head_num"], cfg["kv_head_num"], cfg["head_size"], cfg["inter"], cfg["layers"]
+    layers = []
+    for _ in range(L):
+        layers.append(dict(
+            g1=(1 + 0.1 * rng.standard_normal(h)).astype(np.float32),
+            wqkv=(rng.standard_normal(((H + 2 * Hkv) * d, h)) / np.sqrt(h)).astype(np.float32),
+            bqkv=(0.05 * rng.standard_normal((H + 2 * Hkv) * d)).astype(np.float32) if bias else None,
+            wo=(rng.standard_normal((h, H * d)) / np.sqrt(H * d)).astype(np.float32),
+            bo=(0.05 * rng.standard_normal(h)).astype(np.float32) if bias else None,
+            g2=(1 + 0.1 * rng.standard_normal(h)).astype(np.float32),
+            wgu=(rng.standard_normal((2 * I, h)) / np.sqrt(h)).astype(np.float32),
+            wd=(rng.standard_normal((h, I)) / np.sqrt(I)).astype(np.float32)))
+    return dict(layers=layers, seed=seed)
+
+
+def make_inputs(cfg, batch, step, seed):
+    rng = np.random.default_rng(seed + 1000)
+    Hkv, d, L, S = cfg["kv_head_num"], cfg["head_size"], cfg["layers"], cfg["max_seq"]
+    x = rng.standard_normal((batch, cfg["hidden"])).astype(np.float32)
+    kc = (0.5 * rng.standard_normal((L, batch, Hkv, S, d))).astype(np.float32)
+    vc = (0.5 * rng.standard_normal((L, batch, Hkv, S, d))).astype(np.float32)
+    kc[:, :, :, step - 1:] = 0
+    vc[:, :, :, step - 1:] = 0
+    return x, kc, vc
+
+
+def run_oracle(model, cfg, dtype, batch, step):
+    x, kc, vc = make_inputs(cfg, batch, step, model["seed"])
+    x, kc, vc = rounded(x, dtype), rounded(kc, dtype), rounded(vc, dtype)
+    ocfg = dict(head_num=cfg["head_num"], kv_head_num=cfg["kv_head_num"], head_size=cfg["head_size"], inter=cfg["inter"],
+                eps=cfg["eps"], rot_dim=cfg["head_size"], base=cfg["base"])
+    for l, w in enumerate(model["layers"]):
+        wr = {k: (None if v is None else rounded(v, dtype)) for k, v in w.items()}
+        oracle.decoder_layer(x, wr, kc, vc, ocfg, step, l)
+    return x, kc, vc
+
+
+def build_decoder(model, cfg, dtype, max_batch, w_format=0, group=128):
+    import torch
+
+    mod = b200()
+    dc = mod.DecoderConfig(cfg["hidden"], cfg["head_num"], cfg["kv_head_num"], cfg["head_size"], cfg["inter"], cfg["layers"],
+                           cfg["max_seq"], max_batch, {"f32": 0, "f16": 1, "bf16": 2}[dtype], w_format, group, cfg["eps"],
+                           cfg["head_size"], cfg["base"], 1, 0)
+    dec = mod.Decoder(dc, torch.device("cuda"))
+    for l, w in enumerate(model["layers"]):
+        def lin(a):
+            t = to_dev(a, dtype)
+            if w_format == mod.W_FP8:
+                return mod.quantize_fp8(t)
+            if w_format == mod.W_INT4:
+                return mod.quantize_int4(t, group)
+            return t
+        dec.set_layer(l, dict(g1=to_dev(w["g1"], dtype), qkv=lin(w["wqkv"]), qkv_bias=None if w["bqkv"] is None else to_dev(w["bqkv"], dtype),
+                              o=lin(w["wo"]), o_bias=None if w["bo"] is None else to_dev(w["bo"], dtype), g2=to_dev(w["g2"], dtype),
+                              gate_up=lin(w["wgu"]), down=lin(w["wd"])))
+    return dec
+
+
+def run_engine(model, cfg, dtype, batch, step, max_batch=None, graph=False):
+    import torch
+
+    dec = build_decoder(model, cfg, dtype, max_batch or batch)
+    x, kc, vc = make_inputs(cfg, batch, step, model["seed"])
+    xd, kcd, vcd = to_dev(x, dtype), to_dev(kc, dtype), to_dev(vc, dtype)
+    if graph:
+        x0 = xd.clone()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            dec.step(xd, kcd, vcd, step)  # warm-up: function attributes, caches
+            torch.cuda.synchronize()
+            xd.copy_(x0)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                dec.step(xd, kcd, vcd, step)
+            xd.copy_(x0)
+            g.replay()
+        torch.cuda.synchronize()
+    else:
+        dec.step(xd, kcd, vcd, step)
+        torch.cuda.synchronize()
+    return to_np(xd), to_np(kcd), to_np(vcd)
+
+
+SMALL = dict(hidden=256, head_num=2, kv_head_num=2, head_size=128, inter=384, layers=3, max_seq=64, eps=1e-6, base=10000.0)
+GQA = dict(hidden=512, head_num=4, kv_head_num=1, head_size=128, inter=640, layers=2, max_seq=300, eps=1e-5, base=10000.0)
+TOY = dict(hidden=32, head_num=4, kv_head_num=2, head_size=8, inter=48, layers=2, max_seq=16, eps=1e-6, base=10000.0)  # examples/cpp/self_decoder_example.cpp:26-36
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("cfg,batch,step", [(SMALL, 1, 9), (SMALL, 3, 40), (GQA, 2, 257), (SMALL, 4, 1), (SMALL, 6, 12), (TOY, 2, 3)])
+def test_engine_matches_oracle(cfg, batch, step, dtype):
+    model = make_model(cfg, seed=11)
+    got, kc, vc = run_engine(model, cfg, dtype, batch, step)
+    ref, rkc, rvc = run_oracle(model, cfg, dtype, batch, step)
+    assert_close(got, ref, dtype, "decoder output")
+    # KV cache: untouched positions bit-exact, appended row within tolerance (bit-exact index)
+    mask = np.ones(kc.shape, bool)
+    mask[:, :, :, step - 1] = False
+    assert np.array_equal(kc[mask], rkc[mask]) and np.array_equal(vc[mask], rvc[mask])
+    assert_close(kc[:, :, :, step - 1], rkc[:, :, :, step - 1], dtype, "appended K row")
+    assert_close(vc[:, :, :, step - 1], rvc[:, :, :, step - 1], dtype, "appended V row")
+
+
+@pytest.mark.gpu
+def test_engine_graph_replay_is_bit_identical_to_eager():
+    model = make_model(SMALL, seed=5)
+    a = run_engine(model, SMALL, "bf16", 2, 17)
+    b = run_engine(model, SMALL, "bf16", 2, 17, graph=True)
+    c = run_engine(model, SMALL, "bf16", 2, 17)
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)  # deterministic: fixed split order, no atomics on data
+
+
+@pytest.mark.gpu
+def test_engine_7b_single_layer_fp32_config0():
+    """BASELINE.json configs[0]: Llama-2-7B single decoder layer, batch 1, seq-1 decode, fp32 random weights."""
+    cfg = dict(hidden=4096, head_num=32, kv_head_num=32, head_size=128, inter=11008, layers=1, max_seq=160, eps=1e-6, base=10000.0)
+    model = make_model(cfg, seed=3, bias=False)
+    oracle.set_threads(oracle.max_threads())
+    for step in (1, 128):
+        got, kc, vc = run_engine(model, cfg, "f32", 1, step)
+        ref, rkc, rvc = run_oracle(model, cfg, "f32", 1, step)
+        assert_close(got, ref, "f32", f"7B layer step {step}")
+    got, _, _ = run_engine(model, cfg, "bf16", 1, 100)
+    ref, _, _ = run_oracle(model, cfg, "bf16", 1, 100)
+    assert_close(got, ref, "bf16", "7B layer bf16")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["fp8", "int4"])
+def test_engine_quantised_weights_vs_oracle_on_dequantised(fmt):
+    import torch
+
+    mod = b200()
+    cfg = SMALL
+    dtype = "bf16"
+    model = make_model(cfg, seed=21)
+    w_format = mod.W_FP8 if fmt == "fp8" else mod.W_INT4
+    dec = build_decoder(model, cfg, dtype, 2, w_format=w_format, group=128)
+    # oracle on the weights the device actually holds (dequantised)
+    deq = dict(layers=[], seed=model["seed"])
+    for l, w in enumerate(model["layers"]):
+        kept = dec._keep[l]
+        def dq(t, K):
+            q, s, z = (list(t) + [None])[:3]
+            return to_np(mod.dequantize(q, s, z, w_format, 128, torch.float32 if False else torch_dtype(dtype), K))
+        deq["layers"].append(dict(w, wqkv=dq(kept["qkv"], cfg["hidden"]), wo=dq(kept["o"], cfg["head_num"] * cfg["head_size"]),
+                                  wgu=dq(kept["gate_up"], cfg["hidden"]), wd=dq(kept["down"], cfg["inter"])))
+    batch, step = 2, 20
+    x, kc, vc = make_inputs(cfg, batch, step, model["seed"])
+    xd, kcd, vcd = to_dev(x, dtype), to_dev(kc, dtype), to_dev(vc, dtype)
+    dec.step(xd, kcd, vcd, step)
+    torch.cuda.synchronize()
+    ref, _, _ = run_oracle(deq, cfg, dtype, batch, step)
+    assert_close(to_np(xd), ref, dtype, f"{fmt} engine vs oracle on dequantised weights")
+    # documented separately: quantisation error against the bf16 model
+    full, _, _ = run_oracle(model, cfg, dtype, batch, step)
+    qerr = np.abs(ref - full).max() / np.abs(full).max()
+    print(f"{fmt}: quantisation error vs bf16 model, max-norm relative: {qerr:.3e}")
+    assert qerr < (0.1 if fmt == "fp8" else 0.3)
+
+
+@pytest.mark.gpu
+def test_lm_head_topk_sampling_tail():
+    import torch
+
+    mod = b200()
+    cfg = SMALL
+    dtype = "bf16"
+    V, B, K, step, end_id = 1000, 3, 5, 7, 2
+    rng = np.random.default_rng(9)
+    model = make_model(cfg, seed=1)
+    dec = build_decoder(model, cfg, dtype, B)
+    hidden = rounded(rng.standard_normal((B, cfg["hidden"])), dtype)
+    gamma = rounded(1 + 0.1 * rng.standard_normal(cfg["hidden"]), dtype)
+    lm = rounded(rng.standard_normal((V, cfg["hidden"])) / 16, dtype)
+    dev = torch.device("cuda")
+    bufs = dict(logits=torch.empty((B, V), dtype=torch.float32, device=dev),
+                tmp_ids=torch.empty((B, 8, K), dtype=torch.int32, device=dev), tmp_vals=torch.empty((B, 8, K), dtype=torch.float32, device=dev),
+                topk_ids=torch.empty((B, K), dtype=torch.int32, device=dev), topk_vals=torch.empty((B, K), dtype=torch.float32, device=dev),
+                seq_len=torch.full((B,), 10, dtype=torch.int32, device=dev), finished=torch.zeros(B, dtype=torch.uint8, device=dev),
+                output_id=torch.empty(B, dtype=torch.int32, device=dev))
+    dec.lm_head_topk_sample(to_dev(hidden, dtype), to_dev(gamma, dtype), to_dev(lm, dtype), bufs, K, step, end_id)
+    torch.cuda.synchronize()
+    # oracle: final RMSNorm (rounded to T, as the un-fused reference stores it) -> LM head -> top-k -> sampling
+    xn = hidden.copy()
+    oracle.rmsnorm(xn, None, gamma, cfg["eps"])
+    xn = rounded(xn, dtype)
+    ref_logits = oracle.linear(xn, lm, "nk")
+    got_logits = to_np(bufs["logits"])
+    assert_close(got_logits, ref_logits, "bf16", "logits")
+    # integer work is bit-exact GIVEN IDENTICAL LOGITS: run the oracle's top-k on the device logits
+    ids, vals = oracle.topk(got_logits, K)
+    assert np.array_equal(to_np(bufs["topk_ids"]), ids)
+    u = to_np(mod.xorwow_uniform(B, step, dev))
+    assert abs(u[0] - oracle.xorwow_uniform_subseq0(step)) == 0.0
+    seq = np.full(B, 10, np.int32)
+    fin = np.zeros(B, bool)
+    out = oracle.sampling(ids, vals.copy(), seq, fin, u, end_id, V)
+    assert np.array_equal(to_np(bufs["output_id"]), out)
+    assert np.array_equal(to_np(bufs["seq_len"]), seq) and np.array_equal(to_np(bufs["finished"]).astype(bool), fin)

@@ -1,0 +1,493 @@
+"""Per-launcher parity: every C-ABI entry point against the CPU oracle on identical seeded inputs (and against the
+reference's own fp32 CUDA kernels, oracle/_ref/libref.so, where those are not defective -- SURVEY.md 2.2).
+Bit-exact for integer / index work, BASELINE.md section 5 tolerances for floating point."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from util import assert_close, b200, rounded, to_dev, to_np, torch_dtype
+
+pytestmark = pytest.mark.gpu
+DTYPES = ["f32", "bf16", "f16"]
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ------------------------------------------------------------------ norms / residual
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tokens,hidden", [(64, 4096), (1, 4096), (3, 8192), (5, 20), (2, 24576), (0, 64)])
+def test_rmsnorm(tokens, hidden, dtype):
+    mod = b200()
+    r = rng(1)
+    x = rounded(r.standard_normal((tokens, hidden)), dtype)
+    gamma = rounded(1 + 0.1 * r.standard_normal(hidden), dtype)
+    xd, resd = to_dev(x, dtype), to_dev(np.zeros_like(x), dtype)
+    mod.rmsnorm(xd, resd, to_dev(gamma, dtype), 1e-6)
+    ref, res = x.copy(), np.zeros_like(x)
+    oracle.rmsnorm(ref, res, gamma, 1e-6)
+    assert np.array_equal(to_np(resd), res)  # residual copy is bit-exact
+    assert_close(to_np(xd), ref, dtype, "rmsnorm")
+
+
+def test_rmsnorm_reference_test_inputs():
+    """tests/unit_tests/test_rmsnorm.cu:44-72 inputs, its 1e-3 abs criterion, and the reference CUDA kernel itself."""
+    mod = b200()
+    t, h = 64, 4096
+    idx = np.arange(t * h, dtype=np.int64)
+    x = ((idx * idx) % 3 + 1).astype(np.float32).reshape(t, h)
+    gamma = (np.arange(h) % 3 + 1).astype(np.float32)
+    xd, resd = to_dev(x), to_dev(np.zeros_like(x))
+    mod.rmsnorm(xd, resd, to_dev(gamma), 1e-6)
+    ref = x.copy()
+    oracle.rmsnorm(ref, None, gamma, 1e-6)
+    assert np.abs(to_np(xd) - ref).max() <= 1e-3
+    assert_close(to_np(xd), ref, "f32", "rmsnorm reference inputs")
+    lib = oracle.ref_lib()
+    if lib is not None:
+        rx, rr, rg = to_dev(x), to_dev(np.zeros_like(x)), to_dev(gamma)
+        assert lib.ref_rmsnorm(C.c_void_p(rx.data_ptr()), C.c_void_p(rr.data_ptr()), C.c_void_p(rg.data_ptr()), C.c_float(1e-6), t, h) == 0
+        assert_close(to_np(xd), to_np(rx), "f32", "rmsnorm vs reference CUDA kernel")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tokens,hidden,has_res,has_bias", [(7, 4096, True, True), (1, 8192, True, False), (4, 512, False, True), (2, 36, True, True)])
+def test_fused_add_bias_residual_rmsnorm(tokens, hidden, has_res, has_bias, dtype):
+    mod = b200()
+    r = rng(2)
+    out = rounded(r.standard_normal((tokens, hidden)), dtype)
+    res = rounded(r.standard_normal((tokens, hidden)), dtype) if has_res else None
+    bias = rounded(0.1 * r.standard_normal(hidden), dtype) if has_bias else None
+    gamma = rounded(1 + 0.1 * r.standard_normal(hidden), dtype)
+    od = to_dev(out, dtype)
+    rd = to_dev(res, dtype) if has_res else None
+    mod.fused_add_bias_residual_rmsnorm(rd, od, to_dev(bias, dtype) if has_bias else None, to_dev(gamma, dtype), 1e-5)
+    o, rr = out.copy(), (res.copy() if has_res else None)
+    oracle.fused_add_bias_residual_rmsnorm(rr, o, bias, gamma, 1e-5)
+    if has_res:
+        assert_close(to_np(rd), rr, dtype, "residual (updated before the bias)")
+    assert_close(to_np(od), o, dtype, "fused norm")
+
+
+def test_fused_norm_vs_reference_kernel():
+    lib = oracle.ref_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    mod = b200()
+    r = rng(3)
+    t, h = 5, 4096  # h/4 = 1024 threads: the largest shape the reference launcher supports
+    out, res = r.standard_normal((t, h)).astype(np.float32), r.standard_normal((t, h)).astype(np.float32)
+    bias, gamma = r.standard_normal(h).astype(np.float32), r.standard_normal(h).astype(np.float32)
+    od, rd = to_dev(out), to_dev(res)
+    mod.fused_add_bias_residual_rmsnorm(rd, od, to_dev(bias), to_dev(gamma), 1e-6)
+    ro, rr, rb, rg = to_dev(out), to_dev(res), to_dev(bias), to_dev(gamma)
+    p = lambda t_: C.c_void_p(t_.data_ptr())
+    assert lib.ref_fused_add_bias_residual_rmsnorm(p(rr), p(ro), p(rb), p(rg), C.c_float(1e-6), t, h) == 0
+    assert_close(to_np(od), to_np(ro), "f32", "vs reference CUDA kernel")
+    assert np.array_equal(to_np(rd), to_np(rr))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_add_residual(dtype):
+    mod = b200()
+    r = rng(4)
+    for shape in [(16, 4096), (3, 10)]:
+        a, b_ = rounded(r.standard_normal(shape), dtype), rounded(r.standard_normal(shape), dtype)
+        od = to_dev(a, dtype)
+        mod.add_residual(to_dev(b_, dtype), od)
+        ref = a.copy()
+        oracle.add_residual(b_, ref)
+        assert_close(to_np(od), rounded(ref, dtype), dtype, "add_residual")
+
+
+# ------------------------------------------------------------------ linears
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,K,N", [(1, 4096, 4096), (2, 4096, 1536), (3, 11008, 512), (4, 1024, 1001), (1, 8192, 256), (7, 512, 300),
+                                   (1, 100, 37), (33, 256, 130)])
+@pytest.mark.parametrize("layout", ["nk", "kn"])
+def test_linear_dense(M, K, N, layout, dtype):
+    mod = b200()
+    oracle.set_threads(oracle.max_threads())
+    r = rng(5)
+    x = rounded(r.standard_normal((M, K)), dtype)
+    w = rounded(r.standard_normal((N, K)) / np.sqrt(K), dtype)
+    wmem = w if layout == "nk" else np.ascontiguousarray(w.T)
+    y = mod.linear(to_dev(x, dtype), to_dev(wmem, dtype), mod.LAYOUT_NK if layout == "nk" else mod.LAYOUT_KN)
+    ref = oracle.linear(x, wmem, layout, wide=True)
+    assert_close(to_np(y), ref, dtype, f"linear {layout} M={M} K={K} N={N}")
+
+
+def test_linear_reference_test_inputs_and_kernel():
+    """tests/unit_tests/test_linear.cu:54-82 (small integers) -- CPUlinear layout [N,K]; and the reference GPU path, which reads
+    the same memory as [K,N]: both contracts are served and kept distinct."""
+    mod = b200()
+    r = rng(6)
+    M, K, N = 64, 512, 384
+    x = r.integers(0, 3, (M, K)).astype(np.float32)
+    w = r.integers(0, 3, (N, K)).astype(np.float32)
+    y = mod.linear(to_dev(x), to_dev(w), mod.LAYOUT_NK)
+    assert np.array_equal(to_np(y), oracle.linear(x, w, "nk"))  # integers: exact, == CPUlinear
+    lib = oracle.ref_lib()
+    if lib is not None:
+        wkn = r.standard_normal((K, N)).astype(np.float32)
+        xr = r.standard_normal((4, K)).astype(np.float32)
+        yr = to_dev(np.zeros((4, N), np.float32))
+        xd, wd = to_dev(xr), to_dev(wkn)
+        assert lib.ref_linear(C.c_void_p(xd.data_ptr()), C.c_void_p(wd.data_ptr()), C.c_void_p(yr.data_ptr()), 4, K, N) == 0
+        mine = mod.linear(xd, wd, mod.LAYOUT_KN)
+        assert_close(to_np(mine), to_np(yr), "f32", "KN linear vs reference launchLinearGemm")
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("fmt", ["fp8", "int4"])
+@pytest.mark.parametrize("M,K,N", [(1, 4096, 1024), (2, 11008, 256), (4, 512, 130), (9, 1024, 64), (1, 1536, 48)])
+def test_linear_quantised(M, K, N, fmt, dtype):
+    import torch
+
+    mod = b200()
+    oracle.set_threads(oracle.max_threads())
+    r = rng(7)
+    x = rounded(r.standard_normal((M, K)), dtype)
+    w = rounded(r.standard_normal((N, K)) * 0.02, dtype)
+    wd = to_dev(w, dtype)
+    if fmt == "fp8":
+        q, sc = mod.quantize_fp8(wd)
+        zz, wf, group = None, mod.W_FP8, 0
+        qo, so = oracle.quantize_fp8(w)
+        assert np.array_equal(to_np(q), qo) and np.array_equal(to_np(sc), so)  # device quantiser == oracle quantiser, bit-exact
+        deq_ref = oracle.dequantize_fp8(qo, so)
+    else:
+        group = 128
+        q, sc, zz = mod.quantize_int4(wd, group)
+        wf = mod.W_INT4
+        qo, so, zo = oracle.quantize_int4(w, group, scale_round=1 if dtype == "bf16" else 0)
+        if dtype == "bf16":
+            assert np.array_equal(to_np(zz), zo) and np.array_equal(to_np(sc), so)
+            assert np.array_equal(to_np(q), qo)
+        deq_ref = oracle.dequantize_int4(to_np(q), to_np(sc).astype(np.float32), to_np(zz), group)
+    deq = to_np(mod.dequantize(q, sc, zz, wf, group, torch_dtype(dtype), K))
+    assert np.array_equal(deq, rounded(deq_ref, dtype))
+    y = mod.linear(to_dev(x, dtype), q, mod.LAYOUT_NK, wf, sc, zz, group, N=N)
+    ref = oracle.linear(x, np.ascontiguousarray(deq_ref, np.float32), "nk", wide=True)  # oracle on the dequantised weights
+    assert_close(to_np(y), ref, dtype, f"{fmt} linear")
+
+
+def test_batched_gemm_true_qkt():
+    mod = b200()
+    r = rng(8)
+    a = r.standard_normal((6, 20, 32)).astype(np.float32)
+    bt = r.standard_normal((6, 50, 32)).astype(np.float32)
+    c = mod.batched_gemm(to_dev(a), to_dev(bt), True)
+    assert_close(to_np(c), oracle.batched_gemm(a, bt, True), "f32", "q k^T")
+    p = r.standard_normal((6, 20, 50)).astype(np.float32)
+    v = r.standard_normal((6, 50, 32)).astype(np.float32)
+    c = mod.batched_gemm(to_dev(p), to_dev(v), False)
+    assert_close(to_np(c), oracle.batched_gemm(p, v, False), "f32", "p v")
+
+
+def test_transpose2d_bit_exact():
+    mod = b200()
+    a = rng(9).standard_normal((130, 70)).astype(np.float32)
+    assert np.array_equal(to_np(mod.transpose2d(to_dev(a))), a.T)
+
+
+# ------------------------------------------------------------------ rope / decode attention
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,H,Hkv,d,step", [(1, 32, 32, 128, 1), (2, 8, 2, 128, 1024), (3, 4, 2, 8, 3)])
+def test_rope_decode(B, H, Hkv, d, step, dtype):
+    mod = b200()
+    qkv = rounded(rng(10).standard_normal((B, H + 2 * Hkv, d)), dtype)
+    qd = to_dev(qkv, dtype)
+    mod.rope_decode(qd, H, Hkv, step, d, 10000.0)
+    ref = qkv.copy()
+    oracle.rope_decode(ref, H, Hkv, step, d, 10000.0)
+    got = to_np(qd)
+    assert np.array_equal(got[:, H + Hkv:], qkv[:, H + Hkv:])  # v untouched
+    if dtype == "f32":
+        # sinf/cosf of the device vs libm at |theta| up to `step`: a few ulp of the argument reduction
+        np.testing.assert_allclose(got, ref, rtol=0, atol=4e-6 * np.abs(qkv).max() * 2)
+    else:
+        assert_close(got, rounded(ref, dtype), dtype, "rope")
+
+
+def _mha_case(B, H, Hkv, d, S, L, step, layer, dtype, seed=11, bias=True):
+    r = rng(seed)
+    qkv = rounded(r.standard_normal((B, H + 2 * Hkv, d)), dtype)
+    b_ = rounded(0.1 * r.standard_normal((H + 2 * Hkv) * d), dtype) if bias else None
+    kc = rounded(r.standard_normal((L, B, Hkv, S, d)), dtype)
+    vc = rounded(r.standard_normal((L, B, Hkv, S, d)), dtype)
+    return qkv, b_, kc, vc
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,H,Hkv,d,S,L,step,layer", [
+    (1, 32, 32, 128, 1100, 1, 1, 0), (1, 32, 32, 128, 1100, 2, 127, 1), (1, 32, 32, 128, 1100, 1, 128, 0),
+    (1, 32, 32, 128, 1100, 1, 129, 0), (1, 32, 32, 128, 1100, 1, 1024, 0), (3, 8, 2, 128, 700, 2, 513, 1),
+    (2, 8, 1, 128, 64, 1, 64, 0), (2, 4, 2, 8, 4, 1, 4, 0), (2, 6, 3, 64, 40, 1, 33, 0)])
+def test_decode_mha(B, H, Hkv, d, S, L, step, layer, dtype):
+    mod = b200()
+    qkv, bias, kc, vc = _mha_case(B, H, Hkv, d, S, L, step, layer, dtype)
+    kcd, vcd = to_dev(kc, dtype), to_dev(vc, dtype)
+    out = mod.decode_mha(to_dev(qkv, dtype), to_dev(bias, dtype), kcd, vcd, H, Hkv, step, layer)
+    rk, rv = kc.copy(), vc.copy()
+    ref = oracle.decode_mha(qkv.copy(), bias, rk, rv, H, Hkv, step, layer)
+    assert_close(to_np(out), ref, dtype, "decode mha")
+    # KV-cache indices bit-exact: only [layer, :, :, step-1] changes, and it holds round(k + bias)
+    gk, gv = to_np(kcd), to_np(vcd)
+    assert np.array_equal(gk, rounded(rk, dtype)) and np.array_equal(gv, rounded(rv, dtype))
+
+
+def test_decode_mha_fused_rope_equals_rope_then_mha():
+    mod = b200()
+    B, H, Hkv, d, S, step = 2, 8, 4, 128, 300, 222
+    qkv, bias, kc, vc = _mha_case(B, H, Hkv, d, S, 1, step, 0, "f32", seed=12)
+    k1, v1 = to_dev(kc), to_dev(vc)
+    fused = mod.decode_mha(to_dev(qkv), to_dev(bias), k1, v1, H, Hkv, step, 0, apply_rope=True, rot_dim=d, base=10000.0)
+    q2 = to_dev(qkv)
+    mod.rope_decode(q2, H, Hkv, step, d, 10000.0)
+    k2, v2 = to_dev(kc), to_dev(vc)
+    two = mod.decode_mha(q2, to_dev(bias), k2, v2, H, Hkv, step, 0)
+    assert np.array_equal(to_np(fused), to_np(two)) and np.array_equal(to_np(k1), to_np(k2)) and np.array_equal(to_np(v1), to_np(v2))
+
+
+def test_decode_mha_vs_reference_kernel():
+    """The reference kernel is a valid oracle only for B=1, H==Hkv, step <= head_size."""
+    lib = oracle.ref_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    mod = b200()
+    B, H, d, S, L = 1, 32, 128, 256, 2
+    for step, layer in [(1, 0), (77, 1), (128, 0)]:
+        qkv, bias, kc, vc = _mha_case(B, H, H, d, S, L, step, layer, "f32", seed=13)
+        kcd, vcd = to_dev(kc), to_dev(vc)
+        mine = mod.decode_mha(to_dev(qkv), to_dev(bias), kcd, vcd, H, H, step, layer)
+        rq, rb, rk, rv, ro = to_dev(qkv), to_dev(bias), to_dev(kc), to_dev(vc), to_dev(np.zeros((B, H * d), np.float32))
+        p = lambda t_: C.c_void_p(t_.data_ptr())
+        assert lib.ref_decode_mha(p(rq), p(rb), p(rk), p(rv), p(ro), L, B, H, H, d, S, step, layer) == 0
+        assert_close(to_np(mine), to_np(ro), "f32", f"vs reference MHA kernel step {step}")
+        # cache rows [0, step): identical.  (Rows >= step are scribbled on by the reference kernel: all 128 threads store a float4
+        # at tid*4 from the row start, decoder_self_attention.cu:126,172 -- 3 rows past the appended one.)
+        assert np.array_equal(to_np(kcd)[:, :, :, :step], to_np(rk)[:, :, :, :step])
+        assert np.array_equal(to_np(vcd)[:, :, :, :step], to_np(rv)[:, :, :, :step])
+
+
+# ------------------------------------------------------------------ MLP / embedding / sampling tail
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_silu_and_mul(dtype):
+    mod = b200()
+    for t, inter in [(128, 11008), (3, 13)]:
+        x = rounded(3 * rng(14).standard_normal((t, 2, inter)), dtype)
+        got = mod.silu_and_mul(to_dev(x, dtype))
+        assert_close(to_np(got), oracle.silu_and_mul(x), dtype, "swiglu")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_input_embedding_bit_exact(dtype):
+    mod = b200()
+    r = rng(15)
+    for V, h, T in [(32000, 4096, 64), (50, 6, 9)]:
+        table = rounded(r.standard_normal((V, h)), dtype)
+        ids = r.integers(0, V, T).astype(np.int32)
+        got = mod.input_embedding(to_dev(ids), to_dev(table, dtype))
+        assert np.array_equal(to_np(got), oracle.input_embedding(ids, table))
+
+
+@pytest.mark.parametrize("rows,vocab,k", [(1, 32000, 5), (8, 32000, 5), (3, 1000, 8), (2, 7, 5), (4, 32000, 1)])
+def test_topk_ids_bit_exact(rows, vocab, k):
+    mod = b200()
+    r = rng(16)
+    logits = r.standard_normal((rows, vocab)).astype(np.float32) * 4 - 3  # mostly negative: the reference's sentinel bug territory (D9)
+    ids, vals = mod.topk(to_dev(logits), k)
+    oi, ov = oracle.topk(logits, k)
+    assert np.array_equal(to_np(ids), oi)
+    assert np.array_equal(to_np(vals)[oi >= 0], ov[oi >= 0])
+    # ties resolve to the lower id
+    tie = np.zeros((1, 5000), np.float32)
+    tie[0, [4999, 17, 2500, 3]] = 2.0
+    ids, _ = mod.topk(to_dev(tie), 5)
+    assert to_np(ids)[0].tolist() == [3, 17, 2500, 4999, 0]
+
+
+def test_topk_vs_reference_kernel_on_its_valid_domain():
+    lib = oracle.ref_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    import torch
+
+    mod = b200()
+    logits = np.abs(rng(17).standard_normal((1, 32000))).astype(np.float32) + 0.1  # one row, positive, tie-free
+    ld = to_dev(logits)
+    ids, vals = mod.topk(ld, 5)
+    dev = ld.device
+    ti, tv = torch.zeros((1, 8, 5), dtype=torch.int32, device=dev), torch.zeros((1, 8, 5), dtype=torch.float32, device=dev)
+    fi, fv = torch.zeros((1, 5), dtype=torch.int32, device=dev), torch.zeros((1, 5), dtype=torch.float32, device=dev)
+    p = lambda t_: C.c_void_p(t_.data_ptr())
+    rc = lib.ref_topk(p(ld), p(ti), p(tv), p(fi), p(fv), 1, 32000)
+    if rc != 0:
+        pytest.skip(f"the reference top-k kernel does not launch on sm_100a (cudaError {rc}: 1024 threads x its register footprint)")
+    assert np.array_equal(to_np(ids), to_np(fi)) and np.array_equal(to_np(vals), to_np(fv))
+
+
+def test_sampling_matches_oracle_and_reference():
+    import torch
+
+    mod = b200()
+    r = rng(18)
+    B, K, V, step, end_id = 6, 5, 32000, 41, 2
+    ids = np.sort(r.integers(0, 3 * V, (B, K)).astype(np.int32), axis=1)
+    ids[2, :] = 2  # forces end_id
+    vals = -np.sort(-r.standard_normal((B, K)).astype(np.float32) * 2, axis=1)
+    seq = np.arange(B, dtype=np.int32)
+    fin = np.array([False, True, False, False, True, False])
+    dev = torch.device("cuda")
+    vd, sd, fd = to_dev(vals), to_dev(seq), to_dev(fin.astype(np.uint8))
+    out = mod.sampling(to_dev(ids), vd, sd, fd, step, end_id, V)
+    u = to_np(mod.xorwow_uniform(B, step, dev))
+    assert u[0] == np.float32(oracle.xorwow_uniform_subseq0(step))  # CPU restatement of curand_init/curand_uniform, subsequence 0
+    ov, os_, of = vals.copy(), seq.copy(), fin.copy()
+    oo = oracle.sampling(ids, ov, os_, of, u, end_id, V)
+    assert np.array_equal(to_np(out), oo) and np.array_equal(to_np(sd), os_) and np.array_equal(to_np(fd).astype(bool), of)
+    np.testing.assert_allclose(to_np(vd), ov, rtol=2e-6)
+    lib = oracle.ref_lib()
+    if lib is not None:
+        ri, rv, rs, rf, ro = to_dev(ids), to_dev(vals), to_dev(seq), to_dev(fin), torch.zeros(B, dtype=torch.int32, device=dev)
+        p = lambda t_: C.c_void_p(t_.data_ptr())
+        assert lib.ref_sampling(p(ri), p(rv), p(rs), p(rf), p(ro), B, K, step, end_id, V) == 0
+        assert np.array_equal(to_np(out), to_np(ro)) and np.array_equal(to_np(sd), to_np(rs))
+
+
+# ------------------------------------------------------------------ prefill-side kernels
+def test_padding_offset_bit_exact():
+    mod = b200()
+    for lens, mq in [([4, 3, 5], 5), ([4, 3, 3, 4], 5), ([1], 1), ([7, 0, 2, 9, 9, 1], 9), (list(rng(19).integers(1, 129, 64)), 128)]:
+        lens = np.array(lens, np.int32)
+        po, cum = mod.cal_padding_offset(to_dev(lens), mq, fill=-7)
+        opo, ocum = oracle.cal_padding_offset(lens, mq, fill=-7)
+        assert np.array_equal(to_np(po), opo) and np.array_equal(to_np(cum), ocum)
+    lib = oracle.ref_lib()
+    if lib is not None:
+        import torch
+
+        lens = np.array([4, 3, 5], np.int32)
+        ld = to_dev(lens)
+        po = torch.full((3, 5), -7, dtype=torch.int32, device=ld.device)
+        cum = torch.zeros(4, dtype=torch.int32, device=ld.device)
+        assert lib.ref_cal_padding_offset(C.c_void_p(po.data_ptr()), C.c_void_p(cum.data_ptr()), C.c_void_p(ld.data_ptr()), 3, 5) == 0
+        mine, mcum = mod.cal_padding_offset(ld, 5, fill=-7)
+        assert np.array_equal(to_np(po), to_np(mine)) and np.array_equal(to_np(cum), to_np(mcum))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_causal_mask_bit_exact(dtype):
+    import torch
+
+    mod = b200()
+    r = rng(20)
+    B, mq, mk = 64, 128, 512  # tests/unit_tests/test_build_causal_mask.cu:45-47
+    ql = r.integers(1, mq + 1, B).astype(np.int32)
+    kl = r.integers(1, mk + 1, B).astype(np.int32)
+    m = mod.build_causal_masks(to_dev(ql), to_dev(kl), mq, mk, torch_dtype(dtype))
+    assert np.array_equal(to_np(m), oracle.build_causal_masks(ql, kl, mq, mk))
+
+
+def _prefill_case(dtype, seed=21):
+    r = rng(seed)
+    B, H, Hkv, d, S, L = 3, 4, 2, 128, 96, 2
+    input_len = np.array([17, 5, 32], np.int32)
+    hist = np.array([3, 0, 40], np.int32)
+    mq = int(input_len.max())
+    po, cum = oracle.cal_padding_offset(input_len, mq)
+    T = int(cum[-1])
+    qkv = rounded(r.standard_normal((T, H + 2 * Hkv, d)), dtype)
+    kc = rounded(0.5 * r.standard_normal((L, B, Hkv, S, d)), dtype)
+    vc = rounded(0.5 * r.standard_normal((L, B, Hkv, S, d)), dtype)
+    return dict(B=B, H=H, Hkv=Hkv, d=d, S=S, L=L, input_len=input_len, hist=hist, ctx=input_len + hist, mq=mq, po=po.reshape(-1), T=T,
+                qkv=qkv, kc=kc, vc=vc)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prefill_chain(dtype):
+    """qkv split+RoPE -> KV append -> GQA gather -> scale/mask/softmax -> un-pad, each against the oracle; then the fused
+    context attention against the oracle chain."""
+    mod = b200()
+    c = _prefill_case(dtype)
+    B, H, Hkv, d, mq, T, layer = c["B"], c["H"], c["Hkv"], c["d"], c["mq"], c["T"], 1
+    pod, hd, ild, cld = to_dev(c["po"]), to_dev(c["hist"]), to_dev(c["input_len"]), to_dev(c["ctx"])
+    q, k, v = mod.qkv_bias_transpose_rope(to_dev(c["qkv"], dtype), pod, hd, ild, B, mq, H, Hkv, d, 10000.0)
+    oq, ok, ov = oracle.qkv_bias_transpose_rope(c["qkv"], c["po"], c["hist"], B, mq, H, Hkv, d, 10000.0)
+    assert np.array_equal(to_np(v), ov)  # pure re-layout
+    for got, ref, name in [(q, oq, "q"), (k, ok, "k")]:
+        if dtype == "f32":
+            np.testing.assert_allclose(to_np(got), ref, rtol=0, atol=2e-5)
+        else:
+            assert_close(to_np(got), rounded(ref, dtype), dtype, name)
+    # append (bit-exact copies of what the device produced)
+    kcd, vcd = to_dev(c["kc"], dtype), to_dev(c["vc"], dtype)
+    mod.concat_kv_cache(k, v, kcd, vcd, ild, hd, layer)
+    rk, rv = c["kc"].copy(), c["vc"].copy()
+    oracle.concat_kv_cache(to_np(k), rk, c["input_len"], c["hist"], layer)
+    oracle.concat_kv_cache(to_np(v), rv, c["input_len"], c["hist"], layer)
+    assert np.array_equal(to_np(kcd), rk) and np.array_equal(to_np(vcd), rv)
+    mk = int(c["ctx"].max())
+    kr, vr = mod.repeat_kv_cache(kcd, vcd, cld, layer, H, mk)
+    assert np.array_equal(to_np(kr), oracle.repeat_kv_cache(rk, c["ctx"], layer, H, mk))
+    assert np.array_equal(to_np(vr), oracle.repeat_kv_cache(rv, c["ctx"], layer, H, mk))
+    # scores -> softmax
+    import torch
+
+    qk = mod.batched_gemm(q.reshape(B * H, mq, d), kr.reshape(B * H, mk, d), True).reshape(B, H, mq, mk)
+    mask = mod.build_causal_masks(ild, cld, mq, mk, torch_dtype(dtype))
+    scale = 1.0 / np.sqrt(d)
+    p = mod.scale_mask_softmax(qk, mask, scale)
+    op = oracle.scale_mask_softmax(to_np(qk), to_np(mask), scale)
+    assert_close(to_np(p), op, dtype, "scale-mask-softmax")
+    mod.scale_mask_softmax(qk, mask, scale, out=qk)  # in place, as context_attention.cpp:253-258 calls it
+    assert np.array_equal(to_np(qk), to_np(p))
+    pv = mod.batched_gemm(p.reshape(B * H, mq, mk), vr.reshape(B * H, mk, d), False).reshape(B, H, mq, d)
+    out = mod.transpose_remove_padding(pv, pod, T)
+    assert np.array_equal(to_np(out), oracle.transpose_remove_padding(to_np(pv), c["po"], T))
+    # fused flash-style kernel == the chain (oracle), without materialising [B,H,Sq,Sk]
+    fused = mod.context_attention(q, kcd, vcd, pod, ild, cld, layer, T, scale)
+    ref = oracle.context_attention(to_np(q), rk, rv, c["po"], c["input_len"], c["ctx"], layer, T, mk, scale)
+    assert_close(to_np(fused), ref, dtype, "fused context attention")
+
+
+def test_softmax_vs_reference_kernel():
+    lib = oracle.ref_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    mod = b200()
+    r = rng(22)
+    B, H, ql, kl = 2, 3, 16, 64  # k_len a multiple of 32: the reference's valid domain
+    qk = r.standard_normal((B, H, ql, kl)).astype(np.float32) * 3
+    mask = (r.random((B, ql, kl)) > 0.3).astype(np.float32)
+    mask[:, :, 0] = 1
+    mine = mod.scale_mask_softmax(to_dev(qk), to_dev(mask), 0.125)
+    rq, rm, ro = to_dev(qk), to_dev(mask), to_dev(np.zeros_like(qk))
+    p = lambda t_: C.c_void_p(t_.data_ptr())
+    assert lib.ref_scale_mask_softmax(p(rq), p(rm), p(ro), C.c_float(0.125), B, H, ql, kl) == 0
+    assert_close(to_np(mine), to_np(ro), "f32", "softmax vs reference kernel")
+
+
+# ------------------------------------------------------------------ size-independent properties at BASELINE.json's full sizes
+def test_gemv_full_size_properties():
+    """7B shapes, bf16: linearity in x, determinism, and row-subset consistency (a checksum of checksums)."""
+    import torch
+
+    mod = b200()
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    for K, N in [(4096, 12288), (4096, 22016), (11008, 4096)]:
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        x1 = torch.randn(1, K, device=dev).bfloat16()
+        y1 = mod.linear(x1, w)
+        assert torch.equal(y1, mod.linear(x1, w))  # deterministic
+        y2 = mod.linear(torch.cat([x1, x1 * 2]), w)  # exact scaling by 2 in every format
+        assert torch.equal(y2[0], y1[0]) and torch.equal(y2[1].float(), y1[0].float() * 2)
+        sub = mod.linear(x1, w[1000:1256].contiguous())
+        assert torch.equal(sub[0], y1[0, 1000:1256])
+        ref = (x1.double() @ w.double().T).float()
+        assert_close(y1.float().cpu().numpy(), ref.cpu().numpy(), "bf16", "7B gemv vs fp64 matmul")
