@@ -92,6 +92,11 @@ template <> struct Elem<__nv_bfloat16> {
     __device__ __forceinline__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
 };
 
+// The value a tensor of T holds for the fp32 value v.  The reference's kernels are templates over T and form their
+// intermediate sums in T (out += residual; out += bias; q += bias ...): the fused kernels round at the same points so that
+// fusing does not change which values are representable downstream.
+template <typename T> __device__ __forceinline__ float round_to(float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); }
+
 // 16-byte vector of T unpacked to fp32 lanes.
 template <typename T> struct Vec16 {
     static constexpr int N = Elem<T>::kVec;

@@ -1,4 +1,418 @@
+// gemm_tc.cu -- tcgen05 / TMEM tensor-core GEMM for sm_100a: D[i,j] = sum_k A[i,k] * B[j,k], both operands K-major.
+//
+// Serves the two GEMM-shaped cases of launchLinearGemm (reference src/kernels/linear.cu:10-87) with W packed [N,K]:
+//   * prefill / context linears (M = tokens >= 129):  A = x [M,K],  B = W [N,K],  C[i,j]      (tensor-pipe bound)
+//   * batched decode linears   (5 <= M <= 128):       A = W [N,K],  B = x [M,K],  C[j,i]      ("swap-AB": the weight rows
+//     fill the 128-row MMA M dimension, the few tokens are the MMA N dimension; HBM bound -> split-K so that every SM streams)
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A and B into a ring of smem stages, mbarrier tx counts
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16 per instruction, fp32
+//            accumulate in TMEM), tcgen05.commit releases the smem stage / publishes the accumulator
+//   warp 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter), convert, store; double-buffered
+//            accumulators so the epilogue of tile t overlaps the MMAs of tile t+1
+// Split-K partials go through the library workspace; the last CTA of a tile (self-resetting ticket) adds them in split order
+// (deterministic, no atomics on data).
 #include "gemm_tc.cuh"
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link dependency)
+#include <mutex>
+
 namespace b200 {
-int launch_gemm_tc(const void *, const void *, void *, int, int, int, int, cudaStream_t) { return B200_ERR_UNSUPPORTED; }
+
+constexpr int kBM = 128;   // UMMA M
+constexpr int kBK = 64;    // K elements per stage = one 128-byte swizzle row of a 16-bit type
+constexpr int kUmmaK = 16; // K per tcgen05.mma for 16-bit inputs
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kATileBytes = kBM * kBK * 2;
+
+struct GemmTcParams {
+    void *C;
+    float *partial;
+    unsigned int *tickets;
+    int ldc;
+    int rowsA, rowsB, K;
+    int tilesA, tilesB, ksplit, kb_per_split, kb_total;
+    int bn;        // UMMA N: rows of B per tile, multiple of 16, <= 256
+    int stages;
+    int swap;      // 0: C[i*ldc + j]   1: C[j*ldc + i]
+    int is_bf16;
+    int acc_bufs;  // TMEM accumulators (2 when 2*bn <= 512)
+    unsigned int tmem_cols;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread t = lane base + t)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), descriptor version 1 (sm_100),
+// layout type 2 (SWIZZLE_128B) in bits 61..63; LBO is unused for swizzled K-major layouts (canonical value 1).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, no negate / sparsity / saturation.
+__device__ __forceinline__ uint32_t instr_desc_f16(bool bf16, int m, int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                      // D format: F32
+    d |= (bf16 ? 1u : 0u) << 7;        // A format
+    d |= (bf16 ? 1u : 0u) << 10;       // B format
+    d |= (uint32_t)(n >> 3) << 17;     // N / 8
+    d |= (uint32_t)(m >> 4) << 24;     // M / 16
+    return d;
+}
+
+template <typename T> __device__ __forceinline__ void store_row16(T *dst, const uint32_t (&r)[16], int valid) {
+    // dst: 16 consecutive outputs of one row (32 bytes for 16-bit T); valid = number of in-range columns
+    if (valid >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(r[e]);
+        st_v4(dst, pack16<T>(f));
+        st_v4(dst + 8, pack16<T>(f + 8));
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+            if (e < valid) dst[e] = Elem<T>::from_f(__uint_as_float(r[e]));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: stages x [A tile | B tile] (1024-byte aligned), then barriers, then the TMEM base address
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_tile_bytes = p.bn * kBK * 2;
+    const int stage_bytes = kATileBytes + b_tile_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    const uint32_t full0 = s_u32(bars), empty0 = full0 + 8 * kMaxStages;
+    const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 4);
+    int *flag_slot = reinterpret_cast<int *>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.tilesA * p.tilesB * p.ksplit;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < p.stages; ++s) {
+            bar_init(full0 + 8 * s, 1);
+            bar_init(empty0 + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            bar_init(tfull0 + 8 * a, 1);
+            bar_init(tempty0 + 8 * a, 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    pdl_wait();               // everything below reads (x) or overwrites (C) tensors of the previous kernel
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ================================================= TMA producer
+        if (elect_one()) {
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int ta = item % p.tilesA, tb = (item / p.tilesA) % p.tilesB, ks = item / (p.tilesA * p.tilesB);
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    bar_wait(empty0 + 8 * s, ((it / p.stages) & 1) ^ 1);
+                    const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
+                    bar_expect_tx(full0 + 8 * s, (uint32_t)stage_bytes);
+                    tma_load_2d(sa, &tmA, kb * kBK, ta * kBM, full0 + 8 * s);
+                    tma_load_2d(sa + kATileBytes, &tmB, kb * kBK, tb * p.bn, full0 + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================= MMA issuer
+        const uint32_t idesc = instr_desc_f16(p.is_bf16 != 0, kBM, p.bn);
+        int it = 0, t = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
+            const int ks = item / (p.tilesA * p.tilesB);
+            const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+            const int acc = t % p.acc_bufs;
+            bar_wait(tempty0 + 8 * acc, ((t / p.acc_bufs) & 1) ^ 1);  // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const int s = it % p.stages;
+                bar_wait(full0 + 8 * s, (it / p.stages) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + kATileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (>>4) start-address field
+                        tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty0 + 8 * s);                       // smem stage reusable once these MMAs have read it
+                    if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);  // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int q = warp & 3;
+        const int ep_tid = (warp - 2) * 32 + lane;  // 0..127
+        T *C = reinterpret_cast<T *>(p.C);
+        int t = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
+            const int ta = item % p.tilesA, tb = (item / p.tilesA) % p.tilesB, ks = item / (p.tilesA * p.tilesB);
+            const int acc = t % p.acc_bufs;
+            bar_wait(tfull0 + 8 * acc, (t / p.acc_bufs) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn);
+            const int i = ta * kBM + q * 32 + lane;  // row of A this thread owns
+            const int j0 = tb * p.bn;
+            if (p.ksplit == 1) {
+                for (int c = 0; c < p.bn; c += 16) {
+                    uint32_t r[16];
+                    tc_ld16(taddr + c, r);
+                    tc_wait_ld();
+                    if (i < p.rowsA) {
+                        if (!p.swap) {
+                            const int valid = min(16, p.rowsB - (j0 + c));
+                            if (valid > 0) store_row16<T>(C + (size_t)i * p.ldc + j0 + c, r, valid);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (j0 + c + e < p.rowsB) C[(size_t)(j0 + c + e) * p.ldc + i] = Elem<T>::from_f(__uint_as_float(r[e]));
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(tempty0 + 8 * acc);
+            } else {
+                // split-K: publish this split's fp32 partial [bn][128] (coalesced over lanes), last CTA of the tile reduces
+                const int tile = tb * p.tilesA + ta;
+                float *part = p.partial + ((size_t)tile * p.ksplit + ks) * (size_t)p.bn * kBM;
+                for (int c = 0; c < p.bn; c += 16) {
+                    uint32_t r[16];
+                    tc_ld16(taddr + c, r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) __stcg(part + (size_t)(c + e) * kBM + q * 32 + lane, __uint_as_float(r[e]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(tempty0 + 8 * acc);  // the accumulator is free: the MMA warp may start the next item
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[tile], (unsigned)(p.ksplit - 1)) == (unsigned)(p.ksplit - 1);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = *flag_slot != 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot may be rewritten by the next item
+                if (last) {
+                    __threadfence();
+                    const float *pt = p.partial + (size_t)tile * p.ksplit * (size_t)p.bn * kBM;
+                    const int col = q * 32 + lane;
+                    for (int c = 0; c < p.bn; ++c) {
+                        if (j0 + c >= p.rowsB) break;
+                        float s = 0.0f;
+                        for (int k2 = 0; k2 < p.ksplit; ++k2) s += __ldcg(pt + ((size_t)k2 * p.bn + c) * kBM + col);
+                        if (i < p.rowsA) {
+                            if (p.swap) C[(size_t)(j0 + c) * p.ldc + i] = Elem<T>::from_f(s);
+                            else C[(size_t)i * p.ldc + j0 + c] = Elem<T>::from_f(s);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+// 2-D K-major tensor map: dims {K, rows}, row pitch K * 2 bytes, box {64, box_rows}, 128-byte swizzle, zero fill out of bounds.
+static bool make_map(CUtensorMap *map, const void *ptr, int rows, int K, int box_rows, bool bf16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides,
+              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static unsigned int pow2_cols(int c) {
+    unsigned int v = 32;
+    while ((int)v < c) v <<= 1;
+    return v;
+}
+
+int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, int dtype, cudaStream_t st) {
+    if (dtype != B200_BF16 && dtype != B200_F16) return B200_ERR_UNSUPPORTED;
+    if (M < 1 || K % 8 != 0 || K < kBK || !aligned16(x) || !aligned16(w) || !y) return B200_ERR_UNSUPPORTED;
+    const bool bf16 = dtype == B200_BF16;
+    const bool swap = M <= 128;
+    GemmTcParams p = {};
+    p.C = y, p.ldc = N, p.K = K, p.swap = swap ? 1 : 0, p.is_bf16 = bf16 ? 1 : 0;
+    p.kb_total = (K + kBK - 1) / kBK;
+    const void *a_ptr, *b_ptr;
+    if (swap) {
+        a_ptr = w, b_ptr = x;
+        p.rowsA = N, p.rowsB = M;
+        p.bn = (M + 15) / 16 * 16;
+    } else {
+        a_ptr = x, b_ptr = w;
+        p.rowsA = M, p.rowsB = N;
+        p.bn = N >= 256 ? 256 : (N + 15) / 16 * 16;
+    }
+    p.tilesA = (p.rowsA + kBM - 1) / kBM;
+    p.tilesB = (p.rowsB + p.bn - 1) / p.bn;
+    const int sms = sm_count();
+    const int tiles = p.tilesA * p.tilesB;
+    // split K when the tiles alone cannot occupy every SM (HBM-bound decode shapes); >= 4 k-blocks per split
+    p.ksplit = 1;
+    if (tiles < 2 * sms) {
+        int want = (2 * sms + tiles - 1) / tiles;
+        const int cap = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
+        if (want > cap) want = cap;
+        if (want > 16) want = 16;
+        p.ksplit = want < 1 ? 1 : want;
+    }
+    p.kb_per_split = (p.kb_total + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+    if (p.ksplit > 1) {
+        Workspace ws;
+        if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
+        const size_t need = (size_t)tiles * p.ksplit * p.bn * kBM * sizeof(float);
+        if (need > ws.scratch_bytes || (size_t)tiles > ws.n_tickets) {
+            p.ksplit = 1;
+            p.kb_per_split = p.kb_total;
+        } else {
+            p.partial = reinterpret_cast<float *>(ws.scratch);
+            p.tickets = ws.tickets;
+        }
+    }
+    p.acc_bufs = 2 * p.bn <= 512 ? 2 : 1;
+    p.tmem_cols = pow2_cols(p.acc_bufs * p.bn);
+    const int stage_bytes = kATileBytes + p.bn * kBK * 2;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return B200_ERR_UNSUPPORTED;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+
+    CUtensorMap tmA, tmB;
+    if (!make_map(&tmA, a_ptr, p.rowsA, K, kBM, bf16) || !make_map(&tmB, b_ptr, p.rowsB, K, p.bn, bf16)) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled failed (rows %d/%d, K %d)", p.rowsA, p.rowsB, K);
+        return B200_ERR_CUDA;
+    }
+    const int items = tiles * p.ksplit;
+    const int grid = items < sms ? items : sms;
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, true, tmA, tmB, p);
+    };
+    if (bf16) launch(gemm_tc_kernel<__nv_bfloat16>);
+    else launch(gemm_tc_kernel<__half>);
+    return cuda_status("gemm_tc launch");
+}
+
+}  // namespace b200

@@ -287,7 +287,7 @@ gemv_nk_kernel(const GemvArgs a) {
                 float r[V];
                 unpack16<T>(ld_v4(rin + (size_t)m * K + (size_t)i * V), r);
 #pragma unroll
-                for (int j = 0; j < V; ++j) f[j] += r[j];
+                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
             }
         };
         auto add_bias = [&](int i, float *f) {
@@ -295,7 +295,7 @@ gemv_nk_kernel(const GemvArgs a) {
                 float b[V];
                 unpack16<T>(ld_v4(bias + (size_t)i * V), b);
 #pragma unroll
-                for (int j = 0; j < V; ++j) f[j] += b[j];
+                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + b[j]);
             }
         };
         auto store_xs = [&](int m, int i, const float *f) {

@@ -50,6 +50,34 @@ ORACLE_API int oracle_max_threads(void) {
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Storage type emulation.  The reference's kernels are templates over T (float / half): every tensor they write and
+ * every value they form in T arithmetic is rounded to T.  With oracle_set_storage(1 = fp16, 2 = bf16) the COMPOSED
+ * paths below (oracle_decode_mha's bias add, oracle_fused_add_bias_residual_rmsnorm, oracle_decoder_layer) round to T
+ * at exactly those points, so that a 16-bit device path can be checked element by element instead of only in norm.
+ * 0 (default) = pure fp32, the reference's own fp32 instantiation. */
+static int g_storage = 0;
+ORACLE_API void oracle_set_storage(int t) { g_storage = (t == 1 || t == 2) ? t : 0; }
+ORACLE_API int oracle_get_storage(void) { return g_storage; }
+static float storage_round_bf16(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return f; /* NaN */
+    u += 0x7fffu + ((u >> 16) & 1u);
+    u &= 0xffff0000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static float storage_round(float f) {
+    if (g_storage == 2) return storage_round_bf16(f);
+    if (g_storage == 1) return (float)(_Float16)f; /* IEEE binary16, round-to-nearest-even */
+    return f;
+}
+static void storage_round_n(float *p, size_t n) {
+    if (!g_storage) return;
+    for (size_t i = 0; i < n; ++i) p[i] = storage_round(p[i]);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * RMSNorm: src/kernels/rmsnorm.cu:48-79.  residual <- x (copy), then x <- (x*gamma) * rsqrt(mean+eps).
  * The kernel multiplies by gamma first and by the reciprocal root second (:71-76).
  * Also equals CPUfusedresidandRMSNorm, tests/unit_tests/test_rmsnorm.cu:10-27 up to the order of the
@@ -80,10 +108,10 @@ ORACLE_API void oracle_fused_add_bias_residual_rmsnorm(float *residual, float *o
         for (int j = 0; j < hidden; ++j) {
             float v = o[j];
             if (residual) {
-                v += residual[(size_t)t * hidden + j];
+                v = storage_round(v + residual[(size_t)t * hidden + j]);
                 residual[(size_t)t * hidden + j] = v;
             }
-            if (bias) v += bias[j];
+            if (bias) v = storage_round(v + bias[j]);
             o[j] = v;
             sum += v * v;
         }
@@ -195,7 +223,7 @@ ORACLE_API void oracle_decode_mha(float *qkv, const float *bias, float *k_cache,
     for (int b = 0; b < batch; ++b) {
         float *row = qkv + (size_t)b * qkv_heads * head_size;
         if (bias)
-            for (int i = 0; i < qkv_heads * head_size; ++i) row[i] += bias[i];
+            for (int i = 0; i < qkv_heads * head_size; ++i) row[i] = storage_round(row[i] + bias[i]);
         for (int kvh = 0; kvh < kv_head_num; ++kvh) {
             const size_t c = layer_off + (((size_t)b * kv_head_num + kvh) * max_seq_len + (step - 1)) * head_size;
             memcpy(k_cache + c, row + (size_t)(head_num + kvh) * head_size, sizeof(float) * head_size);
@@ -617,16 +645,27 @@ ORACLE_API void oracle_decoder_layer(float *hidden, const float *g1, const float
     float *mha = (float *)malloc(sizeof(float) * (size_t)batch * qh);
     float *gu = (float *)malloc(sizeof(float) * (size_t)batch * 2 * inter);
     float *act = (float *)malloc(sizeof(float) * (size_t)batch * inter);
+    const size_t nh = (size_t)batch * hidden_units;
     oracle_rmsnorm(hidden, res, g1, eps, batch, hidden_units);
+    storage_round_n(hidden, nh);
     oracle_linear(hidden, wqkv, qkv, batch, hidden_units, qkv_n, 1, 0);
+    storage_round_n(qkv, (size_t)batch * qkv_n);
     oracle_rope_decode(qkv, batch, head_num, kv_head_num, head_size, step, rot_dim, base);
+    storage_round_n(qkv, (size_t)batch * qkv_n);
     oracle_decode_mha(qkv, bqkv, k_cache, v_cache, mha, batch, head_num, kv_head_num, head_size, max_seq_len, step, layer);
+    storage_round_n(mha, (size_t)batch * qh);
     oracle_linear(mha, wo, hidden, batch, qh, hidden_units, 1, 0);
+    storage_round_n(hidden, nh);
     oracle_fused_add_bias_residual_rmsnorm(res, hidden, bo, g2, eps, batch, hidden_units);
+    storage_round_n(hidden, nh);
     oracle_linear(hidden, wgu, gu, batch, hidden_units, 2 * inter, 1, 0);
+    storage_round_n(gu, (size_t)batch * 2 * inter);
     oracle_silu_and_mul(gu, act, batch, inter);
+    storage_round_n(act, (size_t)batch * inter);
     oracle_linear(act, wd, hidden, batch, inter, hidden_units, 1, 0);
+    storage_round_n(hidden, nh);
     oracle_add_residual(res, hidden, batch, hidden_units);
+    storage_round_n(hidden, nh);
     free(res);
     free(qkv);
     free(mha);

@@ -83,6 +83,11 @@ def max_threads():
     return int(lib().oracle_max_threads())
 
 
+def set_storage(dtype):
+    """Storage-type emulation for the composed paths (decoder_layer): 'f32' (default), 'f16' or 'bf16'.  See llama_oracle.c."""
+    lib().oracle_set_storage({"f32": 0, "f16": 1, "bf16": 2}[dtype])
+
+
 def rmsnorm(x, residual, gamma, eps):
     t, h = x.shape
     lib().oracle_rmsnorm(_f(x), _f(residual), _f(gamma), C.c_float(eps), t, h)

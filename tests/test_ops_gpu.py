@@ -328,7 +328,18 @@ def test_topk_vs_reference_kernel_on_its_valid_domain():
     rc = lib.ref_topk(p(ld), p(ti), p(tv), p(fi), p(fv), 1, 32000)
     if rc != 0:
         pytest.skip(f"the reference top-k kernel does not launch on sm_100a (cudaError {rc}: 1024 threads x its register footprint)")
-    assert np.array_equal(to_np(ids), to_np(fi)) and np.array_equal(to_np(vals), to_np(fv))
+    # Round 1 (reduceTopK1, topk.cu:24-63) initialises its queues and is well defined: the 8 per-block top-5 lists must hold
+    # the global top-5, in the same order once merged (descending value; tie-free input).
+    ri, rv = to_np(ti).reshape(-1), to_np(tv).reshape(-1)
+    order = np.argsort(-rv, kind="stable")[:5]
+    assert np.array_equal(to_np(ids)[0], ri[order]) and np.array_equal(to_np(vals)[0], rv[order])
+    # Round 2 (reduceTopK2, topk.cu:82-88) starts from an UNINITIALISED queue: its result is only comparable when
+    # the registers happened to hold a usable sentinel.  Compare when it produced a plausible answer, otherwise record it.
+    rfi = to_np(fi)
+    if (rfi != 0).any():
+        assert np.array_equal(to_np(ids), rfi) and np.array_equal(to_np(vals), to_np(fv))
+    else:
+        print("reference reduceTopK2 returned its uninitialised queue (all-zero ids) on sm_100a: final compare skipped (D9)")
 
 
 def test_sampling_matches_oracle_and_reference():
