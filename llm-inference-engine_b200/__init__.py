@@ -168,8 +168,8 @@ def linear(x, w, layout=LAYOUT_NK, w_format=W_DENSE, scales=None, zeros=None, gr
     if N is None:
         N = w.shape[0] if layout == LAYOUT_NK else w.shape[1]
     y = out if out is not None else torch.empty((M, N), dtype=x.dtype, device=x.device)
-    if layout == LAYOUT_KN:
-        ensure_workspace()
+    if layout == LAYOUT_KN or M > 4:
+        ensure_workspace()  # split-K partials
     check(lib().b200_linear(ptr(x), ptr(w), ptr(scales), ptr(zeros), ptr(y), M, K, N, dtype_code(x), w_format, layout, group, stream()))
     return y
 

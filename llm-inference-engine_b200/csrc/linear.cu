@@ -5,6 +5,8 @@
 //   M <= 4, W dense  [K,N] (the reference's own memory order) -> gemv_kn_kernel (this file)
 //   M  > 4, 16-bit activations, W packed [N,K]   -> tcgen05 / TMEM tensor-core GEMM (gemm_tc.cu)
 //   everything else                              -> gemm_simt_kernel (tiled fp32-accumulate fallback, this file)
+#include <stdlib.h>
+
 #include "gemv.cuh"
 #include "gemm_tc.cuh"
 
@@ -298,9 +300,16 @@ int b200_linear(const void *x, const void *w, const void *scales, const void *ze
     // ---- decode-shaped: weight-streaming GEMV
     if (w_layout == B200_LAYOUT_NK) {
         int done = 0, rc = B200_OK;
-        if (M <= (w_format == B200_W_DENSE ? 8 : 16)) {
-            // M > 4 runs as passes of <= 4 rows (dense: up to 8, then the tensor-core path; quantised: up to 16,
-            // where 4 passes over packed weights still move fewer bytes than one pass over bf16)
+        static const bool force_tc = getenv("B200_FORCE_TC") != nullptr;  // benchmarking aid: tensor-core path for every M
+        // dense 16-bit, M > 4: tcgen05 GEMM (swap-AB + split-K for M <= 128, 128x256 tiles above)
+        if ((M > 4 || force_tc) && dtype != B200_F32 && w_format == B200_W_DENSE) {
+            rc = launch_gemm_tc(x, w, y, M, N, K, dtype, st);
+            if (rc == B200_OK) done = 1;
+            else if (rc != B200_ERR_UNSUPPORTED) return rc;
+        }
+        if (!done && M <= 16) {
+            // weight-streaming GEMV in passes of <= 4 rows (quantised weights with 5..16 rows: 4 passes over packed
+            // weights still move fewer bytes than one pass over bf16)
             for (int m0 = 0; m0 < M; m0 += 4) {
                 GemvArgs a = {};
                 a.w = w, a.scales = scales, a.zeros = zeros;
@@ -310,11 +319,6 @@ int b200_linear(const void *x, const void *w, const void *scales, const void *ze
                 rc = launch_gemv_nk(a, dtype, w_format, false, st);
                 if (rc != B200_OK) break;
             }
-            if (rc == B200_OK) done = 1;
-            else if (rc != B200_ERR_UNSUPPORTED) return rc;
-        }
-        if (!done && dtype != B200_F32 && w_format == B200_W_DENSE) {
-            rc = launch_gemm_tc(x, w, y, M, N, K, dtype, st);
             if (rc == B200_OK) done = 1;
             else if (rc != B200_ERR_UNSUPPORTED) return rc;
         }

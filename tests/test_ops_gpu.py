@@ -120,6 +120,33 @@ def test_linear_dense(M, K, N, layout, dtype):
     assert_close(to_np(y), ref, dtype, f"linear {layout} M={M} K={K} N={N}")
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,K,N", [(5, 64, 128), (8, 4096, 4096), (16, 11008, 512), (33, 1024, 1000), (128, 512, 384), (129, 256, 256),
+                                   (300, 4096, 1024), (1024, 1024, 776), (2048, 4096, 512)])
+def test_linear_tensor_core_gemm(M, K, N, dtype):
+    """M > 4, dense 16-bit, [N,K] weights: the tcgen05 / TMEM GEMM (gemm_tc.cu) -- swap-AB + split-K up to 128 rows, 128x256 tiles
+    above -- against an fp32 matmul of the same (rounded) inputs.  Integer-valued inputs must come out exact."""
+    import torch
+
+    mod = b200()
+    r = rng(55)
+    x = rounded(r.standard_normal((M, K)), dtype)
+    w = rounded(r.standard_normal((N, K)) / np.sqrt(K), dtype)
+    xd, wd = to_dev(x, dtype), to_dev(w, dtype)
+    y = mod.linear(xd, wd, mod.LAYOUT_NK)
+    ref = (xd.float() @ wd.float().T).cpu().numpy()  # fp32 reference of the same op (TF32 is off by default for matmul)
+    if M * N * K <= 64 * 1024 * 1024:
+        oracle.set_threads(oracle.max_threads())
+        assert_close(ref, oracle.linear(x, w, "nk", wide=True), dtype, "torch fp32 reference vs oracle")
+    assert_close(to_np(y), ref, dtype, f"tensor-core linear M={M} K={K} N={N}")
+    xi = r.integers(-2, 3, (M, K)).astype(np.float32)
+    wi = r.integers(-2, 3, (N, K)).astype(np.float32)
+    yi = mod.linear(to_dev(xi, dtype), to_dev(wi, dtype), mod.LAYOUT_NK)
+    exact = xi.astype(np.float64) @ wi.astype(np.float64).T
+    if np.abs(exact).max() < 256:  # representable in bf16 without rounding
+        assert np.array_equal(to_np(yi).astype(np.float64), exact)
+
+
 def test_linear_reference_test_inputs_and_kernel():
     """tests/unit_tests/test_linear.cu:54-82 (small integers) -- CPUlinear layout [N,K]; and the reference GPU path, which reads
     the same memory as [K,N]: both contracts are served and kept distinct."""
