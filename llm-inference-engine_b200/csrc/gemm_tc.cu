@@ -3,7 +3,8 @@
 // Serves the two GEMM-shaped cases of launchLinearGemm (reference src/kernels/linear.cu:10-87) with W packed [N,K]:
 //   * prefill / context linears (M = tokens >= 129):  A = x [M,K],  B = W [N,K],  C[i,j]      (tensor-pipe bound)
 //   * batched decode linears   (5 <= M <= 128):       A = W [N,K],  B = x [M,K],  C[j,i]      ("swap-AB": the weight rows
-//     fill the 128-row MMA M dimension, the few tokens are the MMA N dimension; HBM bound -> split-K so that every SM streams)
+//     fill the 128-row MMA M dimension, the few tokens are the MMA N dimension; HBM bound -> stream-K: the tiles x k-blocks
+//     space is cut into one equal contiguous range per SM so that every SM streams the same number of weight bytes)
 //
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
 //   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A and B into a ring of smem stages, mbarrier tx counts
@@ -11,8 +12,8 @@
 //            accumulate in TMEM), tcgen05.commit releases the smem stage / publishes the accumulator
 //   warp 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter), convert, store; double-buffered
 //            accumulators so the epilogue of tile t overlaps the MMAs of tile t+1
-// Split-K partials go through the library workspace; the last CTA of a tile (self-resetting ticket) adds them in split order
-// (deterministic, no atomics on data).
+// Tiles shared by several CTAs (stream-K) exchange fp32 partials through the library workspace; the last CTA to arrive at a tile
+// (self-resetting ticket) adds the slots in a fixed order (deterministic, no atomics on data).
 #include "gemm_tc.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link dependency)
@@ -33,13 +34,53 @@ struct GemmTcParams {
     unsigned int *tickets;
     int ldc;
     int rowsA, rowsB, K;
-    int tilesA, tilesB, ksplit, kb_per_split, kb_total;
+    int tilesA, tiles, kb_total;
+    int streamk;   // 0: whole tiles dealt round-robin; 1: the tiles x k-blocks space cut into gridDim.x equal contiguous ranges
+    int maxslots;  // stream-K: partial slots reserved per tile
     int bn;        // UMMA N: rows of B per tile, multiple of 16, <= 256
     int stages;
     int swap;      // 0: C[i*ldc + j]   1: C[j*ldc + i]
     int is_bf16;
     int acc_bufs;  // TMEM accumulators (2 when 2*bn <= 512)
     unsigned int tmem_cols;
+};
+
+// One contiguous piece of work of a CTA: k-blocks [kb0, kb1) of one output tile.  nslots > 1: the tile is shared with
+// other CTAs; this CTA's partial goes to slot `slot` and the last arriver (ticket) adds the slots in order.
+struct Seg {
+    int tile, kb0, kb1, slot, nslots;
+};
+struct SegIter {
+    const GemmTcParams &p;
+    long long g, gend, total;
+    int item, G;
+    __device__ SegIter(const GemmTcParams &pp) : p(pp) {
+        G = gridDim.x;
+        total = (long long)p.tiles * p.kb_total;
+        item = blockIdx.x;
+        g = start(blockIdx.x);
+        gend = start(blockIdx.x + 1);
+    }
+    __device__ long long start(int c) const { return (long long)c * total / G; }
+    __device__ int owner(long long gg) const { return (int)(((gg + 1) * G + total - 1) / total) - 1; }  // max c: start(c) <= gg
+    __device__ bool next(Seg &s) {
+        if (!p.streamk) {
+            if (item >= p.tiles) return false;
+            s.tile = item, s.kb0 = 0, s.kb1 = p.kb_total, s.slot = 0, s.nslots = 1;
+            item += G;
+            return true;
+        }
+        if (g >= gend) return false;
+        s.tile = (int)(g / p.kb_total);
+        s.kb0 = (int)(g - (long long)s.tile * p.kb_total);
+        const long long len = min((long long)(p.kb_total - s.kb0), gend - g);
+        s.kb1 = s.kb0 + (int)len;
+        const int first = owner((long long)s.tile * p.kb_total), last = owner((long long)(s.tile + 1) * p.kb_total - 1);
+        s.slot = (int)blockIdx.x - first;
+        s.nslots = last - first + 1;
+        g += len;
+        return true;
+    }
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -154,7 +195,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int *flag_slot = reinterpret_cast<int *>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.tilesA * p.tilesB * p.ksplit;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -184,11 +224,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ================================================= TMA producer
         if (elect_one()) {
+            SegIter si(p);
+            Seg sg;
             int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int ta = item % p.tilesA, tb = (item / p.tilesA) % p.tilesB, ks = item / (p.tilesA * p.tilesB);
-                const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            while (si.next(sg)) {
+                const int ta = sg.tile % p.tilesA, tb = sg.tile / p.tilesA;
+                for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++it) {
                     const int s = it % p.stages;
                     bar_wait(empty0 + 8 * s, ((it / p.stages) & 1) ^ 1);
                     const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
@@ -201,15 +242,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ================================================= MMA issuer
         const uint32_t idesc = instr_desc_f16(p.is_bf16 != 0, kBM, p.bn);
+        SegIter si(p);
+        Seg sg;
         int it = 0, t = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
-            const int ks = item / (p.tilesA * p.tilesB);
-            const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (; si.next(sg); ++t) {
             const int acc = t % p.acc_bufs;
             bar_wait(tempty0 + 8 * acc, ((t / p.acc_bufs) & 1) ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++it) {
                 const int s = it % p.stages;
                 bar_wait(full0 + 8 * s, (it / p.stages) & 1);
                 tc_fence_after();
@@ -219,10 +260,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (>>4) start-address field
-                        tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(empty0 + 8 * s);                       // smem stage reusable once these MMAs have read it
-                    if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);  // accumulator complete
+                    tc_commit(empty0 + 8 * s);                          // smem stage reusable once these MMAs have read it
+                    if (kb == sg.kb1 - 1) tc_commit(tfull0 + 8 * acc);  // accumulator complete
                 }
                 __syncwarp();
             }
@@ -232,16 +273,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int ep_tid = (warp - 2) * 32 + lane;  // 0..127
         T *C = reinterpret_cast<T *>(p.C);
+        SegIter si(p);
+        Seg sg;
         int t = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++t) {
-            const int ta = item % p.tilesA, tb = (item / p.tilesA) % p.tilesB, ks = item / (p.tilesA * p.tilesB);
+        for (; si.next(sg); ++t) {
+            const int ta = sg.tile % p.tilesA, tb = sg.tile / p.tilesA;
             const int acc = t % p.acc_bufs;
             bar_wait(tfull0 + 8 * acc, (t / p.acc_bufs) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn);
             const int i = ta * kBM + q * 32 + lane;  // row of A this thread owns
             const int j0 = tb * p.bn;
-            if (p.ksplit == 1) {
+            if (sg.nslots == 1) {
                 for (int c = 0; c < p.bn; c += 16) {
                     uint32_t r[16];
                     tc_ld16(taddr + c, r);
@@ -261,9 +304,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) bar_arrive(tempty0 + 8 * acc);
             } else {
-                // split-K: publish this split's fp32 partial [bn][128] (coalesced over lanes), last CTA of the tile reduces
-                const int tile = tb * p.tilesA + ta;
-                float *part = p.partial + ((size_t)tile * p.ksplit + ks) * (size_t)p.bn * kBM;
+                // shared tile: publish this CTA's fp32 partial [bn][128] (coalesced over lanes); the last arriver reduces
+                const size_t tile_floats = (size_t)p.bn * kBM;
+                float *part = p.partial + ((size_t)sg.tile * p.maxslots + sg.slot) * tile_floats;
                 for (int c = 0; c < p.bn; c += 16) {
                     uint32_t r[16];
                     tc_ld16(taddr + c, r);
@@ -273,24 +316,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) bar_arrive(tempty0 + 8 * acc);  // the accumulator is free: the MMA warp may start the next item
+                if (lane == 0) bar_arrive(tempty0 + 8 * acc);  // the accumulator is free: the MMA warp may start the next segment
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[tile], (unsigned)(p.ksplit - 1)) == (unsigned)(p.ksplit - 1);
+                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[sg.tile], (unsigned)(sg.nslots - 1)) == (unsigned)(sg.nslots - 1);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const bool last = *flag_slot != 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot may be rewritten by the next item
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot may be rewritten by the next segment
                 if (last) {
                     __threadfence();
-                    const float *pt = p.partial + (size_t)tile * p.ksplit * (size_t)p.bn * kBM;
-                    const int col = q * 32 + lane;
-                    for (int c = 0; c < p.bn; ++c) {
-                        if (j0 + c >= p.rowsB) break;
-                        float s = 0.0f;
-                        for (int k2 = 0; k2 < p.ksplit; ++k2) s += __ldcg(pt + ((size_t)k2 * p.bn + c) * kBM + col);
-                        if (i < p.rowsA) {
-                            if (p.swap) C[(size_t)(j0 + c) * p.ldc + i] = Elem<T>::from_f(s);
-                            else C[(size_t)i * p.ldc + j0 + c] = Elem<T>::from_f(s);
+                    // 128 threads x float4: element f = (column c, 4 consecutive A rows); slots added in order (deterministic)
+                    const float4 *pt = reinterpret_cast<const float4 *>(p.partial + (size_t)sg.tile * p.maxslots * tile_floats);
+                    const int nf = p.bn * (kBM / 4), slot_f4 = (int)(tile_floats / 4);
+                    constexpr int U = 4;
+                    for (int f0 = ep_tid; f0 < nf; f0 += 128 * U) {
+                        float4 sum[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k2 = 0; k2 < sg.nslots; ++k2) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int f = f0 + u * 128;
+                                if (f < nf) {
+                                    const float4 v = __ldcg(pt + (size_t)k2 * slot_f4 + f);
+                                    sum[u].x += v.x, sum[u].y += v.y, sum[u].z += v.z, sum[u].w += v.w;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int f = f0 + u * 128;
+                            if (f >= nf) continue;
+                            const int c = f / (kBM / 4), ii = ta * kBM + (f % (kBM / 4)) * 4;
+                            if (j0 + c >= p.rowsB) continue;
+                            const float v[4] = {sum[u].x, sum[u].y, sum[u].z, sum[u].w};
+                            if (p.swap) {
+                                T *dst = C + (size_t)(j0 + c) * p.ldc + ii;
+                                if (ii + 3 < p.rowsA && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
+                                    uint2 pk;
+                                    const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
+                                    pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+                                    pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
+                                    *reinterpret_cast<uint2 *>(dst) = pk;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (ii + e < p.rowsA) dst[e] = Elem<T>::from_f(v[e]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (ii + e < p.rowsA) C[(size_t)(ii + e) * p.ldc + j0 + c] = Elem<T>::from_f(v[e]);
+                            }
                         }
                     }
                 }
@@ -363,29 +440,25 @@ int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, i
         p.rowsA = M, p.rowsB = N;
         p.bn = N >= 256 ? 256 : (N + 15) / 16 * 16;
     }
-    p.tilesA = (p.rowsA + kBM - 1) / kBM;
-    p.tilesB = (p.rowsB + p.bn - 1) / p.bn;
     const int sms = sm_count();
-    const int tiles = p.tilesA * p.tilesB;
-    // split K when the tiles alone cannot occupy every SM (HBM-bound decode shapes); >= 4 k-blocks per split
-    p.ksplit = 1;
-    if (tiles < 2 * sms) {
-        int want = (2 * sms + tiles - 1) / tiles;
-        const int cap = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
-        if (want > cap) want = cap;
-        if (want > 16) want = 16;
-        p.ksplit = want < 1 ? 1 : want;
-    }
-    p.kb_per_split = (p.kb_total + p.ksplit - 1) / p.ksplit;
-    p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
-    if (p.ksplit > 1) {
+    if (!swap && p.bn == 256 && ((M + kBM - 1) / kBM) * ((N + 255) / 256) * 2 <= sms) p.bn = 128;  // under half a wave: more, smaller tiles
+    p.tilesA = (p.rowsA + kBM - 1) / kBM;
+    const int tilesB = (p.rowsB + p.bn - 1) / p.bn;
+    p.tiles = p.tilesA * tilesB;
+    const long long total = (long long)p.tiles * p.kb_total;
+    int grid = p.tiles < sms ? p.tiles : sms;
+    // Few tiles relative to the SM count (HBM-bound decode shapes): stream-K -- the tiles x k-blocks space is cut into one equal
+    // contiguous range per SM, so every SM streams the same number of weight bytes.
+    p.streamk = 0;
+    if (swap && p.tiles < 4 * sms && total >= 2 * sms) {
+        const int g2 = (int)(total < sms ? total : sms);
+        const long long per = total / g2;  // >= 2 k-blocks per CTA
+        const int maxslots = (int)((p.kb_total + per - 1) / per) + 1;
         Workspace ws;
         if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
-        const size_t need = (size_t)tiles * p.ksplit * p.bn * kBM * sizeof(float);
-        if (need > ws.scratch_bytes || (size_t)tiles > ws.n_tickets) {
-            p.ksplit = 1;
-            p.kb_per_split = p.kb_total;
-        } else {
+        const size_t need = (size_t)p.tiles * maxslots * p.bn * kBM * sizeof(float);
+        if (need <= ws.scratch_bytes && (size_t)p.tiles <= ws.n_tickets) {
+            p.streamk = 1, p.maxslots = maxslots, grid = g2;
             p.partial = reinterpret_cast<float *>(ws.scratch);
             p.tickets = ws.tickets;
         }
@@ -404,8 +477,6 @@ int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, i
         set_error("gemm_tc: cuTensorMapEncodeTiled failed (rows %d/%d, K %d)", p.rowsA, p.rowsB, K);
         return B200_ERR_CUDA;
     }
-    const int items = tiles * p.ksplit;
-    const int grid = items < sms ? items : sms;
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, true, tmA, tmB, p);
