@@ -1,20 +1,26 @@
 // gemv.cuh -- the decode-shaped linear (M <= 4 tokens) for sm_100a: y[M,N] = x[M,K] * W^T, W packed [N,K].
 //
 // HBM-bound by construction: every weight byte is read exactly once per call.  Design:
-//   * persistent grid (a multiple of the SM count); each WARP owns work units of R = 2 weight rows,
-//     dealt round-robin over CTAs first so that every SM streams the same number of bytes (+-1 unit);
-//   * weight rows are contiguous in the [N,K] packing, so they are streamed with 1-D TMA bulk copies
-//     (cp.async.bulk.shared.global, 2 KiB per row chunk) into a PER-WARP shared-memory ring of kGemvStages
-//     stages, completion tracked by one mbarrier per stage: no registers are held by loads in flight and
-//     a single lane issues a whole stage (SASS: UBLKCP + SYNCS);
-//   * the ring is filled BEFORE griddepcontrol.wait, so under programmatic dependent launch the weight
-//     stream of kernel i+1 is already in flight while kernel i drains;
-//   * the activation rows live in shared memory (optionally produced by the fused
-//     add-residual + bias + RMSNorm prologue, reference src/kernels/add_residual_and_rmsnorm.cu:43-121
-//     and src/kernels/rmsnorm.cu:35-80), fp32 accumulation, warp-shuffle reduction, optional SwiGLU
-//     epilogue (reference src/kernels/silu_and_mul.cu:6-41) when the unit's two rows are (gate_i, up_i);
-//   * FP8-e4m3 (per-row fp32 scale) and INT4 (grouped scale + zero point) weights are dequantised in
-//     registers; only their packed bytes cross HBM.
+//   * one persistent CTA per SM: 16 compute warps in 2 groups of 8, plus one TMA-producer warp and one reducer warp per
+//     group (warp-specialised; the compute warps never wait on each other).  A GROUP owns work units of R = 2 weight rows,
+//     dealt round-robin over SMs first; inside a unit the K dimension is split over the group's 8 warps, so a unit is
+//     16 KB of traffic done by 8 warps (not by one) and the last wave of units costs < 1 us: every SM streams the same
+//     number of bytes to within one unit.  Because a warp always works on the same K-slice, its slice of the
+//     activations is held in REGISTERS (no shared-memory read or bf16 unpack of x in the hot loop);
+//   * weight rows are contiguous in the [N,K] packing, so a unit (or an 8 KiB-per-row piece of it when rows are longer) is
+//     fetched with ONE 1-D TMA bulk copy per row (cp.async.bulk.shared.global, up to 8 KiB each) into a group-shared ring
+//     of stages with full/empty mbarriers: no registers are held by loads in flight and a single lane issues a whole
+//     stage (SASS: UBLKCP + SYNCS);
+//   * the ring is filled BEFORE griddepcontrol.wait, so under programmatic dependent launch the weight stream of kernel i+1
+//     is already in flight while kernel i drains;
+//   * the activation rows live in shared memory (optionally produced by the fused add-residual + bias + RMSNorm prologue,
+//     reference src/kernels/add_residual_and_rmsnorm.cu:43-121 and src/kernels/rmsnorm.cu:35-80: one global read pass, the
+//     row cached in registers across the block reduction), fp32 accumulation; the per-lane partial sums of a group's
+//     warps meet in shared memory (double-buffered, ready/free mbarriers) where the reducer warp adds them in a fixed order
+//     (deterministic), reduces across lanes and stores, with the optional SwiGLU epilogue (reference
+//     src/kernels/silu_and_mul.cu:6-41) when the unit's two rows are (gate_i, up_i);
+//   * FP8-e4m3 (per-row fp32 scale) and INT4 (grouped scale + zero point) weights are dequantised in registers; only their
+//     packed bytes cross HBM.
 #pragma once
 #include "common.cuh"
 
@@ -22,12 +28,23 @@ namespace b200 {
 
 enum { WF_DENSE = 0, WF_FP8 = 1, WF_INT4 = 2 };
 
-constexpr int kGemvWarps = 8;
-constexpr int kGemvThreads = kGemvWarps * 32;
-constexpr int kGemvStages = 3;
-constexpr int kGemvRows = 2;           // weight rows per work unit
-constexpr int kGemvChunkBytes = 2048;  // bytes of one row per pipeline stage (128 x 16 B)
-constexpr int kGemvStageBytes = kGemvRows * kGemvChunkBytes;
+constexpr int kGemvGroups = 2;            // groups of compute warps per CTA
+constexpr int kGemvGW = 8;                // compute warps per group (the K split of a unit)
+constexpr int kGemvWarps = kGemvGroups * kGemvGW;                      // compute warps
+constexpr int kGemvThreads = (kGemvWarps + 2 * kGemvGroups) * 32;      // + one producer and one reducer warp per group
+constexpr int kGemvMaxStages = 8;
+constexpr int kGemvRows = 2;             // weight rows per work unit
+constexpr int kGemvPieceBytes = 8192;    // bytes of one row per pipeline stage (one bulk copy)
+constexpr int kGemvXCache = 2;           // 16-byte activation vectors cached per thread across the RMSNorm reduction
+
+// per-launch geometry, computed on the host (gemv_inst.cuh)
+struct GemvGeom {
+    int stages;       // ring depth per group
+    int piece_bytes;  // bytes of a row per stage (<= kGemvPieceBytes, multiple of 512 except for the only piece of a short row)
+    int pieces;       // stages per unit = ceil(row_bytes / piece_bytes)
+    int stage_bytes;  // kGemvRows * row stride inside a stage
+    int cw;           // warp-vectors (32 lanes x 16 B) of a row piece per compute warp
+};
 
 struct GemvArgs {
     const void *w;       // [N, row_bytes]
@@ -56,6 +73,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -204,13 +224,17 @@ __device__ __forceinline__ void dot_rows(const uint4 (&wv)[kGemvRows], const boo
 }
 
 // ------------------------------------------------------------------ the kernel
-// smem: [ xs : MB * Kp * sizeof(XS) | ring : warps * stages * stage_bytes | barriers : warps * stages * 8 ]
-template <typename T, int FMT, int MB, bool kSwiGLU>
-__global__ void __launch_bounds__(kGemvThreads)
-gemv_nk_kernel(const GemvArgs a) {
+// smem: [ xs : MB * Kp * sizeof(XS) | rings : groups * stages * stage_bytes | barriers : groups * (2 * kGemvMaxStages + 4) * 8 |
+//         partial sums : groups * 2 * GW * R*MB * 32 floats ]
+// XV > 0: every compute warp keeps its XV = pieces * cw activation vectors per token in registers (dense formats only).
+template <typename T, int FMT, int MB, bool kSwiGLU, int XV>
+__global__ void __launch_bounds__(kGemvThreads, 1)
+gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
     using WT = WTraits<T, FMT>;
     using XS = typename WT::XS;
     constexpr int EPV = WT::kEPV;
+    constexpr int R = kGemvRows, GW = kGemvGW;
+    constexpr int V = Elem<T>::kVec;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float red[33];
 
@@ -219,69 +243,81 @@ gemv_nk_kernel(const GemvArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t row_bytes = FMT == WF_DENSE ? (size_t)K * sizeof(T) : (FMT == WF_FP8 ? (size_t)K : (size_t)K / 2);
     const int nvec_row = (int)(row_bytes / 16);
-    const int chunks = (nvec_row + 127) / 128;  // pipeline items per unit
     const int units = kSwiGLU ? a.inter : (N + 1) / 2;
-    const int ngroups = FMT == WF_INT4 ? K / a.group : 0;
+    const int ngroups_k = FMT == WF_INT4 ? K / a.group : 0;
+    const int stages = geo.stages, pieces = geo.pieces, cw = geo.cw;
+    const int piece_vecs = geo.piece_bytes / 16, row_stride = geo.stage_bytes / R;
+
+    // ---- roles: warps [0, 16) compute (group = warp / 8), warp 16 + g produces for group g, warp 18 + g reduces for group g
+    const bool is_compute = warp < kGemvWarps;
+    const int grp = is_compute ? warp / GW : (warp - kGemvWarps) % kGemvGroups;
+    const bool is_producer = !is_compute && warp < kGemvWarps + kGemvGroups;
+    const int wg = warp % GW;
+    // group `grp` of this CTA owns units gid, gid + total_groups, ...; a unit is `pieces` ring stages
+    const int gid = grp * gridDim.x + blockIdx.x, total_groups = gridDim.x * kGemvGroups;
+    const int my_units = gid < units ? (units - gid + total_groups - 1) / total_groups : 0;
+    const int my_items = my_units * pieces;
 
     XS *xs = reinterpret_cast<XS *>(smem);
     size_t off = ((size_t)MB * Kp * sizeof(XS) + 127) & ~(size_t)127;
-    unsigned char *ring = smem + off + (size_t)warp * kGemvStages * kGemvStageBytes;
-    off += (size_t)kGemvWarps * kGemvStages * kGemvStageBytes;
-    const uint32_t bars = smem_u32(smem + off) + warp * kGemvStages * 8;
+    unsigned char *ring = smem + off + (size_t)grp * stages * geo.stage_bytes;
+    off += (size_t)kGemvGroups * stages * geo.stage_bytes;
+    const uint32_t full0 = smem_u32(smem + off) + grp * (2 * kGemvMaxStages + 4) * 8, empty0 = full0 + kGemvMaxStages * 8;
+    const uint32_t ready0 = empty0 + kGemvMaxStages * 8, free0 = ready0 + 16;
+    off += (size_t)kGemvGroups * (2 * kGemvMaxStages + 4) * 8;
+    float *gred = reinterpret_cast<float *>(smem + off) + (size_t)grp * 2 * GW * (R * MB) * 32;  // [parity][warp][R*MB][lane]
     const uint32_t ring_u32 = smem_u32(ring);
 
-    // unit u belongs to CTA u % grid, warp (u / grid) % warps: the remainder is spread over CTAs (= SMs) first
-    const int gwarp = warp * gridDim.x + blockIdx.x;
-    const int total_warps = gridDim.x * kGemvWarps;
-    const int my_units = gwarp < units ? (units - gwarp + total_warps - 1) / total_warps : 0;
-    const int my_items = my_units * chunks;
-
     auto unit_row = [&](int u, int r) -> int { return kSwiGLU ? u + r * a.inter : 2 * u + r; };
-    const unsigned char *wbase = reinterpret_cast<const unsigned char *>(a.w);
 
-    // producer: lane 0 arms the stage barrier and issues one bulk copy per row
-    auto issue = [&](int item) {
-        const int s = item % kGemvStages;
-        const int u = gwarp + (item / chunks) * total_warps;
-        const int c = item % chunks;
-        const int vecs = min(128, nvec_row - c * 128);
-        const uint32_t bytes = (uint32_t)vecs * 16u;
-        const uint32_t bar = bars + s * 8;
+    // ---- producer state machine (one lane): arm the stage's full barrier and issue one bulk copy per row
+    int p_un = 0, p_pc = 0, p_item = 0, p_s = 0, p_ph = 0;
+    auto issue_next = [&]() {
+        const int u = gid + p_un * total_groups;
+        const int v0 = p_pc * piece_vecs;
+        const uint32_t bytes = (uint32_t)min(piece_vecs, nvec_row - v0) * 16u;
+        const uint32_t bar = full0 + p_s * 8;
         int nrows = 0;
 #pragma unroll
-        for (int r = 0; r < kGemvRows; ++r) nrows += unit_row(u, r) < N ? 1 : 0;
+        for (int r = 0; r < R; ++r) nrows += unit_row(u, r) < N ? 1 : 0;
         mbar_expect_tx(bar, bytes * nrows);
 #pragma unroll
-        for (int r = 0; r < kGemvRows; ++r) {
+        for (int r = 0; r < R; ++r) {
             const int row = unit_row(u, r);
             if (row < N)
-                bulk_g2s(ring_u32 + s * kGemvStageBytes + r * kGemvChunkBytes,
-                         wbase + (size_t)row * row_bytes + (size_t)c * kGemvChunkBytes, bytes, bar);
+                bulk_g2s(ring_u32 + p_s * geo.stage_bytes + r * row_stride,
+                         reinterpret_cast<const unsigned char *>(a.w) + (size_t)row * row_bytes + (size_t)v0 * 16, bytes, bar);
         }
+        ++p_item;
+        if (++p_pc == pieces) p_pc = 0, ++p_un;
+        if (++p_s == stages) p_s = 0, p_ph ^= 1;
     };
-
-    if (lane == 0) {
-        for (int s = 0; s < kGemvStages; ++s) mbar_init(bars + s * 8, 1);
+    if (is_producer && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full0 + s * 8, 1);
+            mbar_init(empty0 + s * 8, GW);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(ready0 + b * 8, GW);
+            mbar_init(free0 + b * 8, 1);
+        }
         fence_mbar_init();
-    }
-    __syncwarp();
-    // fill the ring before waiting on the previous kernel: the weights do not depend on it
-    if (lane == 0) {
-        for (int it = 0; it < kGemvStages && it < my_items; ++it) issue(it);
+        // fill the ring before waiting on the previous kernel: the weights do not depend on it
+        while (p_item < stages && p_item < my_items) issue_next();
     }
 
     pdl_wait();
 
-    // ---------------- stage the activations (with the fused add-residual / bias / RMSNorm prologue)
+    // ---------------- stage the activations (with the fused add-residual / bias / RMSNorm prologue); all warps help
     {
         const T *xin = reinterpret_cast<const T *>(a.x);
         const T *rin = a.norm ? reinterpret_cast<const T *>(a.res_in) : nullptr;
         T *rout = a.norm ? reinterpret_cast<T *>(a.res_out) : nullptr;
         const T *bias = a.norm ? reinterpret_cast<const T *>(a.bias) : nullptr;
         const T *gamma = a.norm ? reinterpret_cast<const T *>(a.gamma) : nullptr;
-        constexpr int V = Elem<T>::kVec;
         const int nv = K / V;
-        auto prenorm = [&](int m, int i, float *f) {
+        // pre-norm value of vector i of row m: x (+ residual) -> T; residual_out <- that; (+ bias) -> T
+        auto prenorm = [&](int m, int i, float *f, bool write_res) {
             unpack16<T>(ld_v4(xin + (size_t)m * K + (size_t)i * V), f);
             if (rin) {
                 float r[V];
@@ -289,8 +325,7 @@ gemv_nk_kernel(const GemvArgs a) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
             }
-        };
-        auto add_bias = [&](int i, float *f) {
+            if (write_res && rout && blockIdx.x == 0) st_v4(rout + (size_t)m * K + (size_t)i * V, pack16<T>(f));
             if (bias) {
                 float b[V];
                 unpack16<T>(ld_v4(bias + (size_t)i * V), b);
@@ -312,32 +347,58 @@ gemv_nk_kernel(const GemvArgs a) {
             for (int i = K + threadIdx.x; i < Kp; i += kGemvThreads)
                 for (int m = 0; m < MB; ++m) xs[(size_t)m * Kp + xs_perm<EPV>(i)] = 0.0f;
         }
+        const bool cached = nv <= kGemvXCache * kGemvThreads;  // the row fits the per-thread register cache: one global pass
         for (int m = 0; m < MB; ++m) {
             if (m >= a.M) {  // padding rows of the batch tile
                 for (int i = threadIdx.x; i < Kp; i += kGemvThreads) xs[(size_t)m * Kp + i] = XS(0.0f);
                 continue;
             }
-            float ss = 0.0f;
-            for (int i = threadIdx.x; i < nv; i += kGemvThreads) {
-                float f[V];
-                prenorm(m, i, f);
-                if (rout && blockIdx.x == 0) st_v4(rout + (size_t)m * K + (size_t)i * V, pack16<T>(f));
-                add_bias(i, f);
-                if (gamma) {
-#pragma unroll
-                    for (int j = 0; j < V; ++j) ss += f[j] * f[j];
-                } else {
+            if (!gamma) {
+                for (int i = threadIdx.x; i < nv; i += kGemvThreads) {
+                    float f[V];
+                    prenorm(m, i, f, true);
                     store_xs(m, i, f);
                 }
+                continue;
             }
-            if (gamma) {
-                ss = block_sum(ss, red);
-                const float rs = rsqrtf(ss / (float)K + a.eps);
+            float cache[kGemvXCache][V], gm[kGemvXCache][V];
+            float ss = 0.0f;
+            if (cached) {
+#pragma unroll
+                for (int c = 0; c < kGemvXCache; ++c) {
+                    const int i = threadIdx.x + c * kGemvThreads;
+                    if (i < nv) {
+                        unpack16<T>(ld_v4(gamma + (size_t)i * V), gm[c]);  // independent of the reduction: issue it now
+                        prenorm(m, i, cache[c], true);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) ss += cache[c][j] * cache[c][j];
+                    }
+                }
+            } else {
+                for (int i = threadIdx.x; i < nv; i += kGemvThreads) {
+                    float f[V];
+                    prenorm(m, i, f, true);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) ss += f[j] * f[j];
+                }
+            }
+            ss = block_sum(ss, red);
+            const float rs = rsqrtf(ss / (float)K + a.eps);
+            if (cached) {
+#pragma unroll
+                for (int c = 0; c < kGemvXCache; ++c) {
+                    const int i = threadIdx.x + c * kGemvThreads;
+                    if (i < nv) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) cache[c][j] = (cache[c][j] * gm[c][j]) * rs;
+                        store_xs(m, i, cache[c]);
+                    }
+                }
+            } else {
                 // second pass over the (L1/L2-resident) inputs: recompute the pre-norm value and scale it
                 for (int i = threadIdx.x; i < nv; i += kGemvThreads) {
                     float f[V], g[V];
-                    prenorm(m, i, f);
-                    add_bias(i, f);
+                    prenorm(m, i, f, false);
                     unpack16<T>(ld_v4(gamma + (size_t)i * V), g);
 #pragma unroll
                     for (int j = 0; j < V; ++j) f[j] = (f[j] * g[j]) * rs;
@@ -345,72 +406,47 @@ gemv_nk_kernel(const GemvArgs a) {
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();  // xs complete; also publishes the producers' mbarrier initialisation
     }
     pdl_launch_dependents();
 
-    // ---------------- consume
-    float acc[kGemvRows][MB];
-#pragma unroll
-    for (int r = 0; r < kGemvRows; ++r)
-#pragma unroll
-        for (int m = 0; m < MB; ++m) acc[r][m] = 0.0f;
-
-    for (int item = 0; item < my_items; ++item) {
-        const int s = item % kGemvStages;
-        const int u = gwarp + (item / chunks) * total_warps;
-        const int c = item % chunks;
-        bool valid[kGemvRows];
-#pragma unroll
-        for (int r = 0; r < kGemvRows; ++r) valid[r] = unit_row(u, r) < N;
-        mbar_wait(bars + s * 8, (item / kGemvStages) & 1);
-        const unsigned char *st = ring + s * kGemvStageBytes;
-        const int vecs = min(128, nvec_row - c * 128);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int v = j * 32 + lane;
-            if (v < vecs) {
-                uint4 wv[kGemvRows];
-                uint32_t zpk[kGemvRows];
-                float sc[kGemvRows];
-#pragma unroll
-                for (int r = 0; r < kGemvRows; ++r) {
-                    wv[r] = *reinterpret_cast<const uint4 *>(st + r * kGemvChunkBytes + v * 16);
-                    zpk[r] = 0;
-                    sc[r] = 0.0f;
-                    if constexpr (FMT == WF_INT4) {
-                        if (valid[r]) {
-                            // a 32-element vector never straddles a group (group % 32 == 0)
-                            const size_t gi = (size_t)unit_row(u, r) * ngroups + ((c * 128 + v) * EPV) / a.group;
-                            sc[r] = Elem<T>::to_f(__ldg(reinterpret_cast<const T *>(a.scales) + gi));
-                            const uint32_t z = 0x6400u | __ldg(reinterpret_cast<const uint8_t *>(a.zeros) + gi);
-                            zpk[r] = z | (z << 16);
-                        }
-                    }
-                }
-                dot_rows<T, FMT, MB>(wv, valid, xs, Kp, c * 4 + j, lane, zpk, sc, acc);
+    if (is_producer) {
+        // ================================================= TMA producer: refill a stage once all 8 warps have left it
+        if (lane == 0) {
+            int e_s = 0, e_ph = 0;  // stage / phase of the empty barrier to wait on next
+            while (p_item < my_items) {
+                mbar_wait(empty0 + e_s * 8, e_ph);
+                if (++e_s == stages) e_s = 0, e_ph ^= 1;
+                fence_proxy_async();
+                issue_next();
             }
         }
-        __syncwarp();
-        // this stage is free again: refill it with the item kGemvStages ahead
-        if (item + kGemvStages < my_items && lane == 0) {
-            fence_proxy_async();
-            issue(item + kGemvStages);
-        }
-        if (c == chunks - 1) {
-            // ---------------- unit epilogue
-            float out[kGemvRows][MB];
+    } else if (!is_compute) {
+        // ================================================= reducer: add the group's per-lane partials in a fixed order
+        for (int un = 0; un < my_units; ++un) {
+            const int u = gid + un * total_groups;
+            const int b = un & 1;
+            mbar_wait(ready0 + b * 8, (un >> 1) & 1);
+            const float *slot = gred + (size_t)b * GW * (R * MB) * 32;
+            float out[R][MB];
 #pragma unroll
-            for (int r = 0; r < kGemvRows; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int m = 0; m < MB; ++m) {
-                    out[r][m] = warp_sum(acc[r][m]);
-                    acc[r][m] = 0.0f;
+                    float t = 0.0f;
+#pragma unroll
+                    for (int w2 = 0; w2 < GW; ++w2) t += slot[(w2 * (R * MB) + r * MB + m) * 32 + lane];
+                    out[r][m] = warp_sum(t);
                 }
+            __syncwarp();
             if (lane == 0) {
+                mbar_arrive(free0 + b * 8);  // the slot may be overwritten
+                bool valid[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) valid[r] = unit_row(u, r) < N;
                 if constexpr (FMT == WF_FP8) {
 #pragma unroll
-                    for (int r = 0; r < kGemvRows; ++r)
+                    for (int r = 0; r < R; ++r)
                         if (valid[r]) {
                             const float s8 = __ldg(reinterpret_cast<const float *>(a.scales) + unit_row(u, r));
 #pragma unroll
@@ -422,15 +458,14 @@ gemv_nk_kernel(const GemvArgs a) {
                     for (int m = 0; m < MB; ++m)
                         if (m < a.M) {
                             // the un-fused reference stores gate/up in T before SiLU reads them
-                            const float g = Elem<T>::to_f(Elem<T>::from_f(out[0][m]));
-                            const float up = Elem<T>::to_f(Elem<T>::from_f(out[1][m]));
+                            const float g = round_to<T>(out[0][m]), up = round_to<T>(out[1][m]);
                             const float v = (g / (1.0f + expf(-g))) * up;
                             if (a.y_f32) reinterpret_cast<float *>(a.y)[(size_t)m * a.inter + u] = v;
                             else reinterpret_cast<T *>(a.y)[(size_t)m * a.inter + u] = Elem<T>::from_f(v);
                         }
                 } else {
 #pragma unroll
-                    for (int r = 0; r < kGemvRows; ++r)
+                    for (int r = 0; r < R; ++r)
                         if (valid[r]) {
                             const int row = unit_row(u, r);
 #pragma unroll
@@ -442,6 +477,133 @@ gemv_nk_kernel(const GemvArgs a) {
                         }
                 }
             }
+        }
+    } else {
+        // ================================================= compute warps
+        // this warp's slice of the activations, in registers (XV > 0): vector (pc, j) covers k = ((pc*pv32 + wg*cw + j)*32 + lane)*V
+        float xr[XV > 0 ? XV : 1][MB][V];
+        if constexpr (XV > 0) {
+#pragma unroll
+            for (int i = 0; i < XV; ++i) {
+                const int pc = i / 2, j = i % 2;  // XV path: cw <= 2, pieces <= XV / 2
+                const int v = pc * piece_vecs + (wg * cw + j) * 32 + lane;
+#pragma unroll
+                for (int m = 0; m < MB; ++m) {
+                    if (j < cw && pc < pieces && v < nvec_row) {
+                        unpack16<T>(*reinterpret_cast<const uint4 *>(xs + (size_t)m * Kp + (size_t)v * V), xr[i][m]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) xr[i][m][e] = 0.0f;
+                    }
+                }
+            }
+        }
+        float acc[R][MB][2];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int m = 0; m < MB; ++m) acc[r][m][0] = acc[r][m][1] = 0.0f;
+
+        int s = 0, ph = 0;
+        const unsigned char *my_ring = ring + (size_t)(wg * cw * 32 + lane) * 16;
+        for (int un = 0; un < my_units; ++un) {
+            const int u = gid + un * total_groups;
+            if constexpr (XV > 0) {
+                // ---- hot path: fully unrolled over (piece, vector), x in registers, no predication inside the FMAs
+#pragma unroll
+                for (int pc = 0; pc < XV / 2; ++pc) {
+                    if (pc < pieces) {
+                        mbar_wait(full0 + s * 8, ph);
+                        const unsigned char *st = my_ring + (size_t)s * geo.stage_bytes;
+                        const int pv = min(piece_vecs, nvec_row - pc * piece_vecs);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j < cw && (wg * cw + j) * 32 + lane < pv) {
+                                uint4 wv[R];
+#pragma unroll
+                                for (int r = 0; r < R; ++r) wv[r] = *reinterpret_cast<const uint4 *>(st + r * row_stride + j * 512);
+#pragma unroll
+                                for (int r = 0; r < R; ++r) {
+                                    float wf[V];
+                                    unpack16<T>(wv[r], wf);
+#pragma unroll
+                                    for (int m = 0; m < MB; ++m)
+#pragma unroll
+                                        for (int e = 0; e < V; ++e) acc[r][m][j] = fmaf(wf[e], xr[pc * 2 + j][m][e], acc[r][m][j]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty0 + s * 8);  // this warp has left the stage
+                        if (++s == stages) s = 0, ph ^= 1;
+                    }
+                }
+            } else {
+                // ---- generic path: any K / format, x from shared memory
+                const bool all_valid[R] = {true, true};
+                for (int pc = 0; pc < pieces; ++pc) {
+                    mbar_wait(full0 + s * 8, ph);
+                    const unsigned char *st = ring + (size_t)s * geo.stage_bytes;
+                    const int pv = min(piece_vecs, nvec_row - pc * piece_vecs);  // 16-byte vectors per row in this piece
+                    const int wvb = pc * (piece_vecs / 32);                      // absolute warp-vector index of the piece start
+                    for (int j = 0; j < cw; ++j) {
+                        const int wv_i = wg * cw + j;
+                        const int v = wv_i * 32 + lane;
+                        if (v < pv) {
+                            uint4 wv[R];
+                            uint32_t zpk[R];
+                            float sc[R];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                wv[r] = *reinterpret_cast<const uint4 *>(st + r * row_stride + v * 16);
+                                zpk[r] = 0;
+                                sc[r] = 0.0f;
+                                if constexpr (FMT == WF_INT4) {
+                                    const int row = min(unit_row(u, r), N - 1);
+                                    // a 32-element vector never straddles a group (group % 32 == 0)
+                                    const size_t gi = (size_t)row * ngroups_k + ((size_t)(pc * piece_vecs + v) * EPV) / a.group;
+                                    sc[r] = Elem<T>::to_f(__ldg(reinterpret_cast<const T *>(a.scales) + gi));
+                                    const uint32_t z = 0x6400u | __ldg(reinterpret_cast<const uint8_t *>(a.zeros) + gi);
+                                    zpk[r] = z | (z << 16);
+                                }
+                            }
+                            float acc1[R][MB];
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+#pragma unroll
+                                for (int m = 0; m < MB; ++m) acc1[r][m] = (j & 1) ? acc[r][m][1] : acc[r][m][0];
+                            dot_rows<T, FMT, MB>(wv, all_valid, xs, Kp, wvb + wv_i, lane, zpk, sc, acc1);
+                            // same two-accumulator order as the register path: a token's result does not depend on
+                            // which instantiation (batch size) computed it
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+#pragma unroll
+                                for (int m = 0; m < MB; ++m) {
+                                    if (j & 1) acc[r][m][1] = acc1[r][m];
+                                    else acc[r][m][0] = acc1[r][m];
+                                }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + s * 8);
+                    if (++s == stages) s = 0, ph ^= 1;
+                }
+            }
+            // ---- hand the per-lane partial sums to the reducer (double-buffered slot)
+            const int b = un & 1;
+            if (un >= 2) mbar_wait(free0 + b * 8, ((un >> 1) - 1) & 1);
+            float *slot = gred + (size_t)b * GW * (R * MB) * 32;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool ok = unit_row(u, r) < N;  // rows past N were never copied: discard whatever the stage held
+#pragma unroll
+                for (int m = 0; m < MB; ++m) {
+                    slot[(wg * (R * MB) + r * MB + m) * 32 + lane] = ok ? acc[r][m][0] + acc[r][m][1] : 0.0f;
+                    acc[r][m][0] = acc[r][m][1] = 0.0f;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready0 + b * 8);
         }
     }
 }

@@ -5,41 +5,60 @@
 
 namespace b200 {
 
-template <typename T, int FMT> static size_t gemv_smem_bytes(int MB, int K) {
-    using WT = WTraits<T, FMT>;
-    const int Kp = (K + WT::kBlock - 1) / WT::kBlock * WT::kBlock;
-    size_t b = ((size_t)MB * Kp * sizeof(typename WT::XS) + 127) & ~(size_t)127;
-    b += (size_t)kGemvWarps * kGemvStages * kGemvStageBytes;
-    b += (size_t)kGemvWarps * kGemvStages * 8;
-    return b;
+template <typename T, int FMT, int MB, bool SW, int XV>
+static int launch_gemv_geom(const GemvArgs &a, const GemvGeom &g, size_t smem, cudaStream_t st) {
+    auto kern = gemv_nk_kernel<T, FMT, MB, SW, XV>;
+    static thread_local size_t cached_smem[64] = {0};  // per device, per instantiation: opt in to large dynamic smem once
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (cached_smem[dev] < smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return cuda_status("gemv cudaFuncSetAttribute");
+        cached_smem[dev] = smem;
+    }
+    const int units = SW ? a.inter : (a.N + 1) / 2;
+    int grid = sm_count();
+    const int need = (units + kGemvGroups - 1) / kGemvGroups;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    launch_pdl(kern, dim3(grid), dim3(kGemvThreads), smem, st, true, a, g);
+    return cuda_status("gemv_nk launch");
 }
 
 template <typename T, int FMT, int MB, bool SW>
 static int launch_gemv_inst(const GemvArgs &a, cudaStream_t st) {
-    const size_t smem = gemv_smem_bytes<T, FMT>(MB, a.K);
-    if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
-    auto kern = gemv_nk_kernel<T, FMT, MB, SW>;
-    // per-device, per-instantiation setup: opt in to large dynamic smem, find CTAs/SM for this footprint
-    static thread_local size_t cached_smem[64] = {0};
-    static thread_local int cached_occ[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    if (cached_smem[dev] != smem) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return cuda_status("gemv cudaFuncSetAttribute");
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kGemvThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-        cached_occ[dev] = occ > 2 ? 2 : occ;
-        cached_smem[dev] = smem;
+    using WT = WTraits<T, FMT>;
+    const size_t row_bytes = FMT == WF_DENSE ? (size_t)a.K * sizeof(T) : (FMT == WF_FP8 ? (size_t)a.K : (size_t)a.K / 2);
+    GemvGeom g;
+    // a row is cut into equal pieces of <= 8 KiB (multiples of 512 B = one warp-vector), one bulk copy each
+    g.pieces = (int)((row_bytes + kGemvPieceBytes - 1) / kGemvPieceBytes);
+    g.piece_bytes = g.pieces == 1 ? (int)row_bytes : (int)(((row_bytes + g.pieces - 1) / g.pieces + 511) / 512 * 512);
+    g.pieces = (int)((row_bytes + g.piece_bytes - 1) / g.piece_bytes);
+    g.stage_bytes = kGemvRows * ((g.piece_bytes + 127) / 128 * 128);
+    g.cw = ((g.piece_bytes / 16 + 31) / 32 + kGemvGW - 1) / kGemvGW;
+    // shared memory: activations + rings + barriers + per-lane partial sums
+    const int Kp = (a.K + WT::kBlock - 1) / WT::kBlock * WT::kBlock;
+    size_t fixed = ((size_t)MB * Kp * sizeof(typename WT::XS) + 127) & ~(size_t)127;
+    fixed += (size_t)kGemvGroups * (2 * kGemvMaxStages + 4) * 8;
+    fixed += (size_t)kGemvWarps * 2 * kGemvRows * MB * 32 * sizeof(float);
+    const size_t budget = 224 * 1024;
+    const size_t per_stage = (size_t)kGemvGroups * g.stage_bytes;
+    if (fixed + 3 * per_stage > budget) return B200_ERR_UNSUPPORTED;
+    g.stages = (int)((budget - fixed) / per_stage);
+    if (g.stages > kGemvMaxStages) g.stages = kGemvMaxStages;
+    const size_t smem = fixed + (size_t)g.stages * per_stage;
+    // register-resident activations: XV = 2 * pieces vectors per token per warp, at most 6 vectors x tokens in total
+    if constexpr (FMT == WF_DENSE) {
+        if (g.cw <= 2) {
+            if (g.pieces == 1 && MB <= 2) return launch_gemv_geom<T, FMT, MB, SW, 2>(a, g, smem, st);
+            if constexpr (MB == 1) {
+                if (g.pieces == 2) return launch_gemv_geom<T, FMT, MB, SW, 4>(a, g, smem, st);
+                if (g.pieces == 3) return launch_gemv_geom<T, FMT, MB, SW, 6>(a, g, smem, st);
+            }
+        }
     }
-    const int units = SW ? a.inter : (a.N + 1) / 2;
-    int grid = sm_count() * cached_occ[dev];
-    const int need = (units + kGemvWarps - 1) / kGemvWarps;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    launch_pdl(kern, dim3(grid), dim3(kGemvThreads), smem, st, true, a);
-    return cuda_status("gemv_nk launch");
+    return launch_gemv_geom<T, FMT, MB, SW, 0>(a, g, smem, st);
 }
 
 template <typename T, int FMT, bool SW>

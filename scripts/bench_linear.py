@@ -34,7 +34,10 @@ def bench(M, K, N, reps=20, nbuf=None):
     return us, wbytes / us / 1e3, 2.0 * M * N * K / us / 1e6, err
 
 shapes = [("qkv", 4096, 12288), ("o", 4096, 4096), ("gate_up", 4096, 22016), ("down", 11008, 4096), ("lm_head", 4096, 32000)]
-Ms = [int(a) for a in sys.argv[1:]] or [1, 4, 8, 16, 32, 64, 128, 512, 2048]
+only = [a for a in sys.argv[1:] if not a.isdigit()]
+if only:
+    shapes = [sh for sh in shapes if sh[0] in only]
+Ms = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 4, 8, 16, 32, 64, 128, 512, 2048]
 print(f"peaks: HBM {HBM} GB/s, bf16 {TF} TFLOP/s; B200_FORCE_TC={os.environ.get('B200_FORCE_TC')}")
 for M in Ms:
     for name, K, N in shapes:
