@@ -5,10 +5,15 @@
 // softmax with +1e-6 in the denominator and the max-with-0 quirk when step < head_size, P.V).
 //
 // B200 design (HBM-bound: the K and V rows of [0, step) are read exactly once):
-//   * split-KV ("flash-decoding"): grid = (splits, Hkv, B) so that B*Hkv = 32 still fills 148 SMs; every CTA
-//     serves ALL q heads of its kv head (GQA: K/V rows are loaded once per group, not once per q head);
-//   * a K/V row of 128 elements is 16 lanes x 16 bytes (16-bit) or 32 lanes x 16 bytes (fp32): 128-bit coalesced
-//     loads, 4 rows in flight per lane, warp-shuffle dot products;
+//   * split-KV ("flash-decoding"): grid = (splits, Hkv, B), about two CTAs per SM, so that B*Hkv = 32 still fills 148 SMs;
+//     every CTA serves ALL q heads of its kv head (GQA: K/V rows are loaded once per group, not once per q head);
+//   * the K and V rows of a head are contiguous in the [L,B,Hkv,S,d] cache, so a tile of 64 positions is TWO 16 KiB 1-D TMA
+//     bulk copies (cp.async.bulk.shared.global) into a 3-stage shared-memory ring filled by a dedicated producer warp.  Inside the
+//     fused engine the first stages are requested BEFORE griddepcontrol.wait: cached positions do not depend on the QKV
+//     linear that precedes this kernel, so their HBM latency hides behind its tail (programmatic dependent launch);
+//   * one pass over the positions: a K/V row of 128 elements is 16 lanes x 16 bytes (16-bit) or 32 lanes x 16 bytes (fp32);
+//     each row group keeps a private online-softmax state (running max / sum / output slice) -- no block-wide barrier in
+//     the loop; the row groups are merged through shared memory at the end, in a fixed order;
 //   * RoPE + bias + cache append of the new token are fused here (the new K/V row never round-trips through HBM
 //     before being used);
 //   * partial (max, sum, out) per split go to scratch; the last CTA of a (b, kv head) -- elected with a
@@ -48,8 +53,38 @@ __global__ void rope_decode_kernel(T *qkv, int head_num, int kv_head_num, int he
 }
 
 // ------------------------------------------------------------------ fused split-KV decode attention, head_size 128
-constexpr int kAttnThreads = 128;
+constexpr int kAttnWarps = 8;                          // compute warps
+constexpr int kAttnThreads = (kAttnWarps + 1) * 32;    // + one TMA producer warp
 constexpr int kAttnD = 128;
+constexpr int kAttnTileBytes = 16384;                  // bytes of K (and of V) per ring stage: 64 positions (16-bit) / 32 (fp32)
+constexpr int kAttnStages = 3;
+
+__device__ __forceinline__ uint32_t a_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void a_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void a_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void a_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void a_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void a_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 template <typename T> __device__ __forceinline__ float round_t(float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); }
 
@@ -60,29 +95,58 @@ template <typename T, int G>
 __global__ void __launch_bounds__(kAttnThreads)
 decode_attn_kernel(const DecodeAttnArgs a) {
     constexpr int D = kAttnD;
-    constexpr int V = Elem<T>::kVec;          // elements per 16-byte vector
-    constexpr int LPR = D / V;                // lanes per K/V row: 16 (16-bit) or 32 (fp32)
-    constexpr int RG = kAttnThreads / LPR;    // row groups per CTA: 8 or 4
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *qs = reinterpret_cast<float *>(smem_raw);   // [G][D]
-    float *knew = qs + G * D;                          // [D]
-    float *vnew = knew + D;                            // [D]
-    float *ms = vnew + D;                              // [G] chunk max, [G] chunk sum
-    float *ls = ms + 2 * G;                            // [G][chunk]
-    float *red = ls + G * a.chunk;                     // [RG][G][D]
+    constexpr int V = Elem<T>::kVec;                   // elements per 16-byte vector
+    constexpr int LPR = D / V;                         // lanes per K/V row: 16 (16-bit) or 32 (fp32)
+    constexpr int RG = kAttnWarps * 32 / LPR;          // row groups per CTA: 16 or 8
+    constexpr int TP = kAttnTileBytes / (D * (int)sizeof(T));  // positions per tile: 64 or 32
+    constexpr int RPG = TP / RG;                       // rows of a tile per row group: 4
+    constexpr int kStageBytes = 2 * kAttnTileBytes;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *ring = smem_raw;                                                   // [stages][K tile | V tile]
+    float *merge = reinterpret_cast<float *>(smem_raw);                               // aliases the ring after the loop: [RG][G][D+2]
+    float *qs = reinterpret_cast<float *>(smem_raw + kAttnStages * kStageBytes);      // [G][D]
+    float *knew = qs + G * D;                                                         // [D]
+    float *vnew = knew + D;                                                           // [D]
+    float *wts = vnew + D;                                                            // [RG][G] merge weights, then [G] max, [G] sum
+    const uint32_t full0 = a_smem_u32(wts + RG * G + 2 * G + 2), empty0 = full0 + 8 * kAttnStages;
     __shared__ bool is_last;
 
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int H = a.head_num, Hkv = a.kv_head_num;
     const int qkv_heads = H + 2 * Hkv;
     const int step = a.step;
     const int p0 = split * a.chunk, p1 = min(step, p0 + a.chunk);
+    const int ntiles = (p1 - p0 + TP - 1) / TP;
     const bool has_new = p1 == step;  // this CTA owns position step-1 (the token being appended)
     const T *qkv = reinterpret_cast<const T *>(a.qkv) + (size_t)b * qkv_heads * D;
     const T *bias = reinterpret_cast<const T *>(a.bias);
     T *kc = reinterpret_cast<T *>(a.k_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
     T *vc = reinterpret_cast<T *>(a.v_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
+    const bool producer = warp == kAttnWarps && (tid & 31) == 0;
+
+    // ---- producer: one stage = the K rows and the V rows of TP positions (two contiguous byte ranges)
+    int p_t = 0, p_s = 0;
+    auto issue_next = [&]() {
+        const int base = p0 + p_t * TP;
+        const uint32_t bytes = (uint32_t)min(TP, p1 - base) * (uint32_t)(D * sizeof(T));
+        const uint32_t bar = full0 + 8 * p_s, dst = a_smem_u32(ring + (size_t)p_s * kStageBytes);
+        a_mbar_expect_tx(bar, 2 * bytes);
+        a_bulk_g2s(dst, kc + (size_t)base * D, bytes, bar);
+        a_bulk_g2s(dst + kAttnTileBytes, vc + (size_t)base * D, bytes, bar);
+        ++p_t;
+        if (++p_s == kAttnStages) p_s = 0;
+    };
+    if (producer) {
+        for (int s = 0; s < kAttnStages; ++s) {
+            a_mbar_init(full0 + 8 * s, 1);
+            a_mbar_init(empty0 + 8 * s, kAttnWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // cached positions do not depend on the kernel before this one (the QKV linear): request them now
+        if (a.prefetch)
+            while (p_t < kAttnStages && p_t < ntiles) issue_next();
+    }
 
     pdl_wait();
 
@@ -112,139 +176,170 @@ decode_attn_kernel(const DecodeAttnArgs a) {
             vnew[j] = v;
         }
     }
-    __syncthreads();
-    if (has_new) {  // cache append (decoder_self_attention.cu:126,172)
+    __syncthreads();  // q / knew / vnew complete; also publishes the producer's mbarrier initialisation
+    if (has_new) {    // cache append (decoder_self_attention.cu:126,172)
         for (int j = tid; j < D; j += kAttnThreads) {
             kc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(knew[j]);
             vc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(vnew[j]);
         }
+        __threadfence();
     }
     pdl_launch_dependents();
 
-    const int rg = tid / LPR, l = tid % LPR;
-    // shuffles run among the LPR lanes of one row only: the two rows of a warp (16-bit types) may diverge at the chunk tail
-    const unsigned row_mask = LPR == 32 ? 0xffffffffu : (0xffffu << (tid & 16));
-    const float scale = rsqrtf((float)D);
-    // this lane's slice of every q head
-    float qf[G][V];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int e = 0; e < V; ++e) qf[g][e] = qs[g * D + l * V + e];
-
-    // ---- logits for positions [p0, p1)
-    constexpr int U = 4;
-    for (int pb = p0 + rg; pb < p1; pb += RG * U) {
-        uint4 kv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p = pb + u * RG;
-            kv[u] = make_uint4(0, 0, 0, 0);
-            if (p < p1 && p != step - 1) kv[u] = ld_stream_v4(kc + (size_t)p * D + l * V);
+    if (warp == kAttnWarps) {
+        // ================================================= TMA producer
+        if (producer) {
+            if (!a.prefetch)
+                while (p_t < kAttnStages && p_t < ntiles) issue_next();
+            int e_s = 0, e_ph = 0;
+            while (p_t < ntiles) {
+                a_mbar_wait(empty0 + 8 * e_s, e_ph);
+                if (++e_s == kAttnStages) e_s = 0, e_ph ^= 1;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_next();
+            }
         }
+    } else {
+        // ================================================= compute warps: private online softmax per row group
+        const int rg = tid / LPR, l = tid % LPR;
+        const float scale = rsqrtf((float)D);
+        float qf[G][V];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p = pb + u * RG;
-            if (p < p1) {  // uniform across the LPR lanes of a row
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int e = 0; e < V; ++e) qf[g][e] = qs[g * D + l * V + e];
+        float m[G], sum[G], of[G][V];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            m[g] = -INFINITY, sum[g] = 0.0f;
+#pragma unroll
+            for (int e = 0; e < V; ++e) of[g][e] = 0.0f;
+        }
+        int s = 0, ph = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int base = p0 + t * TP;
+            a_mbar_wait(full0 + 8 * s, ph);
+            const unsigned char *kt = ring + (size_t)s * kStageBytes, *vt = kt + kAttnTileBytes;
+            // ---- logits of this row group's RPG rows (rows past the chunk end read as -inf)
+            float lg[G][RPG];
+            bool ok[RPG];
+#pragma unroll
+            for (int i = 0; i < RPG; ++i) {
+                const int r = rg + i * RG, p = base + r;
+                ok[i] = p < p1;
                 float kf[V];
-                if (p == step - 1) {
+                if (has_new && p == step - 1) {
 #pragma unroll
                     for (int e = 0; e < V; ++e) kf[e] = knew[l * V + e];
                 } else {
-                    unpack16<T>(kv[u], kf);
+                    unpack16<T>(*reinterpret_cast<const uint4 *>(kt + (size_t)r * (D * sizeof(T)) + l * 16), kf);
                 }
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    float s = 0.0f;
+                    float d = 0.0f;
 #pragma unroll
-                    for (int e = 0; e < V; ++e) s = fmaf(qf[g][e], kf[e], s);
+                    for (int e = 0; e < V; ++e) d = fmaf(qf[g][e], kf[e], d);
 #pragma unroll
-                    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(row_mask, s, o);
-                    if (l == 0) ls[g * a.chunk + (p - p0)] = s * scale;
+                    for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                    lg[g][i] = ok[i] ? d * scale : -INFINITY;
                 }
             }
-        }
-    }
-    __syncthreads();
-
-    // ---- chunk softmax statistics: one warp per q head
-    {
-        const int warp = tid >> 5, lane = tid & 31, n = p1 - p0;
-        for (int g = warp; g < G; g += kAttnThreads / 32) {
-            float m = -INFINITY;
-            for (int j = lane; j < n; j += 32) m = fmaxf(m, ls[g * a.chunk + j]);
-            m = warp_max(m);
-            float s = 0.0f;
-            for (int j = lane; j < n; j += 32) {
-                const float e = expf(ls[g * a.chunk + j] - m);
-                ls[g * a.chunk + j] = e;
-                s += e;
+            // ---- online softmax update: lane i < RPG of the row computes exp(l_i - m_new), lane RPG the rescale factor
+            float pw[G][RPG];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float mt = m[g];
+#pragma unroll
+                for (int i = 0; i < RPG; ++i) mt = fmaxf(mt, lg[g][i]);
+                const float ms = mt == -INFINITY ? 0.0f : mt;
+                float mine = m[g];
+#pragma unroll
+                for (int i = 0; i < RPG; ++i) mine = l == i ? lg[g][i] : mine;
+                const float ex = expf(mine - ms);  // lanes >= RPG: the rescale factor exp(m_old - m_new)
+                const unsigned lbase = (unsigned)((tid & 31) - l);
+                float ps = 0.0f;
+#pragma unroll
+                for (int i = 0; i < RPG; ++i) {
+                    pw[g][i] = __shfl_sync(0xffffffffu, ex, lbase + i);
+                    ps += pw[g][i];
+                }
+                const float rs = __shfl_sync(0xffffffffu, ex, lbase + RPG);
+                sum[g] = fmaf(sum[g], rs, ps);
+                m[g] = mt;
+#pragma unroll
+                for (int e = 0; e < V; ++e) of[g][e] *= rs;
             }
-            s = warp_sum(s);
-            if (lane == 0) ms[g] = m, ms[G + g] = s;
-        }
-    }
-    __syncthreads();
-
-    // ---- P.V over the chunk
-    float of[G][V];
+            // ---- P.V
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int e = 0; e < V; ++e) of[g][e] = 0.0f;
-    for (int pb = p0 + rg; pb < p1; pb += RG * U) {
-        uint4 vv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p = pb + u * RG;
-            vv[u] = make_uint4(0, 0, 0, 0);
-            if (p < p1 && p != step - 1) vv[u] = ld_stream_v4(vc + (size_t)p * D + l * V);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p = pb + u * RG;
-            if (p < p1) {
+            for (int i = 0; i < RPG; ++i) {
+                const int r = rg + i * RG, p = base + r;
                 float vf[V];
-                if (p == step - 1) {
+                if (has_new && p == step - 1) {  // only the CTA that owns the new token holds knew / vnew
 #pragma unroll
                     for (int e = 0; e < V; ++e) vf[e] = vnew[l * V + e];
+                } else if (ok[i]) {
+                    unpack16<T>(*reinterpret_cast<const uint4 *>(vt + (size_t)r * (D * sizeof(T)) + l * 16), vf);
                 } else {
-                    unpack16<T>(vv[u], vf);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) vf[e] = 0.0f;  // never multiply stale shared memory (could hold NaN bits)
                 }
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float pw = ls[g * a.chunk + (p - p0)];
+                for (int g = 0; g < G; ++g)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) of[g][e] = fmaf(pw, vf[e], of[g][e]);
-                }
+                    for (int e = 0; e < V; ++e) of[g][e] = fmaf(pw[g][i], vf[e], of[g][e]);
             }
+            __syncwarp();
+            if ((tid & 31) == 0) a_mbar_arrive(empty0 + 8 * s);
+            if (++s == kAttnStages) s = 0, ph ^= 1;
         }
+        // ---- publish the row group's state (the ring is dead: every tile has been consumed by every warp after the barrier)
+        asm volatile("bar.sync 1, %0;" ::"r"(kAttnWarps * 32) : "memory");
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float *mp = merge + ((size_t)rg * G + g) * (D + 2);
+#pragma unroll
+            for (int e = 0; e < V; ++e) mp[l * V + e] = of[g][e];
+            if (l == 0) mp[D] = m[g], mp[D + 1] = sum[g];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(kAttnWarps * 32) : "memory");
+        // merge weights exp(m_rg - M) per (rg, g); M and the merged sum per g
+        if (tid < G) {
+            const int g = tid;
+            float M = -INFINITY;
+            for (int r = 0; r < RG; ++r) M = fmaxf(M, merge[((size_t)r * G + g) * (D + 2) + D]);
+            float S = 0.0f;
+            for (int r = 0; r < RG; ++r) {
+                const float *mp = merge + ((size_t)r * G + g) * (D + 2);
+                const float w = expf(mp[D] - M);  // a row group without rows has m = -inf: weight 0
+                wts[r * G + g] = w;
+                S = fmaf(mp[D + 1], w, S);
+            }
+            wts[RG * G + g] = M;
+            wts[RG * G + G + g] = S;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(kAttnWarps * 32) : "memory");
     }
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int e = 0; e < V; ++e) red[((size_t)rg * G + g) * D + l * V + e] = of[g][e];
     __syncthreads();
 
-    // ---- reduce the row groups; single split: finish here, else publish the partial
+    // ---- combine the row groups; single split: finish here, else publish the partial
     float *part = a.partials + (((size_t)b * Hkv + kvh) * a.nsplit + split) * (size_t)G * (D + 2);
     T *out = reinterpret_cast<T *>(a.out) + ((size_t)b * H + (size_t)kvh * G) * D;
     for (int i = tid; i < G * D; i += kAttnThreads) {
         const int g = i / D, d = i % D;
         float o = 0.0f;
 #pragma unroll
-        for (int r = 0; r < RG; ++r) o += red[((size_t)r * G + g) * D + d];
+        for (int r = 0; r < RG; ++r) o = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o);
         if (a.nsplit == 1) {
-            const float m = ms[g], mf = final_max(m, step, D), c = expf(m - mf);
-            out[(size_t)g * D + d] = Elem<T>::from_f(o * c / (ms[G + g] * c + 1e-6f));
+            const float mm = wts[RG * G + g], mf = final_max(mm, step, D), c = expf(mm - mf);
+            out[(size_t)g * D + d] = Elem<T>::from_f(o * c / (wts[RG * G + G + g] * c + 1e-6f));
         } else {
             part[(size_t)g * (D + 2) + d] = o;
         }
     }
     if (a.nsplit == 1) return;
     if (tid < G) {
-        part[(size_t)tid * (D + 2) + D] = ms[tid];
-        part[(size_t)tid * (D + 2) + D + 1] = ms[G + tid];
+        part[(size_t)tid * (D + 2) + D] = wts[RG * G + tid];
+        part[(size_t)tid * (D + 2) + D + 1] = wts[RG * G + G + tid];
     }
     __threadfence();
     __syncthreads();
@@ -257,24 +352,24 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     const float *pbase = a.partials + ((size_t)b * Hkv + kvh) * a.nsplit * (size_t)G * (D + 2);
     for (int i = tid; i < G * D; i += kAttnThreads) {
         const int g = i / D, d = i % D;
-        float m = -INFINITY;
-        for (int s = 0; s < a.nsplit; ++s) m = fmaxf(m, __ldcg(pbase + ((size_t)s * G + g) * (D + 2) + D));
-        m = final_max(m, step, D);
-        float sum = 0.0f, o = 0.0f;
-        for (int s = 0; s < a.nsplit; ++s) {
-            const float *ps = pbase + ((size_t)s * G + g) * (D + 2);
-            const float c = expf(__ldcg(ps + D) - m);
-            sum = fmaf(__ldcg(ps + D + 1), c, sum);
+        float mm = -INFINITY;
+        for (int s2 = 0; s2 < a.nsplit; ++s2) mm = fmaxf(mm, __ldcg(pbase + ((size_t)s2 * G + g) * (D + 2) + D));
+        mm = final_max(mm, step, D);
+        float ssum = 0.0f, o = 0.0f;
+        for (int s2 = 0; s2 < a.nsplit; ++s2) {
+            const float *ps = pbase + ((size_t)s2 * G + g) * (D + 2);
+            const float c = expf(__ldcg(ps + D) - mm);
+            ssum = fmaf(__ldcg(ps + D + 1), c, ssum);
             o = fmaf(__ldcg(ps + d), c, o);
         }
-        out[(size_t)g * D + d] = Elem<T>::from_f(o / (sum + 1e-6f));
+        out[(size_t)g * D + d] = Elem<T>::from_f(o / (ssum + 1e-6f));
     }
 }
 
 // ------------------------------------------------------------------ any head size (toy shapes of the reference's examples)
 template <typename T>
 __global__ void decode_attn_generic_kernel(const DecodeAttnArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int D = a.head_size;
     float *q = reinterpret_cast<float *>(smem_raw);  // [D]
     float *knew = q + D, *vnew = knew + D;           // [D] each
@@ -345,12 +440,12 @@ size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int
 }
 
 int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk) {
-    // enough CTAs for ~4 per SM, chunks of 32..256 positions
-    int want = (4 * sm_count() + batch * kv_head_num - 1) / (batch * kv_head_num);
+    // about two CTAs per SM in ONE wave (never a partial second wave), chunks of >= 32 positions
+    int want = (2 * sm_count()) / (batch * kv_head_num);
+    if (want < 1) want = 1;
     int c = (step + want - 1) / want;
+    c = (c + 3) & ~3;
     if (c < 32) c = 32;
-    if (c > 256) c = 256;
-    c = (c + 7) & ~7;
     *chunk = c;
     return (step + c - 1) / c;
 }
@@ -360,8 +455,9 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
     const int G = a.head_num / a.kv_head_num;
     const bool fast = a.head_size == kAttnD && (G == 1 || G == 2 || G == 4 || G == 8) && aligned16(a.k_cache) && aligned16(a.v_cache);
     if (fast) {
-        const int RG = kAttnThreads / (kAttnD / Elem<T>::kVec);
-        const size_t smem = sizeof(float) * ((size_t)G * kAttnD + 2 * kAttnD + 2 * G + (size_t)G * a.chunk + (size_t)RG * G * kAttnD);
+        const int RG = kAttnWarps * 32 / (kAttnD / Elem<T>::kVec);
+        const size_t smem = (size_t)kAttnStages * 2 * kAttnTileBytes + sizeof(float) * ((size_t)G * kAttnD + 2 * kAttnD + (size_t)RG * G + 2 * G + 2) +
+                            2 * kAttnStages * 8 + 16;
         dim3 grid(a.nsplit, a.kv_head_num, a.batch);
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -16,6 +16,8 @@ struct DecodeAttnArgs {
     int apply_rope, rot_dim;
     float rot_base;
     int nsplit, chunk;
+    int prefetch;  // 1: cached K/V rows may be requested before griddepcontrol.wait (fused engine only: the kernel in front
+                   // of this one does not write the cache)
 };
 
 // number of KV splits (and positions per split) for a decode step

@@ -229,6 +229,7 @@ int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const 
     a.apply_rope = c.rotary_dim > 0, a.rot_dim = c.rotary_dim, a.rot_base = c.rotary_base;
     a.nsplit = decode_attn_plan(batch, c.kv_head_num, step, &a.chunk);
     a.partials = dec->partials, a.tickets = dec->tickets;
+    a.prefetch = 1;  // the kernel in front of this one is the QKV linear: it does not touch the cache
     rc = launch_decode_attn(a, c.dtype, st);
     if (rc != B200_OK) return rc;
     // 3. O projection (row-sharded under TP: `partial` is this rank's partial sum)
