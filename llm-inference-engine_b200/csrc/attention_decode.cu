@@ -21,6 +21,11 @@
 //     normalisation.
 #include "attention_decode.cuh"
 
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+namespace cg = cooperative_groups;
+
 namespace b200 {
 
 // theta denominators exactly as the reference computes them on the host side of its unit tests:
@@ -30,12 +35,27 @@ __device__ __forceinline__ float rope_denominator(float base, int zid, int rot_d
     const float e = (float)zid / (float)rot_dim;
     return (float)pow((double)base, (double)e);
 }
-__device__ __forceinline__ void rope_rotate(float &x0, float &x1, float pos, float denom) {
+__device__ __forceinline__ float2 rope_cos_sin(float pos, float denom) {
     const float th = pos / denom;
-    const float c = cosf(th), s = sinf(th);
+    return make_float2(cosf(th), sinf(th));
+}
+__device__ __forceinline__ void rope_apply(float &x0, float &x1, const float2 cs) {
     const float a = x0, b = x1;
-    x0 = a * c - b * s;
-    x1 = b * c + a * s;
+    x0 = a * cs.x - b * cs.y;
+    x1 = b * cs.x + a * cs.y;
+}
+__device__ __forceinline__ void rope_rotate(float &x0, float &x1, float pos, float denom) { rope_apply(x0, x1, rope_cos_sin(pos, denom)); }
+
+// (cos, sin) table: the same expressions as above, evaluated once per (position, pair) instead of once per head per step
+__global__ void rope_table_kernel(float2 *table, int positions, int rot_dim, float base) {
+    const int half = rot_dim / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < positions * half; i += gridDim.x * blockDim.x)
+        table[i] = rope_cos_sin((float)(i / half), rope_denominator(base, 2 * (i % half), rot_dim));
+}
+int launch_rope_table(float2 *table, int positions, int rot_dim, float rot_base, cudaStream_t st) {
+    if (positions <= 0 || rot_dim < 2) return B200_OK;
+    rope_table_kernel<<<sm_count() * 4, 256, 0, st>>>(table, positions, rot_dim, rot_base);
+    return cuda_status("rope_table launch");
 }
 
 // ------------------------------------------------------------------ standalone decode RoPE (launchRope)
@@ -109,6 +129,9 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     float *vnew = knew + D;                                                           // [D]
     float *wts = vnew + D;                                                            // [RG][G] merge weights, then [G] max, [G] sum
     const uint32_t full0 = a_smem_u32(wts + RG * G + 2 * G + 2), empty0 = full0 + 8 * kAttnStages;
+    // cluster merge: the leader CTA's copy receives every split's (out[G][D], max, sum) -- must not alias the ring, which the
+    // leader may still be reading when a faster CTA of the cluster delivers
+    float *cl_part = wts + RG * G + 2 * G + 2 + 4 * kAttnStages;  // [nsplit <= 8][G][D+2]
     __shared__ bool is_last;
 
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -157,7 +180,9 @@ decode_attn_kernel(const DecodeAttnArgs a) {
         const int head = g < G ? kvh * G + g : H + kvh;
         float x0 = Elem<T>::to_f(qkv[(size_t)head * D + j]), x1 = Elem<T>::to_f(qkv[(size_t)head * D + j + D / 2]);
         if (a.apply_rope && j < a.rot_dim / 2) {
-            rope_rotate(x0, x1, (float)(step - 1), rope_denominator(a.rot_base, 2 * j, a.rot_dim));
+            const float2 cs = a.rope_cs ? __ldg(a.rope_cs + (size_t)(step - 1) * (a.rot_dim / 2) + j)
+                                        : rope_cos_sin((float)(step - 1), rope_denominator(a.rot_base, 2 * j, a.rot_dim));
+            rope_apply(x0, x1, cs);
             x0 = round_t<T>(x0), x1 = round_t<T>(x1);  // launchRope writes T back before the MHA kernel reads it
         }
         if (bias) {
@@ -182,7 +207,6 @@ decode_attn_kernel(const DecodeAttnArgs a) {
             kc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(knew[j]);
             vc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(vnew[j]);
         }
-        __threadfence();
     }
     pdl_launch_dependents();
 
@@ -321,22 +345,61 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     }
     __syncthreads();
 
-    // ---- combine the row groups; single split: finish here, else publish the partial
-    float *part = a.partials + (((size_t)b * Hkv + kvh) * a.nsplit + split) * (size_t)G * (D + 2);
+    // ---- combine the row groups; single split: finish here, else hand the partial to the merge
     T *out = reinterpret_cast<T *>(a.out) + ((size_t)b * H + (size_t)kvh * G) * D;
+    if (a.nsplit == 1) {
+        for (int i = tid; i < G * D; i += kAttnThreads) {
+            const int g = i / D, d = i % D;
+            float o = 0.0f;
+#pragma unroll
+            for (int r = 0; r < RG; ++r) o = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o);
+            const float mm = wts[RG * G + g], mf = final_max(mm, step, D), c = expf(mm - mf);
+            out[(size_t)g * D + d] = Elem<T>::from_f(o * c / (wts[RG * G + G + g] * c + 1e-6f));
+        }
+        return;
+    }
+    if (a.cluster) {
+        // ---- the nsplit CTAs of this (b, kv head) are one thread-block cluster: partials travel through distributed shared memory
+        cg::cluster_group cluster = cg::this_cluster();
+        float *dst = cluster.map_shared_rank(cl_part, 0) + (size_t)split * G * (D + 2);
+        for (int i = tid; i < G * D; i += kAttnThreads) {
+            const int g = i / D, d = i % D;
+            float o = 0.0f;
+#pragma unroll
+            for (int r = 0; r < RG; ++r) o = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o);
+            dst[(size_t)g * (D + 2) + d] = o;
+        }
+        if (tid < G) {
+            dst[(size_t)tid * (D + 2) + D] = wts[RG * G + tid];
+            dst[(size_t)tid * (D + 2) + D + 1] = wts[RG * G + G + tid];
+        }
+        cluster.sync();  // release / acquire: every split's partial is in the leader's shared memory
+        if (split != 0) return;
+        for (int i = tid; i < G * D; i += kAttnThreads) {
+            const int g = i / D, d = i % D;
+            float mm = -INFINITY;
+            for (int s2 = 0; s2 < a.nsplit; ++s2) mm = fmaxf(mm, cl_part[((size_t)s2 * G + g) * (D + 2) + D]);
+            mm = final_max(mm, step, D);
+            float ssum = 0.0f, o = 0.0f;
+            for (int s2 = 0; s2 < a.nsplit; ++s2) {  // split order: deterministic
+                const float *ps = cl_part + ((size_t)s2 * G + g) * (D + 2);
+                const float c = expf(ps[D] - mm);
+                ssum = fmaf(ps[D + 1], c, ssum);
+                o = fmaf(ps[d], c, o);
+            }
+            out[(size_t)g * D + d] = Elem<T>::from_f(o / (ssum + 1e-6f));
+        }
+        return;
+    }
+    // ---- no cluster: partials through global scratch, the last CTA of the (b, kv head) (self-resetting ticket) merges
+    float *part = a.partials + (((size_t)b * Hkv + kvh) * a.nsplit + split) * (size_t)G * (D + 2);
     for (int i = tid; i < G * D; i += kAttnThreads) {
         const int g = i / D, d = i % D;
         float o = 0.0f;
 #pragma unroll
         for (int r = 0; r < RG; ++r) o = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o);
-        if (a.nsplit == 1) {
-            const float mm = wts[RG * G + g], mf = final_max(mm, step, D), c = expf(mm - mf);
-            out[(size_t)g * D + d] = Elem<T>::from_f(o * c / (wts[RG * G + G + g] * c + 1e-6f));
-        } else {
-            part[(size_t)g * (D + 2) + d] = o;
-        }
+        part[(size_t)g * (D + 2) + d] = o;
     }
-    if (a.nsplit == 1) return;
     if (tid < G) {
         part[(size_t)tid * (D + 2) + D] = wts[RG * G + tid];
         part[(size_t)tid * (D + 2) + D + 1] = wts[RG * G + G + tid];
@@ -347,8 +410,6 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-
-    // ---- merge the splits in order (deterministic)
     const float *pbase = a.partials + ((size_t)b * Hkv + kvh) * a.nsplit * (size_t)G * (D + 2);
     for (int i = tid; i < G * D; i += kAttnThreads) {
         const int g = i / D, d = i % D;
@@ -439,10 +500,21 @@ size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int
     return (size_t)batch * kv_head_num * max_splits * (head_num / kv_head_num) * (head_size + 2);
 }
 
+// Two merges of the split-KV partials exist: through global scratch + ticket (default) and through the distributed shared
+// memory of a thread-block cluster (B200_ATTN_CLUSTER=1).  Measured on B200, 7B bf16 B=1 ctx 1024: 2.585 ms/step with the
+// ticket merge (9 splits, 288 CTAs) vs 2.61 ms with clusters of 8 (256 CTAs) -- the cluster launch constrains placement
+// more than the DSMEM hop saves, so it stays opt-in.
+static bool attn_use_cluster() {
+    static const bool on = getenv("B200_ATTN_CLUSTER") != nullptr;
+    return on;
+}
+
 int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk) {
-    // about two CTAs per SM in ONE wave (never a partial second wave), chunks of >= 32 positions
+    // about two CTAs per SM in ONE wave (never a partial second wave), chunks of >= 32 positions; the splits of a
+    // (b, kv head) form one thread-block cluster, so at most 8 (the portable cluster size)
     int want = (2 * sm_count()) / (batch * kv_head_num);
     if (want < 1) want = 1;
+    if (attn_use_cluster() && want > 8) want = 8;
     int c = (step + want - 1) / want;
     c = (c + 3) & ~3;
     if (c < 32) c = 32;
@@ -456,12 +528,13 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
     const bool fast = a.head_size == kAttnD && (G == 1 || G == 2 || G == 4 || G == 8) && aligned16(a.k_cache) && aligned16(a.v_cache);
     if (fast) {
         const int RG = kAttnWarps * 32 / (kAttnD / Elem<T>::kVec);
+        a.cluster = a.nsplit > 1 && a.nsplit <= 8 && attn_use_cluster();
         const size_t smem = (size_t)kAttnStages * 2 * kAttnTileBytes + sizeof(float) * ((size_t)G * kAttnD + 2 * kAttnD + (size_t)RG * G + 2 * G + 2) +
-                            2 * kAttnStages * 8 + 16;
+                            2 * kAttnStages * 8 + (a.cluster ? sizeof(float) * (size_t)a.nsplit * G * (kAttnD + 2) : 0) + 16;
         dim3 grid(a.nsplit, a.kv_head_num, a.batch);
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_pdl(kern, grid, dim3(kAttnThreads), smem, st, true, a);
+            launch_pdl_cluster(kern, grid, dim3(kAttnThreads), smem, st, true, a.cluster ? (unsigned)a.nsplit : 1u, a);
         };
         switch (G) {
             case 1: go(decode_attn_kernel<T, 1>); break;

@@ -10,12 +10,14 @@ struct DecodeAttnArgs {
     void *k_cache;     // layer base: [B, Hkv, S, d]
     void *v_cache;
     void *out;         // [B, H*d]
-    float *partials;   // [B*Hkv][nsplit][G][d+2]
+    float *partials;   // [B*Hkv][nsplit][G][d+2]   (head sizes other than 128 only: the 128 path merges through DSMEM)
     unsigned int *tickets;  // [B*Hkv], zero-initialised, self-resetting
+    const float2 *rope_cs;  // optional (cos, sin) table [max_seq_len][rot_dim/2] made by launch_rope_table(); NULL: compute
     int batch, head_num, kv_head_num, head_size, max_seq_len, step;
     int apply_rope, rot_dim;
     float rot_base;
     int nsplit, chunk;
+    int cluster;   // 1: the nsplit CTAs of a (b, kv head) form a thread-block cluster and merge through distributed shared memory
     int prefetch;  // 1: cached K/V rows may be requested before griddepcontrol.wait (fused engine only: the kernel in front
                    // of this one does not write the cache)
 };
@@ -24,5 +26,7 @@ struct DecodeAttnArgs {
 int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk);
 size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int head_size, int max_splits);
 int launch_decode_attn(const DecodeAttnArgs &a, int dtype, cudaStream_t st);
+// (cos, sin) of pos / base^(2j / rot_dim) for pos < positions, j < rot_dim / 2 -- the values the kernels compute on the fly
+int launch_rope_table(float2 *table, int positions, int rot_dim, float rot_base, cudaStream_t st);
 
 }  // namespace b200

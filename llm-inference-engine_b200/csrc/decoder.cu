@@ -29,6 +29,7 @@ struct b200_decoder {
     void *qkv = nullptr, *attn = nullptr, *y_attn = nullptr, *gu = nullptr, *act = nullptr, *y_ffn = nullptr;
     float *partials = nullptr;
     unsigned int *tickets = nullptr;
+    float2 *rope_cs = nullptr;  // (cos, sin) per (position, rotary pair), filled once by set_scratch
     int max_splits = 0;
     int cur = 0;  // which res[] holds the residual stream
 };
@@ -39,7 +40,7 @@ static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t esize(int dtype) { return dtype == B200_F32 ? 4 : 2; }
 
 struct Carve {
-    size_t res, xn, qkv, attn, y, gu, act, partials, tickets, total;
+    size_t res, xn, qkv, attn, y, gu, act, partials, tickets, rope, total;
 };
 static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     Carve k;
@@ -55,7 +56,8 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     *max_splits = (c.max_seq_len + 31) / 32;
     k.partials = align_up(decode_attn_partials_floats(c.max_batch, c.head_num, c.kv_head_num, c.head_size, *max_splits) * sizeof(float));
     k.tickets = align_up((size_t)c.max_batch * c.kv_head_num * sizeof(unsigned int));
-    k.total = 2 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets;
+    k.rope = c.rotary_dim > 0 ? align_up((size_t)c.max_seq_len * (c.rotary_dim / 2) * sizeof(float2)) : 0;
+    k.total = 2 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.rope;
     return k;
 }
 
@@ -133,6 +135,10 @@ b200_decoder_t *b200_decoder_create(const b200_decoder_config_t *cfg) {
         set_error("decoder_create: bad model shape");
         return nullptr;
     }
+    if (c.rotary_dim < 0 || c.rotary_dim > c.head_size || c.rotary_dim % 2 != 0) {
+        set_error("decoder_create: rotary_dim %d must be even and within [0, head_size]", c.rotary_dim);
+        return nullptr;
+    }
     if (c.dtype != B200_F32 && c.dtype != B200_F16 && c.dtype != B200_BF16) {
         set_error("decoder_create: unknown dtype %d", c.dtype);
         return nullptr;
@@ -194,8 +200,15 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     dec->gu = p, p += k.gu;
     dec->act = p, p += k.act;
     dec->partials = (float *)p, p += k.partials;
-    dec->tickets = (unsigned int *)p;
+    dec->tickets = (unsigned int *)p, p += k.tickets;
     if (cudaMemset(dec->tickets, 0, k.tickets) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
+    dec->rope_cs = nullptr;
+    if (k.rope) {
+        dec->rope_cs = (float2 *)p;
+        const int rc = launch_rope_table(dec->rope_cs, dec->cfg.max_seq_len, dec->cfg.rotary_dim, dec->cfg.rotary_base, nullptr);
+        if (rc != B200_OK) return rc;
+        if (cudaStreamSynchronize(nullptr) != cudaSuccess) return cuda_status("decoder_set_scratch rope table");
+    }
     dec->cur = 0;
     return B200_OK;
 }
@@ -229,6 +242,7 @@ int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const 
     a.apply_rope = c.rotary_dim > 0, a.rot_dim = c.rotary_dim, a.rot_base = c.rotary_base;
     a.nsplit = decode_attn_plan(batch, c.kv_head_num, step, &a.chunk);
     a.partials = dec->partials, a.tickets = dec->tickets;
+    a.rope_cs = dec->rope_cs;
     a.prefetch = 1;  // the kernel in front of this one is the QKV linear: it does not touch the cache
     rc = launch_decode_attn(a, c.dtype, st);
     if (rc != B200_OK) return rc;
