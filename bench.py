@@ -209,6 +209,7 @@ def main():
 
     mod = importlib.import_module("llm-inference-engine_b200")
     mod.lib()  # fails loudly if libb200llm.so is missing
+    tpmod = importlib.import_module("llm-inference-engine_b200.tp")
     tp = world
     assert tp == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE {world}"
     torch.cuda.set_device(local_rank)
@@ -266,15 +267,16 @@ def main():
         mod.check(mod.lib().b200_input_embedding(mod.ptr(ids_dev), mod.ptr(emb), mod.ptr(hidden), B, h, mod.BF16, mod.stream()))
         if tp == 1:
             dec.step(hidden, kc, vc, step)
-        else:
-            pending = None
-            for l in range(L):
-                dec.attn_block(l, hidden, pending, kc, vc, y_attn, step)
-                dist.all_reduce(y_attn)
-                dec.ffn_block(l, y_attn, y_ffn)
-                dist.all_reduce(y_ffn)
-                pending = y_ffn
-            dec.fold(hidden, pending)
+        else:  # one NCCL all-reduce per attention block and per MLP block (llm-inference-engine_b200/tp.py)
+            def attn_block(l, h, pending):
+                dec.attn_block(l, h, pending, kc, vc, y_attn, step)
+                return y_attn
+
+            def ffn_block(l, pending):
+                dec.ffn_block(l, pending, y_ffn)
+                return y_ffn
+
+            tpmod.decode_step_tp(L, hidden, attn_block, ffn_block, lambda h, pending: dec.fold(h, pending), dist.all_reduce)
         dec.lm_head_topk_sample(hidden, final_gamma, lm_head, bufs, K_TOP, step, END_ID)
 
     stream = torch.cuda.Stream(device=dev)
@@ -393,6 +395,14 @@ def main():
         stream.synchronize()
         gemv_ms = r0.elapsed_time(r1) / reps
         achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
+        # DRAM traffic of the same launches from the committed ncu capture (read + write bytes over algorithmic bytes)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if args.config == "7b" and args.wformat == "bf16" and B == 1 and tp == 1:
+                traffic = gemv_bytes * float(tr["traffic_over_algorithmic"])
+        except Exception:
+            pass
 
     if rank == 0:
         cpu = None
@@ -409,7 +419,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "launch_mode": "cuda-graph replay" if graph is not None else "eager",
             "roofline": {"bound": "hbm", "kernel": "gemv_nk_kernel (all %d weight-streaming linears of one step, back to back)" % n_gemv,
-                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
+                         "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write of the QKV/O/gate_up/down launches, scaled to the step)" if traffic else None,
                          "peak_source": peak_src, "bytes_per_step_launches": gemv_bytes, "ms": gemv_ms,
                          "whole_step": {"bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                                         "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak_gbs,

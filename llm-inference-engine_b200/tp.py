@@ -1,0 +1,102 @@
+"""Tensor-parallel sharding of one decoder layer (new -- the reference is single-GPU).
+
+Weights are in the engine's packed [N,K] layout.  Rank r of P owns
+  * q heads  [r*H/P, (r+1)*H/P)  and kv heads [r*Hkv/P, (r+1)*Hkv/P): the matching ROWS of Wqkv (and of its bias),
+  * the matching K-COLUMNS of Wo (row-sharded linear: its output is a partial sum, all-reduced),
+  * FFN columns [r*I/P, (r+1)*I/P): the matching gate rows AND up rows of Wgate_up (paired so SwiGLU stays local),
+    and the matching K-columns of Wdown (partial sum, all-reduced),
+  * KV-cache heads [r*Hkv/P, ...): cache [L, B, Hkv/P, S, d].
+Norm gammas, the residual stream and the o-bias are replicated (the bias is added once, after the reduce).
+Works on numpy arrays and torch tensors alike (pure slicing + concatenation)."""
+
+
+def _cat(parts):
+    try:
+        import torch
+
+        if isinstance(parts[0], torch.Tensor):
+            return torch.cat(list(parts), dim=0).contiguous()
+    except ImportError:
+        pass
+    import numpy as np
+
+    return np.ascontiguousarray(np.concatenate(list(parts), axis=0))
+
+
+def _contig(a):
+    if hasattr(a, "contiguous"):
+        return a.contiguous()
+    import numpy as np
+
+    return np.ascontiguousarray(a)
+
+
+def check_divisible(head_num, kv_head_num, inter, world):
+    if head_num % world or kv_head_num % world or inter % world:
+        raise ValueError(f"tensor-parallel degree {world} must divide head_num {head_num}, kv_head_num {kv_head_num} and inter {inter}")
+
+
+def shard_qkv_rows(wqkv, head_num, kv_head_num, head_size, rank, world):
+    """Rows of Wqkv [(H+2Hkv)*d, K] (or entries of the qkv bias [(H+2Hkv)*d]) owned by `rank`: its q heads, k heads, v heads."""
+    hq, hk, d = head_num // world, kv_head_num // world, head_size
+    q0, k0, v0 = 0, head_num * d, (head_num + kv_head_num) * d
+    return _cat([wqkv[q0 + rank * hq * d: q0 + (rank + 1) * hq * d], wqkv[k0 + rank * hk * d: k0 + (rank + 1) * hk * d],
+                 wqkv[v0 + rank * hk * d: v0 + (rank + 1) * hk * d]])
+
+
+def shard_o_cols(wo, head_num, head_size, rank, world):
+    """K-columns of Wo [h, H*d] that multiply this rank's attention heads."""
+    n = head_num // world * head_size
+    return _contig(wo[:, rank * n:(rank + 1) * n])
+
+
+def shard_gate_up_rows(wgu, inter, rank, world):
+    """Rows of Wgate_up [2I, K]: this rank's gate rows followed by its up rows."""
+    n = inter // world
+    return _cat([wgu[rank * n:(rank + 1) * n], wgu[inter + rank * n: inter + (rank + 1) * n]])
+
+
+def shard_down_cols(wd, inter, rank, world):
+    n = inter // world
+    return _contig(wd[:, rank * n:(rank + 1) * n])
+
+
+def shard_kv_cache(cache, kv_head_num, rank, world):
+    """cache [L, B, Hkv, S, d] -> [L, B, Hkv/P, S, d]"""
+    n = kv_head_num // world
+    return _contig(cache[:, :, rank * n:(rank + 1) * n])
+
+
+def shard_layer(w, cfg, rank, world):
+    """w: dict(g1, wqkv, bqkv|None, wo, bo|None, g2, wgu, wd) in [N,K] layout; cfg: dict(head_num, kv_head_num, head_size, inter).
+    Returns this rank's dict with the same keys.  The o bias stays whole: it is applied once, after the all-reduce."""
+    H, Hkv, d, I = cfg["head_num"], cfg["kv_head_num"], cfg["head_size"], cfg["inter"]
+    check_divisible(H, Hkv, I, world)
+    out = dict(w)
+    out["wqkv"] = shard_qkv_rows(w["wqkv"], H, Hkv, d, rank, world)
+    out["bqkv"] = None if w.get("bqkv") is None else shard_qkv_rows(w["bqkv"], H, Hkv, d, rank, world)
+    out["wo"] = shard_o_cols(w["wo"], H, d, rank, world)
+    out["wgu"] = shard_gate_up_rows(w["wgu"], I, rank, world)
+    out["wd"] = shard_down_cols(w["wd"], I, rank, world)
+    return out
+
+
+def local_cfg(cfg, world):
+    """Per-rank shape: what goes into b200_decoder_config_t (head_num, kv_head_num, inter_size are per-rank counts)."""
+    check_divisible(cfg["head_num"], cfg["kv_head_num"], cfg["inter"], world)
+    out = dict(cfg)
+    out["head_num"], out["kv_head_num"], out["inter"] = cfg["head_num"] // world, cfg["kv_head_num"] // world, cfg["inter"] // world
+    return out
+
+
+def decode_step_tp(layers, hidden, attn_block, ffn_block, fold, all_reduce):
+    """The tensor-parallel decode step: the call sequence bench.py and the C ABI (b200_decoder_attn_block / _ffn_block / _fold)
+    share.  attn_block(l, hidden, pending) -> partial; ffn_block(l, pending) -> partial; all_reduce(t) sums t over ranks in place."""
+    pending = None
+    for l in range(layers):
+        y = attn_block(l, hidden, pending)
+        all_reduce(y)
+        z = ffn_block(l, y)
+        all_reduce(z)
+        pending = z
+    return fold(hidden, pending)

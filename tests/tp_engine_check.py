@@ -1,0 +1,83 @@
+"""Run under torchrun (N ranks, one GPU each): the tensor-parallel fused engine (b200_decoder_attn_block / _ffn_block + one NCCL
+all-reduce per block) against the UN-SHARDED CPU oracle on the same seeded model.  Exits non-zero on mismatch.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/tp_engine_check.py"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle
+    from test_decoder_engine import make_inputs, make_model, run_oracle
+    from util import assert_close, rounded, to_dev, to_np
+
+    mod = importlib.import_module("llm-inference-engine_b200")
+    tp = importlib.import_module("llm-inference-engine_b200.tp")
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(hidden=1024, head_num=8, kv_head_num=8 if world <= 8 else world, head_size=128, inter=2048, layers=3, max_seq=160, eps=1e-6, base=10000.0)
+    ok = True
+    for dtype, batch, step in (("f32", 2, 37), ("bf16", 1, 130), ("bf16", 4, 64)):
+        model = make_model(cfg, seed=17)
+        lcfg = tp.local_cfg(dict(head_num=cfg["head_num"], kv_head_num=cfg["kv_head_num"], head_size=cfg["head_size"], inter=cfg["inter"]), world)
+        dc = mod.DecoderConfig(cfg["hidden"], lcfg["head_num"], lcfg["kv_head_num"], cfg["head_size"], lcfg["inter"], cfg["layers"], cfg["max_seq"],
+                               batch, {"f32": 0, "f16": 1, "bf16": 2}[dtype], 0, 128, cfg["eps"], cfg["head_size"], cfg["base"], world, rank)
+        dec = mod.Decoder(dc, dev)
+        for l, w in enumerate(model["layers"]):
+            s = tp.shard_layer(w, cfg, rank, world)
+            dec.set_layer(l, dict(g1=to_dev(s["g1"], dtype), qkv=to_dev(s["wqkv"], dtype), qkv_bias=to_dev(s["bqkv"], dtype), o=to_dev(s["wo"], dtype),
+                                  o_bias=to_dev(s["bo"], dtype), g2=to_dev(s["g2"], dtype), gate_up=to_dev(s["wgu"], dtype), down=to_dev(s["wd"], dtype)))
+        x, kc, vc = make_inputs(cfg, batch, step, model["seed"])
+        hidden = to_dev(x, dtype)
+        kcd = to_dev(tp.shard_kv_cache(kc, cfg["kv_head_num"], rank, world), dtype)
+        vcd = to_dev(tp.shard_kv_cache(vc, cfg["kv_head_num"], rank, world), dtype)
+        y_attn, y_ffn = torch.empty_like(hidden), torch.empty_like(hidden)
+
+        def attn_block(l, h, pending):
+            dec.attn_block(l, h, pending, kcd, vcd, y_attn, step)
+            return y_attn
+
+        def ffn_block(l, pending):
+            dec.ffn_block(l, pending, y_ffn)
+            return y_ffn
+
+        def fold(h, pending):
+            dec.fold(h, pending)
+            return h
+
+        tp.decode_step_tp(cfg["layers"], hidden, attn_block, ffn_block, fold, dist.all_reduce)
+        torch.cuda.synchronize()
+        got = to_np(hidden)
+        ref, rkc, rvc = run_oracle(model, cfg, dtype, batch, step, storage="f32")
+        try:
+            if dtype == "f32":
+                assert_close(got, ref, "f32", f"TP-{world} engine")
+            else:
+                fro = np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ref)
+                assert fro <= 1e-2, f"TP-{world} {dtype} engine vs fp32 oracle: {fro:.3e}"
+            mine = to_np(kcd)[:, :, :, step - 1]
+            want = rounded(tp.shard_kv_cache(rkc, cfg["kv_head_num"], rank, world), dtype)[:, :, :, step - 1]
+            assert_close(mine, want, dtype, "appended K rows of this rank's heads")
+            print(f"[rank {rank}] TP-{world} {dtype} batch {batch} step {step}: OK", flush=True)
+        except AssertionError as e:
+            ok = False
+            print(f"[rank {rank}] FAILED: {e}", flush=True)
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
