@@ -430,7 +430,12 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if tp > 1:
-        dist.destroy_process_group()
+        # every rank is done once rank 0 has printed; leave without the NCCL teardown (observed to hang after graph-captured
+        # collectives on this stack) so the launcher returns immediately
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

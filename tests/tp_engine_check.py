@@ -66,17 +66,20 @@ def main():
             else:
                 fro = np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ref)
                 assert fro <= 1e-2, f"TP-{world} {dtype} engine vs fp32 oracle: {fro:.3e}"
-            mine = to_np(kcd)[:, :, :, step - 1]
-            want = rounded(tp.shard_kv_cache(rkc, cfg["kv_head_num"], rank, world), dtype)[:, :, :, step - 1]
-            assert_close(mine, want, dtype, "appended K rows of this rank's heads")
+            mine = to_np(kcd)[:, :, :, step - 1].astype(np.float64)
+            want = tp.shard_kv_cache(rkc, cfg["kv_head_num"], rank, world)[:, :, :, step - 1]
+            kerr = np.linalg.norm(mine - want) / np.linalg.norm(want)
+            assert kerr <= (1e-5 if dtype == "f32" else 1e-2), f"appended K rows of this rank's heads: {kerr:.3e}"
             print(f"[rank {rank}] TP-{world} {dtype} batch {batch} step {step}: OK", flush=True)
         except AssertionError as e:
             ok = False
             print(f"[rank {rank}] FAILED: {e}", flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
-    dist.destroy_process_group()
-    sys.exit(1 if int(flag.item()) else 0)
+    code = 1 if int(flag.item()) else 0
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(code)  # skip NCCL teardown: it is not what is under test and can outlast the job
 
 
 if __name__ == "__main__":
