@@ -1,0 +1,422 @@
+// context_attn_tc.cu -- prefill ("context") attention on tcgen05 / TMEM for sm_100a, head_size 128, 16-bit activations.
+//
+// Semantics: the reference chain src/layers/context_attention.cpp:221-289 with a true QK^T (launchRepeatKVCache ->
+// launchLinearStridedBatchGemm -> launchFusedScaleMaskAndSoftmax -> launchLinearStridedBatchGemm ->
+// launchFusedTransposeAndRemovePadding), i.e. per (batch b, head h, query row i):
+//   s_k = scale * q_i.k_k for keys k < context_len[b] with k <= i + context_len[b] - input_len[b]   (others carry the additive
+//   -10000 of the mask and vanish: expf(-10000 + ...) == 0 in fp32), p = exp(s - max(max_k s, FLT_MIN)) / (sum + 1e-6), out = p.V
+// without materialising [B,H,Sq,Sk] scores or the GQA-repeated K/V, output already un-padded [T, H, d].
+//
+// One CTA = 128 query rows of one (b, h).  192 threads, warp-specialised:
+//   warp 4   TMA producer: Q tile once, then K and V tiles of 128 keys (cp.async.bulk.tensor.2d, 128-byte swizzle) in a 2-stage ring
+//   warp 5   MMA issuer:  S = Q.K^T (128x128x128, tcgen05.mma kind::f16, fp32 in TMEM, two S buffers so the logits of tile j+1 are
+//            computed while the softmax threads work on tile j) and O_j = P_j.V_j (V is the MN-major B operand)
+//   warps 0-3 softmax + epilogue: thread t owns query row t (TMEM lane t): tcgen05.ld its row of S, mask, online softmax, writes P
+//            (bf16/fp16) into shared memory in the 128-byte-swizzled K-major layout the second MMA reads, then tcgen05.ld the tile's
+//            P.V and accumulates the rescaled output row in registers.
+// Causal structure: q tiles visit only the key tiles up to their diagonal; heavy (late) q tiles are scheduled first.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <float.h>
+#include <mutex>
+
+namespace b200 {
+
+namespace catc {
+
+constexpr int kRows = 128;   // query rows per CTA = UMMA M
+constexpr int kKeys = 128;   // keys per tile = UMMA N of the first MMA, K extent of the second
+constexpr int kD = 128;      // head size
+constexpr int kThreads = 192;
+constexpr int kHalfBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 elements (128 B)
+constexpr int kTileBytes = 2 * kHalfBytes;
+constexpr int kKvStages = 2;
+
+struct Params {
+    void *out;                  // [T, H, d]
+    const int *seq_off;         // [B] padded-slot minus token index of each sequence
+    const int *input_len, *context_len;
+    int head_num, kv_head_num, max_q_len, max_seq_len;
+    float scale;
+    int is_bf16;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// Shared-memory matrix descriptors (sm_100 format: version 1 at bit 46, layout type in bits 61..63, 2 = SWIZZLE_128B).
+// K-major operand (rows of 128 bytes along K, 8-row atoms of 1024 bytes): SBO = 1024, LBO unused (1).
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// MN-major operand (V: rows = keys (the MMA K dimension), 128 bytes = 64 head dims contiguous along N): 8 keys = one 1024-byte
+// group (SBO), the next 64 head dims live in the second TMA box, kHalfBytes further (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(kHalfBytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint32_t idesc_f16(bool bf16, int m, int n, bool b_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;                   // D: F32
+    d |= (bf16 ? 1u : 0u) << 7;     // A format
+    d |= (bf16 ? 1u : 0u) << 10;    // B format
+    d |= (b_mn_major ? 1u : 0u) << 16;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(m >> 4) << 24;
+    return d;
+}
+
+// smem: [Q 32K][K ring 2x32K][V ring 2x32K][P 32K][barriers][tmem slot]
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                       const Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sQ = smem, *sK = sQ + kTileBytes, *sV = sK + kKvStages * kTileBytes, *sP = sV + kKvStages * kTileBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kTileBytes);
+    // barriers: q_full, kv_full[2], kv_empty[2], s_full[2], p_ready, o_full, o_taken
+    const uint32_t q_full = s_u32(bars), kv_full0 = q_full + 8, kv_empty0 = kv_full0 + 16, s_full0 = kv_empty0 + 16, p_ready = s_full0 + 16,
+                   o_full = p_ready + 8, o_taken = o_full + 8, s_free0 = o_taken + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) tiles first
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qt * kRows;
+
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+        bar_init(q_full, 1);
+        for (int s = 0; s < kKvStages; ++s) {
+            bar_init(kv_full0 + 8 * s, 1);
+            bar_init(kv_empty0 + 8 * s, 1);   // released by tcgen05.commit of the P.V MMA
+            bar_init(s_full0 + 8 * s, 1);
+            bar_init(s_free0 + 8 * s, 128);   // all softmax threads have read S[s]
+        }
+        bar_init(p_ready, 128);
+        bar_init(o_full, 1);
+        bar_init(o_taken, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;  // columns: S0 [0,128) S1 [128,256) O_tile [256,384)
+
+    pdl_wait();
+    pdl_launch_dependents();
+
+    const int qlen = p.input_len[b], klen = p.context_len[b];
+    const bool active = q0 < qlen;  // CTA-uniform
+    // last key any row of this tile may see (exclusive)
+    const int q_hi = min(q0 + kRows, qlen) - 1;
+    const int k_hi = active ? min(klen, q_hi + (klen - qlen) + 1) : 0;
+    const int ntiles = (k_hi + kKeys - 1) / kKeys;
+    const int kvh = h / (p.head_num / p.kv_head_num);
+    const int q_row0 = (b * p.head_num + h) * p.max_q_len + q0;
+    const int kv_row0 = (b * p.kv_head_num + kvh) * p.max_seq_len;
+
+    if (warp == 4) {
+        // ================================================= TMA producer
+        if (ntiles > 0 && elect_one()) {
+            bar_expect_tx(q_full, kTileBytes);
+            tma_load_2d(s_u32(sQ), &tmQ, 0, q_row0, q_full);
+            tma_load_2d(s_u32(sQ) + kHalfBytes, &tmQ, 64, q_row0, q_full);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % kKvStages;
+                bar_wait(kv_empty0 + 8 * s, ((j / kKvStages) & 1) ^ 1);
+                bar_expect_tx(kv_full0 + 8 * s, 2 * kTileBytes);
+                const uint32_t dk = s_u32(sK + s * kTileBytes), dv = s_u32(sV + s * kTileBytes);
+                tma_load_2d(dk, &tmK, 0, kv_row0 + j * kKeys, kv_full0 + 8 * s);
+                tma_load_2d(dk + kHalfBytes, &tmK, 64, kv_row0 + j * kKeys, kv_full0 + 8 * s);
+                tma_load_2d(dv, &tmV, 0, kv_row0 + j * kKeys, kv_full0 + 8 * s);
+                tma_load_2d(dv + kHalfBytes, &tmV, 64, kv_row0 + j * kKeys, kv_full0 + 8 * s);
+            }
+        }
+    } else if (warp == 5) {
+        // ================================================= MMA issuer
+        if (ntiles > 0) {
+            const uint32_t id_qk = idesc_f16(p.is_bf16 != 0, kRows, kKeys, false);
+            const uint32_t id_pv = idesc_f16(p.is_bf16 != 0, kRows, kD, true);
+            auto issue_qk = [&](int j) {  // S[j % 2] = Q . K_j^T
+                const int s = j % kKvStages, sb = j & 1;
+                bar_wait(kv_full0 + 8 * s, (j / kKvStages) & 1);
+                bar_wait(s_free0 + 8 * sb, ((j >> 1) & 1) ^ 1);  // the softmax threads are done with what S[sb] held (tile j - 2)
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t aq = s_u32(sQ), bk = s_u32(sK + s * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kD / 16; ++k) {
+                        const uint32_t off = (uint32_t)(k / 4) * kHalfBytes + (uint32_t)(k % 4) * 32;
+                        tc_mma_f16(tmem + (uint32_t)(sb * kKeys), desc_kmajor(aq + off), desc_kmajor(bk + off), id_qk, k > 0 ? 1u : 0u);
+                    }
+                    tc_commit(s_full0 + 8 * sb);
+                }
+                __syncwarp();
+            };
+            bar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) issue_qk(j + 1);  // next tile's logits while the softmax threads work on tile j
+                const int s = j % kKvStages;
+                bar_wait(p_ready, j & 1);                       // P_j is in shared memory (and V_j has landed: waited in issue_qk(j))
+                bar_wait(o_taken, (j & 1) ^ 1);                 // the previous tile's P.V has been read out of TMEM
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t ap = s_u32(sP), bv = s_u32(sV + s * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kKeys / 16; ++k) {
+                        const uint32_t aoff = (uint32_t)(k / 4) * kHalfBytes + (uint32_t)(k % 4) * 32;  // P: K-major over keys
+                        const uint32_t boff = (uint32_t)k * 16 * 128;                                    // V: 16 keys = 2048 bytes further
+                        tc_mma_f16(tmem + 2 * kKeys, desc_kmajor(ap + aoff), desc_mnmajor(bv + boff), id_pv, k > 0 ? 1u : 0u);
+                    }
+                    tc_commit(kv_empty0 + 8 * s);  // K_j / V_j (and P_j) may be overwritten
+                    tc_commit(o_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================= softmax + epilogue: thread = query row
+        const int row = threadIdx.x;           // 0..127 == TMEM lane
+        const int qi = q0 + row;
+        const int lim = qi + (klen - qlen);    // keys <= lim are visible to this row
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        float m_run = FLT_MIN, l_run = 0.0f;   // the reference's running max starts at FLT_MIN (scale_and_mask_and_softmax.cu:86-126)
+        float o[kD];
+#pragma unroll
+        for (int e = 0; e < kD; ++e) o[e] = 0.0f;
+        for (int j = 0; j < ntiles; ++j) {
+            const int sb = j & 1, k0 = j * kKeys;
+            bar_wait(s_full0 + 8 * sb, (j >> 1) & 1);
+            tc_fence_after();
+            // pass 1: row max over the visible keys of this tile
+            float mx = m_run;
+#pragma unroll 1
+            for (int c = 0; c < kKeys; c += 32) {
+                uint32_t r[32];
+                tc_ld32(lane_addr + (uint32_t)(sb * kKeys + c), r);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int kg = k0 + c + e;
+                    const float sv = (kg < klen && kg <= lim) ? p.scale * __uint_as_float(r[e]) : -INFINITY;
+                    mx = fmaxf(mx, sv);
+                }
+            }
+            const float corr = expf(m_run - mx);
+            // the previous tile's P must have been consumed by its MMA before P is overwritten: that MMA's completion is what
+            // o_full signalled and this thread waited for at the end of the previous iteration.
+            // pass 2: p = exp(s - max) -> shared memory (K-major, 128-byte swizzle: 16-byte chunk index XOR (row % 8))
+            float psum = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < kKeys; c += 32) {
+                uint32_t r[32];
+                tc_ld32(lane_addr + (uint32_t)(sb * kKeys + c), r);
+                tc_wait_ld();
+                uint32_t packed[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float pv[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int kg = k0 + c + e + u;
+                        const bool vis = kg < klen && kg <= lim;
+                        const float sv = p.scale * __uint_as_float(r[e + u]);
+                        // round to T first: the reference stores the probabilities in T before the second GEMM reads them
+                        pv[u] = vis ? Elem<T>::to_f(Elem<T>::from_f(expf(sv - mx))) : 0.0f;
+                        psum += vis ? expf(sv - mx) : 0.0f;
+                    }
+                    const T a0 = Elem<T>::from_f(pv[0]), a1 = Elem<T>::from_f(pv[1]);
+                    packed[e / 2] = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) |
+                                    ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+                }
+                // 32 keys = 4 chunks of 16 bytes; key c lives in half c / 64, chunk (c % 64) / 8
+                unsigned char *prow = sP + (c / 64) * kHalfBytes + row * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = ((c % 64) / 8 + q) ^ (row & 7);
+                    *reinterpret_cast<uint4 *>(prow + chunk * 16) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                }
+            }
+            tc_fence_before();
+            bar_arrive(s_free0 + 8 * sb);  // S[sb] may be overwritten by the logits of tile j + 2
+            // rows of V past the context must not reach the tensor core: 0 * NaN would poison the row (the cache beyond
+            // context_len is not initialised by anybody).  Row r of the tile is key k0 + r.
+            if (k0 + row >= klen) {
+                bar_wait(kv_full0 + 8 * (j % kKvStages), (j / kKvStages) & 1);
+                unsigned char *vrow = sV + (j % kKvStages) * kTileBytes + row * 128;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    *reinterpret_cast<uint4 *>(vrow + q * 16) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(vrow + kHalfBytes + q * 16) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of P / V visible to the MMA (async proxy)
+            bar_arrive(p_ready);
+            l_run = l_run * corr + psum;
+            m_run = mx;
+#pragma unroll
+            for (int e = 0; e < kD; ++e) o[e] *= corr;
+            // ---- this tile's P.V
+            bar_wait(o_full, j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < kD; c += 32) {
+                uint32_t r[32];
+                tc_ld32(lane_addr + (uint32_t)(2 * kKeys + c), r);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[c + e] += __uint_as_float(r[e]);
+            }
+            tc_fence_before();
+            bar_arrive(o_taken);
+        }
+        if (active && qi < qlen) {
+            const int t = b * p.max_q_len + qi - p.seq_off[b];  // un-padded token index
+            T *dst = reinterpret_cast<T *>(p.out) + ((size_t)t * p.head_num + h) * kD;
+            const float inv = 1.0f / (l_run + 1e-6f);
+#pragma unroll
+            for (int e = 0; e < kD; e += 8) {
+                float f[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = o[e + u] * inv;
+                st_v4(dst + e, pack16<T>(f));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+// rows x 128 matrix of a 16-bit type, boxes of 128 rows x 64 columns, 128-byte swizzle
+static bool make_map(CUtensorMap *map, const void *ptr, size_t rows, bool bf16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kD * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace catc
+
+// q [B, H, max_q_len, 128]; k/v: LAYER base of the cache [B, Hkv, S, 128]; out [T, H, 128]; seq_off [B] (device).
+// Returns B200_ERR_UNSUPPORTED (no error text) when the shape / type cannot use the tensor-core kernel.
+int launch_context_attention_tc(const void *q, const void *k_layer, const void *v_layer, void *out, const int *seq_off, const int *input_len,
+                                const int *context_len, int batch, int head_num, int kv_head_num, int max_q_len, int max_seq_len, int head_size,
+                                float scale, int dtype, cudaStream_t st) {
+    using namespace catc;
+    if ((dtype != B200_BF16 && dtype != B200_F16) || head_size != kD) return B200_ERR_UNSUPPORTED;
+    if (!aligned16(q) || !aligned16(k_layer) || !aligned16(v_layer) || !aligned16(out)) return B200_ERR_UNSUPPORTED;
+    const bool bf16 = dtype == B200_BF16;
+    CUtensorMap tmQ, tmK, tmV;
+    if (!make_map(&tmQ, q, (size_t)batch * head_num * max_q_len, bf16) || !make_map(&tmK, k_layer, (size_t)batch * kv_head_num * max_seq_len, bf16) ||
+        !make_map(&tmV, v_layer, (size_t)batch * kv_head_num * max_seq_len, bf16)) {
+        set_error("context_attention: cuTensorMapEncodeTiled failed");
+        return B200_ERR_CUDA;
+    }
+    Params p = {};
+    p.out = out, p.seq_off = seq_off, p.input_len = input_len, p.context_len = context_len;
+    p.head_num = head_num, p.kv_head_num = kv_head_num, p.max_q_len = max_q_len, p.max_seq_len = max_seq_len;
+    p.scale = scale, p.is_bf16 = bf16 ? 1 : 0;
+    const size_t smem = (size_t)(2 + 2 * kKvStages) * kTileBytes + 1024 + 16 * 8 + 16;
+    dim3 grid((max_q_len + kRows - 1) / kRows, head_num, batch);
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        launch_pdl(kern, grid, dim3(kThreads), smem, st, true, tmQ, tmK, tmV, p);
+    };
+    if (bf16) go(context_attn_tc_kernel<__nv_bfloat16>);
+    else go(context_attn_tc_kernel<__half>);
+    return cuda_status("context_attention (tcgen05) launch");
+}
+
+}  // namespace b200

@@ -5,9 +5,15 @@
 // The index kernels are bit-exact by construction (pure copies / integer arithmetic).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <float.h>
 
 namespace b200 {
+
+int launch_context_attention_tc(const void *q, const void *k_layer, const void *v_layer, void *out, const int *seq_off, const int *input_len,
+                                const int *context_len, int batch, int head_num, int kv_head_num, int max_q_len, int max_seq_len, int head_size,
+                                float scale, int dtype, cudaStream_t st);
 
 __device__ __forceinline__ float rope_denominator_p(float base, int zid, int rot_dim) {
     const float e = (float)zid / (float)rot_dim;
@@ -400,6 +406,13 @@ int b200_context_attention(const void *q, const void *k_cache, const void *v_cac
                                          (size_t)kCaRows * kCaKeys);
     const size_t eb = dtype == B200_F32 ? 4 : 2;
     const size_t loff = (size_t)layer * batch * kv_head_num * max_seq_len * head_size * eb;
+    // head size 128, 16-bit: tcgen05 / TMEM flash attention (context_attn_tc.cu); everything else: the SIMT tiles below
+    static const bool force_simt = getenv("B200_CTX_ATTN_SIMT") != nullptr;
+    if (!force_simt) {
+        const int rc = launch_context_attention_tc(q, (const char *)k_cache + loff, (const char *)v_cache + loff, out, seq_off, input_len,
+                                                   context_len, batch, head_num, kv_head_num, max_q_len, max_seq_len, head_size, scale, dtype, st);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
     dim3 grid((max_q_len + kCaRows - 1) / kCaRows, head_num, batch);
     B200_DISPATCH_DTYPE(dtype, {
         cudaFuncSetAttribute(context_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

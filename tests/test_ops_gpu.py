@@ -493,6 +493,48 @@ def test_prefill_chain(dtype):
     assert_close(to_np(fused), ref, dtype, "fused context attention")
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("B,H,Hkv,S,input_len,hist", [
+    (2, 8, 2, 700, [300, 129], [290, 0]),       # 3 query tiles, 5 key tiles, GQA 4:1, ragged batch, history
+    (1, 4, 4, 256, [256], [0]),                 # exact tiles, pure causal prefill
+    (3, 2, 1, 130, [1, 128, 2], [0, 2, 127]),   # single-row prompts, tile-edge lengths
+])
+def test_context_attention_tensor_core(B, H, Hkv, S, input_len, hist, dtype):
+    """The tcgen05 / TMEM context attention (head size 128, 16-bit) against the oracle chain; cache rows past context_len hold NaN
+    bit patterns (nobody initialises them): they must not leak into the result."""
+    import torch
+
+    mod = b200()
+    r = rng(77)
+    d, L, layer = 128, 2, 1
+    input_len, hist = np.array(input_len, np.int32), np.array(hist, np.int32)
+    ctx = input_len + hist
+    mq, mk = int(input_len.max()), int(ctx.max())
+    po, cum = oracle.cal_padding_offset(input_len, mq)
+    T = int(cum[-1])
+    q = np.zeros((B, H, mq, d), np.float32)
+    for b in range(B):
+        q[b, :, :input_len[b]] = r.standard_normal((H, input_len[b], d))
+    q = rounded(q, dtype)
+    kc = rounded(0.5 * r.standard_normal((L, B, Hkv, S, d)), dtype)
+    vc = rounded(0.5 * r.standard_normal((L, B, Hkv, S, d)), dtype)
+    kcd, vcd = to_dev(kc, dtype), to_dev(vc, dtype)
+    for b in range(B):  # poison what lies beyond the context
+        kcd[:, b, :, ctx[b]:] = float("nan")
+        vcd[:, b, :, ctx[b]:] = float("nan")
+    scale = 1.0 / np.sqrt(d)
+    got = mod.context_attention(to_dev(q, dtype), kcd, vcd, to_dev(po.reshape(-1)), to_dev(input_len), to_dev(ctx), layer, T, scale)
+    ref = oracle.context_attention(q, kc, vc, po.reshape(-1), input_len, ctx, layer, T, mk, scale)
+    # The probabilities reach the second MMA in T (as in the reference, whose softmax output tensor is T): an entry of a peaked row
+    # carries 2^-9 relative rounding, i.e. up to ~1e-3 absolute on the output, whatever the output's own magnitude.  Bars: 1e-2 in
+    # norm, and 1e-2 of the tensor's range per element.
+    g, rf = to_np(got).astype(np.float64), ref.astype(np.float64)
+    assert np.isfinite(g).all(), "non-finite output (NaN rows of the cache leaked)"
+    fro = np.linalg.norm(g - rf) / np.linalg.norm(rf)
+    assert fro <= 1e-2, f"||err||/||ref|| = {fro:.3e}"
+    assert np.abs(g - rf).max() <= 1e-2 * np.abs(rf).max(), f"max abs err {np.abs(g - rf).max():.3e} vs range {np.abs(rf).max():.3e}"
+
+
 def test_softmax_vs_reference_kernel():
     lib = oracle.ref_lib()
     if lib is None:
