@@ -296,6 +296,18 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes);
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch,
                       int step, int layer_begin, int layer_end, b200_stream_t stream);
 
+/* Prefill ("context") pass over layers [layer_begin, layer_end): LlamaContextDecoder<T>::forward
+ * (src/layers/context_decoder.cpp:58-199): padding offsets -> per layer RMSNorm -> QKV linear -> split/transpose/RoPE ->
+ * KV append at history_len -> causal attention over context_len keys -> O linear -> add-bias-residual-RMSNorm -> gate/up ->
+ * SwiGLU -> down -> add-residual.  hidden[num_tokens, h] in/out (un-padded tokens, sequences back to back);
+ * input_len / history_len / context_len: device int[batch] (context = history + input); max_q_len >= max(input_len).
+ * The cache batch dimension is the engine's max_batch.  `scratch`: caller-owned device memory of at least
+ * b200_decoder_prefill_scratch_bytes(); linears run on the tensor-core GEMM (library workspace must be set). */
+size_t b200_decoder_prefill_scratch_bytes(const b200_decoder_t *dec, int batch, int max_q_len, int num_tokens);
+int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len,
+                         const int *history_len, const int *context_len, int batch, int max_q_len, int num_tokens,
+                         void *scratch, size_t scratch_bytes, int layer_begin, int layer_end, b200_stream_t stream);
+
 /* Tensor-parallel halves of one layer.  Each leaves this rank's PARTIAL sum of the row-sharded linear
  * in partial[B,h] (`dtype`); the caller all-reduces it (NCCL) and passes the reduced tensor as
  * `pending` to the next call, which folds it into the residual stream (hidden += pending) before its

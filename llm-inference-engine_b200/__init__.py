@@ -80,13 +80,15 @@ SIGNATURES = {
     "b200_decoder_scratch_bytes": [_P],
     "b200_decoder_set_scratch": [_P, _P, _SZ],
     "b200_decoder_step": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_decoder_prefill_scratch_bytes": [_P, _I, _I, _I],
+    "b200_decoder_prefill": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _SZ, _I, _I, _P],
     "b200_decoder_attn_block": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P],
     "b200_decoder_ffn_block": [_P, _I, _P, _P, _P, _I, _P],
     "b200_decoder_fold": [_P, _P, _P, _I, _P],
     "b200_lm_head_topk_sample": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_workspace_default_bytes": _SZ, "b200_decoder_create": _P,
-             "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ}
+             "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ, "b200_decoder_prefill_scratch_bytes": _SZ}
 
 _lib = None
 
@@ -385,6 +387,19 @@ class Decoder:
         layer_end = self.cfg.num_layers if layer_end is None else layer_end
         check(lib().b200_decoder_step(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], step, layer_begin, layer_end,
                                       stream()))
+
+    def prefill(self, hidden, k_cache, v_cache, input_len, history_len, context_len, max_q_len, layer_begin=0, layer_end=None):
+        """hidden [T, h] in/out; input_len / history_len / context_len: int32 device tensors [B]."""
+        torch = _torch()
+        ensure_workspace()
+        layer_end = self.cfg.num_layers if layer_end is None else layer_end
+        B, T = input_len.shape[0], hidden.shape[0]
+        nbytes = lib().b200_decoder_prefill_scratch_bytes(self.handle, B, max_q_len, T)
+        if getattr(self, "_prefill_scratch", None) is None or self._prefill_scratch.numel() < nbytes + 256:
+            self._prefill_scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=hidden.device)
+        base = (self._prefill_scratch.data_ptr() + 255) // 256 * 256
+        check(lib().b200_decoder_prefill(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), ptr(input_len), ptr(history_len), ptr(context_len),
+                                         B, max_q_len, T, C.c_void_p(base), nbytes, layer_begin, layer_end, stream()))
 
     def attn_block(self, layer, hidden, pending, k_cache, v_cache, partial, step):
         batch = partial.shape[0]

