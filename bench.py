@@ -171,6 +171,56 @@ def run_reference(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank):
+    """BASELINE configs[2], first half: a T-token prompt per sequence through all layers (b200_decoder_prefill): tensor-core linears +
+    tcgen05 context attention.  Prints one JSON line: prefill tokens/s and the fraction of the measured bf16 tensor peak."""
+    import torch
+
+    h, H, Hkv, d, I, L = (cfg[k] for k in ("hidden", "head_num", "kv_head_num", "head_size", "inter", "layers"))
+    B, Tq = args.batch, args.prefill_tokens
+    T = B * Tq
+    assert Tq <= kc.shape[3], "KV cache too short for the prompt: raise --ctx"
+    x0 = torch.randn(T, h, device=dev).to(dt)
+    x = x0.clone()
+    il = torch.full((B,), Tq, dtype=torch.int32, device=dev)
+    hl = torch.zeros(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            x.copy_(x0)
+            dec.prefill(x, kc, vc, il, hl, il, Tq)
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(dev.index or 0) as clocks:
+            e0.record(stream)
+            for _ in range(args.steps):
+                dec.prefill(x, kc, vc, il, hl, il, Tq)
+            e1.record(stream)
+            stream.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+    params = h * (H + 2 * Hkv) * d + H * d * h + 3 * h * I
+    flops_lin = 2.0 * T * params * L
+    flops_attn = 4.0 * B * H * Tq * Tq * d * L / 2  # causal: only the lower triangle is computed
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved = (flops_lin + flops_attn) / (ms * 1e-3) / 1e12
+    if rank == 0:
+        print(json.dumps({
+            "metric": "prefill tokens/s", "value": T * 1e3 / ms, "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{cfg['name']} {L}-layer bf16 prefill, batch {B} x {Tq} tokens", "batch": B, "prompt_tokens": Tq,
+                       "cache_policy": "weights (13 GB) larger than L2"},
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel + context_attn_tc_kernel (whole prefill pass)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1400",
+                         "flops": {"linears": flops_lin, "attention_causal": flops_attn}},
+            "clocks": clocks.summary()}), flush=True)
+
+
 def workload_config(args, cfg):
     return {"workload": f"{cfg['name']} {cfg['layers']}-layer {args.wformat} decode, batch {args.batch}, {args.ctx}-token context",
             "batch": args.batch, "context": args.ctx, "weights": args.wformat, "kv_cache": "bf16",
@@ -189,10 +239,15 @@ def main():
     ap.add_argument("--ctx", type=int, default=1024)
     ap.add_argument("--wformat", default="bf16", choices=list(WBYTES))
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only: makes the number INVALID)")
+    ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
+                    help="decode (default, the BASELINE metric) or prefill: one pass of --prefill-tokens tokens through all layers")
+    ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.mode == "prefill":
+        args.ctx = max(args.ctx, args.prefill_tokens)
     cfg = dict(CONFIGS[args.config])
     if args.layers:
         cfg["layers"] = args.layers
@@ -261,6 +316,10 @@ def main():
                 topk_vals=torch.empty((B, K_TOP), dtype=torch.float32, device=dev), seq_len=torch.full((B,), ctx, dtype=torch.int32, device=dev),
                 finished=torch.zeros(B, dtype=torch.uint8, device=dev), output_id=torch.zeros(B, dtype=torch.int32, device=dev))
     launches_per_step = 1 + L * 5 + 1 + (B + 3) // 4 + 2 + 1
+
+    if args.mode == "prefill":
+        run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank)
+        return
 
     def decode_step():
         """embedding -> L layers -> fold -> final norm + LM head -> top-k -> sampling; all on the current stream."""

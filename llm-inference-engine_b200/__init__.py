@@ -358,6 +358,7 @@ class Decoder:
         torch = _torch()
         self.cfg = cfg
         self.device = device
+        ensure_workspace()  # split-K / stream-K partials of the batched (M > 4) linears
         self.handle = lib().b200_decoder_create(C.byref(cfg))
         if not self.handle:
             raise B200Error(lib().b200_last_error_string().decode())

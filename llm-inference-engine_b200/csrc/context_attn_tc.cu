@@ -7,13 +7,15 @@
 //   -10000 of the mask and vanish: expf(-10000 + ...) == 0 in fp32), p = exp(s - max(max_k s, FLT_MIN)) / (sum + 1e-6), out = p.V
 // without materialising [B,H,Sq,Sk] scores or the GQA-repeated K/V, output already un-padded [T, H, d].
 //
-// One CTA = 128 query rows of one (b, h).  192 threads, warp-specialised:
-//   warp 4   TMA producer: Q tile once, then K and V tiles of 128 keys (cp.async.bulk.tensor.2d, 128-byte swizzle) in a 2-stage ring
-//   warp 5   MMA issuer:  S = Q.K^T (128x128x128, tcgen05.mma kind::f16, fp32 in TMEM, two S buffers so the logits of tile j+1 are
+// One CTA = 128 query rows of one (b, h).  576 threads, warp-specialised:
+//   warp 16  TMA producer: Q tile once, then K and V tiles of 128 keys (cp.async.bulk.tensor.2d, 128-byte swizzle) in a 2-stage ring
+//   warp 17  MMA issuer:  S = Q.K^T (128x128x128, tcgen05.mma kind::f16, fp32 in TMEM, two S buffers so the logits of tile j+1 are
 //            computed while the softmax threads work on tile j) and O_j = P_j.V_j (V is the MN-major B operand)
-//   warps 0-3 softmax + epilogue: thread t owns query row t (TMEM lane t): tcgen05.ld its row of S, mask, online softmax, writes P
-//            (bf16/fp16) into shared memory in the 128-byte-swizzled K-major layout the second MMA reads, then tcgen05.ld the tile's
-//            P.V and accumulates the rescaled output row in registers.
+//   warps 0-15 softmax + epilogue: warp w owns TMEM lanes 32*(w%4).. (query rows) and columns 32*(w/4).. : four threads share a
+//            row, 32 keys / 32 output dims each (16 warps keep the SM's four schedulers busy; with one thread per row the softmax
+//            ran at one warp per scheduler and took 6x longer than the MMAs).  tcgen05.ld the logits once into registers, mask,
+//            exchange the row max through shared memory, p = ex2(s - max) -> shared memory (bf16/fp16, the 128-byte-swizzled
+//            K-major layout the second MMA reads), then tcgen05.ld the tile's P.V slice and accumulate the rescaled output.
 // Causal structure: q tiles visit only the key tiles up to their diagonal; heavy (late) q tiles are scheduled first.
 #include "common.cuh"
 
@@ -28,7 +30,9 @@ namespace catc {
 constexpr int kRows = 128;   // query rows per CTA = UMMA M
 constexpr int kKeys = 128;   // keys per tile = UMMA N of the first MMA, K extent of the second
 constexpr int kD = 128;      // head size
-constexpr int kThreads = 192;
+constexpr int kSoftmaxWarps = 16;
+constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;  // 4 threads per query row
+constexpr int kThreads = kSoftmaxThreads + 64;      // + producer warp + MMA warp
 constexpr int kHalfBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 elements (128 B)
 constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kKvStages = 2;
@@ -123,7 +127,7 @@ __device__ __forceinline__ uint32_t idesc_f16(bool bf16, int m, int n, bool b_mn
     return d;
 }
 
-// smem: [Q 32K][K ring 2x32K][V ring 2x32K][P 32K][barriers][tmem slot]
+// smem: [Q 32K][K ring 2x32K][V ring 2x32K][P 32K][barriers][tmem slot][row-max / row-sum exchange 2x128x4 floats]
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -136,13 +140,14 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t q_full = s_u32(bars), kv_full0 = q_full + 8, kv_empty0 = kv_full0 + 16, s_full0 = kv_empty0 + 16, p_ready = s_full0 + 16,
                    o_full = p_ready + 8, o_taken = o_full + 8, s_free0 = o_taken + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    float *red = reinterpret_cast<float *>(bars + 14);  // [2][128][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) tiles first
     const int h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * kRows;
 
-    if (warp == 4 && lane == 0) {
+    if (warp == kSoftmaxWarps && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
@@ -151,14 +156,14 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             bar_init(kv_full0 + 8 * s, 1);
             bar_init(kv_empty0 + 8 * s, 1);   // released by tcgen05.commit of the P.V MMA
             bar_init(s_full0 + 8 * s, 1);
-            bar_init(s_free0 + 8 * s, 128);   // all softmax threads have read S[s]
+            bar_init(s_free0 + 8 * s, kSoftmaxThreads);   // all softmax threads have read S[s]
         }
-        bar_init(p_ready, 128);
+        bar_init(p_ready, kSoftmaxThreads);
         bar_init(o_full, 1);
-        bar_init(o_taken, 128);
+        bar_init(o_taken, kSoftmaxThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == kSoftmaxWarps + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -180,7 +185,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int q_row0 = (b * p.head_num + h) * p.max_q_len + q0;
     const int kv_row0 = (b * p.kv_head_num + kvh) * p.max_seq_len;
 
-    if (warp == 4) {
+    if (warp == kSoftmaxWarps) {
         // ================================================= TMA producer
         if (ntiles > 0 && elect_one()) {
             bar_expect_tx(q_full, kTileBytes);
@@ -197,7 +202,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 tma_load_2d(dv + kHalfBytes, &tmV, 64, kv_row0 + j * kKeys, kv_full0 + 8 * s);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kSoftmaxWarps + 1) {
         // ================================================= MMA issuer
         if (ntiles > 0) {
             const uint32_t id_qk = idesc_f16(p.is_bf16 != 0, kRows, kKeys, false);
@@ -241,107 +246,96 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             }
         }
     } else {
-        // ================================================= softmax + epilogue: thread = query row
-        const int row = threadIdx.x;           // 0..127 == TMEM lane
+        // ================================================= softmax + epilogue: 4 threads per query row, 32 columns each
+        const int quarter = warp & 3, cg = warp >> 2;
+        const int row = quarter * 32 + lane;   // == TMEM lane
         const int qi = q0 + row;
         const int lim = qi + (klen - qlen);    // keys <= lim are visible to this row
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        float m_run = FLT_MIN, l_run = 0.0f;   // the reference's running max starts at FLT_MIN (scale_and_mask_and_softmax.cu:86-126)
-        float o[kD];
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cg * 32);
+        const float sl2 = p.scale * 1.4426950408889634f;  // logits in the log2 domain: exp(x) = ex2(x * log2 e)
+        // the reference's running max starts at FLT_MIN (scale_and_mask_and_softmax.cu:86-126)
+        float m_run = FLT_MIN * 1.4426950408889634f, l_part = 0.0f;
+        float o[32];
 #pragma unroll
-        for (int e = 0; e < kD; ++e) o[e] = 0.0f;
+        for (int e = 0; e < 32; ++e) o[e] = 0.0f;
         for (int j = 0; j < ntiles; ++j) {
-            const int sb = j & 1, k0 = j * kKeys;
+            const int sb = j & 1, k0 = j * kKeys + cg * 32;
             bar_wait(s_full0 + 8 * sb, (j >> 1) & 1);
             tc_fence_after();
-            // pass 1: row max over the visible keys of this tile
-            float mx = m_run;
-#pragma unroll 1
-            for (int c = 0; c < kKeys; c += 32) {
-                uint32_t r[32];
-                tc_ld32(lane_addr + (uint32_t)(sb * kKeys + c), r);
-                tc_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int kg = k0 + c + e;
-                    const float sv = (kg < klen && kg <= lim) ? p.scale * __uint_as_float(r[e]) : -INFINITY;
-                    mx = fmaxf(mx, sv);
-                }
-            }
-            const float corr = expf(m_run - mx);
-            // the previous tile's P must have been consumed by its MMA before P is overwritten: that MMA's completion is what
-            // o_full signalled and this thread waited for at the end of the previous iteration.
-            // pass 2: p = exp(s - max) -> shared memory (K-major, 128-byte swizzle: 16-byte chunk index XOR (row % 8))
-            float psum = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < kKeys; c += 32) {
-                uint32_t r[32];
-                tc_ld32(lane_addr + (uint32_t)(sb * kKeys + c), r);
-                tc_wait_ld();
-                uint32_t packed[16];
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float pv[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int kg = k0 + c + e + u;
-                        const bool vis = kg < klen && kg <= lim;
-                        const float sv = p.scale * __uint_as_float(r[e + u]);
-                        // round to T first: the reference stores the probabilities in T before the second GEMM reads them
-                        pv[u] = vis ? Elem<T>::to_f(Elem<T>::from_f(expf(sv - mx))) : 0.0f;
-                        psum += vis ? expf(sv - mx) : 0.0f;
-                    }
-                    const T a0 = Elem<T>::from_f(pv[0]), a1 = Elem<T>::from_f(pv[1]);
-                    packed[e / 2] = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) |
-                                    ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
-                }
-                // 32 keys = 4 chunks of 16 bytes; key c lives in half c / 64, chunk (c % 64) / 8
-                unsigned char *prow = sP + (c / 64) * kHalfBytes + row * 128;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = ((c % 64) / 8 + q) ^ (row & 7);
-                    *reinterpret_cast<uint4 *>(prow + chunk * 16) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-                }
-            }
+            uint32_t r[32];
+            tc_ld32(lane_addr + (uint32_t)(sb * kKeys), r);
+            tc_wait_ld();
             tc_fence_before();
-            bar_arrive(s_free0 + 8 * sb);  // S[sb] may be overwritten by the logits of tile j + 2
-            // rows of V past the context must not reach the tensor core: 0 * NaN would poison the row (the cache beyond
-            // context_len is not initialised by anybody).  Row r of the tile is key k0 + r.
-            if (k0 + row >= klen) {
-                bar_wait(kv_full0 + 8 * (j % kKvStages), (j / kKvStages) & 1);
-                unsigned char *vrow = sV + (j % kKvStages) * kTileBytes + row * 128;
+            bar_arrive(s_free0 + 8 * sb);  // the logits are in registers: S[sb] may be overwritten by tile j + 2
+            float sv[32], mloc = -INFINITY;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    *reinterpret_cast<uint4 *>(vrow + q * 16) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(vrow + kHalfBytes + q * 16) = make_uint4(0, 0, 0, 0);
-                }
+            for (int e = 0; e < 32; ++e) {
+                const int kg = k0 + e;
+                sv[e] = (kg < klen && kg <= lim) ? sl2 * __uint_as_float(r[e]) : -INFINITY;
+                mloc = fmaxf(mloc, sv[e]);
+            }
+            float *rx = red + ((size_t)(j & 1) * kRows + row) * 4;
+            rx[cg] = mloc;
+            asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxThreads) : "memory");
+            const float4 m4 = *reinterpret_cast<const float4 *>(rx);
+            const float mx = fmaxf(fmaxf(m_run, fmaxf(m4.x, m4.y)), fmaxf(m4.z, m4.w));
+            float corr;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"(m_run - mx));
+            // p = ex2(s - max): masked keys are -inf -> 0.  Rounded to T for the MMA (the reference's probabilities are a T tensor);
+            // the row sum uses the unrounded values.  Shared memory: K-major, 128-byte swizzle (16-byte chunk index XOR (row % 8)).
+            float psum = 0.0f;
+            uint32_t packed[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(sv[e] - mx));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(sv[e + 1] - mx));
+                psum += p0 + p1;
+                const T a0 = Elem<T>::from_f(p0), a1 = Elem<T>::from_f(p1);
+                packed[e / 2] = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+            }
+            unsigned char *prow = sP + (cg >> 1) * kHalfBytes + row * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int chunk = ((cg & 1) * 4 + q) ^ (row & 7);
+                *reinterpret_cast<uint4 *>(prow + chunk * 16) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            }
+            // rows of V past the context must not reach the tensor core: 0 * NaN would poison the output (the cache beyond
+            // context_len is not initialised by anybody).  Row r of the tile is key j*128 + r; each of the row's 4 threads clears
+            // its quarter of the 256 bytes.
+            if (j * kKeys + row >= klen) {
+                bar_wait(kv_full0 + 8 * (j % kKvStages), (j / kKvStages) & 1);
+                unsigned char *vrow = sV + (j % kKvStages) * kTileBytes + (cg >> 1) * kHalfBytes + row * 128 + (cg & 1) * 64;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4 *>(vrow + q * 16) = make_uint4(0, 0, 0, 0);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of P / V visible to the MMA (async proxy)
             bar_arrive(p_ready);
-            l_run = l_run * corr + psum;
+            l_part = fmaf(l_part, corr, psum);
             m_run = mx;
 #pragma unroll
-            for (int e = 0; e < kD; ++e) o[e] *= corr;
-            // ---- this tile's P.V
+            for (int e = 0; e < 32; ++e) o[e] *= corr;
+            // ---- this tile's P.V, this thread's 32 output dims
             bar_wait(o_full, j & 1);
             tc_fence_after();
+            tc_ld32(lane_addr + (uint32_t)(2 * kKeys), r);
+            tc_wait_ld();
 #pragma unroll
-            for (int c = 0; c < kD; c += 32) {
-                uint32_t r[32];
-                tc_ld32(lane_addr + (uint32_t)(2 * kKeys + c), r);
-                tc_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) o[c + e] += __uint_as_float(r[e]);
-            }
+            for (int e = 0; e < 32; ++e) o[e] += __uint_as_float(r[e]);
             tc_fence_before();
             bar_arrive(o_taken);
         }
+        // row sum across the row's 4 threads
+        float *rx = red + ((size_t)(ntiles & 1) * kRows + row) * 4;
+        rx[cg] = l_part;
+        asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxThreads) : "memory");
         if (active && qi < qlen) {
+            const float4 l4 = *reinterpret_cast<const float4 *>(rx);
+            const float inv = 1.0f / (((l4.x + l4.y) + (l4.z + l4.w)) + 1e-6f);
             const int t = b * p.max_q_len + qi - p.seq_off[b];  // un-padded token index
-            T *dst = reinterpret_cast<T *>(p.out) + ((size_t)t * p.head_num + h) * kD;
-            const float inv = 1.0f / (l_run + 1e-6f);
+            T *dst = reinterpret_cast<T *>(p.out) + ((size_t)t * p.head_num + h) * kD + cg * 32;
 #pragma unroll
-            for (int e = 0; e < kD; e += 8) {
+            for (int e = 0; e < 32; e += 8) {
                 float f[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) f[u] = o[e + u] * inv;
@@ -352,7 +346,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kSoftmaxWarps + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
@@ -408,7 +402,7 @@ int launch_context_attention_tc(const void *q, const void *k_layer, const void *
     p.out = out, p.seq_off = seq_off, p.input_len = input_len, p.context_len = context_len;
     p.head_num = head_num, p.kv_head_num = kv_head_num, p.max_q_len = max_q_len, p.max_seq_len = max_seq_len;
     p.scale = scale, p.is_bf16 = bf16 ? 1 : 0;
-    const size_t smem = (size_t)(2 + 2 * kKvStages) * kTileBytes + 1024 + 16 * 8 + 16;
+    const size_t smem = (size_t)(2 + 2 * kKvStages) * kTileBytes + 1024 + 16 * 8 + 16 + 2 * kRows * 4 * sizeof(float);
     dim3 grid((max_q_len + kRows - 1) / kRows, head_num, batch);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

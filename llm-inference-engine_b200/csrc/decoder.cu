@@ -37,6 +37,10 @@ struct b200_decoder {
 
 namespace b200 {
 
+int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const int *padding_offset, const int *history_len,
+                                  int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size, int max_seq_len, int rot_dim,
+                                  float base, int dtype, cudaStream_t st);
+
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t esize(int dtype) { return dtype == B200_F32 ? 4 : 2; }
 
@@ -365,11 +369,17 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
         rc = launch_norm_any(c.dtype, pending ? pending : hidden, xn, pending ? res : nullptr, res, nullptr, w.attn_norm_gamma, c.rmsnorm_eps, T, h, st);
         if (rc != B200_OK) return rc;
         if ((rc = linear(xn, w.qkv, qkv, h, qkv_n)) != B200_OK) return rc;
-        rc = b200_qkv_bias_transpose_rope(qp, kp, vp, qkv, w.qkv_bias, padding_offset, history_len, input_len, batch, max_q_len, T, c.head_num,
-                                          c.kv_head_num, c.head_size, c.rotary_dim, c.rotary_base, c.dtype, stream);
-        if (rc != B200_OK) return rc;
-        rc = b200_concat_kv_cache(kp, vp, k_cache, v_cache, input_len, history_len, l, batch, c.kv_head_num, max_q_len, c.max_seq_len, c.head_size,
-                                  c.dtype, stream);
+        // split + RoPE + KV append: one fused pass (k / v go straight into the cache); un-vectorisable shapes take the two launchers
+        const size_t layer_off = (size_t)l * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
+        rc = launch_prefill_qkv_rope_cache(qp, (char *)k_cache + layer_off, (char *)v_cache + layer_off, qkv, padding_offset, history_len, max_q_len, T,
+                                           c.head_num, c.kv_head_num, c.head_size, c.max_seq_len, c.rotary_dim, c.rotary_base, c.dtype, st);
+        if (rc == B200_ERR_UNSUPPORTED) {
+            rc = b200_qkv_bias_transpose_rope(qp, kp, vp, qkv, w.qkv_bias, padding_offset, history_len, input_len, batch, max_q_len, T, c.head_num,
+                                              c.kv_head_num, c.head_size, c.rotary_dim, c.rotary_base, c.dtype, stream);
+            if (rc != B200_OK) return rc;
+            rc = b200_concat_kv_cache(kp, vp, k_cache, v_cache, input_len, history_len, l, batch, c.kv_head_num, max_q_len, c.max_seq_len,
+                                      c.head_size, c.dtype, stream);
+        }
         if (rc != B200_OK) return rc;
         rc = b200_context_attention(qp, k_cache, v_cache, attn, padding_offset, input_len, context_len, l, batch, c.head_num, c.kv_head_num,
                                     max_q_len, c.max_seq_len, c.head_size, T, scale, c.dtype, stream);

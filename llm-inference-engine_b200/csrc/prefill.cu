@@ -90,6 +90,75 @@ __global__ void qkv_rope_kernel(T *q, T *k, T *v, const T *__restrict__ qkv, con
     if ((head_size & 1) && threadIdx.x == 0) d[head_size - 1] = src[head_size - 1];
 }
 
+// ---------------------------------------------------------------- engine prefill: QKV split + RoPE + KV append in ONE pass
+// launchFusedQKVAddBiasAndTransposeAndRope + launchConcatKVCache fused: one CTA per token, 128-bit vectors; q goes to the padded
+// [B,H,max_q,d] buffer the attention reads, k and v go STRAIGHT into the cache at history_len[b] + s (the padded k/v buffers and
+// the second pass over them disappear).  cos/sin of the token's position are evaluated once per CTA (same expressions as above).
+template <typename T>
+__global__ void __launch_bounds__(256)
+prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict__ qkv, const int *__restrict__ padding_offset,
+                              const int *__restrict__ history_len, int seq_len, int head_num, int kv_head_num, int head_size, int max_seq_len,
+                              int rot_dim, float base) {
+    constexpr int V = Elem<T>::kVec;
+    extern __shared__ float2 cs[];  // [head_size / 2] (cos, sin); identity past rot_dim / 2
+    const int t = blockIdx.x;
+    const int half = head_size / 2, vph = half / V;  // vector pairs per head
+    pdl_wait();
+    const int dst = t + padding_offset[t];
+    const int b = dst / seq_len, s = dst % seq_len;
+    const int pos_i = history_len[b] + s;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        float2 v = make_float2(1.0f, 0.0f);
+        if (i < rot_dim / 2) {
+            const float th = (float)pos_i / rope_denominator_p(base, 2 * i, rot_dim);
+            v = make_float2(cosf(th), sinf(th));
+        }
+        cs[i] = v;
+    }
+    __syncthreads();
+    const int heads = head_num + 2 * kv_head_num;
+    const T *src_tok = qkv + (size_t)t * heads * head_size;
+    for (int w = threadIdx.x; w < heads * vph; w += blockDim.x) {
+        const int head = w / vph, i0 = (w % vph) * V;  // dims [i0, i0 + V) and [i0 + half, ...)
+        const T *src = src_tok + (size_t)head * head_size;
+        float lo[V], hi[V];
+        unpack16<T>(ld_stream_v4(src + i0), lo);
+        unpack16<T>(ld_stream_v4(src + i0 + half), hi);
+        T *d;
+        if (head < head_num) {
+            d = q + (((size_t)b * head_num + head) * seq_len + s) * head_size;
+        } else if (head < head_num + kv_head_num) {
+            d = k_cache + (((size_t)b * kv_head_num + (head - head_num)) * max_seq_len + pos_i) * head_size;
+        } else {
+            d = v_cache + (((size_t)b * kv_head_num + (head - head_num - kv_head_num)) * max_seq_len + pos_i) * head_size;
+        }
+        if (head < head_num + kv_head_num) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float2 c = cs[i0 + e];
+                const float a = lo[e], bb = hi[e];
+                lo[e] = a * c.x - bb * c.y;
+                hi[e] = bb * c.x + a * c.y;
+            }
+        }
+        st_v4(d + i0, pack16<T>(lo));
+        st_v4(d + i0 + half, pack16<T>(hi));
+    }
+}
+
+// q [B,H,max_q,d]; k_cache / v_cache: LAYER base [B,Hkv,S,d].  B200_ERR_UNSUPPORTED when the shape cannot be vectorised.
+int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const int *padding_offset, const int *history_len,
+                                  int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size, int max_seq_len, int rot_dim,
+                                  float base, int dtype, cudaStream_t st) {
+    const int vec = dtype == B200_F32 ? 4 : 8;
+    if (head_size % (2 * vec) != 0 || !aligned16(q) || !aligned16(k_layer) || !aligned16(v_layer) || !aligned16(qkv)) return B200_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(float2) * (size_t)(head_size / 2);
+    B200_DISPATCH_DTYPE(dtype, launch_pdl(prefill_qkv_rope_cache_kernel<T>, dim3(num_tokens), dim3(256), smem, st, true, (T *)q, (T *)k_layer,
+                                          (T *)v_layer, (const T *)qkv, padding_offset, history_len, seq_len, head_num, kv_head_num, head_size,
+                                          max_seq_len, rot_dim, base));
+    return cuda_status("prefill_qkv_rope_cache launch");
+}
+
 // ---------------------------------------------------------------- KV append (concat_past_kv.cu:10-42), K and V in one launch
 // grid (max_q_len, Hkv, 2*B)
 template <typename T>
