@@ -316,6 +316,16 @@ def main():
                 topk_vals=torch.empty((B, K_TOP), dtype=torch.float32, device=dev), seq_len=torch.full((B,), ctx, dtype=torch.int32, device=dev),
                 finished=torch.zeros(B, dtype=torch.uint8, device=dev), output_id=torch.zeros(B, dtype=torch.int32, device=dev))
     launches_per_step = 1 + L * 5 + 1 + (B + 3) // 4 + 2 + 1
+    tp_mode = "none"
+    if tp > 1:
+        tp_mode = "nccl all-reduce"
+        if not os.environ.get("B200_TP_NCCL"):
+            try:  # one-shot all-reduce over NVLink peer memory, fused into the consuming kernels (no NCCL call on the path)
+                dec.tp_attach(dist)
+                tp_mode = "fused NVLink peer-memory exchange"
+                launches_per_step += 1
+            except Exception as e:
+                print(f"[bench] fused tensor-parallel exchange unavailable ({e}); using NCCL all-reduce", file=sys.stderr)
 
     if args.mode == "prefill":
         run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank)
@@ -326,6 +336,8 @@ def main():
         mod.check(mod.lib().b200_input_embedding(mod.ptr(ids_dev), mod.ptr(emb), mod.ptr(hidden), B, h, mod.BF16, mod.stream()))
         if tp == 1:
             dec.step(hidden, kc, vc, step)
+        elif tp_mode.startswith("fused"):
+            dec.step_tp(hidden, kc, vc, step)
         else:  # one NCCL all-reduce per attention block and per MLP block (llm-inference-engine_b200/tp.py)
             def attn_block(l, h, pending):
                 dec.attn_block(l, h, pending, kc, vc, y_attn, step)
@@ -477,6 +489,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4 * B, "ms_per_step": ms_e2e},
             "gpu_launches": launches_per_step * args.steps,
             "launch_mode": "cuda-graph replay" if graph is not None else "eager",
+            "tp_exchange": tp_mode,
             "roofline": {"bound": "hbm", "kernel": "gemv_nk_kernel (all %d weight-streaming linears of one step, back to back)" % n_gemv,
                          "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                          "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write of the QKV/O/gate_up/down launches, scaled to the step)" if traffic else None,
@@ -488,6 +501,8 @@ def main():
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
+    if tp > 1 and tp_mode.startswith("fused") and dec.tp_error():
+        print(f"[bench] rank {rank}: the tensor-parallel exchange timed out on a peer: the number above is INVALID", file=sys.stderr)
     if tp > 1:
         # every rank is done once rank 0 has printed; leave without the NCCL teardown (observed to hang after graph-captured
         # collectives on this stack) so the launcher returns immediately

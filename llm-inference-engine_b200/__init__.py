@@ -85,10 +85,17 @@ SIGNATURES = {
     "b200_decoder_attn_block": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P],
     "b200_decoder_ffn_block": [_P, _I, _P, _P, _P, _I, _P],
     "b200_decoder_fold": [_P, _P, _P, _I, _P],
+    "b200_decoder_tp_buffer_bytes": [_P],
+    "b200_tp_alloc_exported": [_SZ, C.POINTER(C.c_void_p), _P],
+    "b200_tp_open": [_P, C.POINTER(C.c_void_p)],
+    "b200_decoder_tp_attach": [_P, _I, _I, C.POINTER(C.c_void_p)],
+    "b200_decoder_tp_error": [_P],
+    "b200_decoder_step_tp": [_P, _P, _P, _P, _I, _I, _P],
     "b200_lm_head_topk_sample": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_workspace_default_bytes": _SZ, "b200_decoder_create": _P,
-             "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ, "b200_decoder_prefill_scratch_bytes": _SZ}
+             "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ, "b200_decoder_prefill_scratch_bytes": _SZ,
+             "b200_decoder_tp_buffer_bytes": _SZ}
 
 _lib = None
 
@@ -401,6 +408,34 @@ class Decoder:
         base = (self._prefill_scratch.data_ptr() + 255) // 256 * 256
         check(lib().b200_decoder_prefill(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), ptr(input_len), ptr(history_len), ptr(context_len),
                                          B, max_q_len, T, C.c_void_p(base), nbytes, layer_begin, layer_end, stream()))
+
+    def tp_attach(self, dist_module):
+        """Fused tensor-parallel exchange: allocate this rank's exchange buffer, swap CUDA-IPC handles with the other ranks of the
+        node through torch.distributed (host-side plumbing only) and map theirs."""
+        world, rank = self.cfg.tp_world, self.cfg.tp_rank
+        nbytes = lib().b200_decoder_tp_buffer_bytes(self.handle)
+        mine = C.c_void_p()
+        handle = (C.c_char * 64)()
+        check(lib().b200_tp_alloc_exported(nbytes, C.byref(mine), handle))
+        handles = [None] * world
+        dist_module.all_gather_object(handles, bytes(handle.raw))
+        bases = (C.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                bases[r] = mine.value
+            else:
+                p = C.c_void_p()
+                buf = (C.c_char * 64).from_buffer_copy(handles[r])
+                check(lib().b200_tp_open(buf, C.byref(p)))
+                bases[r] = p.value
+        check(lib().b200_decoder_tp_attach(self.handle, world, rank, bases))
+        dist_module.barrier()  # every rank has mapped every buffer before anybody signals into one
+
+    def step_tp(self, hidden, k_cache, v_cache, step):
+        check(lib().b200_decoder_step_tp(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], step, stream()))
+
+    def tp_error(self):
+        return lib().b200_decoder_tp_error(self.handle)
 
     def attn_block(self, layer, hidden, pending, k_cache, v_cache, partial, step):
         batch = partial.shape[0]

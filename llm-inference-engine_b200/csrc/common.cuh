@@ -40,7 +40,26 @@ struct Workspace {
 // Returns false (and sets the error) if no workspace is available.
 bool get_workspace(Workspace *ws);
 
+// ------------------------------------------------------------------ tensor-parallel exchange over NVLink peer memory
+// One-shot all-reduce fused into the CONSUMER of a row-sharded linear: every rank left its partial sum [B,h] in its own
+// exchange buffer (peer-mapped on every other rank through CUDA IPC); the first kernel of the next block signals "my
+// partial is complete" into every peer's flag word, waits for every peer's signal, then reads all P partials with peer loads
+// and adds them in rank order (identical on every rank, deterministic).  No NCCL call, no extra launch, no extra pass.
+// Flag values grow monotonically: epoch (bumped once per decode step by a one-thread kernel) * 4096 + block sequence number.
+constexpr int kTpMaxWorld = 8;
+struct TpExchange {
+    const void *peer_x[kTpMaxWorld];        // every rank's partial buffer of this slot, rank order ([rank] is local memory)
+    unsigned int *peer_flags[kTpMaxWorld];  // in every rank's buffer: the flag word (this slot, written by THIS rank)
+    const unsigned int *my_flags;           // this rank's flag words of this slot: [world], one per writer
+    const unsigned int *epoch;              // this rank's step counter (device memory)
+    unsigned int *error;                    // set to 1 if a peer never signalled (time-out instead of a hang)
+    int world, rank, seq;                   // world <= 1: exchange disabled
+};
+
 // out = gamma * (o + bias) * rsqrt(mean((o+bias)^2)+eps), o = in (+ rin); rout <- o.  in == NULL: in place on out.
+// tp (optional, world > 1): `in` is replaced by the sum over ranks of tp->peer_x[*] (see TpExchange).
+int launch_norm_tp(int dtype, const void *in, void *out, const void *rin, void *rout, const void *bias, const void *gamma, float eps,
+                   int tokens, int hidden, const TpExchange *tp, cudaStream_t st);
 // gamma == NULL: out = o + bias.  (norm.cu)
 int launch_norm_any(int dtype, const void *in, void *out, const void *rin, void *rout, const void *bias, const void *gamma,
                     float eps, int tokens, int hidden, cudaStream_t st);
@@ -84,6 +103,38 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ tensor-parallel exchange (device)
+// Called by EVERY thread of EVERY CTA of the consuming kernel, after griddepcontrol.wait (so this rank's producer is complete).
+__device__ __forceinline__ void tp_exchange_sync(const TpExchange &t) {
+    if (t.world <= 1) return;
+    const unsigned int want = *t.epoch * 4096u + (unsigned int)t.seq;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < t.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flags[threadIdx.x]), "r"(want) : "memory");
+    }
+    if ((int)threadIdx.x < t.world) {
+        const unsigned int *f = t.my_flags + threadIdx.x;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - want) >= 0) break;
+            if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died; leave a mark instead of hanging the GPU
+                atomicExch(t.error, 1u);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+// 16 bytes of every rank's partial at byte offset `off`; peer memory is read uncached (it changes between kernels)
+__device__ __forceinline__ uint4 tp_ld_v4(const void *base, size_t off) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"((const char *)base + off));
+    return r;
 }
 
 // ------------------------------------------------------------------ element traits

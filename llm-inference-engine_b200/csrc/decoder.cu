@@ -33,6 +33,9 @@ struct b200_decoder {
     float2 *rope_cs = nullptr;  // (cos, sin) per (position, rotary pair), filled once by set_scratch
     int max_splits = 0;
     int cur = 0;  // which res[] holds the residual stream
+    // fused tensor-parallel exchange (b200_decoder_tp_attach): every rank's exchange buffer as mapped in this process
+    char *tp_base[b200::kTpMaxWorld] = {};
+    bool tp_attached = false;
 };
 
 namespace b200 {
@@ -66,9 +69,36 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     return k;
 }
 
-// prologue (add residual / bias / RMSNorm) + linear (+ SwiGLU): fused GEMV for M <= 4, un-fused otherwise
+// ---- exchange buffer of the fused tensor-parallel path (one per rank, peer-mapped everywhere):
+//      [0, 256)    flag words: [2 slots][kTpMaxWorld writers]
+//      [256, 512)  this rank's step counter (epoch) and error word
+//      [512, ...)  two partial-sum slots of max_batch * hidden elements
+constexpr size_t kTpFlagsOff = 0, kTpEpochOff = 256, kTpErrorOff = 260, kTpDataOff = 512;
+static size_t tp_slot_bytes(const b200_decoder_config_t &c) { return align_up((size_t)c.max_batch * c.hidden * esize(c.dtype)); }
+static void *tp_slot(const b200_decoder *d, int rank, int seq) { return d->tp_base[rank] + kTpDataOff + (size_t)(seq & 1) * tp_slot_bytes(d->cfg); }
+// descriptor for the consumer of block `seq` (seq >= 1)
+static TpExchange tp_consume(const b200_decoder *d, int seq) {
+    TpExchange t = {};
+    const b200_decoder_config_t &c = d->cfg;
+    t.world = c.tp_world, t.rank = c.tp_rank, t.seq = seq;
+    for (int r = 0; r < c.tp_world; ++r) {
+        t.peer_x[r] = tp_slot(d, r, seq);
+        t.peer_flags[r] = reinterpret_cast<unsigned int *>(d->tp_base[r] + kTpFlagsOff) + (seq & 1) * kTpMaxWorld + c.tp_rank;
+    }
+    t.my_flags = reinterpret_cast<const unsigned int *>(d->tp_base[c.tp_rank] + kTpFlagsOff) + (seq & 1) * kTpMaxWorld;
+    t.epoch = reinterpret_cast<const unsigned int *>(d->tp_base[c.tp_rank] + kTpEpochOff);
+    t.error = reinterpret_cast<unsigned int *>(d->tp_base[c.tp_rank] + kTpErrorOff);
+    return t;
+}
+__global__ void tp_begin_step_kernel(unsigned int *epoch) {
+    pdl_wait();
+    if (threadIdx.x == 0) *epoch += 1;
+}
+
+// prologue (add residual / bias / RMSNorm) + linear (+ SwiGLU): fused GEMV for M <= 4, un-fused otherwise.
+// tp (optional): x is the fused all-reduce of every rank's partial (TpExchange) instead of a local tensor.
 static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void *res_out, const void *bias, const void *gamma,
-                       const b200_linear_weight_t &w, int K, int N, bool swiglu, void *y, int M, cudaStream_t st) {
+                       const b200_linear_weight_t &w, int K, int N, bool swiglu, void *y, int M, cudaStream_t st, const TpExchange *tp = nullptr) {
     const b200_decoder_config_t &c = d->cfg;
     if (M <= 4) {
         GemvArgs a = {};
@@ -76,10 +106,11 @@ static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void 
         a.x = x, a.y = y;
         a.res_in = res_in, a.res_out = res_out, a.bias = bias, a.gamma = gamma, a.eps = c.rmsnorm_eps, a.norm = 1;
         a.M = M, a.K = K, a.N = N, a.group = c.group, a.inter = swiglu ? N / 2 : 0;
+        if (tp) a.tp = *tp;
         const int rc = launch_gemv_nk(a, c.dtype, c.w_format, swiglu, st);
         if (rc != B200_ERR_UNSUPPORTED) return rc;
     }
-    int rc = launch_norm_any(c.dtype, x, d->xn, res_in, res_out, bias, gamma, c.rmsnorm_eps, M, K, st);
+    int rc = launch_norm_tp(c.dtype, x, d->xn, res_in, res_out, bias, gamma, c.rmsnorm_eps, M, K, tp, st);
     if (rc != B200_OK) return rc;
     if (!swiglu) return b200_linear(d->xn, w.w, w.scales, w.zeros, y, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
     rc = b200_linear(d->xn, w.w, w.scales, w.zeros, d->gu, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
@@ -101,10 +132,31 @@ static int plain_linear(b200_decoder *d, const void *x, const b200_linear_weight
 }
 
 template <typename T>
-__global__ void fold_kernel(T *out, const T *a, const T *b, size_t n) {
+__global__ void fold_kernel(T *out, const T *a, const T *b, size_t n, const TpExchange tp) {
     pdl_wait();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = Elem<T>::from_f(Elem<T>::to_f(a[i]) + (b ? Elem<T>::to_f(b[i]) : 0.0f));
+    tp_exchange_sync(tp);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float add = 0.0f;
+        if (tp.world > 1) {  // fused all-reduce of the last FFN partial, rank order, rounded to T
+            for (int r = 0; r < tp.world; ++r) {
+                unsigned short u;
+                asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(u) : "l"(reinterpret_cast<const char *>(tp.peer_x[r]) + i * sizeof(T)));
+                if constexpr (sizeof(T) == 2) {
+                    T v;
+                    *reinterpret_cast<unsigned short *>(&v) = u;
+                    add += Elem<T>::to_f(v);
+                } else {
+                    unsigned int w32;
+                    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w32) : "l"(reinterpret_cast<const char *>(tp.peer_x[r]) + i * sizeof(T)));
+                    add += __uint_as_float(w32);
+                }
+            }
+            add = round_to<T>(add);
+        } else if (b) {
+            add = Elem<T>::to_f(b[i]);
+        }
+        out[i] = Elem<T>::from_f(Elem<T>::to_f(a[i]) + add);
+    }
 }
 
 static int check_ready(const b200_decoder *d, int batch) {
@@ -218,8 +270,8 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     return B200_OK;
 }
 
-int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache,
-                            void *partial, int batch, int step, b200_stream_t stream) {
+static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache, void *partial,
+                           int batch, int step, b200_stream_t stream, const TpExchange *tp) {
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
     const b200_decoder_config_t &c = dec->cfg;
@@ -233,7 +285,7 @@ int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const 
     // 1. residual fold + RMSNorm + QKV
     void *res_out = dec->res[dec->cur ^ 1];
     rc = norm_linear(dec, pending ? pending : hidden, pending ? dec->res[dec->cur] : nullptr, res_out, nullptr, w.attn_norm_gamma, w.qkv,
-                     c.hidden, qkv_n, false, dec->qkv, batch, st);
+                     c.hidden, qkv_n, false, dec->qkv, batch, st, pending ? tp : nullptr);
     if (rc != B200_OK) return rc;
     dec->cur ^= 1;
     // 2. attention
@@ -255,9 +307,13 @@ int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const 
     return plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, partial, batch, st);
 }
 
-int b200_decoder_ffn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *partial, int batch,
-                           b200_stream_t stream) {
-    (void)hidden;
+int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache,
+                            void *partial, int batch, int step, b200_stream_t stream) {
+    return attn_block_impl(dec, layer, hidden, pending, k_cache, v_cache, partial, batch, step, stream, nullptr);
+}
+
+static int ffn_block_impl(b200_decoder_t *dec, int layer, const void *pending, void *partial, int batch, b200_stream_t stream,
+                          const TpExchange *tp) {
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
     const b200_decoder_config_t &c = dec->cfg;
@@ -268,22 +324,115 @@ int b200_decoder_ffn_block(b200_decoder_t *dec, int layer, void *hidden, const v
     // 4. residual += attention output; + o bias (tp rank 0 semantics: bias is replicated, added after the reduce);
     //    RMSNorm; gate/up; SwiGLU
     rc = norm_linear(dec, pending, dec->res[dec->cur], dec->res[dec->cur ^ 1], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
-                     2 * c.inter_size, true, dec->act, batch, st);
+                     2 * c.inter_size, true, dec->act, batch, st, tp);
     if (rc != B200_OK) return rc;
     dec->cur ^= 1;
     // 5. down projection
     return plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, partial, batch, st);
 }
 
-int b200_decoder_fold(b200_decoder_t *dec, void *hidden, const void *pending, int batch, b200_stream_t stream) {
+int b200_decoder_ffn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *partial, int batch,
+                           b200_stream_t stream) {
+    (void)hidden;
+    return ffn_block_impl(dec, layer, pending, partial, batch, stream, nullptr);
+}
+
+static int fold_impl(b200_decoder_t *dec, void *hidden, const void *pending, int batch, b200_stream_t stream, const TpExchange *tpx) {
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
     B200_REQUIRE(hidden, "decoder_fold: null pointer");
     const size_t n = (size_t)batch * dec->cfg.hidden;
     const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    TpExchange tp = {};
+    if (tpx) tp = *tpx;
     B200_DISPATCH_DTYPE(dec->cfg.dtype, launch_pdl(fold_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), true, (T *)hidden,
-                                                   (const T *)dec->res[dec->cur], (const T *)pending, n));
+                                                   (const T *)dec->res[dec->cur], (const T *)pending, n, tp));
     return cuda_status("decoder_fold launch");
+}
+
+int b200_decoder_fold(b200_decoder_t *dec, void *hidden, const void *pending, int batch, b200_stream_t stream) {
+    return fold_impl(dec, hidden, pending, batch, stream, nullptr);
+}
+
+// ---------------------------------------------------------------- fused tensor-parallel step (no NCCL on the path)
+size_t b200_decoder_tp_buffer_bytes(const b200_decoder_t *dec) {
+    if (!dec) return 0;
+    return kTpDataOff + 2 * tp_slot_bytes(dec->cfg);
+}
+
+int b200_tp_alloc_exported(size_t bytes, void **ptr, void *handle64) {
+    B200_REQUIRE(ptr && handle64 && bytes > 0, "tp_alloc_exported: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return cuda_status("tp_alloc_exported cudaMalloc");
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) return cuda_status("tp_alloc_exported memset");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+        const int rc = cuda_status("cudaIpcGetMemHandle");
+        cudaFree(p);
+        return rc;
+    }
+    memcpy(handle64, &h, 64);
+    if (cudaDeviceSynchronize() != cudaSuccess) return cuda_status("tp_alloc_exported sync");
+    *ptr = p;
+    return B200_OK;
+}
+
+int b200_tp_open(const void *handle64, void **ptr) {
+    B200_REQUIRE(ptr && handle64, "tp_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return cuda_status("cudaIpcOpenMemHandle");
+    *ptr = p;
+    return B200_OK;
+}
+
+int b200_decoder_tp_attach(b200_decoder_t *dec, int world, int rank, void *const *bases) {
+    B200_REQUIRE(dec && bases, "decoder_tp_attach: null argument");
+    B200_REQUIRE(world == dec->cfg.tp_world && rank == dec->cfg.tp_rank, "decoder_tp_attach: world/rank differ from the decoder config");
+    B200_REQUIRE(world >= 2 && world <= kTpMaxWorld, "decoder_tp_attach: world %d outside [2, %d]", world, kTpMaxWorld);
+    B200_REQUIRE((dec->cfg.hidden * esize(dec->cfg.dtype)) % 16 == 0, "decoder_tp_attach: hidden rows must be 16-byte multiples");
+    for (int r = 0; r < world; ++r) {
+        B200_REQUIRE(bases[r] != nullptr && ((uintptr_t)bases[r] & 255) == 0, "decoder_tp_attach: buffer of rank %d is null or unaligned", r);
+        dec->tp_base[r] = (char *)bases[r];
+    }
+    dec->tp_attached = true;
+    return B200_OK;
+}
+
+int b200_decoder_tp_error(const b200_decoder_t *dec) {
+    if (!dec || !dec->tp_attached) return 0;
+    unsigned int e = 0;
+    if (cudaMemcpy(&e, dec->tp_base[dec->cfg.tp_rank] + kTpErrorOff, sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)e;
+}
+
+int b200_decoder_step_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, b200_stream_t stream) {
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    B200_REQUIRE(dec->tp_attached, "decoder_step_tp: call b200_decoder_tp_attach first");
+    B200_REQUIRE(hidden && k_cache && v_cache, "decoder_step_tp: null pointer");
+    const b200_decoder_config_t &c = dec->cfg;
+    B200_REQUIRE(2 * c.num_layers + 1 < 4096, "decoder_step_tp: too many layers for the flag encoding");
+    cudaStream_t st = as_stream(stream);
+    launch_pdl(tp_begin_step_kernel, dim3(1), dim3(32), 0, st, true, reinterpret_cast<unsigned int *>(dec->tp_base[c.tp_rank] + kTpEpochOff));
+    if ((rc = cuda_status("tp_begin_step launch")) != B200_OK) return rc;
+    int seq = 0;  // sequence number of the last partial produced in this step
+    for (int l = 0; l < c.num_layers; ++l) {
+        // attention block: consumes the previous layer's FFN partial (seq), leaves its O-projection partial in slot seq + 1
+        TpExchange tin = seq ? tp_consume(dec, seq) : TpExchange{};
+        rc = attn_block_impl(dec, l, hidden, seq ? tp_slot(dec, c.tp_rank, seq) : nullptr, k_cache, v_cache, tp_slot(dec, c.tp_rank, seq + 1), batch, step,
+                             stream, seq ? &tin : nullptr);
+        if (rc != B200_OK) return rc;
+        ++seq;
+        TpExchange tmid = tp_consume(dec, seq);
+        rc = ffn_block_impl(dec, l, tp_slot(dec, c.tp_rank, seq), tp_slot(dec, c.tp_rank, seq + 1), batch, stream, &tmid);
+        if (rc != B200_OK) return rc;
+        ++seq;
+    }
+    TpExchange tlast = tp_consume(dec, seq);
+    return fold_impl(dec, hidden, tp_slot(dec, c.tp_rank, seq), batch, stream, &tlast);
 }
 
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin,

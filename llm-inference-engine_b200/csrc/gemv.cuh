@@ -64,6 +64,7 @@ struct GemvArgs {
     int group;
     int inter;  // SwiGLU: rows (i, inter + i) form a unit, n_out = inter
     int y_f32;
+    TpExchange tp;  // world > 1: x is the sum over ranks of tp.peer_x[*] (fused one-shot all-reduce), `x` itself is ignored
 };
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy PTX
@@ -317,8 +318,24 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
         const T *gamma = a.norm ? reinterpret_cast<const T *>(a.gamma) : nullptr;
         const int nv = K / V;
         // pre-norm value of vector i of row m: x (+ residual) -> T; residual_out <- that; (+ bias) -> T
+        tp_exchange_sync(a.tp);
         auto prenorm = [&](int m, int i, float *f, bool write_res) {
-            unpack16<T>(ld_v4(xin + (size_t)m * K + (size_t)i * V), f);
+            if (a.tp.world > 1) {
+                // one-shot all-reduce: add every rank's partial in rank order, round to T as an all-reduced tensor of T would be
+                const size_t off = ((size_t)m * K + (size_t)i * V) * sizeof(T);
+#pragma unroll
+                for (int j = 0; j < V; ++j) f[j] = 0.0f;
+                for (int r2 = 0; r2 < a.tp.world; ++r2) {
+                    float g[V];
+                    unpack16<T>(tp_ld_v4(a.tp.peer_x[r2], off), g);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) f[j] += g[j];
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
+            } else {
+                unpack16<T>(ld_v4(xin + (size_t)m * K + (size_t)i * V), f);
+            }
             if (rin) {
                 float r[V];
                 unpack16<T>(ld_v4(rin + (size_t)m * K + (size_t)i * V), r);

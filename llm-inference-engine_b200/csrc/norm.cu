@@ -16,7 +16,7 @@ constexpr int kNormMaxVec = 8;  // 16-byte vectors cached per thread
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kNormThreads)
 norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T *__restrict__ bias,
-            const T *__restrict__ gamma, float eps, int hidden) {
+            const T *__restrict__ gamma, float eps, int hidden, const TpExchange tp) {
     constexpr int V = kVec ? Elem<T>::kVec : 1;
     __shared__ float red[33];
     const int row = blockIdx.x;
@@ -27,10 +27,25 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
     T *rout = residual_out ? residual_out + (size_t)row * hidden : nullptr;
 
     pdl_wait();
+    tp_exchange_sync(tp);
     // pre-norm value of vector i: o (+ residual); residual_out <- that; (+ bias)
     auto prenorm = [&](int i, float *f) {
         if constexpr (kVec) {
-            unpack16<T>(ld_v4(x + (size_t)i * V), f);
+            if (tp.world > 1) {  // fused one-shot all-reduce of the row-sharded linear's partial sums (rank order)
+                const size_t off = ((size_t)row * hidden + (size_t)i * V) * sizeof(T);
+#pragma unroll
+                for (int j = 0; j < V; ++j) f[j] = 0.0f;
+                for (int r2 = 0; r2 < tp.world; ++r2) {
+                    float g[V];
+                    unpack16<T>(tp_ld_v4(tp.peer_x[r2], off), g);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) f[j] += g[j];
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
+            } else {
+                unpack16<T>(ld_v4(x + (size_t)i * V), f);
+            }
             if (rin) {
                 float r[V];
                 unpack16<T>(ld_v4(rin + (size_t)i * V), r);
@@ -120,21 +135,32 @@ add_residual_kernel(T *__restrict__ out, const T *__restrict__ residual, size_t 
 
 template <typename T>
 static int launch_norm(const T *in, T *out, const T *rin, T *rout, const T *bias, const T *gamma, float eps, int tokens,
-                       int hidden, cudaStream_t st) {
+                       int hidden, cudaStream_t st, const TpExchange *tpx = nullptr) {
     const bool vec = hidden % Elem<T>::kVec == 0 && aligned16(out) && (!in || aligned16(in)) && (!rin || aligned16(rin)) &&
                      (!rout || aligned16(rout)) && (!bias || aligned16(bias)) && (!gamma || aligned16(gamma));
+    TpExchange tp = {};
+    if (tpx) tp = *tpx;
+    if (tp.world > 1 && !vec) {
+        set_error("norm: the fused tensor-parallel exchange needs 16-byte aligned rows");
+        return B200_ERR_UNSUPPORTED;
+    }
     cudaError_t e;
-    if (vec) e = launch_pdl(norm_kernel<T, true>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden);
-    else e = launch_pdl(norm_kernel<T, false>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden);
+    if (vec) e = launch_pdl(norm_kernel<T, true>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
+    else e = launch_pdl(norm_kernel<T, false>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
     (void)e;
     return cuda_status("norm kernel launch");
 }
 
+int launch_norm_tp(int dtype, const void *in, void *out, const void *rin, void *rout, const void *bias, const void *gamma, float eps,
+                   int tokens, int hidden, const TpExchange *tp, cudaStream_t st) {
+    B200_DISPATCH_DTYPE(dtype, return launch_norm<T>((const T *)in, (T *)out, (const T *)rin, (T *)rout, (const T *)bias,
+                                                     (const T *)gamma, eps, tokens, hidden, st, tp));
+    return B200_OK;
+}
+
 int launch_norm_any(int dtype, const void *in, void *out, const void *rin, void *rout, const void *bias, const void *gamma,
                     float eps, int tokens, int hidden, cudaStream_t st) {
-    B200_DISPATCH_DTYPE(dtype, return launch_norm<T>((const T *)in, (T *)out, (const T *)rin, (T *)rout, (const T *)bias,
-                                                     (const T *)gamma, eps, tokens, hidden, st));
-    return B200_OK;
+    return launch_norm_tp(dtype, in, out, rin, rout, bias, gamma, eps, tokens, hidden, nullptr, st);
 }
 
 }  // namespace b200

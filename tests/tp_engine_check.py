@@ -28,7 +28,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     cfg = dict(hidden=1024, head_num=8, kv_head_num=8 if world <= 8 else world, head_size=128, inter=2048, layers=3, max_seq=160, eps=1e-6, base=10000.0)
     ok = True
-    for dtype, batch, step in (("f32", 2, 37), ("bf16", 1, 130), ("bf16", 4, 64)):
+    for mode, dtype, batch, step in (("nccl", "f32", 2, 37), ("nccl", "bf16", 1, 130), ("fused", "f32", 2, 37), ("fused", "bf16", 1, 130),
+                                     ("fused", "bf16", 4, 64), ("fused", "bf16", 6, 21)):
         model = make_model(cfg, seed=17)
         lcfg = tp.local_cfg(dict(head_num=cfg["head_num"], kv_head_num=cfg["kv_head_num"], head_size=cfg["head_size"], inter=cfg["inter"]), world)
         dc = mod.DecoderConfig(cfg["hidden"], lcfg["head_num"], lcfg["kv_head_num"], cfg["head_size"], lcfg["inter"], cfg["layers"], cfg["max_seq"],
@@ -56,13 +57,18 @@ def main():
             dec.fold(h, pending)
             return h
 
-        tp.decode_step_tp(cfg["layers"], hidden, attn_block, ffn_block, fold, dist.all_reduce)
+        if mode == "nccl":
+            tp.decode_step_tp(cfg["layers"], hidden, attn_block, ffn_block, fold, dist.all_reduce)
+        else:  # one-shot all-reduce over NVLink peer memory fused into the consuming kernels: no NCCL call on the path
+            dec.tp_attach(dist)
+            dec.step_tp(hidden, kcd, vcd, step)
         torch.cuda.synchronize()
+        assert mode == "nccl" or dec.tp_error() == 0, "a peer never signalled (exchange timed out)"
         got = to_np(hidden)
         ref, rkc, rvc = run_oracle(model, cfg, dtype, batch, step, storage="f32")
         try:
             if dtype == "f32":
-                assert_close(got, ref, "f32", f"TP-{world} engine")
+                assert_close(got, ref, "f32", f"TP-{world} {mode} engine")
             else:
                 fro = np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ref)
                 assert fro <= 1e-2, f"TP-{world} {dtype} engine vs fp32 oracle: {fro:.3e}"
@@ -70,10 +76,10 @@ def main():
             want = tp.shard_kv_cache(rkc, cfg["kv_head_num"], rank, world)[:, :, :, step - 1]
             kerr = np.linalg.norm(mine - want) / np.linalg.norm(want)
             assert kerr <= (1e-5 if dtype == "f32" else 1e-2), f"appended K rows of this rank's heads: {kerr:.3e}"
-            print(f"[rank {rank}] TP-{world} {dtype} batch {batch} step {step}: OK", flush=True)
+            print(f"[rank {rank}] TP-{world} {mode} {dtype} batch {batch} step {step}: OK", flush=True)
         except AssertionError as e:
             ok = False
-            print(f"[rank {rank}] FAILED: {e}", flush=True)
+            print(f"[rank {rank}] {mode} {dtype} batch {batch} FAILED: {e}", flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     code = 1 if int(flag.item()) else 0
