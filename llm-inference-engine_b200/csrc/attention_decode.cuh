@@ -17,6 +17,8 @@ struct DecodeAttnArgs {
     int apply_rope, rot_dim;
     float rot_base;
     int nsplit, chunk;
+    const void *l2_prefetch;    // optional: bytes the NEXT kernel will stream (the O-projection weights); pulled into L2 while the
+    size_t l2_prefetch_bytes;   // attention's dependent chain leaves HBM idle
     int cluster;   // 1: the nsplit CTAs of a (b, kv head) form a thread-block cluster and merge through distributed shared memory
     int prefetch;  // 1: cached K/V rows may be requested before griddepcontrol.wait (fused engine only: the kernel in front
                    // of this one does not write the cache)

@@ -44,6 +44,8 @@ struct GemvGeom {
     int pieces;       // stages per unit = ceil(row_bytes / piece_bytes)
     int stage_bytes;  // kGemvRows * row stride inside a stage
     int cw;           // warp-vectors (32 lanes x 16 B) of a row piece per compute warp
+    int groups;       // groups of 8 compute warps in a CTA: 2 (one CTA fills the SM) or 1 (half-size CTA: the next kernel's CTA can be
+                      // co-resident and prefetch its weights while this one streams)
 };
 
 struct GemvArgs {
@@ -250,22 +252,23 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
     const int piece_vecs = geo.piece_bytes / 16, row_stride = geo.stage_bytes / R;
 
     // ---- roles: warps [0, 16) compute (group = warp / 8), warp 16 + g produces for group g, warp 18 + g reduces for group g
-    const bool is_compute = warp < kGemvWarps;
-    const int grp = is_compute ? warp / GW : (warp - kGemvWarps) % kGemvGroups;
-    const bool is_producer = !is_compute && warp < kGemvWarps + kGemvGroups;
+    const int n_groups = geo.groups, n_compute = n_groups * GW, n_threads = (int)blockDim.x;
+    const bool is_compute = warp < n_compute;
+    const int grp = is_compute ? warp / GW : (warp - n_compute) % n_groups;
+    const bool is_producer = !is_compute && warp < n_compute + n_groups;
     const int wg = warp % GW;
     // group `grp` of this CTA owns units gid, gid + total_groups, ...; a unit is `pieces` ring stages
-    const int gid = grp * gridDim.x + blockIdx.x, total_groups = gridDim.x * kGemvGroups;
+    const int gid = grp * gridDim.x + blockIdx.x, total_groups = gridDim.x * n_groups;
     const int my_units = gid < units ? (units - gid + total_groups - 1) / total_groups : 0;
     const int my_items = my_units * pieces;
 
     XS *xs = reinterpret_cast<XS *>(smem);
     size_t off = ((size_t)MB * Kp * sizeof(XS) + 127) & ~(size_t)127;
     unsigned char *ring = smem + off + (size_t)grp * stages * geo.stage_bytes;
-    off += (size_t)kGemvGroups * stages * geo.stage_bytes;
+    off += (size_t)n_groups * stages * geo.stage_bytes;
     const uint32_t full0 = smem_u32(smem + off) + grp * (2 * kGemvMaxStages + 4) * 8, empty0 = full0 + kGemvMaxStages * 8;
     const uint32_t ready0 = empty0 + kGemvMaxStages * 8, free0 = ready0 + 16;
-    off += (size_t)kGemvGroups * (2 * kGemvMaxStages + 4) * 8;
+    off += (size_t)n_groups * (2 * kGemvMaxStages + 4) * 8;
     float *gred = reinterpret_cast<float *>(smem + off) + (size_t)grp * 2 * GW * (R * MB) * 32;  // [parity][warp][R*MB][lane]
     const uint32_t ring_u32 = smem_u32(ring);
 
@@ -361,17 +364,17 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
             }
         };
         if constexpr (FMT != WF_DENSE) {
-            for (int i = K + threadIdx.x; i < Kp; i += kGemvThreads)
+            for (int i = K + threadIdx.x; i < Kp; i += n_threads)
                 for (int m = 0; m < MB; ++m) xs[(size_t)m * Kp + xs_perm<EPV>(i)] = 0.0f;
         }
-        const bool cached = nv <= kGemvXCache * kGemvThreads;  // the row fits the per-thread register cache: one global pass
+        const bool cached = nv <= kGemvXCache * n_threads;  // the row fits the per-thread register cache: one global pass
         for (int m = 0; m < MB; ++m) {
             if (m >= a.M) {  // padding rows of the batch tile
-                for (int i = threadIdx.x; i < Kp; i += kGemvThreads) xs[(size_t)m * Kp + i] = XS(0.0f);
+                for (int i = threadIdx.x; i < Kp; i += n_threads) xs[(size_t)m * Kp + i] = XS(0.0f);
                 continue;
             }
             if (!gamma) {
-                for (int i = threadIdx.x; i < nv; i += kGemvThreads) {
+                for (int i = threadIdx.x; i < nv; i += n_threads) {
                     float f[V];
                     prenorm(m, i, f, true);
                     store_xs(m, i, f);
@@ -383,7 +386,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
             if (cached) {
 #pragma unroll
                 for (int c = 0; c < kGemvXCache; ++c) {
-                    const int i = threadIdx.x + c * kGemvThreads;
+                    const int i = threadIdx.x + c * n_threads;
                     if (i < nv) {
                         unpack16<T>(ld_v4(gamma + (size_t)i * V), gm[c]);  // independent of the reduction: issue it now
                         prenorm(m, i, cache[c], true);
@@ -392,7 +395,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
                     }
                 }
             } else {
-                for (int i = threadIdx.x; i < nv; i += kGemvThreads) {
+                for (int i = threadIdx.x; i < nv; i += n_threads) {
                     float f[V];
                     prenorm(m, i, f, true);
 #pragma unroll
@@ -404,7 +407,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
             if (cached) {
 #pragma unroll
                 for (int c = 0; c < kGemvXCache; ++c) {
-                    const int i = threadIdx.x + c * kGemvThreads;
+                    const int i = threadIdx.x + c * n_threads;
                     if (i < nv) {
 #pragma unroll
                         for (int j = 0; j < V; ++j) cache[c][j] = (cache[c][j] * gm[c][j]) * rs;
@@ -413,7 +416,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
                 }
             } else {
                 // second pass over the (L1/L2-resident) inputs: recompute the pre-norm value and scale it
-                for (int i = threadIdx.x; i < nv; i += kGemvThreads) {
+                for (int i = threadIdx.x; i < nv; i += n_threads) {
                     float f[V], g[V];
                     prenorm(m, i, f, false);
                     unpack16<T>(ld_v4(gamma + (size_t)i * V), g);

@@ -1,6 +1,8 @@
 // gemv_inst.cuh -- host-side launch of gemv_nk_kernel for one activation type (included by gemv_<type>.cu so that
 // the three element types compile in parallel).
 #pragma once
+#include <stdlib.h>
+
 #include "gemv.cuh"
 
 namespace b200 {
@@ -19,10 +21,10 @@ static int launch_gemv_geom(const GemvArgs &a, const GemvGeom &g, size_t smem, c
     }
     const int units = SW ? a.inter : (a.N + 1) / 2;
     int grid = sm_count();
-    const int need = (units + kGemvGroups - 1) / kGemvGroups;
+    const int need = (units + g.groups - 1) / g.groups;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    launch_pdl(kern, dim3(grid), dim3(kGemvThreads), smem, st, true, a, g);
+    launch_pdl(kern, dim3(grid), dim3((g.groups * kGemvGW + 2 * g.groups) * 32), smem, st, true, a, g);
     return cuda_status("gemv_nk launch");
 }
 
@@ -37,13 +39,17 @@ static int launch_gemv_inst(const GemvArgs &a, cudaStream_t st) {
     g.pieces = (int)((row_bytes + g.piece_bytes - 1) / g.piece_bytes);
     g.stage_bytes = kGemvRows * ((g.piece_bytes + 127) / 128 * 128);
     g.cw = ((g.piece_bytes / 16 + 31) / 32 + kGemvGW - 1) / kGemvGW;
+    // B200_GEMV_HALF=1: half-size CTAs (one group of 8 compute warps, half the ring) so that two DIFFERENT kernels' CTAs fit on an
+    // SM and kernel i+1 prefetches its weights under kernel i (experiment)
+    static const bool half = getenv("B200_GEMV_HALF") != nullptr;
+    g.groups = half ? 1 : kGemvGroups;
     // shared memory: activations + rings + barriers + per-lane partial sums
     const int Kp = (a.K + WT::kBlock - 1) / WT::kBlock * WT::kBlock;
     size_t fixed = ((size_t)MB * Kp * sizeof(typename WT::XS) + 127) & ~(size_t)127;
-    fixed += (size_t)kGemvGroups * (2 * kGemvMaxStages + 4) * 8;
-    fixed += (size_t)kGemvWarps * 2 * kGemvRows * MB * 32 * sizeof(float);
-    const size_t budget = 224 * 1024;
-    const size_t per_stage = (size_t)kGemvGroups * g.stage_bytes;
+    fixed += (size_t)g.groups * (2 * kGemvMaxStages + 4) * 8;
+    fixed += (size_t)g.groups * kGemvGW * 2 * kGemvRows * MB * 32 * sizeof(float);
+    const size_t budget = half ? 111 * 1024 : 224 * 1024;
+    const size_t per_stage = (size_t)g.groups * g.stage_bytes;
     if (fixed + 3 * per_stage > budget) return B200_ERR_UNSUPPORTED;
     g.stages = (int)((budget - fixed) / per_stage);
     if (g.stages > kGemvMaxStages) g.stages = kGemvMaxStages;
