@@ -323,10 +323,11 @@ int b200_decoder_fold(b200_decoder_t *dec, void *hidden, const void *pending, in
 
 /* Fused tensor-parallel decode step: no NCCL on the path.  Every rank owns one EXCHANGE BUFFER (b200_decoder_tp_buffer_bytes) that all
  * other ranks of the node map through CUDA IPC (b200_tp_alloc_exported on the owner, b200_tp_open on the peers; the 64-byte handles
- * travel over any host channel, e.g. torch.distributed.all_gather_object).  The row-sharded O / down linears leave their partial sums
- * there; the first kernel of the next block signals completion into every peer's flag word, waits for every peer (bounded: ~2 s, then
- * b200_decoder_tp_error() reads non-zero), loads all partials over NVLink and adds them in rank order -- a one-shot all-reduce fused
- * into the residual-add + RMSNorm prologue of the consuming linear.  bases[r] = rank r's buffer as mapped in THIS process. */
+ * travel over any host channel, e.g. torch.distributed.all_gather_object).  The row-sharded O / down linears PUSH their partial sums
+ * into every rank's buffer from their epilogue (posted NVLink stores); the first kernel of the next block signals completion into
+ * every peer's flag word, waits for every peer (bounded: ~2 s, then b200_decoder_tp_error() reads non-zero), and adds the P partials
+ * -- now all in local memory -- in rank order: a one-shot all-reduce fused into the producing linear's epilogue and the
+ * residual-add + RMSNorm prologue of the consuming one.  bases[r] = rank r's buffer as mapped in THIS process. */
 size_t b200_decoder_tp_buffer_bytes(const b200_decoder_t *dec);
 int b200_tp_alloc_exported(size_t bytes, void **ptr, void *handle64);
 int b200_tp_open(const void *handle64, void **ptr);

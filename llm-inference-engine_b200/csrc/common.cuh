@@ -41,14 +41,17 @@ struct Workspace {
 bool get_workspace(Workspace *ws);
 
 // ------------------------------------------------------------------ tensor-parallel exchange over NVLink peer memory
-// One-shot all-reduce fused into the CONSUMER of a row-sharded linear: every rank left its partial sum [B,h] in its own
-// exchange buffer (peer-mapped on every other rank through CUDA IPC); the first kernel of the next block signals "my
-// partial is complete" into every peer's flag word, waits for every peer's signal, then reads all P partials with peer loads
-// and adds them in rank order (identical on every rank, deterministic).  No NCCL call, no extra launch, no extra pass.
+// One-shot all-reduce fused into the producer AND the consumer of a row-sharded linear.  Every rank owns an exchange buffer that
+// all other ranks of the node map through CUDA IPC.  PUSH: the producing linear's epilogue stores this rank's partial sum [B,h]
+// straight into EVERY rank's buffer (slot [source rank]; posted NVLink writes, no round trip).  The first kernel of the next block
+// then signals "my partial is complete" into every peer's flag word, waits for every peer's signal, reads the P partials from its
+// OWN memory and adds them in rank order (identical on every rank, deterministic).  No NCCL call, no extra launch, no remote read.
+// (A first version pulled the partials with peer loads from every CTA: 148 CTAs x (P-1) peers x 8 KB per exchange and one NVLink
+// round trip per peer made TP-8 slower than one GPU.)
 // Flag values grow monotonically: epoch (bumped once per decode step by a one-thread kernel) * 4096 + block sequence number.
 constexpr int kTpMaxWorld = 8;
 struct TpExchange {
-    const void *peer_x[kTpMaxWorld];        // every rank's partial buffer of this slot, rank order ([rank] is local memory)
+    const void *peer_x[kTpMaxWorld];        // the P partials of this slot, one per source rank, all in THIS rank's exchange buffer
     unsigned int *peer_flags[kTpMaxWorld];  // in every rank's buffer: the flag word (this slot, written by THIS rank)
     const unsigned int *my_flags;           // this rank's flag words of this slot: [world], one per writer
     const unsigned int *epoch;              // this rank's step counter (device memory)

@@ -73,23 +73,36 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
 // ---- exchange buffer of the fused tensor-parallel path (one per rank, peer-mapped everywhere):
 //      [0, 256)    flag words: [2 slots][kTpMaxWorld writers]
 //      [256, 512)  this rank's step counter (epoch) and error word
-//      [512, ...)  two partial-sum slots of max_batch * hidden elements
+//      [512, ...)  partial sums: [2 slots][world source ranks][max_batch * hidden elements]
 constexpr size_t kTpFlagsOff = 0, kTpEpochOff = 256, kTpErrorOff = 260, kTpDataOff = 512;
 static size_t tp_slot_bytes(const b200_decoder_config_t &c) { return align_up((size_t)c.max_batch * c.hidden * esize(c.dtype)); }
-static void *tp_slot(const b200_decoder *d, int rank, int seq) { return d->tp_base[rank] + kTpDataOff + (size_t)(seq & 1) * tp_slot_bytes(d->cfg); }
-// descriptor for the consumer of block `seq` (seq >= 1)
+// where the partial of block `seq` produced by rank `src` lives inside rank `owner`'s buffer
+static void *tp_slot(const b200_decoder *d, int owner, int seq, int src) {
+    return d->tp_base[owner] + kTpDataOff + ((size_t)(seq & 1) * d->cfg.tp_world + src) * tp_slot_bytes(d->cfg);
+}
+// descriptor for the consumer of block `seq` (seq >= 1): P local partials + the flag words
 static TpExchange tp_consume(const b200_decoder *d, int seq) {
     TpExchange t = {};
     const b200_decoder_config_t &c = d->cfg;
     t.world = c.tp_world, t.rank = c.tp_rank, t.seq = seq;
     for (int r = 0; r < c.tp_world; ++r) {
-        t.peer_x[r] = tp_slot(d, r, seq);
+        t.peer_x[r] = tp_slot(d, c.tp_rank, seq, r);
         t.peer_flags[r] = reinterpret_cast<unsigned int *>(d->tp_base[r] + kTpFlagsOff) + (seq & 1) * kTpMaxWorld + c.tp_rank;
     }
     t.my_flags = reinterpret_cast<const unsigned int *>(d->tp_base[c.tp_rank] + kTpFlagsOff) + (seq & 1) * kTpMaxWorld;
     t.epoch = reinterpret_cast<const unsigned int *>(d->tp_base[c.tp_rank] + kTpEpochOff);
     t.error = reinterpret_cast<unsigned int *>(d->tp_base[c.tp_rank] + kTpErrorOff);
     return t;
+}
+// batched (M > 4) path: the tensor-core GEMM wrote this rank's partial into its own buffer; copy it to every peer's
+template <typename T>
+__global__ void tp_push_kernel(const T *src, TpExchange dsts, size_t n_vec) {
+    pdl_wait();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = ld_v4(reinterpret_cast<const char *>(src) + i * 16);
+        for (int r = 0; r < dsts.world; ++r)
+            if (r != dsts.rank) st_v4(reinterpret_cast<char *>(const_cast<void *>(dsts.peer_x[r])) + i * 16, v);
+    }
 }
 __global__ void tp_begin_step_kernel(unsigned int *epoch) {
     pdl_wait();
@@ -119,17 +132,31 @@ static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void 
     return b200_silu_and_mul(d->gu, y, M, N / 2, c.dtype, st);
 }
 
-static int plain_linear(b200_decoder *d, const void *x, const b200_linear_weight_t &w, int K, int N, void *y, int M, cudaStream_t st) {
+// push_seq > 0 (fused tensor-parallel path): y is the partial of block push_seq and must reach every rank's exchange buffer
+static int plain_linear(b200_decoder *d, const void *x, const b200_linear_weight_t &w, int K, int N, void *y, int M, cudaStream_t st,
+                        int push_seq = 0) {
     const b200_decoder_config_t &c = d->cfg;
     if (M <= 4) {
         GemvArgs a = {};
         a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
         a.x = x, a.y = y;
         a.M = M, a.K = K, a.N = N, a.group = c.group;
+        if (push_seq > 0) {
+            a.n_push = c.tp_world;
+            for (int r = 0; r < c.tp_world; ++r) a.y_push[r] = tp_slot(d, r, push_seq, c.tp_rank);
+        }
         const int rc = launch_gemv_nk(a, c.dtype, c.w_format, false, st);
         if (rc != B200_ERR_UNSUPPORTED) return rc;
     }
-    return b200_linear(x, w.w, w.scales, w.zeros, y, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
+    int rc = b200_linear(x, w.w, w.scales, w.zeros, y, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
+    if (rc != B200_OK || push_seq <= 0) return rc;
+    TpExchange dsts = {};
+    dsts.world = c.tp_world, dsts.rank = c.tp_rank;
+    for (int r = 0; r < c.tp_world; ++r) dsts.peer_x[r] = tp_slot(d, r, push_seq, c.tp_rank);
+    const size_t n_vec = (size_t)M * N * esize(c.dtype) / 16;
+    const int grid = (int)((n_vec + 255) / 256 < 64 ? (n_vec + 255) / 256 : 64);
+    B200_DISPATCH_DTYPE(c.dtype, launch_pdl(tp_push_kernel<T>, dim3(grid), dim3(256), 0, st, true, (const T *)y, dsts, n_vec));
+    return cuda_status("tp_push launch");
 }
 
 template <typename T>
@@ -272,7 +299,7 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
 }
 
 static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache, void *partial,
-                           int batch, int step, b200_stream_t stream, const TpExchange *tp) {
+                           int batch, int step, b200_stream_t stream, const TpExchange *tp, int push_seq = 0) {
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
     const b200_decoder_config_t &c = dec->cfg;
@@ -314,7 +341,7 @@ static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const v
     rc = launch_decode_attn(a, c.dtype, st);
     if (rc != B200_OK) return rc;
     // 3. O projection (row-sharded under TP: `partial` is this rank's partial sum)
-    return plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, partial, batch, st);
+    return plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, partial, batch, st, push_seq);
 }
 
 int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache,
@@ -323,7 +350,7 @@ int b200_decoder_attn_block(b200_decoder_t *dec, int layer, void *hidden, const 
 }
 
 static int ffn_block_impl(b200_decoder_t *dec, int layer, const void *pending, void *partial, int batch, b200_stream_t stream,
-                          const TpExchange *tp) {
+                          const TpExchange *tp, int push_seq = 0) {
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
     const b200_decoder_config_t &c = dec->cfg;
@@ -338,7 +365,7 @@ static int ffn_block_impl(b200_decoder_t *dec, int layer, const void *pending, v
     if (rc != B200_OK) return rc;
     dec->cur ^= 1;
     // 5. down projection
-    return plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, partial, batch, st);
+    return plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, partial, batch, st, push_seq);
 }
 
 int b200_decoder_ffn_block(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *partial, int batch,
@@ -367,7 +394,7 @@ int b200_decoder_fold(b200_decoder_t *dec, void *hidden, const void *pending, in
 // ---------------------------------------------------------------- fused tensor-parallel step (no NCCL on the path)
 size_t b200_decoder_tp_buffer_bytes(const b200_decoder_t *dec) {
     if (!dec) return 0;
-    return kTpDataOff + 2 * tp_slot_bytes(dec->cfg);
+    return kTpDataOff + 2 * (size_t)dec->cfg.tp_world * tp_slot_bytes(dec->cfg);
 }
 
 int b200_tp_alloc_exported(size_t bytes, void **ptr, void *handle64) {
@@ -429,20 +456,21 @@ int b200_decoder_step_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void 
     launch_pdl(tp_begin_step_kernel, dim3(1), dim3(32), 0, st, true, reinterpret_cast<unsigned int *>(dec->tp_base[c.tp_rank] + kTpEpochOff));
     if ((rc = cuda_status("tp_begin_step launch")) != B200_OK) return rc;
     int seq = 0;  // sequence number of the last partial produced in this step
+    const int me = c.tp_rank;
     for (int l = 0; l < c.num_layers; ++l) {
-        // attention block: consumes the previous layer's FFN partial (seq), leaves its O-projection partial in slot seq + 1
+        // attention block: consumes the previous layer's FFN partials (seq), pushes its O-projection partial as block seq + 1
         TpExchange tin = seq ? tp_consume(dec, seq) : TpExchange{};
-        rc = attn_block_impl(dec, l, hidden, seq ? tp_slot(dec, c.tp_rank, seq) : nullptr, k_cache, v_cache, tp_slot(dec, c.tp_rank, seq + 1), batch, step,
-                             stream, seq ? &tin : nullptr);
+        rc = attn_block_impl(dec, l, hidden, seq ? tp_slot(dec, me, seq, me) : nullptr, k_cache, v_cache, tp_slot(dec, me, seq + 1, me), batch, step,
+                             stream, seq ? &tin : nullptr, seq + 1);
         if (rc != B200_OK) return rc;
         ++seq;
         TpExchange tmid = tp_consume(dec, seq);
-        rc = ffn_block_impl(dec, l, tp_slot(dec, c.tp_rank, seq), tp_slot(dec, c.tp_rank, seq + 1), batch, stream, &tmid);
+        rc = ffn_block_impl(dec, l, tp_slot(dec, me, seq, me), tp_slot(dec, me, seq + 1, me), batch, stream, &tmid, seq + 1);
         if (rc != B200_OK) return rc;
         ++seq;
     }
     TpExchange tlast = tp_consume(dec, seq);
-    return fold_impl(dec, hidden, tp_slot(dec, c.tp_rank, seq), batch, stream, &tlast);
+    return fold_impl(dec, hidden, tp_slot(dec, me, seq, me), batch, stream, &tlast);
 }
 
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin,

@@ -67,6 +67,10 @@ struct GemvArgs {
     int inter;  // SwiGLU: rows (i, inter + i) form a unit, n_out = inter
     int y_f32;
     TpExchange tp;  // world > 1: x is the sum over ranks of tp.peer_x[*] (fused one-shot all-reduce), `x` itself is ignored
+    // n_push > 0: y is this rank's PARTIAL sum of a row-sharded linear; the reducer stores it into every rank's exchange buffer
+    // (y_push[p], peer-mapped memory: posted NVLink writes) instead of `y`, so that the consumers read only local memory
+    void *y_push[kTpMaxWorld];
+    int n_push;
 };
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy PTX
@@ -328,12 +332,18 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
                 const size_t off = ((size_t)m * K + (size_t)i * V) * sizeof(T);
 #pragma unroll
                 for (int j = 0; j < V; ++j) f[j] = 0.0f;
-                for (int r2 = 0; r2 < a.tp.world; ++r2) {
-                    float g[V];
-                    unpack16<T>(tp_ld_v4(a.tp.peer_x[r2], off), g);
+                uint4 raw[kTpMaxWorld];
 #pragma unroll
-                    for (int j = 0; j < V; ++j) f[j] += g[j];
-                }
+                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)  // all loads in flight before the first add
+                    if (r2 < a.tp.world) raw[r2] = tp_ld_v4(a.tp.peer_x[r2], off);
+#pragma unroll
+                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
+                    if (r2 < a.tp.world) {
+                        float g[V];
+                        unpack16<T>(raw[r2], g);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) f[j] += g[j];
+                    }
 #pragma unroll
                 for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
             } else {
@@ -491,8 +501,14 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
 #pragma unroll
                             for (int m = 0; m < MB; ++m)
                                 if (m < a.M) {
-                                    if (a.y_f32) reinterpret_cast<float *>(a.y)[(size_t)m * N + row] = out[r][m];
-                                    else reinterpret_cast<T *>(a.y)[(size_t)m * N + row] = Elem<T>::from_f(out[r][m]);
+                                    if (a.n_push > 0) {
+                                        const T v = Elem<T>::from_f(out[r][m]);
+                                        for (int pp = 0; pp < a.n_push; ++pp) reinterpret_cast<T *>(a.y_push[pp])[(size_t)m * N + row] = v;
+                                    } else if (a.y_f32) {
+                                        reinterpret_cast<float *>(a.y)[(size_t)m * N + row] = out[r][m];
+                                    } else {
+                                        reinterpret_cast<T *>(a.y)[(size_t)m * N + row] = Elem<T>::from_f(out[r][m]);
+                                    }
                                 }
                         }
                 }

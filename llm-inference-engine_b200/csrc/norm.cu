@@ -35,12 +35,18 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
                 const size_t off = ((size_t)row * hidden + (size_t)i * V) * sizeof(T);
 #pragma unroll
                 for (int j = 0; j < V; ++j) f[j] = 0.0f;
-                for (int r2 = 0; r2 < tp.world; ++r2) {
-                    float g[V];
-                    unpack16<T>(tp_ld_v4(tp.peer_x[r2], off), g);
+                uint4 raw[kTpMaxWorld];
 #pragma unroll
-                    for (int j = 0; j < V; ++j) f[j] += g[j];
-                }
+                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
+                    if (r2 < tp.world) raw[r2] = tp_ld_v4(tp.peer_x[r2], off);
+#pragma unroll
+                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
+                    if (r2 < tp.world) {
+                        float g[V];
+                        unpack16<T>(raw[r2], g);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) f[j] += g[j];
+                    }
 #pragma unroll
                 for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
             } else {
