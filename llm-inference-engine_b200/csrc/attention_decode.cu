@@ -169,18 +169,6 @@ decode_attn_kernel(const DecodeAttnArgs a) {
         // cached positions do not depend on the kernel before this one (the QKV linear): request them now
         if (a.prefetch)
             while (p_t < kAttnStages && p_t < ntiles) issue_next();
-        // this kernel moves 17 MB and then waits on a chain of dependent steps: use the idle HBM time to pull the weights of the
-        // NEXT kernel (the O projection, 33.5 MB << 126 MB of L2) into L2 -- every CTA prefetches its slice
-        if (a.l2_prefetch && a.l2_prefetch_bytes) {
-            const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
-            const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-            const size_t per = ((a.l2_prefetch_bytes + ncta - 1) / ncta + 127) & ~(size_t)127;
-            const size_t lo = cta * per, hi = lo + per < a.l2_prefetch_bytes ? lo + per : a.l2_prefetch_bytes;
-            for (size_t o = lo; o < hi; o += 16384) {
-                const unsigned int n = (unsigned int)((hi - o < 16384 ? hi - o : 16384) & ~(size_t)15);
-                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)a.l2_prefetch + o), "r"(n) : "memory");
-            }
-        }
     }
 
     pdl_wait();
@@ -233,6 +221,20 @@ decode_attn_kernel(const DecodeAttnArgs a) {
                 if (++e_s == kAttnStages) e_s = 0, e_ph ^= 1;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue_next();
+            }
+            // (opt-in) once this CTA's last K/V tile has LANDED, HBM idles while the softmax / merge chain finishes: pull this CTA's
+            // slice of the next kernel's weights (the O projection, 33.5 MB << 126 MB of L2) into L2
+            if (a.l2_prefetch && a.l2_prefetch_bytes && ntiles > 0) {
+                const int last = ntiles - 1;
+                a_mbar_wait(full0 + 8 * (last % kAttnStages), (last / kAttnStages) & 1);
+                const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+                const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+                const size_t per = ((a.l2_prefetch_bytes + ncta - 1) / ncta + 127) & ~(size_t)127;
+                const size_t lo = cta * per, hi = lo + per < a.l2_prefetch_bytes ? lo + per : a.l2_prefetch_bytes;
+                for (size_t o = lo; o < hi; o += 16384) {
+                    const unsigned int n = (unsigned int)((hi - o < 16384 ? hi - o : 16384) & ~(size_t)15);
+                    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)a.l2_prefetch + o), "r"(n) : "memory");
+                }
             }
         }
     } else {

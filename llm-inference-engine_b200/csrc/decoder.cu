@@ -109,12 +109,15 @@ __global__ void tp_begin_step_kernel(unsigned int *epoch) {
     if (threadIdx.x == 0) *epoch += 1;
 }
 
-// prologue (add residual / bias / RMSNorm) + linear (+ SwiGLU): fused GEMV for M <= 4, un-fused otherwise.
+// rows one fused GEMV launch can take: 4 (SIMT kernels), 8 for weight-only quantised 16-bit models (tensor-core dequant kernel)
+static int gemv_max_rows(const b200_decoder_config_t &c) { return (c.w_format != B200_W_DENSE && c.dtype != B200_F32) ? 8 : 4; }
+
+// prologue (add residual / bias / RMSNorm) + linear (+ SwiGLU): fused GEMV for M <= 4 (8 quantised), un-fused otherwise.
 // tp (optional): x is the fused all-reduce of every rank's partial (TpExchange) instead of a local tensor.
 static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void *res_out, const void *bias, const void *gamma,
                        const b200_linear_weight_t &w, int K, int N, bool swiglu, void *y, int M, cudaStream_t st, const TpExchange *tp = nullptr) {
     const b200_decoder_config_t &c = d->cfg;
-    if (M <= 4) {
+    if (M <= gemv_max_rows(c)) {
         GemvArgs a = {};
         a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
         a.x = x, a.y = y;
@@ -136,7 +139,7 @@ static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void 
 static int plain_linear(b200_decoder *d, const void *x, const b200_linear_weight_t &w, int K, int N, void *y, int M, cudaStream_t st,
                         int push_seq = 0) {
     const b200_decoder_config_t &c = d->cfg;
-    if (M <= 4) {
+    if (M <= gemv_max_rows(c)) {
         GemvArgs a = {};
         a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
         a.x = x, a.y = y;

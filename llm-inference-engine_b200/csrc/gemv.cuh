@@ -230,6 +230,118 @@ __device__ __forceinline__ void dot_rows(const uint4 (&wv)[kGemvRows], const boo
     }
 }
 
+// ------------------------------------------------------------------ activation staging shared by the GEMV kernels
+// For every token row m < a.M and every 16-byte vector i of the row: x (or, under tensor parallelism, the fused all-reduce of every
+// rank's partial -- TpExchange) (+ residual) -> T; residual_out <- that (CTA 0 only); (+ bias) -> T; RMSNorm with gamma when given
+// (reference src/kernels/rmsnorm.cu:35-80, add_residual_and_rmsnorm.cu:43-121).  The V fp32 values of each vector are handed to
+// store(m, i, f).  One global read pass when the row fits the per-thread register cache.  Every thread of the CTA must call;
+// `red` = shared float[33].  The caller synchronises afterwards.
+template <typename T, typename Store>
+__device__ __forceinline__ void gemv_stage_activations(const GemvArgs &a, int n_threads, float *red, Store store) {
+    constexpr int V = Elem<T>::kVec;
+    const int K = a.K;
+    const T *xin = reinterpret_cast<const T *>(a.x);
+    const T *rin = a.norm ? reinterpret_cast<const T *>(a.res_in) : nullptr;
+    T *rout = a.norm ? reinterpret_cast<T *>(a.res_out) : nullptr;
+    const T *bias = a.norm ? reinterpret_cast<const T *>(a.bias) : nullptr;
+    const T *gamma = a.norm ? reinterpret_cast<const T *>(a.gamma) : nullptr;
+    const int nv = K / V;
+    tp_exchange_sync(a.tp);
+    // pre-norm value of vector i of row m
+    auto prenorm = [&](int m, int i, float *f, bool write_res) {
+        if (a.tp.world > 1) {
+            // one-shot all-reduce: add every rank's partial in rank order, round to T as an all-reduced tensor of T would be
+            const size_t off = ((size_t)m * K + (size_t)i * V) * sizeof(T);
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[j] = 0.0f;
+            uint4 raw[kTpMaxWorld];
+#pragma unroll
+            for (int r2 = 0; r2 < kTpMaxWorld; ++r2)  // all loads in flight before the first add
+                if (r2 < a.tp.world) raw[r2] = tp_ld_v4(a.tp.peer_x[r2], off);
+#pragma unroll
+            for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
+                if (r2 < a.tp.world) {
+                    float g[V];
+                    unpack16<T>(raw[r2], g);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) f[j] += g[j];
+                }
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
+        } else {
+            unpack16<T>(ld_v4(xin + (size_t)m * K + (size_t)i * V), f);
+        }
+        if (rin) {
+            float r[V];
+            unpack16<T>(ld_v4(rin + (size_t)m * K + (size_t)i * V), r);
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
+        }
+        if (write_res && rout && blockIdx.x == 0) st_v4(rout + (size_t)m * K + (size_t)i * V, pack16<T>(f));
+        if (bias) {
+            float b[V];
+            unpack16<T>(ld_v4(bias + (size_t)i * V), b);
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + b[j]);
+        }
+    };
+    const bool cached = nv <= kGemvXCache * n_threads;  // the row fits the per-thread register cache: one global pass
+    for (int m = 0; m < a.M; ++m) {
+        if (!gamma) {
+            for (int i = threadIdx.x; i < nv; i += n_threads) {
+                float f[V];
+                prenorm(m, i, f, true);
+                store(m, i, f);
+            }
+            continue;
+        }
+        float cache[kGemvXCache][V], gm[kGemvXCache][V];
+        float ss = 0.0f;
+        if (cached) {
+#pragma unroll
+            for (int c = 0; c < kGemvXCache; ++c) {
+                const int i = threadIdx.x + c * n_threads;
+                if (i < nv) {
+                    unpack16<T>(ld_v4(gamma + (size_t)i * V), gm[c]);  // independent of the reduction: issue it now
+                    prenorm(m, i, cache[c], true);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) ss += cache[c][j] * cache[c][j];
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < nv; i += n_threads) {
+                float f[V];
+                prenorm(m, i, f, true);
+#pragma unroll
+                for (int j = 0; j < V; ++j) ss += f[j] * f[j];
+            }
+        }
+        ss = block_sum(ss, red);
+        const float rs = rsqrtf(ss / (float)K + a.eps);
+        if (cached) {
+#pragma unroll
+            for (int c = 0; c < kGemvXCache; ++c) {
+                const int i = threadIdx.x + c * n_threads;
+                if (i < nv) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) cache[c][j] = (cache[c][j] * gm[c][j]) * rs;
+                    store(m, i, cache[c]);
+                }
+            }
+        } else {
+            // second pass over the (L1/L2-resident) inputs: recompute the pre-norm value and scale it
+            for (int i = threadIdx.x; i < nv; i += n_threads) {
+                float f[V], g[V];
+                prenorm(m, i, f, false);
+                unpack16<T>(ld_v4(gamma + (size_t)i * V), g);
+#pragma unroll
+                for (int j = 0; j < V; ++j) f[j] = (f[j] * g[j]) * rs;
+                store(m, i, f);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 // smem: [ xs : MB * Kp * sizeof(XS) | rings : groups * stages * stage_bytes | barriers : groups * (2 * kGemvMaxStages + 4) * 8 |
 //         partial sums : groups * 2 * GW * R*MB * 32 floats ]
@@ -318,52 +430,13 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
 
     // ---------------- stage the activations (with the fused add-residual / bias / RMSNorm prologue); all warps help
     {
-        const T *xin = reinterpret_cast<const T *>(a.x);
-        const T *rin = a.norm ? reinterpret_cast<const T *>(a.res_in) : nullptr;
-        T *rout = a.norm ? reinterpret_cast<T *>(a.res_out) : nullptr;
-        const T *bias = a.norm ? reinterpret_cast<const T *>(a.bias) : nullptr;
-        const T *gamma = a.norm ? reinterpret_cast<const T *>(a.gamma) : nullptr;
-        const int nv = K / V;
-        // pre-norm value of vector i of row m: x (+ residual) -> T; residual_out <- that; (+ bias) -> T
-        tp_exchange_sync(a.tp);
-        auto prenorm = [&](int m, int i, float *f, bool write_res) {
-            if (a.tp.world > 1) {
-                // one-shot all-reduce: add every rank's partial in rank order, round to T as an all-reduced tensor of T would be
-                const size_t off = ((size_t)m * K + (size_t)i * V) * sizeof(T);
-#pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = 0.0f;
-                uint4 raw[kTpMaxWorld];
-#pragma unroll
-                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)  // all loads in flight before the first add
-                    if (r2 < a.tp.world) raw[r2] = tp_ld_v4(a.tp.peer_x[r2], off);
-#pragma unroll
-                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
-                    if (r2 < a.tp.world) {
-                        float g[V];
-                        unpack16<T>(raw[r2], g);
-#pragma unroll
-                        for (int j = 0; j < V; ++j) f[j] += g[j];
-                    }
-#pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
-            } else {
-                unpack16<T>(ld_v4(xin + (size_t)m * K + (size_t)i * V), f);
-            }
-            if (rin) {
-                float r[V];
-                unpack16<T>(ld_v4(rin + (size_t)m * K + (size_t)i * V), r);
-#pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
-            }
-            if (write_res && rout && blockIdx.x == 0) st_v4(rout + (size_t)m * K + (size_t)i * V, pack16<T>(f));
-            if (bias) {
-                float b[V];
-                unpack16<T>(ld_v4(bias + (size_t)i * V), b);
-#pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + b[j]);
-            }
-        };
-        auto store_xs = [&](int m, int i, const float *f) {
+        if constexpr (FMT != WF_DENSE) {
+            for (int i = K + threadIdx.x; i < Kp; i += n_threads)
+                for (int m = 0; m < MB; ++m) xs[(size_t)m * Kp + xs_perm<EPV>(i)] = 0.0f;
+        }
+        for (int m = a.M; m < MB; ++m)  // padding rows of the batch tile
+            for (int i = threadIdx.x; i < Kp; i += n_threads) xs[(size_t)m * Kp + i] = XS(0.0f);
+        gemv_stage_activations<T>(a, n_threads, red, [&](int m, int i, const float *f) {
             if constexpr (FMT == WF_DENSE) {
                 *reinterpret_cast<uint4 *>(xs + (size_t)m * Kp + (size_t)i * V) = pack16<T>(f);
             } else {
@@ -372,70 +445,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) xs[(size_t)m * Kp + xs_perm<EPV>(i * V + j)] = g[j];
             }
-        };
-        if constexpr (FMT != WF_DENSE) {
-            for (int i = K + threadIdx.x; i < Kp; i += n_threads)
-                for (int m = 0; m < MB; ++m) xs[(size_t)m * Kp + xs_perm<EPV>(i)] = 0.0f;
-        }
-        const bool cached = nv <= kGemvXCache * n_threads;  // the row fits the per-thread register cache: one global pass
-        for (int m = 0; m < MB; ++m) {
-            if (m >= a.M) {  // padding rows of the batch tile
-                for (int i = threadIdx.x; i < Kp; i += n_threads) xs[(size_t)m * Kp + i] = XS(0.0f);
-                continue;
-            }
-            if (!gamma) {
-                for (int i = threadIdx.x; i < nv; i += n_threads) {
-                    float f[V];
-                    prenorm(m, i, f, true);
-                    store_xs(m, i, f);
-                }
-                continue;
-            }
-            float cache[kGemvXCache][V], gm[kGemvXCache][V];
-            float ss = 0.0f;
-            if (cached) {
-#pragma unroll
-                for (int c = 0; c < kGemvXCache; ++c) {
-                    const int i = threadIdx.x + c * n_threads;
-                    if (i < nv) {
-                        unpack16<T>(ld_v4(gamma + (size_t)i * V), gm[c]);  // independent of the reduction: issue it now
-                        prenorm(m, i, cache[c], true);
-#pragma unroll
-                        for (int j = 0; j < V; ++j) ss += cache[c][j] * cache[c][j];
-                    }
-                }
-            } else {
-                for (int i = threadIdx.x; i < nv; i += n_threads) {
-                    float f[V];
-                    prenorm(m, i, f, true);
-#pragma unroll
-                    for (int j = 0; j < V; ++j) ss += f[j] * f[j];
-                }
-            }
-            ss = block_sum(ss, red);
-            const float rs = rsqrtf(ss / (float)K + a.eps);
-            if (cached) {
-#pragma unroll
-                for (int c = 0; c < kGemvXCache; ++c) {
-                    const int i = threadIdx.x + c * n_threads;
-                    if (i < nv) {
-#pragma unroll
-                        for (int j = 0; j < V; ++j) cache[c][j] = (cache[c][j] * gm[c][j]) * rs;
-                        store_xs(m, i, cache[c]);
-                    }
-                }
-            } else {
-                // second pass over the (L1/L2-resident) inputs: recompute the pre-norm value and scale it
-                for (int i = threadIdx.x; i < nv; i += n_threads) {
-                    float f[V], g[V];
-                    prenorm(m, i, f, false);
-                    unpack16<T>(ld_v4(gamma + (size_t)i * V), g);
-#pragma unroll
-                    for (int j = 0; j < V; ++j) f[j] = (f[j] * g[j]) * rs;
-                    store_xs(m, i, f);
-                }
-            }
-        }
+        });
         __syncthreads();  // xs complete; also publishes the producers' mbarrier initialisation
     }
     pdl_launch_dependents();

@@ -1,13 +1,24 @@
+#include <stdlib.h>
+
 #include "gemv_inst.cuh"
 namespace b200 {
 int launch_gemv_nk_f32(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st) { return launch_gemv_t<float, false>(a, fmt, swiglu, st); }
 int launch_gemv_nk_bf16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
 int launch_gemv_nk_f16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
+int launch_gemv_q_bf16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
+int launch_gemv_q_f16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
 int launch_gemv_nk(const GemvArgs &a, int dtype, int fmt, bool swiglu, cudaStream_t st) {
     if (swiglu && (a.N != 2 * a.inter)) {
         set_error("gemv: SwiGLU epilogue needs N == 2*inter");
         return B200_ERR_INVALID_ARG;
     }
+    // weight-only quantised, 16-bit activations, M <= 8: dequant into tensor-core fragments (gemv_q.cuh)
+    static const bool no_q = getenv("B200_GEMV_Q_SIMT") != nullptr;  // A/B knob: force the SIMT dequant path
+    if (fmt != WF_DENSE && !no_q && (dtype == B200_BF16 || dtype == B200_F16)) {
+        const int rc = dtype == B200_BF16 ? launch_gemv_q_bf16(a, fmt, swiglu, st) : launch_gemv_q_f16(a, fmt, swiglu, st);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+    if (a.M > 4) return B200_ERR_UNSUPPORTED;
     switch (dtype) {
         case B200_F32: return launch_gemv_nk_f32(a, fmt, swiglu, st);
         case B200_F16: return launch_gemv_nk_f16(a, fmt, swiglu, st);

@@ -307,20 +307,24 @@ int b200_linear(const void *x, const void *w, const void *scales, const void *ze
             if (rc == B200_OK) done = 1;
             else if (rc != B200_ERR_UNSUPPORTED) return rc;
         }
-        if (!done && M <= 16) {
-            // weight-streaming GEMV in passes of <= 4 rows (quantised weights with 5..16 rows: 4 passes over packed
-            // weights still move fewer bytes than one pass over bf16)
-            for (int m0 = 0; m0 < M; m0 += 4) {
-                GemvArgs a = {};
-                a.w = w, a.scales = scales, a.zeros = zeros;
-                a.x = (const char *)x + (size_t)m0 * K * elem_bytes(dtype);
-                a.y = (char *)y + (size_t)m0 * N * elem_bytes(dtype);
-                a.M = M - m0 < 4 ? M - m0 : 4, a.K = K, a.N = N, a.group = group;
-                rc = launch_gemv_nk(a, dtype, w_format, false, st);
-                if (rc != B200_OK) break;
+        if (!done && M <= 32) {
+            // weight-streaming GEMV in passes: quantised weights take up to 8 rows per pass (tensor-core dequant kernel, gemv_q.cuh;
+            // 4 passes over packed weights still move fewer bytes than one pass over bf16), the SIMT kernels 4 rows
+            for (int step = (w_format != B200_W_DENSE && dtype != B200_F32) ? 8 : 4; step >= 4 && !done; step -= 4) {
+                if (M > 4 * step) continue;
+                rc = B200_OK;
+                for (int m0 = 0; m0 < M; m0 += step) {
+                    GemvArgs a = {};
+                    a.w = w, a.scales = scales, a.zeros = zeros;
+                    a.x = (const char *)x + (size_t)m0 * K * elem_bytes(dtype);
+                    a.y = (char *)y + (size_t)m0 * N * elem_bytes(dtype);
+                    a.M = M - m0 < step ? M - m0 : step, a.K = K, a.N = N, a.group = group;
+                    rc = launch_gemv_nk(a, dtype, w_format, false, st);
+                    if (rc != B200_OK) break;
+                }
+                if (rc == B200_OK) done = 1;
+                else if (rc != B200_ERR_UNSUPPORTED) return rc;
             }
-            if (rc == B200_OK) done = 1;
-            else if (rc != B200_ERR_UNSUPPORTED) return rc;
         }
         if (done) return B200_OK;
     } else if (M <= 4 && N % (16 / elem_bytes(dtype)) == 0 && aligned16(w)) {

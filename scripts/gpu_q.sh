@@ -1,0 +1,5 @@
+set -x
+timeout -k 5 400 python -m pytest tests/test_ops_gpu.py tests/test_decoder_engine.py -m gpu -q -k "quantis" --timeout 200 --timeout-method=thread -p no:cacheprovider > gpurun_out/test_q.log 2>&1; tail -25 gpurun_out/test_q.log | cut -c1-250
+for wf in fp8 int4; do for b in 1 16; do
+timeout 300 python bench.py --wformat $wf --batch $b --steps 32 --warmup 3 --no-cpu-baseline 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$wf b$b', round(d['value'],1),'tok/s', round(d['ms_per_step'],3),'ms', 'gemv GB/s', round(d['roofline']['achieved']), 'whole frac', round(d['roofline']['whole_step']['frac'],3))"
+done; done

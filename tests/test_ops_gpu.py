@@ -170,7 +170,8 @@ def test_linear_reference_test_inputs_and_kernel():
 
 @pytest.mark.parametrize("dtype", ["bf16", "f16"])
 @pytest.mark.parametrize("fmt", ["fp8", "int4"])
-@pytest.mark.parametrize("M,K,N", [(1, 4096, 1024), (2, 11008, 256), (4, 512, 130), (9, 1024, 64), (1, 1536, 48)])
+@pytest.mark.parametrize("M,K,N", [(1, 4096, 1024), (2, 11008, 256), (4, 512, 130), (9, 1024, 64), (1, 1536, 48), (8, 4096, 520), (16, 2048, 256),
+                                   (3, 384, 40)])
 def test_linear_quantised(M, K, N, fmt, dtype):
     import torch
 
