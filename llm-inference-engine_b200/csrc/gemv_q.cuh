@@ -17,11 +17,12 @@ namespace b200 {
 
 constexpr int kQRows = 16;         // weight rows per unit = mma M
 constexpr int kQTok = 8;           // token slots = mma N
-constexpr int kQPieceK = 1024;     // k elements of a row per ring stage; each of the 8 warps of a group owns 128 of them
-constexpr int kQWarpK = kQPieceK / kGemvGW;
+constexpr int kQPieceBytes = 2048;  // preferred bytes of a row per ring stage = one bulk copy (1 KiB copies cap the kernel near 3.3 TB/s:
+                                    // the copy engine is request-rate bound); 1024 when shared memory is short (long rows, many tokens)
 constexpr int kQRowPad = 16;       // bytes added to a stage row: keeps ldmatrix rows on different banks
 
 struct GemvQGeom {
+    int piece_bytes;  // bytes of a row per ring stage: 2048 or 1024; each of the 8 warps of a group owns 1/8 of them
     int stages;
     int pieces;       // stages per unit = ceil(K / kQPieceK)
     int row_stride;   // bytes between rows inside a stage
@@ -51,7 +52,7 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
     constexpr int GW = kGemvGW, R = kQRows;
     constexpr int V = Elem<T>::kVec;
     constexpr int kBytesPerK8 = FMT == WF_FP8 ? 8 : 4;            // bytes of 8 consecutive k of one row
-    constexpr int kWarpBytes = kQWarpK * kBytesPerK8 / 8;          // bytes of a row a warp owns per stage: 128 (FP8) / 64 (INT4)
+    constexpr int kBlkBytes = 128 * kBytesPerK8 / 8;               // bytes of one 128-k block of a row: 128 / 64
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float red[33];
 
@@ -61,6 +62,9 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
     const int units = kSwiGLU ? (a.inter + 7) / 8 : (N + R - 1) / R;
     const int stages = geo.stages, pieces = geo.pieces;
     const int n_threads = (int)blockDim.x;
+    const int kQPieceK = geo.piece_bytes * 8 / kBytesPerK8;   // k per stage
+    const int kQWarpK = kQPieceK / kGemvGW;                   // k per warp per stage (a multiple of 128)
+    const int kWarpBytes = geo.piece_bytes / kGemvGW;         // bytes of a row a warp owns per stage
 
     const bool is_compute = warp < kGemvWarps;
     const int grp = is_compute ? warp / GW : (warp - kGemvWarps) % kGemvGroups;
@@ -222,24 +226,26 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
             for (int pc = 0; pc < pieces; ++pc) {
                 mbar_wait(full0 + s * 8, ph);
                 const int kw = pc * kQPieceK + wg * kQWarpK;  // first k of this warp's slice
-                if (kw < K) {
-                    const uint32_t st = ring_u32 + (uint32_t)s * geo.stage_bytes + lm_off;
+                const uint32_t st = ring_u32 + (uint32_t)s * geo.stage_bytes + lm_off;
+                for (int bk = 0; bk < kQWarpK / 128; ++bk) {  // 128-k blocks of the slice (K is a multiple of 128)
+                    const int kb = kw + bk * 128;
+                    if (kb >= K) break;
                     if constexpr (FMT == WF_FP8) {
 #pragma unroll
-                        for (int j = 0; j < kQWarpK / 32; ++j) {  // 32 k per ldmatrix.x4 = two mma k-steps
+                        for (int j = 0; j < 4; ++j) {  // 32 k per ldmatrix.x4 = two mma k-steps
                             uint32_t r[4];
-                            ldmatrix_x4(r, st + j * 32);
+                            ldmatrix_x4(r, st + bk * kBlkBytes + j * 32);
                             // r0: row g, fp8 k = 4t..4t+3 of the first 16 k; r1: row g+8; r2 / r3: the next 16 k.
                             // k is permuted consistently for A and B: mma slots (2t, 2t+1) <- k (4t, 4t+1), slots (2t+8, 2t+9) <- (4t+2, 4t+3)
-                            uint2 b01 = *reinterpret_cast<const uint2 *>(xrow + kw + j * 32 + 4 * t);
-                            uint2 b23 = *reinterpret_cast<const uint2 *>(xrow + kw + j * 32 + 16 + 4 * t);
+                            uint2 b01 = *reinterpret_cast<const uint2 *>(xrow + kb + j * 32 + 4 * t);
+                            uint2 b23 = *reinterpret_cast<const uint2 *>(xrow + kb + j * 32 + 16 + 4 * t);
                             if (!tok) b01 = make_uint2(0u, 0u), b23 = make_uint2(0u, 0u);
                             mma_f16(acc, e4m3x2_to_f16x2(r[0]), e4m3x2_to_f16x2(r[1]), e4m3x2_to_f16x2(r[0] >> 16), e4m3x2_to_f16x2(r[1] >> 16), b01.x, b01.y);
                             mma_f16(acc, e4m3x2_to_f16x2(r[2]), e4m3x2_to_f16x2(r[3]), e4m3x2_to_f16x2(r[2] >> 16), e4m3x2_to_f16x2(r[3] >> 16), b23.x, b23.y);
                         }
                     } else {
-                        // the warp's 128 k are exactly one quantisation group (group == 128) of every row
-                        const int grp_k = kw / a.group;
+                        // a 128-k block is exactly one quantisation group (group == 128) of every row
+                        const int grp_k = kb / a.group;
                         float sc[2];
                         uint32_t zpk[2];
 #pragma unroll
@@ -252,14 +258,14 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
                         }
                         float ag[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int j = 0; j < kQWarpK / 64; ++j) {  // 64 k per ldmatrix.x4 = four mma k-steps
+                        for (int j = 0; j < 2; ++j) {  // 64 k per ldmatrix.x4 = four mma k-steps
                             uint32_t r[4];
-                            ldmatrix_x4(r, st + j * 32);
+                            ldmatrix_x4(r, st + bk * kBlkBytes + j * 32);
                             // r0: row g, nibbles k = 8t..8t+7 of the first 32 k; r1: row g+8; r2 / r3: the next 32 k
 #pragma unroll
                             for (int q = 0; q < 2; ++q) {
                                 const uint32_t w0 = r[2 * q], w1 = r[2 * q + 1];
-                                uint4 xb = *reinterpret_cast<const uint4 *>(xrow + kw + j * 64 + q * 32 + 8 * t);  // (k0,k4)(k1,k5)(k2,k6)(k3,k7)
+                                uint4 xb = *reinterpret_cast<const uint4 *>(xrow + kb + j * 64 + q * 32 + 8 * t);  // (k0,k4)(k1,k5)(k2,k6)(k3,k7)
                                 if (!tok) xb = make_uint4(0u, 0u, 0u, 0u);
                                 auto deq = [&](uint32_t w, int shift, uint32_t z) -> uint32_t {
                                     const uint32_t hbits = ((w >> shift) & 0x000f000fu) | 0x64006400u;  // {1024 + n_i, 1024 + n_{i+4}}
@@ -296,15 +302,21 @@ template <typename T, int FMT, bool SW>
 static int launch_gemv_q_inst(const GemvArgs &a, cudaStream_t st) {
     GemvQGeom g;
     const int bytes_per_k8 = FMT == WF_FP8 ? 8 : 4;
-    g.pieces = (a.K + kQPieceK - 1) / kQPieceK;
-    g.row_stride = kQPieceK * bytes_per_k8 / 8 + kQRowPad;
-    g.stage_bytes = kQRows * g.row_stride;
     g.xs_stride = a.K + (FMT == WF_FP8 ? 16 : 32);  // token rows shifted by 8 (64-bit B loads) / 16 (128-bit) banks: conflict-free
     size_t fixed = ((size_t)a.M * g.xs_stride * sizeof(__half) + 127) & ~(size_t)127;
     fixed += (size_t)kGemvGroups * (2 * kGemvMaxStages + 4) * 8;
     fixed += (size_t)kGemvWarps * 2 * kQRows * kQTok * sizeof(float);
-    const size_t budget = 224 * 1024, per_stage = (size_t)kGemvGroups * g.stage_bytes;
-    if (fixed + 3 * per_stage > budget) return B200_ERR_UNSUPPORTED;
+    const size_t budget = 224 * 1024;
+    size_t per_stage = 0;
+    for (g.piece_bytes = kQPieceBytes; g.piece_bytes >= 1024; g.piece_bytes /= 2) {  // 2 KiB pieces if >= 3 stages fit, else 1 KiB
+        g.row_stride = g.piece_bytes + kQRowPad;
+        g.stage_bytes = kQRows * g.row_stride;
+        per_stage = (size_t)kGemvGroups * g.stage_bytes;
+        if (fixed + 3 * per_stage <= budget) break;
+    }
+    if (g.piece_bytes < 1024) return B200_ERR_UNSUPPORTED;
+    const int piece_k = g.piece_bytes * 8 / bytes_per_k8;
+    g.pieces = (a.K + piece_k - 1) / piece_k;
     g.stages = (int)((budget - fixed) / per_stage);
     if (g.stages > kGemvMaxStages) g.stages = kGemvMaxStages;
     const size_t smem = fixed + (size_t)g.stages * per_stage;

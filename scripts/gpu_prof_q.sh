@@ -1,0 +1,4 @@
+set -x
+CMD="python bench.py --wformat fp8 --steps 2 --warmup 3 --no-cpu-baseline --no-graph"
+timeout 300 $CMD > gpurun_out/plain_q.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemv_q_kernel -s 640 -c 3 -o gpurun_out/prof_gemvq $CMD > gpurun_out/ncu_q.log 2>&1
+tail -3 gpurun_out/ncu_q.log
