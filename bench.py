@@ -53,53 +53,113 @@ def algorithmic_bytes(cfg, batch, ctx, wformat, tp=1, group=128):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled in-process every ~2 ms
+    (a timed region can be a few tens of ms); `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
 
-    def __init__(self, index):
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+               ("hw_power_brake_slowdown", 0x80))
+
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.rows = []
+        self.uuid = uuid
+        self.rows = []  # (sm_mhz, sm_max_mhz, reasons bitmask)
         self.proc = None
+        self.thread = None
+        self.stop = threading.Event()
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        if self.uuid:
+            for u in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(u if isinstance(u, bytes) else u.encode())
+                except Exception:
+                    try:
+                        return pynvml, pynvml.nvmlDeviceGetHandleByUUID(u)
+                    except Exception:
+                        pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll_nvml(self, nv, h):
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while True:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            if self.stop.wait(0.002):
+                break
+
+    def _poll_smi(self):
+        names = [n for n, _ in self.REASONS[:4]]
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                mask = 0
+                for (n, bit), v in zip(self.REASONS[:4], r[2:6]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(r[0]), float(r[1]), mask))
+            except Exception:
+                pass
 
     def __enter__(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        try:
+            nv, h = self._nvml_handle()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            pass
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._poll_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        mask = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            mask |= r[2]
+        reasons = sorted(n for n, bit in self.REASONS if mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "source": self.source}
 
 
 def cpu_reference_tokens_per_s(cfg, batch, ctx, threads, budget_s=20.0):
@@ -151,12 +211,15 @@ def run_reference(args, cfg, rank):
     threads = oracle.max_threads()
     vals = []
     t_all = time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        budget = max(4.0, 150.0 / (args.warmup + args.steps))
-        v, sample, cores = cpu_reference_tokens_per_s(cfg, args.batch, args.ctx, threads, budget_s=min(budget, 20.0))
+    # each "step" is a bounded sample of the workload (one decoder layer timed a few times + the LM head, extrapolated to all layers);
+    # the whole arm stays under ~100 s whatever --steps says
+    n = args.warmup + args.steps
+    for i in range(n):
+        budget = min(20.0, max(1.5, 80.0 / n))
+        v, sample, cores = cpu_reference_tokens_per_s(cfg, args.batch, args.ctx, threads, budget_s=budget)
         if i >= args.warmup:
             vals.append(v)
-        if time.perf_counter() - t_all > 200:
+        if time.perf_counter() - t_all > 90 and vals:
             break
     vals = vals or [v]
     value = sum(vals) / len(vals)
@@ -191,7 +254,7 @@ def run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank):
             dec.prefill(x, kc, vc, il, hl, il, Tq)
         stream.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(dev.index or 0) as clocks:
+        with ClockSampler(dev.index or 0, gpu_uuid(dev)) as clocks:
             e0.record(stream)
             for _ in range(args.steps):
                 dec.prefill(x, kc, vc, il, hl, il, Tq)
@@ -221,6 +284,15 @@ def run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank):
             "clocks": clocks.summary()}), flush=True)
 
 
+def gpu_uuid(dev):
+    try:
+        import torch
+
+        return str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        return None
+
+
 def workload_config(args, cfg):
     return {"workload": f"{cfg['name']} {cfg['layers']}-layer {args.wformat} decode, batch {args.batch}, {args.ctx}-token context",
             "batch": args.batch, "context": args.ctx, "weights": args.wformat, "kv_cache": "bf16",
@@ -231,8 +303,8 @@ def workload_config(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="7b", choices=list(CONFIGS))
     ap.add_argument("--batch", type=int, default=1)
@@ -242,6 +314,7 @@ def main():
     ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
                     help="decode (default, the BASELINE metric) or prefill: one pass of --prefill-tokens tokens through all layers")
     ap.add_argument("--prefill-tokens", type=int, default=2048)
+    ap.add_argument("--preheat", type=float, default=1.5, help="seconds of untimed steps before the warm-up (clock ramp)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -387,11 +460,26 @@ def main():
             return float(t.item())
 
         # ---------------- value: device-resident, CUDA events, max over ranks
+        # pre-heat: an idle GPU sits at low clocks and a few warm-up steps (tens of ms) do not bring it up; run untimed steps for
+        # ~1.5 s first (every rank the same count), then the W warm-up steps the contract asks for
+        preheat_steps = 0
+        if tp > 1:  # ranks meet inside every step (exchange flags / all-reduce): every rank must run the same number of steps
+            preheat_steps = 384 if args.preheat > 0 else 0
+            for _ in range(preheat_steps):
+                run_step()
+            stream.synchronize()
+        else:
+            t_pre = time.perf_counter()
+            while time.perf_counter() - t_pre < args.preheat:
+                for _ in range(32):
+                    run_step()
+                stream.synchronize()
+                preheat_steps += 32
         for _ in range(args.warmup):
             run_step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clocks:
+        with ClockSampler(local_rank, gpu_uuid(dev)) as clocks:
             e0.record(stream)
             for _ in range(args.steps):
                 run_step()
@@ -488,7 +576,7 @@ def main():
             "config": workload_config(args, cfg),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4 * B, "ms_per_step": ms_e2e},
             "gpu_launches": launches_per_step * args.steps,
-            "launch_mode": "cuda-graph replay" if graph is not None else "eager",
+            "launch_mode": "cuda-graph replay" if graph is not None else "eager", "preheat_steps": preheat_steps,
             "tp_exchange": tp_mode,
             "roofline": {"bound": "hbm", "kernel": "gemv_nk_kernel (all %d weight-streaming linears of one step, back to back)" % n_gemv,
                          "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,

@@ -236,7 +236,7 @@ __device__ __forceinline__ void dot_rows(const uint4 (&wv)[kGemvRows], const boo
 // (reference src/kernels/rmsnorm.cu:35-80, add_residual_and_rmsnorm.cu:43-121).  The V fp32 values of each vector are handed to
 // store(m, i, f).  One global read pass when the row fits the per-thread register cache.  Every thread of the CTA must call;
 // `red` = shared float[33].  The caller synchronises afterwards.
-template <typename T, typename Store>
+template <typename T, int MB, typename Store>
 __device__ __forceinline__ void gemv_stage_activations(const GemvArgs &a, int n_threads, float *red, Store store) {
     constexpr int V = Elem<T>::kVec;
     const int K = a.K;
@@ -286,7 +286,9 @@ __device__ __forceinline__ void gemv_stage_activations(const GemvArgs &a, int n_
         }
     };
     const bool cached = nv <= kGemvXCache * n_threads;  // the row fits the per-thread register cache: one global pass
-    for (int m = 0; m < a.M; ++m) {
+    // MB == 1: a single trip known at compile time (keeps the B = 1 instantiation spill-free); otherwise a rolled run-time loop
+#pragma unroll 1
+    for (int m = 0; m < (MB == 1 ? 1 : a.M); ++m) {
         if (!gamma) {
             for (int i = threadIdx.x; i < nv; i += n_threads) {
                 float f[V];
@@ -436,7 +438,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
         }
         for (int m = a.M; m < MB; ++m)  // padding rows of the batch tile
             for (int i = threadIdx.x; i < Kp; i += n_threads) xs[(size_t)m * Kp + i] = XS(0.0f);
-        gemv_stage_activations<T>(a, n_threads, red, [&](int m, int i, const float *f) {
+        gemv_stage_activations<T, MB>(a, n_threads, red, [&](int m, int i, const float *f) {
             if constexpr (FMT == WF_DENSE) {
                 *reinterpret_cast<uint4 *>(xs + (size_t)m * Kp + (size_t)i * V) = pack16<T>(f);
             } else {

@@ -128,7 +128,7 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
     // ---------------- stage the activations as f16 (a.M token rows); INT4 stores every 8 k in the order
     //                  [k0 k4 k1 k5 k2 k6 k3 k7] -- the order in which the nibble pairs come out of a 32-bit word
     {
-        gemv_stage_activations<T>(a, n_threads, red, [&](int m, int i, const float *f) {
+        gemv_stage_activations<T, 0>(a, n_threads, red, [&](int m, int i, const float *f) {
             float g[V];
             unpack16<T>(pack16<T>(f), g);  // the un-fused reference hands the GEMM a tensor of T
             __half *dst = xs + (size_t)m * geo.xs_stride + (size_t)i * V;
