@@ -80,6 +80,8 @@ SIGNATURES = {
     "b200_decoder_scratch_bytes": [_P],
     "b200_decoder_set_scratch": [_P, _P, _SZ],
     "b200_decoder_step": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_decoder_linears_only": [_P, _I, C.POINTER(C.c_int), _P],
+    "b200_decoder_debug_trace": [_P, _P, _SZ],
     "b200_decoder_prefill_scratch_bytes": [_P, _I, _I, _I],
     "b200_decoder_prefill": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _SZ, _I, _I, _P],
     "b200_decoder_attn_block": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P],
@@ -95,7 +97,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_workspace_default_bytes": _SZ, "b200_decoder_create": _P,
              "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ, "b200_decoder_prefill_scratch_bytes": _SZ,
-             "b200_decoder_tp_buffer_bytes": _SZ}
+             "b200_decoder_tp_buffer_bytes": _SZ, "b200_decoder_debug_trace": _SZ}
 
 _lib = None
 
@@ -395,6 +397,25 @@ class Decoder:
         layer_end = self.cfg.num_layers if layer_end is None else layer_end
         check(lib().b200_decoder_step(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], step, layer_begin, layer_end,
                                       stream()))
+
+    def debug_trace(self, enable=True):
+        """Diagnostics: returns a uint64 tensor [layers, SMs, 4, 8] the chained GEMV kernels fill with %globaltimer stamps."""
+        import torch
+
+        if not enable:
+            lib().b200_decoder_debug_trace(self.handle, None, 0)
+            self._trace = None
+            return None
+        nbytes = lib().b200_decoder_debug_trace(self.handle, None, 0)
+        self._trace = torch.zeros(nbytes // 8, dtype=torch.int64, device=self.device)
+        lib().b200_decoder_debug_trace(self.handle, C.c_void_p(self._trace.data_ptr()), nbytes)
+        return self._trace
+
+    def linears_only(self, batch):
+        """Diagnostic: the weight-streaming launches of one decode step (no attention, no fold); returns the number of launches."""
+        n = C.c_int(0)
+        check(lib().b200_decoder_linears_only(self.handle, batch, C.byref(n), stream()))
+        return n.value
 
     def prefill(self, hidden, k_cache, v_cache, input_len, history_len, context_len, max_q_len, layer_begin=0, layer_end=None):
         """hidden [T, h] in/out; input_len / history_len / context_len: int32 device tensors [B]."""

@@ -101,8 +101,11 @@ __device__ __forceinline__ void a_mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 __device__ __forceinline__ void a_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
+    // read-once per step: evict-first in L2 (see gemv.cuh l2_evict_first_policy)
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
                  : "memory");
 }
 

@@ -13,6 +13,7 @@
 // the same kernel still reads.
 #include "attention_decode.cuh"
 #include "gemv.cuh"
+#include "gemv_chain.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -31,6 +32,8 @@ struct b200_decoder {
     void *qkv = nullptr, *attn = nullptr, *y_attn = nullptr, *gu = nullptr, *act = nullptr, *y_ffn = nullptr;
     float *partials = nullptr;
     unsigned int *tickets = nullptr;
+    unsigned long long *chain_trace = nullptr;  // optional diagnostics buffer (b200_decoder_debug_trace)
+    unsigned int *chain_sync = nullptr;  // [num_layers][kChainMaxPhases] grid-barrier counters of the chained GEMV kernel
     float2 *rope_cs = nullptr;  // (cos, sin) per (position, rotary pair), filled once by set_scratch
     int max_splits = 0;
     int cur = 0;  // which res[] holds the residual stream
@@ -49,7 +52,7 @@ static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t esize(int dtype) { return dtype == B200_F32 ? 4 : 2; }
 
 struct Carve {
-    size_t res, xn, qkv, attn, y, gu, act, partials, tickets, rope, total;
+    size_t res, xn, qkv, attn, y, gu, act, partials, tickets, chain, rope, total;
 };
 static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     Carve k;
@@ -65,8 +68,9 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     *max_splits = (c.max_seq_len + 31) / 32;
     k.partials = align_up(decode_attn_partials_floats(c.max_batch, c.head_num, c.kv_head_num, c.head_size, *max_splits) * sizeof(float));
     k.tickets = align_up((size_t)c.max_batch * c.kv_head_num * sizeof(unsigned int));
+    k.chain = align_up((size_t)c.num_layers * kChainMaxPhases * sizeof(unsigned int));
     k.rope = c.rotary_dim > 0 ? align_up((size_t)c.max_seq_len * (c.rotary_dim / 2) * sizeof(float2)) : 0;
-    k.total = 2 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.rope;
+    k.total = 2 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.chain + k.rope;
     return k;
 }
 
@@ -290,6 +294,8 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     dec->partials = (float *)p, p += k.partials;
     dec->tickets = (unsigned int *)p, p += k.tickets;
     if (cudaMemset(dec->tickets, 0, k.tickets) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
+    dec->chain_sync = (unsigned int *)p, p += k.chain;
+    if (cudaMemset(dec->chain_sync, 0, k.chain) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
     dec->rope_cs = nullptr;
     if (k.rope) {
         dec->rope_cs = (float2 *)p;
@@ -301,25 +307,10 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     return B200_OK;
 }
 
-static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache, void *partial,
-                           int batch, int step, b200_stream_t stream, const TpExchange *tp, int push_seq = 0) {
-    int rc = check_ready(dec, batch);
-    if (rc != B200_OK) return rc;
+// RoPE + qkv bias + KV append + split-KV attention + merge for one layer: dec->qkv -> dec->attn
+static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache, void *v_cache, int batch, int step, cudaStream_t st) {
     const b200_decoder_config_t &c = dec->cfg;
-    B200_REQUIRE(layer >= 0 && layer < c.num_layers && dec->layer_set[layer], "decoder: layer %d not set", layer);
-    B200_REQUIRE(k_cache && v_cache && partial, "decoder_attn_block: null pointer");
-    B200_REQUIRE(pending || hidden, "decoder_attn_block: need `hidden` (first block) or `pending`");
-    B200_REQUIRE(step >= 1 && step <= c.max_seq_len, "decoder: step %d outside [1, %d]", step, c.max_seq_len);
-    cudaStream_t st = as_stream(stream);
     const b200_layer_weights_t &w = dec->layers[layer];
-    const int qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size;
-    // 1. residual fold + RMSNorm + QKV
-    void *res_out = dec->res[dec->cur ^ 1];
-    rc = norm_linear(dec, pending ? pending : hidden, pending ? dec->res[dec->cur] : nullptr, res_out, nullptr, w.attn_norm_gamma, w.qkv,
-                     c.hidden, qkv_n, false, dec->qkv, batch, st, pending ? tp : nullptr);
-    if (rc != B200_OK) return rc;
-    dec->cur ^= 1;
-    // 2. attention
     DecodeAttnArgs a = {};
     const size_t layer_off = (size_t)layer * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
     a.qkv = dec->qkv, a.bias = w.qkv_bias;
@@ -341,7 +332,29 @@ static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const v
         static const bool l2 = getenv("B200_L2_PREFETCH") != nullptr;
         if (!l2) a.l2_prefetch_bytes = 0;
     }
-    rc = launch_decode_attn(a, c.dtype, st);
+    return launch_decode_attn(a, c.dtype, st);
+}
+
+static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const void *pending, void *k_cache, void *v_cache, void *partial,
+                           int batch, int step, b200_stream_t stream, const TpExchange *tp, int push_seq = 0) {
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    const b200_decoder_config_t &c = dec->cfg;
+    B200_REQUIRE(layer >= 0 && layer < c.num_layers && dec->layer_set[layer], "decoder: layer %d not set", layer);
+    B200_REQUIRE(k_cache && v_cache && partial, "decoder_attn_block: null pointer");
+    B200_REQUIRE(pending || hidden, "decoder_attn_block: need `hidden` (first block) or `pending`");
+    B200_REQUIRE(step >= 1 && step <= c.max_seq_len, "decoder: step %d outside [1, %d]", step, c.max_seq_len);
+    cudaStream_t st = as_stream(stream);
+    const b200_layer_weights_t &w = dec->layers[layer];
+    const int qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size;
+    // 1. residual fold + RMSNorm + QKV
+    void *res_out = dec->res[dec->cur ^ 1];
+    rc = norm_linear(dec, pending ? pending : hidden, pending ? dec->res[dec->cur] : nullptr, res_out, nullptr, w.attn_norm_gamma, w.qkv,
+                     c.hidden, qkv_n, false, dec->qkv, batch, st, pending ? tp : nullptr);
+    if (rc != B200_OK) return rc;
+    dec->cur ^= 1;
+    // 2. attention
+    rc = launch_layer_attention(dec, layer, k_cache, v_cache, batch, step, st);
     if (rc != B200_OK) return rc;
     // 3. O projection (row-sharded under TP: `partial` is this rank's partial sum)
     return plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, partial, batch, st, push_seq);
@@ -476,6 +489,84 @@ int b200_decoder_step_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void 
     return fold_impl(dec, hidden, tp_slot(dec, me, seq, me), batch, stream, &tlast);
 }
 
+// The chained GEMV kernel of layer l: O -> [norm] gate/up + SwiGLU -> down (-> [norm] QKV of layer l + 1 when next_qkv).
+// `cur` = which res[] holds the residual stream before the chain; returns the index after it.
+static int build_chain(b200_decoder_t *dec, int l, bool next_qkv, int batch, int cur, ChainArgs *out) {
+    const b200_decoder_config_t &c = dec->cfg;
+    const b200_layer_weights_t &w = dec->layers[l];
+    ChainArgs a = {};
+    a.M = batch, a.eps = c.rmsnorm_eps;
+    a.sync = dec->chain_sync + (size_t)l * kChainMaxPhases;
+    a.trace = dec->chain_trace ? dec->chain_trace + (size_t)l * sm_count() * kChainMaxPhases * 8 : nullptr;
+    int n = 0;
+    {   // O projection (reference self_attention.cpp:131-138)
+        ChainPhase &P = a.ph[n++];
+        P.w = w.o.w, P.x = dec->attn, P.y = dec->y_attn, P.K = c.head_num * c.head_size, P.N = c.hidden;
+    }
+    {   // residual += attention output; + o bias; RMSNorm; gate/up; SwiGLU (self_decoder.cpp:92-100, ffn.cpp:105-131)
+        ChainPhase &P = a.ph[n++];
+        P.w = w.gate_up.w, P.x = dec->y_attn, P.y = dec->act, P.K = c.hidden, P.N = 2 * c.inter_size, P.inter = c.inter_size, P.swiglu = 1;
+        P.res_in = dec->res[cur], P.res_out = dec->res[cur ^ 1], P.bias = w.o_bias, P.gamma = w.ffn_norm_gamma, P.norm = 1;
+        cur ^= 1;
+    }
+    {   // down projection (ffn.cpp:132-139)
+        ChainPhase &P = a.ph[n++];
+        P.w = w.down.w, P.x = dec->act, P.y = dec->y_ffn, P.K = c.inter_size, P.N = c.hidden;
+    }
+    if (next_qkv) {  // residual += FFN output; RMSNorm(gamma1 of layer l + 1); QKV (self_decoder.cpp:104-116 + 76-86 of the next layer)
+        const b200_layer_weights_t &wn = dec->layers[l + 1];
+        ChainPhase &P = a.ph[n++];
+        P.w = wn.qkv.w, P.x = dec->y_ffn, P.y = dec->qkv, P.K = c.hidden, P.N = (c.head_num + 2 * c.kv_head_num) * c.head_size;
+        P.res_in = dec->res[cur], P.res_out = dec->res[cur ^ 1], P.gamma = wn.attn_norm_gamma, P.norm = 1;
+        cur ^= 1;
+    }
+    a.n_phases = n;
+    *out = a;
+    return cur;
+}
+
+// batch <= 4, dense weights, one GPU: two launches per layer (attention + one chained GEMV kernel) instead of five
+static bool chain_usable(b200_decoder_t *dec, int batch, int layer_begin, int layer_end) {
+    static const bool off = getenv("B200_NO_CHAIN") != nullptr;
+    const b200_decoder_config_t &c = dec->cfg;
+    if (off || c.tp_world > 1 || c.w_format != B200_W_DENSE || batch > 4 || !dec->chain_sync) return false;
+    for (int l = layer_begin; l < layer_end; ++l) {
+        if (!dec->layer_set[l]) return false;
+        ChainArgs a;
+        build_chain(dec, l, l + 1 < layer_end, batch, 0, &a);
+        if (launch_gemv_chain(a, c.dtype, nullptr, true) != B200_OK) return false;
+    }
+    return true;
+}
+
+static int step_chained(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin, int layer_end,
+                        b200_stream_t stream) {
+    const b200_decoder_config_t &c = dec->cfg;
+    B200_REQUIRE(step >= 1 && step <= c.max_seq_len, "decoder: step %d outside [1, %d]", step, c.max_seq_len);
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(dec->chain_sync, 0, (size_t)c.num_layers * kChainMaxPhases * sizeof(unsigned int), st) != cudaSuccess)
+        return cuda_status("decoder_step memset");
+    // first layer's QKV: residual <- hidden; RMSNorm; QKV
+    const b200_layer_weights_t &w0 = dec->layers[layer_begin];
+    int rc = norm_linear(dec, hidden, nullptr, dec->res[dec->cur ^ 1], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden,
+                         (c.head_num + 2 * c.kv_head_num) * c.head_size, false, dec->qkv, batch, st);
+    if (rc != B200_OK) return rc;
+    dec->cur ^= 1;
+    for (int l = layer_begin; l < layer_end; ++l) {
+        rc = launch_layer_attention(dec, l, k_cache, v_cache, batch, step, st);
+        if (rc != B200_OK) return rc;
+        ChainArgs a;
+        dec->cur = build_chain(dec, l, l + 1 < layer_end, batch, dec->cur, &a);
+        rc = launch_gemv_chain(a, c.dtype, st);
+        if (rc == B200_ERR_UNSUPPORTED) {
+            set_error("decoder_step: chained GEMV rejected layer %d after accepting it", l);
+            return B200_ERR_STATE;
+        }
+        if (rc != B200_OK) return rc;
+    }
+    return b200_decoder_fold(dec, hidden, dec->y_ffn, batch, stream);
+}
+
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin,
                       int layer_end, b200_stream_t stream) {
     int rc = check_ready(dec, batch);
@@ -483,6 +574,7 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
     B200_REQUIRE(dec->cfg.tp_world <= 1, "decoder_step: tensor-parallel engines drive attn_block / ffn_block themselves");
     B200_REQUIRE(hidden && k_cache && v_cache, "decoder_step: null pointer");
     B200_REQUIRE(layer_begin >= 0 && layer_end <= dec->cfg.num_layers && layer_begin < layer_end, "decoder_step: bad layer range");
+    if (chain_usable(dec, batch, layer_begin, layer_end)) return step_chained(dec, hidden, k_cache, v_cache, batch, step, layer_begin, layer_end, stream);
     const void *pending = nullptr;
     for (int l = layer_begin; l < layer_end; ++l) {
         rc = b200_decoder_attn_block(dec, l, hidden, pending, k_cache, v_cache, dec->y_attn, batch, step, stream);
@@ -492,6 +584,61 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
         pending = dec->y_ffn;
     }
     return b200_decoder_fold(dec, hidden, pending, batch, stream);
+}
+
+// Diagnostic for roofline measurements: exactly the weight-streaming launches of b200_decoder_step (first QKV + per layer the chained
+// GEMV kernel, or the four separate GEMVs when the chain is not usable) without the attention kernels and the final fold.  The
+// activations are whatever the scratch buffers hold: call it after at least one real step; results are meaningless, timing is not.
+int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b200_stream_t stream) {
+    int rc = check_ready(dec, batch);
+    if (rc != B200_OK) return rc;
+    const b200_decoder_config_t &c = dec->cfg;
+    B200_REQUIRE(c.tp_world <= 1, "decoder_linears_only: single-GPU engines only");
+    cudaStream_t st = as_stream(stream);
+    const int L = c.num_layers, qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size;
+    for (int l = 0; l < L; ++l) B200_REQUIRE(dec->layer_set[l], "decoder_linears_only: layer %d not set", l);
+    int launches = 0;
+    if (chain_usable(dec, batch, 0, L)) {
+        if (cudaMemsetAsync(dec->chain_sync, 0, (size_t)L * kChainMaxPhases * sizeof(unsigned int), st) != cudaSuccess)
+            return cuda_status("decoder_linears_only memset");
+        const b200_layer_weights_t &w0 = dec->layers[0];
+        rc = norm_linear(dec, dec->y_ffn, nullptr, dec->res[dec->cur ^ 1], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden, qkv_n, false, dec->qkv,
+                         batch, st);
+        if (rc != B200_OK) return rc;
+        dec->cur ^= 1, ++launches;
+        for (int l = 0; l < L; ++l) {
+            ChainArgs a;
+            dec->cur = build_chain(dec, l, l + 1 < L, batch, dec->cur, &a);
+            if ((rc = launch_gemv_chain(a, c.dtype, st)) != B200_OK) return rc;
+            ++launches;
+        }
+    } else {
+        for (int l = 0; l < L; ++l) {
+            const b200_layer_weights_t &w = dec->layers[l];
+            rc = norm_linear(dec, dec->y_ffn, dec->res[dec->cur], dec->res[dec->cur ^ 1], nullptr, w.attn_norm_gamma, w.qkv, c.hidden, qkv_n, false,
+                             dec->qkv, batch, st);
+            if (rc != B200_OK) return rc;
+            dec->cur ^= 1;
+            if ((rc = plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, dec->y_attn, batch, st)) != B200_OK) return rc;
+            rc = norm_linear(dec, dec->y_attn, dec->res[dec->cur], dec->res[dec->cur ^ 1], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
+                             2 * c.inter_size, true, dec->act, batch, st);
+            if (rc != B200_OK) return rc;
+            dec->cur ^= 1;
+            if ((rc = plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, dec->y_ffn, batch, st)) != B200_OK) return rc;
+            launches += 4;
+        }
+    }
+    if (n_launches) *n_launches = launches;
+    return B200_OK;
+}
+
+// Diagnostics: device buffer of num_layers * SMs * 4 phases * 8 uint64 globaltimer stamps written by the chained GEMV kernels
+// (NULL switches tracing off).  Returns the bytes such a buffer needs when ptr == NULL and bytes == 0.
+size_t b200_decoder_debug_trace(b200_decoder_t *dec, void *ptr, size_t bytes) {
+    if (!dec) return 0;
+    const size_t need = (size_t)dec->cfg.num_layers * sm_count() * kChainMaxPhases * 8 * sizeof(unsigned long long);
+    dec->chain_trace = (ptr && bytes >= need) ? (unsigned long long *)ptr : nullptr;
+    return need;
 }
 
 static size_t prefill_carve(const b200_decoder_config_t &c, int batch, int mq, int T, size_t *off /*[11]*/) {
