@@ -527,7 +527,7 @@ static int build_chain(b200_decoder_t *dec, int l, bool next_qkv, int batch, int
 
 // batch <= 4, dense weights, one GPU: two launches per layer (attention + one chained GEMV kernel) instead of five
 static bool chain_usable(b200_decoder_t *dec, int batch, int layer_begin, int layer_end) {
-    static const bool off = getenv("B200_NO_CHAIN") != nullptr;
+    static const bool off = getenv("B200_NO_CHAIN") != nullptr || getenv("B200_CHAIN") == nullptr;  // opt-in until it beats the separate launches
     const b200_decoder_config_t &c = dec->cfg;
     if (off || c.tp_world > 1 || c.w_format != B200_W_DENSE || batch > 4 || !dec->chain_sync) return false;
     for (int l = layer_begin; l < layer_end; ++l) {
