@@ -27,16 +27,17 @@ struct b200_decoder {
     // scratch carve-up
     char *scratch = nullptr;
     size_t scratch_bytes = 0;
-    void *res[2] = {nullptr, nullptr};
+    void *res[3] = {nullptr, nullptr, nullptr};  // the residual stream rotates over three buffers (see next_res)
     void *xn = nullptr;      // normalised activations (un-fused path)
     void *qkv = nullptr, *attn = nullptr, *y_attn = nullptr, *gu = nullptr, *act = nullptr, *y_ffn = nullptr;
     float *partials = nullptr;
     unsigned int *tickets = nullptr;
     unsigned long long *chain_trace = nullptr;  // optional diagnostics buffer (b200_decoder_debug_trace)
-    unsigned int *chain_sync = nullptr;  // [num_layers][kChainMaxPhases] grid-barrier counters of the chained GEMV kernel
     float2 *rope_cs = nullptr;  // (cos, sin) per (position, rotary pair), filled once by set_scratch
     int max_splits = 0;
     int cur = 0;  // which res[] holds the residual stream
+    char *chain_ll = nullptr;   // per-layer chained-GEMV exchange area: claim counters + LL activation buffers (zeroed every step)
+    size_t chain_ll_layer = 0;  // bytes per layer
     // fused tensor-parallel exchange (b200_decoder_tp_attach): every rank's exchange buffer as mapped in this process
     char *tp_base[b200::kTpMaxWorld] = {};
     bool tp_attached = false;
@@ -49,11 +50,19 @@ int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const v
                                   float base, int dtype, cudaStream_t st);
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+// A kernel never writes the residual buffer other CTAs of the same launch still read: outputs go to the next buffer of the rotation
+// (three, because the chained GEMV kernel forms two successive residuals in one launch).
+static int next_res(int cur) { return (cur + 1) % 3; }
 static size_t esize(int dtype) { return dtype == B200_F32 ? 4 : 2; }
 
 struct Carve {
     size_t res, xn, qkv, attn, y, gu, act, partials, tickets, chain, rope, total;
 };
+// per-layer exchange area of the chained GEMV kernel: [claim counters: 256 B][y_attn LL][act LL][y_ffn LL], 8-byte {payload, flag} words
+static size_t chain_ll_words(const b200_decoder_config_t &c, int n) { return (size_t)c.max_batch * n / (esize(c.dtype) == 2 ? 2 : 1); }
+static size_t chain_layer_bytes(const b200_decoder_config_t &c) {
+    return 256 + align_up(chain_ll_words(c, c.hidden) * 8) * 2 + align_up(chain_ll_words(c, c.inter_size) * 8);
+}
 static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     Carve k;
     const size_t e = esize(c.dtype), B = c.max_batch;
@@ -68,9 +77,9 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     *max_splits = (c.max_seq_len + 31) / 32;
     k.partials = align_up(decode_attn_partials_floats(c.max_batch, c.head_num, c.kv_head_num, c.head_size, *max_splits) * sizeof(float));
     k.tickets = align_up((size_t)c.max_batch * c.kv_head_num * sizeof(unsigned int));
-    k.chain = align_up((size_t)c.num_layers * kChainMaxPhases * sizeof(unsigned int));
+    k.chain = (size_t)c.num_layers * chain_layer_bytes(c);
     k.rope = c.rotary_dim > 0 ? align_up((size_t)c.max_seq_len * (c.rotary_dim / 2) * sizeof(float2)) : 0;
-    k.total = 2 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.chain + k.rope;
+    k.total = 3 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.chain + k.rope;
     return k;
 }
 
@@ -284,6 +293,7 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     dec->scratch = p, dec->scratch_bytes = bytes, dec->max_splits = ms;
     dec->res[0] = p, p += k.res;
     dec->res[1] = p, p += k.res;
+    dec->res[2] = p, p += k.res;
     dec->xn = p, p += k.xn;
     dec->qkv = p, p += k.qkv;
     dec->attn = p, p += k.attn;
@@ -294,8 +304,9 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     dec->partials = (float *)p, p += k.partials;
     dec->tickets = (unsigned int *)p, p += k.tickets;
     if (cudaMemset(dec->tickets, 0, k.tickets) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
-    dec->chain_sync = (unsigned int *)p, p += k.chain;
-    if (cudaMemset(dec->chain_sync, 0, k.chain) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
+    dec->chain_ll = p, p += k.chain;
+    dec->chain_ll_layer = chain_layer_bytes(dec->cfg);
+    if (cudaMemset(dec->chain_ll, 0, k.chain) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
     dec->rope_cs = nullptr;
     if (k.rope) {
         dec->rope_cs = (float2 *)p;
@@ -348,11 +359,11 @@ static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const v
     const b200_layer_weights_t &w = dec->layers[layer];
     const int qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size;
     // 1. residual fold + RMSNorm + QKV
-    void *res_out = dec->res[dec->cur ^ 1];
+    void *res_out = dec->res[next_res(dec->cur)];
     rc = norm_linear(dec, pending ? pending : hidden, pending ? dec->res[dec->cur] : nullptr, res_out, nullptr, w.attn_norm_gamma, w.qkv,
                      c.hidden, qkv_n, false, dec->qkv, batch, st, pending ? tp : nullptr);
     if (rc != B200_OK) return rc;
-    dec->cur ^= 1;
+    dec->cur = next_res(dec->cur);
     // 2. attention
     rc = launch_layer_attention(dec, layer, k_cache, v_cache, batch, step, st);
     if (rc != B200_OK) return rc;
@@ -376,10 +387,10 @@ static int ffn_block_impl(b200_decoder_t *dec, int layer, const void *pending, v
     const b200_layer_weights_t &w = dec->layers[layer];
     // 4. residual += attention output; + o bias (tp rank 0 semantics: bias is replicated, added after the reduce);
     //    RMSNorm; gate/up; SwiGLU
-    rc = norm_linear(dec, pending, dec->res[dec->cur], dec->res[dec->cur ^ 1], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
+    rc = norm_linear(dec, pending, dec->res[dec->cur], dec->res[next_res(dec->cur)], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
                      2 * c.inter_size, true, dec->act, batch, st, tp);
     if (rc != B200_OK) return rc;
-    dec->cur ^= 1;
+    dec->cur = next_res(dec->cur);
     // 5. down projection
     return plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, partial, batch, st, push_seq);
 }
@@ -496,29 +507,41 @@ static int build_chain(b200_decoder_t *dec, int l, bool next_qkv, int batch, int
     const b200_layer_weights_t &w = dec->layers[l];
     ChainArgs a = {};
     a.M = batch, a.eps = c.rmsnorm_eps;
-    a.sync = dec->chain_sync + (size_t)l * kChainMaxPhases;
+    static const int poll_ns = getenv("B200_CHAIN_POLL_NS") ? atoi(getenv("B200_CHAIN_POLL_NS")) : 40;
+    a.poll_ns = poll_ns;
+    static const int l2_ahead = getenv("B200_CHAIN_L2_AHEAD") ? atoi(getenv("B200_CHAIN_L2_AHEAD")) : 0;
+    a.l2_ahead = l2_ahead;
+    char *area = dec->chain_ll + (size_t)l * dec->chain_ll_layer;
+    a.claim = reinterpret_cast<unsigned int *>(area);
+    uint2 *y_attn_ll = reinterpret_cast<uint2 *>(area + 256);
+    uint2 *y_ffn_ll = reinterpret_cast<uint2 *>(area + 256 + align_up(chain_ll_words(c, c.hidden) * 8));
+    uint2 *act_ll = reinterpret_cast<uint2 *>(area + 256 + 2 * align_up(chain_ll_words(c, c.hidden) * 8));
     a.trace = dec->chain_trace ? dec->chain_trace + (size_t)l * sm_count() * kChainMaxPhases * 8 : nullptr;
+    const int r0 = cur, r1 = next_res(cur), r2 = next_res(r1);  // residual before the chain, after the attention block, after the FFN
     int n = 0;
     {   // O projection (reference self_attention.cpp:131-138)
         ChainPhase &P = a.ph[n++];
-        P.w = w.o.w, P.x = dec->attn, P.y = dec->y_attn, P.K = c.head_num * c.head_size, P.N = c.hidden;
+        P.w = w.o.w, P.x = dec->attn, P.y_ll = y_attn_ll, P.K = c.head_num * c.head_size, P.N = c.hidden;
     }
     {   // residual += attention output; + o bias; RMSNorm; gate/up; SwiGLU (self_decoder.cpp:92-100, ffn.cpp:105-131)
         ChainPhase &P = a.ph[n++];
-        P.w = w.gate_up.w, P.x = dec->y_attn, P.y = dec->act, P.K = c.hidden, P.N = 2 * c.inter_size, P.inter = c.inter_size, P.swiglu = 1;
-        P.res_in = dec->res[cur], P.res_out = dec->res[cur ^ 1], P.bias = w.o_bias, P.gamma = w.ffn_norm_gamma, P.norm = 1;
-        cur ^= 1;
+        P.w = w.gate_up.w, P.x_ll = y_attn_ll, P.y_ll = act_ll, P.K = c.hidden, P.N = 2 * c.inter_size, P.inter = c.inter_size, P.swiglu = 1;
+        P.res_in = dec->res[r0], P.res_out = dec->res[r1], P.bias = w.o_bias, P.gamma = w.ffn_norm_gamma, P.norm = 1;
+        cur = r1;
     }
     {   // down projection (ffn.cpp:132-139)
         ChainPhase &P = a.ph[n++];
-        P.w = w.down.w, P.x = dec->act, P.y = dec->y_ffn, P.K = c.inter_size, P.N = c.hidden;
+        P.w = w.down.w, P.x_ll = act_ll, P.K = c.inter_size, P.N = c.hidden;
+        if (next_qkv) P.y_ll = y_ffn_ll;
+        else P.y = dec->y_ffn;
     }
     if (next_qkv) {  // residual += FFN output; RMSNorm(gamma1 of layer l + 1); QKV (self_decoder.cpp:104-116 + 76-86 of the next layer)
         const b200_layer_weights_t &wn = dec->layers[l + 1];
         ChainPhase &P = a.ph[n++];
-        P.w = wn.qkv.w, P.x = dec->y_ffn, P.y = dec->qkv, P.K = c.hidden, P.N = (c.head_num + 2 * c.kv_head_num) * c.head_size;
-        P.res_in = dec->res[cur], P.res_out = dec->res[cur ^ 1], P.gamma = wn.attn_norm_gamma, P.norm = 1;
-        cur ^= 1;
+        P.w = wn.qkv.w, P.x_ll = y_ffn_ll, P.y = dec->qkv, P.K = c.hidden, P.N = (c.head_num + 2 * c.kv_head_num) * c.head_size;
+        // the residual after the attention block is re-formed from its two terms: nothing another CTA wrote in this launch is read plain
+        P.res_in = dec->res[r0], P.res_ll = y_attn_ll, P.res_out = dec->res[r2], P.gamma = wn.attn_norm_gamma, P.norm = 1;
+        cur = r2;
     }
     a.n_phases = n;
     *out = a;
@@ -529,7 +552,7 @@ static int build_chain(b200_decoder_t *dec, int l, bool next_qkv, int batch, int
 static bool chain_usable(b200_decoder_t *dec, int batch, int layer_begin, int layer_end) {
     static const bool off = getenv("B200_NO_CHAIN") != nullptr || getenv("B200_CHAIN") == nullptr;  // opt-in until it beats the separate launches
     const b200_decoder_config_t &c = dec->cfg;
-    if (off || c.tp_world > 1 || c.w_format != B200_W_DENSE || batch > 4 || !dec->chain_sync) return false;
+    if (off || c.tp_world > 1 || c.w_format != B200_W_DENSE || batch > 4 || !dec->chain_ll) return false;
     for (int l = layer_begin; l < layer_end; ++l) {
         if (!dec->layer_set[l]) return false;
         ChainArgs a;
@@ -544,14 +567,14 @@ static int step_chained(b200_decoder_t *dec, void *hidden, void *k_cache, void *
     const b200_decoder_config_t &c = dec->cfg;
     B200_REQUIRE(step >= 1 && step <= c.max_seq_len, "decoder: step %d outside [1, %d]", step, c.max_seq_len);
     cudaStream_t st = as_stream(stream);
-    if (cudaMemsetAsync(dec->chain_sync, 0, (size_t)c.num_layers * kChainMaxPhases * sizeof(unsigned int), st) != cudaSuccess)
-        return cuda_status("decoder_step memset");
+    // claim counters and LL flags of every layer: one memset
+    if (cudaMemsetAsync(dec->chain_ll, 0, (size_t)c.num_layers * dec->chain_ll_layer, st) != cudaSuccess) return cuda_status("decoder_step memset");
     // first layer's QKV: residual <- hidden; RMSNorm; QKV
     const b200_layer_weights_t &w0 = dec->layers[layer_begin];
-    int rc = norm_linear(dec, hidden, nullptr, dec->res[dec->cur ^ 1], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden,
+    int rc = norm_linear(dec, hidden, nullptr, dec->res[next_res(dec->cur)], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden,
                          (c.head_num + 2 * c.kv_head_num) * c.head_size, false, dec->qkv, batch, st);
     if (rc != B200_OK) return rc;
-    dec->cur ^= 1;
+    dec->cur = next_res(dec->cur);
     for (int l = layer_begin; l < layer_end; ++l) {
         rc = launch_layer_attention(dec, l, k_cache, v_cache, batch, step, st);
         if (rc != B200_OK) return rc;
@@ -599,13 +622,12 @@ int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b
     for (int l = 0; l < L; ++l) B200_REQUIRE(dec->layer_set[l], "decoder_linears_only: layer %d not set", l);
     int launches = 0;
     if (chain_usable(dec, batch, 0, L)) {
-        if (cudaMemsetAsync(dec->chain_sync, 0, (size_t)L * kChainMaxPhases * sizeof(unsigned int), st) != cudaSuccess)
-            return cuda_status("decoder_linears_only memset");
+        if (cudaMemsetAsync(dec->chain_ll, 0, (size_t)L * dec->chain_ll_layer, st) != cudaSuccess) return cuda_status("decoder_linears_only memset");
         const b200_layer_weights_t &w0 = dec->layers[0];
-        rc = norm_linear(dec, dec->y_ffn, nullptr, dec->res[dec->cur ^ 1], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden, qkv_n, false, dec->qkv,
+        rc = norm_linear(dec, dec->y_ffn, nullptr, dec->res[next_res(dec->cur)], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden, qkv_n, false, dec->qkv,
                          batch, st);
         if (rc != B200_OK) return rc;
-        dec->cur ^= 1, ++launches;
+        dec->cur = next_res(dec->cur), ++launches;
         for (int l = 0; l < L; ++l) {
             ChainArgs a;
             dec->cur = build_chain(dec, l, l + 1 < L, batch, dec->cur, &a);
@@ -615,15 +637,15 @@ int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b
     } else {
         for (int l = 0; l < L; ++l) {
             const b200_layer_weights_t &w = dec->layers[l];
-            rc = norm_linear(dec, dec->y_ffn, dec->res[dec->cur], dec->res[dec->cur ^ 1], nullptr, w.attn_norm_gamma, w.qkv, c.hidden, qkv_n, false,
+            rc = norm_linear(dec, dec->y_ffn, dec->res[dec->cur], dec->res[next_res(dec->cur)], nullptr, w.attn_norm_gamma, w.qkv, c.hidden, qkv_n, false,
                              dec->qkv, batch, st);
             if (rc != B200_OK) return rc;
-            dec->cur ^= 1;
+            dec->cur = next_res(dec->cur);
             if ((rc = plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, dec->y_attn, batch, st)) != B200_OK) return rc;
-            rc = norm_linear(dec, dec->y_attn, dec->res[dec->cur], dec->res[dec->cur ^ 1], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
+            rc = norm_linear(dec, dec->y_attn, dec->res[dec->cur], dec->res[next_res(dec->cur)], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
                              2 * c.inter_size, true, dec->act, batch, st);
             if (rc != B200_OK) return rc;
-            dec->cur ^= 1;
+            dec->cur = next_res(dec->cur);
             if ((rc = plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, dec->y_ffn, batch, st)) != B200_OK) return rc;
             launches += 4;
         }

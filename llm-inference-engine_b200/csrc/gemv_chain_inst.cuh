@@ -26,13 +26,19 @@ static int launch_chain_mb(const ChainArgs &a, size_t smem, cudaStream_t st) {
 template <typename T>
 static int launch_gemv_chain_t(ChainArgs &a, cudaStream_t st, bool dry) {
     constexpr int V = Elem<T>::kVec;
-    if (a.n_phases < 1 || a.n_phases > kChainMaxPhases || a.M < 1 || a.M > 4 || !a.sync) return B200_ERR_UNSUPPORTED;
+    if (a.n_phases < 1 || a.n_phases > kChainMaxPhases || a.M < 1 || a.M > 4 || !a.claim) return B200_ERR_UNSUPPORTED;
     const int MB = a.M <= 1 ? 1 : (a.M <= 2 ? 2 : 4);
     int stage_bytes = 0, max_k = 0;
     for (int p = 0; p < a.n_phases; ++p) {
         ChainPhase &P = a.ph[p];
         const size_t row_bytes = (size_t)P.K * sizeof(T);
-        if (P.K < V || row_bytes % 16 != 0 || P.K % V != 0 || !aligned16(P.w) || !aligned16(P.x) || !P.y) return B200_ERR_UNSUPPORTED;
+        if (P.K < V || row_bytes % 16 != 0 || P.K % V != 0 || !aligned16(P.w)) return B200_ERR_UNSUPPORTED;
+        if (P.x_ll ? !aligned16(P.x_ll) : (!P.x || !aligned16(P.x))) return B200_ERR_UNSUPPORTED;
+        if (P.y_ll ? !aligned16(P.y_ll) : !P.y) return B200_ERR_UNSUPPORTED;
+        if (P.res_ll && (!P.res_in || !aligned16(P.res_ll))) return B200_ERR_UNSUPPORTED;
+        // an LL output is read back in whole 16-byte vectors of T; a pair of 16-bit rows shares one LL word
+        const int n_out = P.swiglu ? P.inter : P.N;
+        if (P.y_ll && (n_out % V != 0 || (!P.swiglu && P.N % 2 != 0))) return B200_ERR_UNSUPPORTED;
         if (P.norm && ((P.res_in && !aligned16(P.res_in)) || (P.res_out && !aligned16(P.res_out)) || (P.bias && !aligned16(P.bias)) ||
                        (P.gamma && !aligned16(P.gamma))))
             return B200_ERR_UNSUPPORTED;
@@ -58,6 +64,8 @@ static int launch_gemv_chain_t(ChainArgs &a, cudaStream_t st, bool dry) {
     a.xs_elems = (max_k + V - 1) / V * V;
     size_t fixed = ((size_t)MB * a.xs_elems * sizeof(T) + 127) & ~(size_t)127;
     fixed += (size_t)kGemvGroups * (2 * kGemvMaxStages + 4) * 8;
+    fixed += 128;  // unit ids of the ring stages and partial-sum slots
+    static_assert(kGemvGroups * (kGemvMaxStages + 3) * sizeof(int) <= 128, "unit-id area");
     fixed += (size_t)kGemvGroups * kGemvGW * 2 * kGemvRows * MB * 32 * sizeof(float);
     const size_t budget = 224 * 1024;
     const size_t per_stage = (size_t)kGemvGroups * stage_bytes;

@@ -58,18 +58,30 @@ for p in range(4):
     print(f"--- phase {p} ({names[p]})")
     if p > 0:
         Tp = t[lay, :, p - 1, :]
-        print("  compute warp0 idle until barrier seen (t1-t0)      ", stat(T[..., 1] - T[..., 0]))
-        last_arrive = Tp[..., 6].max(axis=1, keepdims=True)
-        first_done = Tp[..., 4].min(axis=1, keepdims=True)
-        print("  last reducer arrival - first compute-done (skew)   ", stat(last_arrive - first_done))
-        print("  barrier seen - last reducer arrival (propagation)  ", stat(T[..., 1] - last_arrive))
+        print("  compute-done skew over the grid (max t4 - min t4)  ", stat(Tp[..., 4].max(axis=1) - Tp[..., 4].min(axis=1)))
         print("  reducer: last store - compute warp0 done (t5-t4)   ", stat(Tp[..., 5] - Tp[..., 4]))
-        print("  reducer: fence + atomic (t6-t5)                    ", stat(Tp[..., 6] - Tp[..., 5]))
-    print("  CTA-local barrier wait (t2-t1)                     ", stat(T[..., 2] - T[..., 1]))
-    print("  staging (t3-t2)                                    ", stat(T[..., 3] - T[..., 2]))
+        print("  staging done - last reducer store of the grid      ", stat(T[..., 3] - Tp[..., 5].max(axis=1, keepdims=True)))
+    print("  CTA-local barrier wait (t2-t0)                     ", stat(T[..., 2] - T[..., 0]))
+    print("  staging incl. polling (t3-t2)                      ", stat(T[..., 3] - T[..., 2]))
     print("  compute (t4-t3)                                    ", stat(T[..., 4] - T[..., 3]))
     print("  phase span over the grid: max(t4) - min(t3)        ", stat(T[..., 4].max(axis=1) - T[..., 3].min(axis=1)))
+    print("  producer: start issuing - compute start (t1-t3)    ", stat(T[..., 1] - T[..., 3]))
+    print("  producer: last copy issued - compute end (t6-t4)   ", stat(T[..., 6] - T[..., 4]))
 tot = t[lay, :, 3, 4].max(axis=1) - t[lay, :, 0, 0].min(axis=1)
 print("chain kernel span (first t0 .. last qkv compute end)   ", stat(tot))
-res = np.diff(np.unique(t[10, :, :, :4].ravel()))
-print("globaltimer resolution (smallest non-zero step)", res[res > 0].min() if (res > 0).any() else None)
+gap = t[5:28, :, 0, 0].min(axis=1) - t[4:27, :, 3, 4].max(axis=1)
+print("between chain kernels (attention + 2 boundaries)       ", stat(gap))
+# is the per-SM speed systematic?  compute time of the gate_up phase per smid, correlation between layers
+smid = t[10, :, 1, 7]
+gu = (t[lay, :, 1, 4] - t[lay, :, 1, 3]).astype(np.float64)  # [layers, cta]
+order = np.argsort(smid)
+print("smid range", smid.min(), smid.max(), "unique", len(np.unique(smid)))
+same_map = all((t[l, :, 1, 7] == smid).all() for l in range(4, 28))
+print("blockIdx -> smid mapping identical in every layer:", same_map)
+m = gu.mean(axis=0)
+c = np.corrcoef(gu)
+print("gate_up compute time per CTA: mean over layers min/median/max", m.min(), np.median(m), m.max(),
+      "; mean pairwise correlation between layers", (c.sum() - len(c)) / (len(c) * (len(c) - 1)))
+print("per-smid mean gate_up compute time (us), sorted by smid:")
+print(" ".join(f"{int(s)}:{v / 1e3:.1f}" for s, v in zip(smid[order], m[order])))
+np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "chain_trace.npz"), t=t)
