@@ -285,6 +285,8 @@ typedef struct {
 
 b200_decoder_t *b200_decoder_create(const b200_decoder_config_t *cfg);
 void b200_decoder_destroy(b200_decoder_t *dec);
+/* Copies the configuration the engine was created with. */
+int b200_decoder_get_config(const b200_decoder_t *dec, b200_decoder_config_t *cfg);
 int b200_decoder_set_layer(b200_decoder_t *dec, int layer, const b200_layer_weights_t *w);
 /* Device scratch the engine needs (activations, split-KV partials); caller-owned. */
 size_t b200_decoder_scratch_bytes(const b200_decoder_t *dec);
@@ -353,6 +355,35 @@ int b200_lm_head_topk_sample(b200_decoder_t *dec, const void *hidden, const void
                              int *topk_ids, float *topk_vals, int *seq_len, uint8_t *finished,
                              int *output_id, int batch, int k, int step, int end_id,
                              b200_stream_t stream);
+
+/* ========================================== generation loop ========================================= */
+
+/* The loop LlamaModel<T>::response / generateFirstToken / generateNextToken / LMHeadAndTopKSample intend
+ * (src/models/llama/llama.cpp:165-398; dead code in the reference -- SURVEY.md 8f rank 2):
+ * prompt -> launchInputEmbedding -> context decoder (KV cache filled from position 0) -> final RMSNorm + LM head on the last prompt
+ * token -> top-k -> sampling; then per new token: embedding of the sampled id -> self decoder step -> the same tail.
+ * `step` (sampling seed and 1-based position count) starts at the prompt length and grows by one per token, as in the reference. */
+typedef struct {
+    const void *embedding;   /* [vocab, hidden] of the engine's dtype (pre_decoder_embedding_weight)          */
+    const void *final_gamma; /* [hidden] (out_rmsnorm_weight)                                                */
+    const void *lm_head;     /* [vocab, hidden] dense, engine dtype (post_decoder_embedding_weight)          */
+    int vocab;
+    int top_k;               /* 1..B200_TOPK_MAX_K; 1 = greedy                                               */
+    int end_id;
+    int max_new_tokens;      /* tokens to produce per sequence, including the one sampled from the prompt    */
+    int check_every;         /* poll the finished flags every this many steps (0: always run max_new_tokens) */
+} b200_generate_params_t;
+
+/* Device workspace b200_generate needs for this batch / prompt length (0 on a bad argument: see b200_last_error_string). */
+size_t b200_generate_workspace_bytes(const b200_decoder_t *dec, const b200_generate_params_t *p, int batch, int prompt_len);
+
+/* prompt_ids: HOST int[batch, prompt_len] (every sequence the same length; batch must equal the engine's max_batch, which is the
+ * cache's batch dimension).  k_cache / v_cache: caller-owned [L, batch, Hkv, max_seq_len, d], overwritten from position 0.
+ * out_ids: HOST int[batch, max_new_tokens]: the sampled ids; everything from a sequence's first end_id on is end_id.
+ * n_generated (optional): HOST int[batch], tokens before the first end_id.  Synchronises the stream before returning. */
+int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const int *prompt_ids, int batch, int prompt_len,
+                  void *k_cache, void *v_cache, void *workspace, size_t workspace_bytes, int *out_ids, int *n_generated,
+                  b200_stream_t stream);
 
 #ifdef __cplusplus
 }

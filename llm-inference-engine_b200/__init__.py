@@ -41,6 +41,12 @@ class LayerWeights(C.Structure):
                 ("o_bias", C.c_void_p), ("ffn_norm_gamma", C.c_void_p), ("gate_up", LinearWeight), ("down", LinearWeight)]
 
 
+class GenerateParams(C.Structure):
+    """b200_generate_params_t (include/b200llm.h)."""
+    _fields_ = [("embedding", C.c_void_p), ("final_gamma", C.c_void_p), ("lm_head", C.c_void_p), ("vocab", C.c_int), ("top_k", C.c_int),
+                ("end_id", C.c_int), ("max_new_tokens", C.c_int), ("check_every", C.c_int)]
+
+
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 # name -> argtypes (restype int unless listed in _RESTYPES); must list every symbol of include/b200llm.h
 SIGNATURES = {
@@ -76,6 +82,9 @@ SIGNATURES = {
     "b200_xorwow_uniform": [_P, _I, C.c_ulonglong, _P],
     "b200_decoder_create": [C.POINTER(DecoderConfig)],
     "b200_decoder_destroy": [_P],
+    "b200_decoder_get_config": [_P, C.POINTER(DecoderConfig)],
+    "b200_generate_workspace_bytes": [_P, C.POINTER(GenerateParams), _I, _I],
+    "b200_generate": [_P, C.POINTER(GenerateParams), _P, _I, _I, _P, _P, _P, _SZ, _P, _P, _P],
     "b200_decoder_set_layer": [_P, _I, C.POINTER(LayerWeights)],
     "b200_decoder_scratch_bytes": [_P],
     "b200_decoder_set_scratch": [_P, _P, _SZ],
@@ -97,7 +106,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_workspace_default_bytes": _SZ, "b200_decoder_create": _P,
              "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ, "b200_decoder_prefill_scratch_bytes": _SZ,
-             "b200_decoder_tp_buffer_bytes": _SZ, "b200_decoder_debug_trace": _SZ}
+             "b200_decoder_tp_buffer_bytes": _SZ, "b200_decoder_debug_trace": _SZ, "b200_generate_workspace_bytes": _SZ}
 
 _lib = None
 
@@ -410,6 +419,27 @@ class Decoder:
         self._trace = torch.zeros(nbytes // 8, dtype=torch.int64, device=self.device)
         lib().b200_decoder_debug_trace(self.handle, C.c_void_p(self._trace.data_ptr()), nbytes)
         return self._trace
+
+    def generate(self, prompt_ids, embedding, final_gamma, lm_head, k_cache, v_cache, max_new_tokens, top_k=1, end_id=2, check_every=0):
+        """The generation loop (b200_generate): prompt_ids = int array [batch, prompt_len] on the HOST; returns (ids [batch, max_new_tokens],
+        n_generated [batch]) as numpy arrays.  embedding / lm_head: [vocab, hidden] tensors of the engine's dtype."""
+        import numpy as np
+
+        torch = _torch()
+        prompt = np.ascontiguousarray(np.asarray(prompt_ids, dtype=np.int32))
+        B, T = prompt.shape
+        gp = GenerateParams(C.c_void_p(embedding.data_ptr()), C.c_void_p(final_gamma.data_ptr()), C.c_void_p(lm_head.data_ptr()),
+                            int(lm_head.shape[0]), int(top_k), int(end_id), int(max_new_tokens), int(check_every))
+        nbytes = lib().b200_generate_workspace_bytes(self.handle, C.byref(gp), B, T)
+        if nbytes == 0:
+            raise B200Error(lib().b200_last_error_string().decode())
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        out = np.empty((B, max_new_tokens), dtype=np.int32)
+        ngen = np.empty(B, dtype=np.int32)
+        check(lib().b200_generate(self.handle, C.byref(gp), prompt.ctypes.data_as(C.c_void_p), B, T, ptr(k_cache), ptr(v_cache),
+                                  C.c_void_p(base), nbytes, out.ctypes.data_as(C.c_void_p), ngen.ctypes.data_as(C.c_void_p), stream()))
+        return out, ngen
 
     def linears_only(self, batch):
         """Diagnostic: the weight-streaming launches of one decode step (no attention, no fold); returns the number of launches."""

@@ -263,6 +263,12 @@ b200_decoder_t *b200_decoder_create(const b200_decoder_config_t *cfg) {
 
 void b200_decoder_destroy(b200_decoder_t *dec) { delete dec; }
 
+int b200_decoder_get_config(const b200_decoder_t *dec, b200_decoder_config_t *cfg) {
+    B200_REQUIRE(dec && cfg, "decoder_get_config: null argument");
+    *cfg = dec->cfg;
+    return B200_OK;
+}
+
 int b200_decoder_set_layer(b200_decoder_t *dec, int layer, const b200_layer_weights_t *w) {
     B200_REQUIRE(dec && w, "decoder_set_layer: null argument");
     B200_REQUIRE(layer >= 0 && layer < dec->cfg.num_layers, "decoder_set_layer: layer %d out of range", layer);
