@@ -311,8 +311,10 @@ def main():
     ap.add_argument("--ctx", type=int, default=1024)
     ap.add_argument("--wformat", default="bf16", choices=list(WBYTES))
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only: makes the number INVALID)")
-    ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
-                    help="decode (default, the BASELINE metric) or prefill: one pass of --prefill-tokens tokens through all layers")
+    ap.add_argument("--mode", default="decode", choices=["decode", "prefill", "generate"],
+                    help="decode (default, the BASELINE metric); prefill: one pass of --prefill-tokens tokens through all layers; generate: "
+                         "the whole loop through b200_generate (prompt of --prefill-tokens tokens, --new-tokens sampled tokens, host in / host out)")
+    ap.add_argument("--new-tokens", type=int, default=128)
     ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--preheat", type=float, default=1.5, help="seconds of untimed steps before the warm-up (clock ramp)")
     ap.add_argument("--no-graph", action="store_true")
@@ -321,6 +323,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.mode == "prefill":
         args.ctx = max(args.ctx, args.prefill_tokens)
+    if args.mode == "generate":
+        args.ctx = max(args.ctx, args.prefill_tokens + args.new_tokens)
     cfg = dict(CONFIGS[args.config])
     if args.layers:
         cfg["layers"] = args.layers
@@ -402,6 +406,24 @@ def main():
 
     if args.mode == "prefill":
         run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank)
+        return
+    if args.mode == "generate":
+        # end to end through the generation loop of the C ABI: host prompt ids in, host token ids out; eager launches (the position
+        # changes every step), prefill included in the time
+        assert tp == 1, "generate mode is single-GPU"
+        prompt = np.random.default_rng(0).integers(3, V, size=(B, args.prefill_tokens)).astype(np.int32)
+        times = []
+        for i in range(max(args.warmup, 1) + args.steps):
+            t0 = time.perf_counter()
+            ids, ngen = dec.generate(prompt, emb, final_gamma, lm_head, kc, vc, args.new_tokens, top_k=K_TOP, end_id=-1)
+            times.append(time.perf_counter() - t0)
+        tt = sorted(times[max(args.warmup, 1):])
+        sec = tt[len(tt) // 2]
+        print(json.dumps({"metric": "generate tokens/s (end to end, prefill included)", "value": B * args.new_tokens / sec, "unit": "tokens/s",
+                          "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_call": sec * 1e3,
+                          "ms_per_new_token": sec * 1e3 / args.new_tokens, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"{cfg['name']} {L}-layer {args.wformat} b200_generate, batch {B}, prompt {args.prefill_tokens}, "
+                                                 f"{args.new_tokens} new tokens", "launch_mode": "eager (PDL-chained)", "sampled": int(ngen.sum())}}), flush=True)
         return
 
     def decode_step():

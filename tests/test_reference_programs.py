@@ -83,3 +83,19 @@ def test_reference_program_runs_against_the_shim(name):
                   f"shim result recorded, not asserted")
     else:
         assert not failed or ref_failed, f"{name}: failure lines with the shim but not with the reference: {failed[:3]}"
+
+
+OWN_DIR = os.path.join(ROOT, "llm-inference-engine_b200", "shim", "_own_programs")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_llama_model_example_runs(dtype):
+    """The shim's LlamaModel<T> (reference src/models/llama/llama.h:13-214, dead code there) driving b200_generate: one conversation
+    round on dummy weights; the example checks that response() and generateIds() agree and respect the token limit."""
+    exe = os.path.join(OWN_DIR, "llama_model_example")
+    if not os.path.exists(exe):
+        pytest.skip("shim/_own_programs not built (run __graft_entry__.build())")
+    p = subprocess.run([exe, dtype, "10"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=180)
+    out = p.stdout.decode(errors="replace")
+    assert p.returncode == 0 and "llama_model_example passed" in out, out[-3000:]
