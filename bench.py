@@ -591,7 +591,7 @@ def main():
         # DRAM traffic of the same launches from the committed ncu capture (read + write bytes over algorithmic bytes)
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
             if args.config == "7b" and args.wformat == "bf16" and B == 1 and tp == 1:
                 traffic = gemv_bytes * float(tr["traffic_over_algorithmic"])
         except Exception:
@@ -614,7 +614,7 @@ def main():
             "tp_exchange": tp_mode,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "launches": n_gemv, "avg_launch_us": gemv_ms * 1e3 / n_gemv,
                          "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                         "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write of the QKV/O/gate_up/down launches, scaled to the step)" if traffic else None,
+                         "traffic_source": "profiles/r1c_traffic.json (ncu dram__bytes_read+write of the QKV/O/gate_up/down launches, scaled to the step)" if traffic else None,
                          "peak_source": peak_src, "bytes_per_step_launches": gemv_bytes, "ms": gemv_ms,
                          "whole_step": {"bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                                         "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak_gbs,
