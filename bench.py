@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     "7b": dict(name="Llama-2-7B", hidden=4096, head_num=32, kv_head_num=32, head_size=128, inter=11008, layers=32, vocab=32000),
     "70b": dict(name="Llama-2-70B-shaped", hidden=8192, head_num=64, kv_head_num=8, head_size=128, inter=28672, layers=80, vocab=32000),
+    # diagnostics: ONE rank's shard of the 70B-shaped model under TP-8, run on one GPU without the exchange (kernel-level profiling)
+    "70b-tp8-rank": dict(name="Llama-2-70B-shaped, one TP-8 shard", hidden=8192, head_num=8, kv_head_num=1, head_size=128, inter=3584, layers=80, vocab=32000),
 }
 WBYTES = {"bf16": 2.0, "fp8": 1.0, "int4": 0.5}
 
