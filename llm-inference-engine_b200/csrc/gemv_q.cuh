@@ -128,21 +128,26 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
     // ---------------- stage the activations as f16 (a.M token rows); INT4 stores every 8 k in the order
     //                  [k0 k4 k1 k5 k2 k6 k3 k7] -- the order in which the nibble pairs come out of a 32-bit word
     {
-        gemv_stage_activations<T, 0>(a, n_threads, red, [&](int m, int i, const float *f) {
+        auto store = [&](int m, int i, const float *f) {
             float g[V];
             unpack16<T>(pack16<T>(f), g);  // the un-fused reference hands the GEMM a tensor of T
-            __half *dst = xs + (size_t)m * geo.xs_stride + (size_t)i * V;
-            if constexpr (FMT == WF_FP8) {
+            // one 16-byte store per vector of 8 k (V == 8 for the 16-bit types this kernel is instantiated for)
+            float o[8];
 #pragma unroll
-                for (int j = 0; j < V; ++j) dst[j] = __float2half_rn(g[j]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const int k8 = j & 7;
-                    dst[(j & ~7) + ((k8 & 3) * 2 + (k8 >> 2))] = __float2half_rn(g[j]);
-                }
+            for (int j = 0; j < 8; ++j) {
+                const int dstj = FMT == WF_FP8 ? j : ((j & 3) * 2 + (j >> 2));
+                o[dstj] = g[j];
             }
-        });
+            const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+            const __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&h0), pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+            pk.z = *reinterpret_cast<const uint32_t *>(&h2), pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(xs + (size_t)m * geo.xs_stride + (size_t)i * V) = pk;
+        };
+        static_assert(V == 8, "gemv_q_kernel: 16-bit activation types only");
+        if (a.M == 1) gemv_stage_activations<T, 1>(a, n_threads, red, store);  // single-trip instantiation: no spills in the B = 1 prologue
+        else gemv_stage_activations<T, 0>(a, n_threads, red, store);
         __syncthreads();
     }
     pdl_launch_dependents();
@@ -224,8 +229,36 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
             const int u = gid + un * total_groups;
             acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
             for (int pc = 0; pc < pieces; ++pc) {
-                mbar_wait(full0 + s * 8, ph);
                 const int kw = pc * kQPieceK + wg * kQWarpK;  // first k of this warp's slice
+                // INT4: the group scales / zero points of this warp's (<= 4) consecutive 128-k blocks, for rows g and g+8, requested BEFORE
+                // waiting for the stage and kept packed (4 x T in a uint2, 4 x u8 in a uint32): fetched block by block inside the loop
+                // they put a ~600-cycle dependent L2 load in front of every block, which bounded the INT4 kernel near 1.8 TB/s
+                uint2 sraw[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+                uint32_t zraw[2] = {0u, 0u};
+                if constexpr (FMT == WF_INT4) {
+                    const int nblk = min(kQWarpK, max(K - kw, 0)) / 128;  // blocks of this slice that exist
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int row = min(unit_row(u, g + 8 * h), N - 1);
+                        const size_t gi = (size_t)row * ngroups_k + kw / a.group;
+                        const T *sp = reinterpret_cast<const T *>(a.scales) + gi;
+                        const uint8_t *zp = reinterpret_cast<const uint8_t *>(a.zeros) + gi;
+                        if (nblk == 4 && (ngroups_k & 3) == 0) {  // 8-byte / 4-byte aligned: one load each
+                            sraw[h] = __ldg(reinterpret_cast<const uint2 *>(sp));
+                            zraw[h] = __ldg(reinterpret_cast<const uint32_t *>(zp));
+                        } else {
+                            uint32_t s16[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                            for (int bk = 0; bk < 4; ++bk)
+                                if (bk < nblk) {
+                                    s16[bk] = __ldg(reinterpret_cast<const unsigned short *>(sp) + bk);
+                                    zraw[h] |= (uint32_t)__ldg(zp + bk) << (8 * bk);
+                                }
+                            sraw[h] = make_uint2(s16[0] | (s16[1] << 16), s16[2] | (s16[3] << 16));
+                        }
+                    }
+                }
+                mbar_wait(full0 + s * 8, ph);
                 const uint32_t st = ring_u32 + (uint32_t)s * geo.stage_bytes + lm_off;
                 for (int bk = 0; bk < kQWarpK / 128; ++bk) {  // 128-k blocks of the slice (K is a multiple of 128)
                     const int kb = kw + bk * 128;
@@ -245,15 +278,14 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
                         }
                     } else {
                         // a 128-k block is exactly one quantisation group (group == 128) of every row
-                        const int grp_k = kb / a.group;
                         float sc[2];
                         uint32_t zpk[2];
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const int row = min(unit_row(u, g + 8 * h), N - 1);
-                            const size_t gi = (size_t)row * ngroups_k + grp_k;
-                            sc[h] = Elem<T>::to_f(__ldg(reinterpret_cast<const T *>(a.scales) + gi));
-                            const uint32_t z = 0x6400u | __ldg(reinterpret_cast<const uint8_t *>(a.zeros) + gi);
+                            const uint32_t pair = bk < 2 ? sraw[h].x : sraw[h].y;
+                            const unsigned short s16 = (unsigned short)((bk & 1) ? (pair >> 16) : (pair & 0xffffu));
+                            sc[h] = Elem<T>::to_f(*reinterpret_cast<const T *>(&s16));
+                            const uint32_t z = 0x6400u | ((zraw[h] >> (8 * bk)) & 0xffu);
                             zpk[h] = z | (z << 16);  // f16x2 {1024 + z, 1024 + z}
                         }
                         float ag[4] = {0.f, 0.f, 0.f, 0.f};
