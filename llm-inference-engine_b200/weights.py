@@ -14,13 +14,13 @@ Sources
 
 Products
   * `fused` : dict(layers=[dict(g1, wqkv, bqkv, wo, bo, g2, wgu, wd)], embed, final_gamma, lm_head), fp32 numpy, linears in the engine's
-    [N, K] orientation -- the same dict the CPU oracle consumes, so parity on a converted checkpoint needs no second loader;
+    [N, K] orientation -- the same dict the parity tests feed to their CPU checker, so a converted checkpoint needs no second loader;
   * `export_reference_bins`: the reference's directory from `fused` (what its `loadWeights(path)` reads);
   * `save_packed` / `load_packed`: the engine's own format -- per rank, per tensor raw files of the PACKED bytes (bf16 / fp16 / fp32 dense,
     FP8-e4m3 + per-row scale, INT4-g128 + scales + zero points, all [N, K]) plus a JSON manifest: quantisation and tensor-parallel
     sharding happen once, offline; loading is a read + H2D copy;
   * `build_decoder`: a ready `Decoder` (+ embedding, final gamma, LM head on the device) from `fused` or from a packed directory.
-Quantisers are the library's (`b200_quantize_fp8` / `b200_quantize_int4`, bit-exact against the oracle's), so this module needs a GPU only
+Quantisers are the library's (`b200_quantize_fp8` / `b200_quantize_int4`), so this module needs a GPU only
 for FP8 / INT4 packing and for `build_decoder`; everything else is numpy.
 """
 import importlib
