@@ -38,6 +38,30 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// (a & b) | c in one instruction (the compiler emits two LOP3 when b and c are immediates)
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// The 8 nibbles of a 32-bit word as four f16x2 pairs {n_i - z, n_{i+4} - z}, i = 0..3, exact integers:
+//   i even: ((w' & 0x000f000f) | 0x64006400) = {1024 + n, 1024 + n} minus {1024 + z};
+//   i odd : ((w' & 0x00f000f0) | 0x64006400) = {1024 + 16 n, ...}: one HFMA2 with 1/16 and -(64 + z) (exact: 64 + n is an f16 integer);
+//   w' = w for i = 0, 1 and w >> 8 for i = 2, 3: one shift per word instead of three.
+struct Int4Consts {
+    uint32_t m_lo, m_hi, magic, sixteenth;  // 0x000f000f, 0x00f000f0, 0x64006400, f16x2 {1/16, 1/16}
+};
+__device__ __forceinline__ void deq_int4_word(uint32_t w, uint32_t zpk, uint32_t nz64, const Int4Consts &c, uint32_t (&d)[4]) {
+    const uint32_t w8 = w >> 8;
+    const uint32_t h0 = lop3_and_or(w, c.m_lo, c.magic), h1 = lop3_and_or(w, c.m_hi, c.magic);
+    const uint32_t h2 = lop3_and_or(w8, c.m_lo, c.magic), h3 = lop3_and_or(w8, c.m_hi, c.magic);
+    const __half2 z = *reinterpret_cast<const __half2 *>(&zpk), nz = *reinterpret_cast<const __half2 *>(&nz64);
+    const __half2 s16 = *reinterpret_cast<const __half2 *>(&c.sixteenth);
+    const __half2 r0 = __hsub2(*reinterpret_cast<const __half2 *>(&h0), z), r2 = __hsub2(*reinterpret_cast<const __half2 *>(&h2), z);
+    const __half2 r1 = __hfma2(*reinterpret_cast<const __half2 *>(&h1), s16, nz), r3 = __hfma2(*reinterpret_cast<const __half2 *>(&h3), s16, nz);
+    d[0] = *reinterpret_cast<const uint32_t *>(&r0), d[1] = *reinterpret_cast<const uint32_t *>(&r1);
+    d[2] = *reinterpret_cast<const uint32_t *>(&r2), d[3] = *reinterpret_cast<const uint32_t *>(&r3);
+}
 __device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint32_t two_bytes) {
     uint32_t h;
     asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h) : "h"((unsigned short)two_bytes));
@@ -220,10 +244,13 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
         const int g = lane >> 2, t = lane & 3;
         // ldmatrix.x4 row addresses: lanes 0-7 rows 0-7 (first 16 bytes), 8-15 rows 8-15, 16-23 rows 0-7 (+16 bytes), 24-31 rows 8-15 (+16)
         const uint32_t lm_off = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * geo.row_stride + (uint32_t)(lane >> 4) * 16 + (uint32_t)wg * kWarpBytes;
-        const bool tok = g < a.M;                                              // B fragments: token g (zero past the batch)
-        const __half *xrow = xs + (size_t)(tok ? g : 0) * geo.xs_stride;
+        // B fragments: token g; slots past the batch read token 0 (their accumulator columns are never reduced)
+        const __half *xrow = xs + (size_t)(g < a.M ? g : 0) * geo.xs_stride;
         const int ngroups_k = FMT == WF_INT4 ? K / a.group : 0;
         float acc[4];
+        Int4Consts i4c;
+        i4c.m_lo = 0x000f000fu, i4c.m_hi = 0x00f000f0u, i4c.magic = 0x64006400u, i4c.sixteenth = 0x2c002c00u;  // f16 1/16 = 0x2c00
+        (void)i4c;
         int s = 0, ph = 0;
         for (int un = 0; un < my_units; ++un) {
             const int u = gid + un * total_groups;
@@ -272,21 +299,23 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
                             // k is permuted consistently for A and B: mma slots (2t, 2t+1) <- k (4t, 4t+1), slots (2t+8, 2t+9) <- (4t+2, 4t+3)
                             uint2 b01 = *reinterpret_cast<const uint2 *>(xrow + kb + j * 32 + 4 * t);
                             uint2 b23 = *reinterpret_cast<const uint2 *>(xrow + kb + j * 32 + 16 + 4 * t);
-                            if (!tok) b01 = make_uint2(0u, 0u), b23 = make_uint2(0u, 0u);
                             mma_f16(acc, e4m3x2_to_f16x2(r[0]), e4m3x2_to_f16x2(r[1]), e4m3x2_to_f16x2(r[0] >> 16), e4m3x2_to_f16x2(r[1] >> 16), b01.x, b01.y);
                             mma_f16(acc, e4m3x2_to_f16x2(r[2]), e4m3x2_to_f16x2(r[3]), e4m3x2_to_f16x2(r[2] >> 16), e4m3x2_to_f16x2(r[3] >> 16), b23.x, b23.y);
                         }
                     } else {
                         // a 128-k block is exactly one quantisation group (group == 128) of every row
                         float sc[2];
-                        uint32_t zpk[2];
+                        uint32_t zpk[2], nz64[2];
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const uint32_t pair = bk < 2 ? sraw[h].x : sraw[h].y;
                             const unsigned short s16 = (unsigned short)((bk & 1) ? (pair >> 16) : (pair & 0xffffu));
                             sc[h] = Elem<T>::to_f(*reinterpret_cast<const T *>(&s16));
-                            const uint32_t z = 0x6400u | ((zraw[h] >> (8 * bk)) & 0xffu);
+                            const uint32_t zq = (zraw[h] >> (8 * bk)) & 0xffu;
+                            const uint32_t z = 0x6400u | zq;
                             zpk[h] = z | (z << 16);  // f16x2 {1024 + z, 1024 + z}
+                            const __half2 n2 = __float2half2_rn(-(64.0f + (float)zq));
+                            nz64[h] = *reinterpret_cast<const uint32_t *>(&n2);  // f16x2 {-(64 + z), -(64 + z)}
                         }
                         float ag[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -296,16 +325,13 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
                             // r0: row g, nibbles k = 8t..8t+7 of the first 32 k; r1: row g+8; r2 / r3: the next 32 k
 #pragma unroll
                             for (int q = 0; q < 2; ++q) {
-                                const uint32_t w0 = r[2 * q], w1 = r[2 * q + 1];
-                                uint4 xb = *reinterpret_cast<const uint4 *>(xrow + kb + j * 64 + q * 32 + 8 * t);  // (k0,k4)(k1,k5)(k2,k6)(k3,k7)
-                                if (!tok) xb = make_uint4(0u, 0u, 0u, 0u);
-                                auto deq = [&](uint32_t w, int shift, uint32_t z) -> uint32_t {
-                                    const uint32_t hbits = ((w >> shift) & 0x000f000fu) | 0x64006400u;  // {1024 + n_i, 1024 + n_{i+4}}
-                                    const __half2 d = __hsub2(*reinterpret_cast<const __half2 *>(&hbits), *reinterpret_cast<const __half2 *>(&z));
-                                    return *reinterpret_cast<const uint32_t *>(&d);
-                                };
-                                mma_f16(ag, deq(w0, 0, zpk[0]), deq(w1, 0, zpk[1]), deq(w0, 4, zpk[0]), deq(w1, 4, zpk[1]), xb.x, xb.y);
-                                mma_f16(ag, deq(w0, 8, zpk[0]), deq(w1, 8, zpk[1]), deq(w0, 12, zpk[0]), deq(w1, 12, zpk[1]), xb.z, xb.w);
+                                uint32_t d0[4], d1[4];
+                                deq_int4_word(r[2 * q], zpk[0], nz64[0], i4c, d0);
+                                deq_int4_word(r[2 * q + 1], zpk[1], nz64[1], i4c, d1);
+                                // token slots past the batch read token 0's activations: their accumulator columns are never reduced
+                                const uint4 xb = *reinterpret_cast<const uint4 *>(xrow + kb + j * 64 + q * 32 + 8 * t);  // (k0,k4)(k1,k5)(k2,k6)(k3,k7)
+                                mma_f16(ag, d0[0], d1[0], d0[1], d1[1], xb.x, xb.y);
+                                mma_f16(ag, d0[2], d1[2], d0[3], d1[3], xb.z, xb.w);
                             }
                         }
                         acc[0] = fmaf(sc[0], ag[0], acc[0]), acc[1] = fmaf(sc[0], ag[1], acc[1]);
