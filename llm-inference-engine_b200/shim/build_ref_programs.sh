@@ -1,5 +1,5 @@
 #!/bin/bash
-# Compile the REFERENCE's own unit tests (tests/unit_tests/*.cu) and layer examples (examples/cpp/*.cpp), unmodified, against
+# Compile the REFERENCE's own unit tests (tests/unit_tests/*.cu), layer examples (examples/cpp/*.cpp) and chat entry (user_entry.cpp), unmodified, against
 # the shim headers of this directory and libb200llm.so.  This is the drop-in check of the boundary: the reference sources
 # include "../../src/<...>" relative to their own location, so a scratch tree of SYMLINKS is laid out in which tests/ and
 # examples/ point at the reference files and src/ points at shim/src -- nothing is copied into the repository.
@@ -19,6 +19,7 @@ mkdir -p "$TREE/tests/unit_tests" "$TREE/examples/cpp" "$OUT"
 ln -s "$HERE/src" "$TREE/src"
 for f in "$REF"/tests/unit_tests/*.cu; do ln -s "$f" "$TREE/tests/unit_tests/$(basename "$f")"; done
 for f in "$REF"/examples/cpp/*.cpp; do ln -s "$f" "$TREE/examples/cpp/$(basename "$f")"; done
+[ -f "$REF/user_entry.cpp" ] && ln -s "$REF/user_entry.cpp" "$TREE/user_entry.cpp"   # the chat entry: includes "src/utils/model_utils.h"
 fail=0
 build_one() {  # $1 = source (in the symlink tree), $2 = output name
     "$NVCC" -std=c++17 -O2 -w -x cu -gencode arch=compute_100a,code=sm_100a -I"$ROOT/include" -I"$TREE" \
@@ -28,6 +29,7 @@ build_one() {  # $1 = source (in the symlink tree), $2 = output name
 pids=()
 for f in "$TREE"/tests/unit_tests/*.cu; do build_one "$f" "$(basename "$f" .cu)" & pids+=($!); done
 for f in "$TREE"/examples/cpp/*.cpp; do build_one "$f" "$(basename "$f" .cpp)" & pids+=($!); done
+[ -f "$TREE/user_entry.cpp" ] && { build_one "$TREE/user_entry.cpp" user_entry & pids+=($!); }
 for p in "${pids[@]}"; do wait "$p"; done
 ls "$OUT"/*.build.log > /dev/null 2>&1 && { echo "some reference programs did not compile against the shim"; exit 1; }
 echo "all reference programs compiled against the shim -> $OUT"

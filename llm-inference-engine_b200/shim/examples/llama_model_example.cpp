@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include "../src/models/llama/llama.h"
+#include "../src/utils/model_utils.h"
 
 template <typename T> static int run(int limit) {
     const int head_num = 4, kv_head_num = 2, head_size = 128, inter_size = 768, num_layers = 2, vocab = 32000, max_seq_len = 64;
@@ -35,7 +36,33 @@ template <typename T> static int run(int limit) {
     return ok ? 0 : 1;
 }
 
+// the reference's chat entry without the terminal: factory -> two rounds of MakeInput / Response / MakeHistory (user_entry.cpp:9-46)
+static int run_factory(const char *config_json) {
+    setenv("LLAMA_CONFIG_JSON", config_json, 1);
+    srand(7);
+    BaseModel *model = llm::createModelWithName<float>("llama");
+    model->loadWeightsFromDummy();
+    LlamaModel<float> *lm = dynamic_cast<LlamaModel<float> *>(model);
+    lm->setTopK(1);
+    lm->setOutputTokenLimit(6);
+    std::string history = "";
+    int tokens = 0;
+    for (int round = 0; round < 2; ++round) {
+        const std::string input = round == 0 ? "first question" : "second question";
+        std::string ret = model->Response(model->MakeInput(history, round, input), [&](int index, const char *content) {
+            if (index >= 0) ++tokens;
+        });
+        history = model->MakeHistory(history, round, input, ret);
+        printf("round %d: %s\n", round, ret.c_str());
+    }
+    const bool ok = tokens == 12 && history.find("second question") != std::string::npos;
+    printf(ok ? "chat factory passed\n" : "chat factory FAILED (%d tokens)\n", tokens);
+    delete model;
+    return ok ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 2 && !strcmp(argv[1], "factory")) return run_factory(argv[2]);
     const int limit = argc > 2 ? atoi(argv[2]) : 12;
     if (argc > 1 && !strcmp(argv[1], "f16")) return run<half>(limit);
     return run<float>(limit);

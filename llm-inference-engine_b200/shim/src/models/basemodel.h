@@ -34,4 +34,11 @@ public:
     virtual std::vector<std::string> makeInput(const std::string &history, int round, const std::string &input) const = 0;
     virtual std::string makeHistory(const std::string &history, int round, const std::string &input, const std::string &output) const = 0;
     virtual std::string response(const std::vector<std::string> &input, CallBack printRes) = 0;
+
+    // the spellings the reference's chat entry uses (user_entry.cpp:25-42)
+    std::vector<std::string> MakeInput(const std::string &history, int round, const std::string &input) const { return makeInput(history, round, input); }
+    std::string MakeHistory(const std::string &history, int round, const std::string &input, const std::string &output) const {
+        return makeHistory(history, round, input, output);
+    }
+    std::string Response(const std::vector<std::string> &input, CallBack printRes) { return response(input, printRes); }
 };

@@ -26,7 +26,8 @@ PASS_LINE = {
     "test_rmsnorm": "RMSNorm passed",
     "test_silu_and_mul": "Test passed",
 }
-NEEDS_EXTERNAL_FILE = {"context_decoder_example": "/home/llama2-7b-tokenizer.bin"}  # hard-coded path in the reference example
+NEEDS_EXTERNAL_FILE = {"context_decoder_example": "/home/llama2-7b-tokenizer.bin",  # hard-coded paths in the reference programs
+                       "user_entry": "/home/llamaweight/model.norm.weight.bin"}  # (and user_entry is an interactive REPL)
 
 
 def programs():
@@ -54,7 +55,7 @@ def test_reference_programs_were_built_when_the_reference_is_present():
 
     __graft_entry__.build()
     names = programs()
-    assert len(names) == 21, f"expected the reference's 16 unit tests + 5 examples compiled against the shim, got {len(names)}: {names}"
+    assert len(names) == 22, f"expected the reference's 16 unit tests + 5 examples + user_entry compiled against the shim, got {len(names)}: {names}"
     assert not [f for f in os.listdir(SHIM_DIR) if f.endswith(".build.log")]
 
 
@@ -99,3 +100,18 @@ def test_llama_model_example_runs(dtype):
     p = subprocess.run([exe, dtype, "10"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=180)
     out = p.stdout.decode(errors="replace")
     assert p.returncode == 0 and "llama_model_example passed" in out, out[-3000:]
+
+
+@pytest.mark.gpu
+def test_chat_factory_two_rounds(tmp_path):
+    """The model factory of the reference's chat entry (src/utils/model_utils.h:14-94 -> shim/src/utils/model_utils.h): config JSON ->
+    LlamaModel -> two conversation rounds through MakeInput / Response / MakeHistory, non-interactively."""
+    exe = os.path.join(OWN_DIR, "llama_model_example")
+    if not os.path.exists(exe):
+        pytest.skip("shim/_own_programs not built (run __graft_entry__.build())")
+    cfg = tmp_path / "llama_config.json"
+    cfg.write_text('{"head_num": 4, "kv_head_num": 2, "head_size": 128, "inter_size": 768, "num_layers": 2, "max_seq_len": 96, "vocab_size": 32000,\n'
+                   ' "attn_bias": false, "rotary_embedding_dim": 128, "rotary_embedding_base": 10000, "max_position_embeddings": 4096, "use_dynamic_ntk": false}')
+    p = subprocess.run([exe, "factory", str(cfg)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=180)
+    out = p.stdout.decode(errors="replace")
+    assert p.returncode == 0 and "chat factory passed" in out, out[-3000:]
