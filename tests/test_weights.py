@@ -149,3 +149,41 @@ def test_converted_checkpoint_runs_on_the_engine(tmp_path, wformat):
         oracle.decoder_layer(ref, ww, kc, vc, ocfg, step, l)
     got = to_np(xd)
     assert rel_fro(got, ref) <= 1e-2, f"{wformat}: {rel_fro(got, ref):.3e}"
+
+
+def test_converter_cli_on_cpu(tmp_path):
+    """scripts/convert_weights.py end to end without a GPU: a Hugging Face style checkpoint file -> the reference's .bin directory ->
+    the packed bf16 engine format for two tensor-parallel ranks."""
+    import subprocess
+    import sys
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shape = dict(SHAPE, head_num=2, kv_head_num=2)
+    sd = {k: torch.from_numpy(v) for k, v in fake_hf_state_dict(shape, seed=21).items()}
+    ckpt = tmp_path / "hf"
+    ckpt.mkdir()
+    torch.save(sd, str(ckpt / "pytorch_model.bin"))
+    spec = ",".join(str(shape[k]) for k in ("hidden", "head_num", "kv_head_num", "head_size", "inter", "layers", "vocab"))
+    ref_prefix = str(tmp_path / "refbins") + "/"
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "convert_weights.py"), "--hf", str(ckpt), "--shape", spec,
+                        "--export-ref-bins", ref_prefix], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
+    assert p.returncode == 0, p.stdout.decode()[-2000:]
+    assert os.path.exists(ref_prefix + "model.layers.1.mlp.down_proj.weight.bin")
+    out = str(tmp_path / "packed")
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "convert_weights.py"), "--ref-bins", ref_prefix, "--shape", spec, "--out", out,
+                        "--tp", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
+    assert p.returncode == 0, p.stdout.decode()[-2000:]
+    fused = W.fuse_hf_state_dict(fake_hf_state_dict(shape, seed=21), shape)
+    for r in range(2):
+        packed, manifest = W.load_packed(out, torch.device("cpu"), r)
+        assert manifest["tp"] == 2 and manifest["rank"] == r and manifest["wformat"] == "bf16"
+        want = torch.from_numpy(fused["layers"][0]["wd"]).to(torch.bfloat16)
+        I2 = shape["inter"] // 2
+        assert torch.equal(packed["layers"][0]["down"], want[:, r * I2:(r + 1) * I2].contiguous())
+    # FP8 / INT4 packing uses the library's device quantisers: refused (not silently done on the CPU) without a GPU
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "convert_weights.py"), "--ref-bins", ref_prefix, "--shape", spec, "--out", out + "8",
+                        "--wformat", "fp8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
+    assert p.returncode != 0 and b"needs a GPU" in p.stdout
