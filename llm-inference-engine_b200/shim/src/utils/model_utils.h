@@ -48,34 +48,62 @@ inline std::string readConfigText() {
     return "";
 }
 
+// everything the factory needs to know about the model, with Llama-2-7B defaults (src/models/llama/llama_config.json)
+struct ModelShape {
+    int head_num = 32, kv_head_num = 32, head_size = 128, inter_size = 11008, num_layers = 32, max_seq_len = 64, vocab_size = 32000;
+    int rotary_embedding_dim = 128, max_position_embeddings = 4096;
+    float rotary_embedding_base = 10000.0f;
+    bool use_dynamic_ntk = false;
+
+    static ModelShape fromJson(const std::string &text) {
+        ModelShape m;
+        struct Field {
+            const char *key;
+            int *dst;
+        };
+        const Field ints[] = {{"head_num", &m.head_num},       {"kv_head_num", &m.kv_head_num}, {"head_size", &m.head_size},
+                              {"inter_size", &m.inter_size},   {"num_layers", &m.num_layers},   {"max_seq_len", &m.max_seq_len},
+                              {"vocab_size", &m.vocab_size},   {"rotary_embedding_dim", &m.rotary_embedding_dim},
+                              {"max_position_embeddings", &m.max_position_embeddings}};
+        for (const Field &f : ints) *f.dst = (int)configNumber(text, f.key, *f.dst);
+        m.rotary_embedding_base = (float)configNumber(text, "rotary_embedding_base", m.rotary_embedding_base);
+        m.use_dynamic_ntk = configNumber(text, "use_dynamic_ntk", m.use_dynamic_ntk ? 1.0 : 0.0) != 0.0;
+        return m;
+    }
+};
+
+// helpers the model borrows for its whole life: created once per process (the reference lets them die with the factory call)
+struct ModelRuntime {
+    cublasHandle_t cublas = nullptr;
+    cublasLtHandle_t cublaslt = nullptr;
+    CublasWrapper *wrapper = nullptr;
+    BaseAllocator *allocator = nullptr;
+    cudaDeviceProp prop;
+
+    static ModelRuntime &get() {
+        static ModelRuntime rt;
+        if (!rt.wrapper) {
+            cublasCreate(&rt.cublas);
+            cublasLtCreate(&rt.cublaslt);
+            cublasSetMathMode(rt.cublas, CUBLAS_DEFAULT_MATH);
+            rt.wrapper = new CublasWrapper(rt.cublas, rt.cublaslt);
+            rt.wrapper->setFP32GemmConfig();
+            rt.allocator = new CudaAllocator;
+            cudaGetDeviceProperties(&rt.prop, 0);
+        }
+        return rt;
+    }
+};
+
 template <typename T> BaseModel *createModelWithName(const std::string &model_name) {
     LLM_CHECK_WITH_INFO(model_name == "llama", "Currently, only llama models are supported!");
-    const std::string cfg = readConfigText();
-    const int head_num = (int)configNumber(cfg, "head_num", 32), kv_head_num = (int)configNumber(cfg, "kv_head_num", 32);
-    const int head_size = (int)configNumber(cfg, "head_size", 128), inter_size = (int)configNumber(cfg, "inter_size", 11008);
-    const int num_layers = (int)configNumber(cfg, "num_layers", 32), max_seq_len = (int)configNumber(cfg, "max_seq_len", 64);
-    const int vocab_size = (int)configNumber(cfg, "vocab_size", 32000);
-    LlamaAttentionStaticParams attn_static_params = {};
-    attn_static_params.rotary_embedding_dim = (int)configNumber(cfg, "rotary_embedding_dim", 128);
-    attn_static_params.rotary_embedding_base = (float)configNumber(cfg, "rotary_embedding_base", 10000);
-    attn_static_params.max_position_embeddings = (int)configNumber(cfg, "max_position_embeddings", 4096);
-    attn_static_params.use_dynamic_ntk = configNumber(cfg, "use_dynamic_ntk", 0) != 0.0;
-
-    // process-lifetime helpers: the model keeps raw pointers to them
-    static cublasHandle_t cublas_handle = nullptr;
-    static cublasLtHandle_t cublaslt_handle = nullptr;
-    if (!cublas_handle) {
-        cublasCreate(&cublas_handle);
-        cublasLtCreate(&cublaslt_handle);
-        cublasSetMathMode(cublas_handle, CUBLAS_DEFAULT_MATH);
-    }
-    static CublasWrapper *cublas_wrapper = new CublasWrapper(cublas_handle, cublaslt_handle);
-    cublas_wrapper->setFP32GemmConfig();
-    static BaseAllocator *allocator = new CudaAllocator;
-    static cudaDeviceProp device_prop;
-    cudaGetDeviceProperties(&device_prop, 0);
-    return new LlamaModel<T>(head_num, kv_head_num, head_size, inter_size, num_layers, vocab_size, attn_static_params, max_seq_len, nullptr,
-                             cublas_wrapper, allocator, &device_prop);
+    const ModelShape m = ModelShape::fromJson(readConfigText());
+    LlamaAttentionStaticParams rope = {};
+    rope.rotary_embedding_dim = m.rotary_embedding_dim, rope.rotary_embedding_base = m.rotary_embedding_base;
+    rope.max_position_embeddings = m.max_position_embeddings, rope.use_dynamic_ntk = m.use_dynamic_ntk;
+    ModelRuntime &rt = ModelRuntime::get();
+    return new LlamaModel<T>(m.head_num, m.kv_head_num, m.head_size, m.inter_size, m.num_layers, m.vocab_size, rope, m.max_seq_len, nullptr, rt.wrapper,
+                             rt.allocator, &rt.prop);
 }
 
 template <typename T> BaseModel *createDummyLLMModel(const std::string &tokenizer_file) {

@@ -1,6 +1,3 @@
-// Drop-in for the reference's src/utils/params.h.
+// include path of the reference kept for its callers; the aliases live in b200_params.h
 #pragma once
-#include <string>
-#include <unordered_map>
-using MapStringToInt = std::unordered_map<std::string, int>;
-using MapStringToFloat = std::unordered_map<std::string, float>;
+#include "b200_params.h"

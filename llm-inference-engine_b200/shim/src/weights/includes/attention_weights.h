@@ -1,7 +1,3 @@
-// Drop-in for the reference's src/weights/includes/attention_weights.h.
+// include path of the reference kept for its callers; the type itself lives in b200_model_types.h
 #pragma once
-#include "base_weights.h"
-template <typename T> struct LlamaAttentionWeights {
-    BaseWeight<T> qkv;     // [h, (H + 2 Hkv) d] as [K,N]
-    BaseWeight<T> output;  // [H d, h] as [K,N]; .bias = o-proj bias
-};
+#include "b200_model_types.h"

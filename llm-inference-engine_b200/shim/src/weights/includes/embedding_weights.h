@@ -1,4 +1,3 @@
-// Drop-in for the reference's src/weights/includes/embedding_weights.h.
+// include path of the reference kept for its callers; the type itself lives in b200_model_types.h
 #pragma once
-#include "base_weights.h"
-template <typename T> struct EmbeddingWeight : public BaseWeight<T> {};
+#include "b200_model_types.h"

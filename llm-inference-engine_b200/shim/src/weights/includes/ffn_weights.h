@@ -1,9 +1,3 @@
-// Drop-in for the reference's src/weights/includes/ffn_weights.h.
+// include path of the reference kept for its callers; the type itself lives in b200_model_types.h
 #pragma once
-#include "base_weights.h"
-template <typename T> struct LlamaFFNWeights {
-    BaseWeight<T> gate;
-    BaseWeight<T> up;
-    BaseWeight<T> down;         // [I, h] as [K,N]
-    BaseWeight<T> gate_and_up;  // [h, 2 I] as [K,N]: gate columns then up columns
-};
+#include "b200_model_types.h"

@@ -1,8 +1,3 @@
-// Drop-in for the reference's src/weights/includes/weight.h.
+// include path of the reference kept for its callers; the type itself lives in b200_model_types.h
 #pragma once
-#include <string>
-class Weight {
-public:
-    virtual ~Weight() = default;
-    virtual void loadWeightsFromFile(const std::string &weight_path) = 0;
-};
+#include "b200_model_types.h"
