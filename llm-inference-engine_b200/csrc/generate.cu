@@ -8,8 +8,8 @@
 //                                                                                                                 (llama.cpp:219-257)
 //
 // Differences from the reference's loop, all on the host side: no per-kernel device synchronisation, no allocation inside the loop,
-// the sampled id never visits the host between steps (the next embedding reads it from device memory), and the finished flags are
-// polled every `check_every` steps instead of every step.  `step` follows the reference: the sampling seed of the first token is the
+// the sampled id never visits the host between steps (the next embedding reads it from device memory), and the recorded ids are
+// scanned for the end id every `check_every` steps instead of every step.  `step` follows the reference: the sampling seed of the first token is the
 // prompt length, then it is incremented once per token (llama.cpp:353,372) and is also the self decoder's 1-based position count.
 #include "common.cuh"
 
@@ -129,7 +129,7 @@ int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const in
     if (rc != B200_OK) return rc;
 
     // ---- the decode loop: the sampled ids stay on the device
-    std::vector<uint8_t> fin(batch);
+    std::vector<int> poll((size_t)batch * N);
     int produced = 1;
     for (int i = 1; i <= N; ++i) {
         // record token i-1 (column i-1 of out_dev[batch, N])
@@ -137,12 +137,18 @@ int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const in
             cudaSuccess)
             return cuda_status("generate record");
         if (i == N) break;
-        if (p->check_every > 0 && i % p->check_every == 0) {  // stop early once every sequence has produced end_id
-            if (cudaMemcpyAsync(fin.data(), finished, (size_t)batch, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        if (p->check_every > 0 && i % p->check_every == 0) {
+            // stop early once every sequence HAS produced end_id: decided from the recorded ids, not from the `finished` flags -- the
+            // sampling kernel keeps the reference's flag semantics (finished = "the token sampled just now is end_id"), which is not sticky
+            if (cudaMemcpyAsync(poll.data(), out_dev, poll.size() * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaStreamSynchronize(st) != cudaSuccess)
                 return cuda_status("generate poll");
             bool all = true;
-            for (int b = 0; b < batch; ++b) all = all && fin[b];
+            for (int b = 0; b < batch && all; ++b) {
+                bool hit = false;
+                for (int t = 0; t < i && !hit; ++t) hit = poll[(size_t)b * N + t] == p->end_id;
+                all = hit;
+            }
             if (all) break;
         }
         ++step;  // llama.cpp:372
