@@ -10,6 +10,7 @@ from util import b200, rounded, to_dev, to_np
 
 CFG = dict(hidden=256, head_num=2, kv_head_num=2, head_size=128, inter=384, layers=2, max_seq=48, eps=1e-6, base=10000.0)
 V, END = 500, 2
+GOLDEN = dict(model_seed=3, tail_seed=4, prompt_seed=11, batch=2, prompt_len=7, new_tokens=6)  # tests/golden/generate_golden.npz
 
 
 def tail_weights(seed, dtype):
@@ -51,6 +52,22 @@ def oracle_generate(model, emb, gamma, lm, prompt, n_new):
     return np.stack(out, axis=1), logits_all
 
 
+def golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generate_golden.npz"))
+
+
+def test_checker_loop_reproduces_the_golden_fixture():
+    """CPU only: the checker's generation loop against the committed fixture (tests/golden/make_generate_golden.py)."""
+    g = golden()
+    model = make_model(CFG, seed=GOLDEN["model_seed"], bias=False)
+    emb, gamma, lm = tail_weights(GOLDEN["tail_seed"], "f32")
+    ids, logits = oracle_generate(model, emb, gamma, lm, g["prompt"], GOLDEN["new_tokens"])
+    assert np.array_equal(ids, g["ids"])
+    assert np.allclose(logits[-1], g["last_logits"], rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.gpu
 def test_generate_greedy_matches_oracle_fp32():
     import torch
@@ -77,6 +94,8 @@ def test_generate_greedy_matches_oracle_fp32():
         if len(hit):
             expect[b, hit[0]:] = END
     assert np.array_equal(ids, expect), f"{ids} vs {expect}"
+    g = golden()  # same seeds as the fixture: the engine also reproduces the committed ids
+    assert np.array_equal(prompt, g["prompt"]) and np.array_equal(ref, g["ids"])
     assert np.array_equal(ngen, [(np.where(expect[b] == END)[0][0] if (expect[b] == END).any() else N) for b in range(B)])
 
 
