@@ -10,7 +10,7 @@ from oracle import oracle
 
 tp = importlib.import_module("llm-inference-engine_b200.tp")
 W = importlib.import_module("llm-inference-engine_b200.weights")
-SET = settings(max_examples=25, deadline=None)
+SET = settings(max_examples=25, deadline=None, derandomize=True, database=None)  # same examples on every run
 
 
 @SET
