@@ -21,4 +21,13 @@ template <typename T> inline std::string arr2str(const T *const &arr, size_t siz
     ss << ")";
     return ss.str();
 }
-template <typename T> inline std::string vec2str(const std::vector<T> &vec) { return arr2str(vec.data(), vec.size()); }
+// The reference's vec2str (string_utils.h:24-36) writes every element followed by ", " and then the LAST element once more:
+// {5, 7} prints as "(5, 7, 7)".  Kept, so that tensor descriptions and the key list of a failed TensorMap lookup read the same.
+template <typename T> inline std::string vec2str(const std::vector<T> &vec) {
+    std::ostringstream ss;
+    ss << "(";
+    for (size_t i = 0; i < vec.size(); ++i) ss << vec[i] << ", ";
+    if (!vec.empty()) ss << vec.back();
+    ss << ")";
+    return ss.str();
+}

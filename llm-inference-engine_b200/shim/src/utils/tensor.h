@@ -118,11 +118,17 @@ public:
     std::unordered_map<std::string, Tensor *> tensor_map;
 
     TensorMap() = default;
+    // brace-initialised maps are checked: an entry with size() == 0 (null data or empty shape) is an error (tensor.h:198-212)
     TensorMap(std::initializer_list<std::pair<std::string, Tensor *>> init) {
-        for (const auto &kv : init) insert(kv.first, kv.second);
+        for (const auto &kv : init) {
+            LLM_CHECK_WITH_INFO(isValid(kv.second), fmtstr("%s is not a valid tensor, skipping insert into TensorMap", kv.first.c_str()));
+            insert(kv.first, kv.second);
+        }
     }
-    explicit TensorMap(const std::unordered_map<std::string, Tensor *> &init) {
-        for (const auto &kv : init) insert(kv.first, kv.second);
+    // maps copied from an unordered_map silently drop such entries (tensor.h:214-220)
+    TensorMap(const std::unordered_map<std::string, Tensor *> &init) {
+        for (const auto &kv : init)
+            if (isValid(kv.second)) insert(kv.first, kv.second);
     }
     ~TensorMap() = default;  // does not own its tensors
 
@@ -130,12 +136,9 @@ public:
     inline bool isExist(const std::string &key) const { return tensor_map.find(key) != tensor_map.end(); }
     inline bool isValid(const Tensor *tensor) const { return tensor != nullptr && tensor->size() > 0; }
 
-    // like the reference (tensor.h:198-212,237-239): tensors with size() == 0 are rejected
-    inline void insert(const std::string &key, Tensor *value) {
-        LLM_CHECK_WITH_INFO(isValid(value), fmtstr("%s is not a valid tensor, skipping insert into TensorMap", key.c_str()));
-        tensor_map[key] = value;
-    }
-    inline void insert(std::pair<std::string, Tensor *> p) { insert(p.first, p.second); }
+    // as in the reference (tensor.h:237-243): (key, value) overwrites and does not validate; a pair keeps an existing entry
+    inline void insert(const std::string &key, Tensor *value) { tensor_map[key] = value; }
+    inline void insert(const std::pair<std::string, Tensor *> &kv) { tensor_map.insert(kv); }
 
     inline Tensor *at(const std::string &key) const {
         LLM_CHECK_WITH_INFO(isExist(key), fmtstr("Cannot find a tensor of name %s in the tensor map (keys: %s)", key.c_str(),
@@ -152,7 +155,8 @@ public:
 
     std::string toString() const {
         std::string s = "{";
-        for (const auto &k : keys()) s += k + ": " + at(k)->toString() + ", ";
+        const std::vector<std::string> names = keys();
+        for (size_t i = 0; i < names.size(); ++i) s += names[i] + ": " + at(names[i])->toString() + (i + 1 < names.size() ? ", " : "");
         return s + "}";
     }
 };
