@@ -133,7 +133,7 @@ public:
             if (l > 0) {
                 ids[l] = l;
                 id_tensors.push_back(new TensorWrapper<int>(Device::CPU, getTensorType<int>(), std::vector<int>{1}, &ids[l]));
-                context_attention_inputs.insert({"layer_id", id_tensors.back()});
+                context_attention_inputs.insert("layer_id", id_tensors.back());  // (key, value): overwrites -- a pair would keep layer 0 (tensor.h:241-243)
             }
             Tensor *x = context_attention_inputs.at("attention_input");
             launchRMSNorm(x->wrap<T>(), decoder_residual, &layer_weights->at(l)->attention_norm_weight, rmsnorm_eps);
@@ -146,7 +146,7 @@ public:
             attention_dynamic_params->is_context = true;  // reference context_decoder.cpp:172
             ffn->forward(&ffn_inputs, &ffn_outputs, &layer_weights->at(l)->ffn_weight, attention_dynamic_params);
             launchAddResidual(decoder_residual, decoder_output->wrap<T>());
-            context_attention_inputs.insert({"attention_input", decoder_output});
+            context_attention_inputs.insert("attention_input", decoder_output);
         }
         for (TensorWrapper<int> *t : id_tensors) delete t;
     }

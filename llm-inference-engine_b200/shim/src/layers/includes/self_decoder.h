@@ -170,7 +170,7 @@ public:
             if (l > 0) {
                 ids[l] = l;
                 id_tensors.push_back(new TensorWrapper<int>(Device::CPU, getTensorType<int>(), std::vector<int>{1}, &ids[l]));
-                self_attention_inputs.insert({"layer_id", id_tensors.back()});
+                self_attention_inputs.insert("layer_id", id_tensors.back());  // (key, value): overwrites -- a pair would keep layer 0 (tensor.h:241-243)
             }
             Tensor *x = self_attention_inputs.at("attention_input");
             launchRMSNorm(x->wrap<T>(), decoder_residual, &layer_weights->at(l)->attention_norm_weight, rmsnorm_eps);
@@ -181,7 +181,7 @@ public:
             TensorMap ffn_outputs{{"ffn_output", decoder_output}};
             ffn->forward(&ffn_inputs, &ffn_outputs, &layer_weights->at(l)->ffn_weight, dynamic_params);
             launchAddResidual(decoder_residual, decoder_output->wrap<T>(), true);
-            self_attention_inputs.insert({"attention_input", decoder_output});
+            self_attention_inputs.insert("attention_input", decoder_output);
         }
         for (TensorWrapper<int> *t : id_tensors) delete t;  // views of ids[]: nothing else is freed (TensorMap does not own)
     }
