@@ -33,3 +33,40 @@ for f in "$TREE"/examples/cpp/*.cpp; do build_one "$f" "$(basename "$f" .cpp)" &
 for p in "${pids[@]}"; do wait "$p"; done
 ls "$OUT"/*.build.log > /dev/null 2>&1 && { echo "some reference programs did not compile against the shim"; exit 1; }
 echo "all reference programs compiled against the shim -> $OUT"
+
+# ---- second configuration: the reference's OWN layer sources (src/layers/*.cpp + src/layers/includes/*.h, unmodified) on top of the shim's
+#      launchers.  north_star: "keeps the repo's C++ launch-function ... API surface so it drops into src/layers ... unchanged".  In this tree
+#      src/layers points at the reference, src/{kernels,utils,weights,memory,models} at the shim; the five layer examples are linked against
+#      the resulting library.  Output: shim/_ref_programs/ref_layers.d/{libref_layers_on_b200.so,<example>}
+TREE2=$(mktemp -d /tmp/b200shim_tree2.XXXXXX)
+trap 'rm -rf "$TREE" "$TREE2"' EXIT
+OUT2=$OUT/ref_layers.d
+rm -rf "$OUT2"
+mkdir -p "$TREE2/src/layers/includes" "$TREE2/examples/cpp" "$TREE2/obj" "$OUT2"
+for d in kernels utils weights memory models; do ln -s "$HERE/src/$d" "$TREE2/src/$d"; done
+for f in "$REF"/src/layers/*.cpp; do ln -s "$f" "$TREE2/src/layers/$(basename "$f")"; done
+for f in "$REF"/src/layers/includes/*.h; do ln -s "$f" "$TREE2/src/layers/includes/$(basename "$f")"; done
+for f in "$REF"/examples/cpp/*.cpp; do ln -s "$f" "$TREE2/examples/cpp/$(basename "$f")"; done
+pids=()
+for f in "$TREE2"/src/layers/*.cpp; do
+    n=$(basename "$f" .cpp)
+    ( "$NVCC" -std=c++17 -O2 -w -x cu -gencode arch=compute_100a,code=sm_100a -I"$ROOT/include" -I"$TREE2" -Xcompiler -fPIC -c "$f" -o "$TREE2/obj/$n.o" \
+        > "$OUT2/$n.build.log" 2>&1 && rm -f "$OUT2/$n.build.log" ) & pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+if ! ls "$OUT2"/*.build.log > /dev/null 2>&1; then
+    "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT2/libref_layers_on_b200.so" "$TREE2"/obj/*.o -L"$LIBDIR" -lb200llm -lcublas -lcublasLt \
+        -Xlinker -rpath -Xlinker '$ORIGIN/../../../lib' > "$OUT2/libref_layers_on_b200.build.log" 2>&1 && rm -f "$OUT2/libref_layers_on_b200.build.log"
+fi
+if ! ls "$OUT2"/*.build.log > /dev/null 2>&1; then
+    pids=()
+    for f in "$TREE2"/examples/cpp/*.cpp; do
+        n=$(basename "$f" .cpp)
+        ( "$NVCC" -std=c++17 -O2 -w -x cu -gencode arch=compute_100a,code=sm_100a -I"$ROOT/include" -I"$TREE2" "$f" -o "$OUT2/$n" -L"$OUT2" -lref_layers_on_b200 \
+            -L"$LIBDIR" -lb200llm -lcublas -lcublasLt -Xlinker -rpath -Xlinker '$ORIGIN' -Xlinker -rpath -Xlinker '$ORIGIN/../../../lib' \
+            > "$OUT2/$n.build.log" 2>&1 && rm -f "$OUT2/$n.build.log" ) & pids+=($!)
+    done
+    for p in "${pids[@]}"; do wait "$p"; done
+fi
+ls "$OUT2"/*.build.log > /dev/null 2>&1 && { echo "the reference's layer sources did not build on the shim's launchers (see $OUT2/*.build.log)"; exit 1; }
+echo "the reference's own src/layers/*.cpp + layer examples built on the shim's launchers -> $OUT2"

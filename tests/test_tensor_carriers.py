@@ -30,3 +30,25 @@ def test_golden_is_what_the_reference_headers_print():
     if not os.path.exists(REF):
         pytest.skip("oracle/_ref/tensor_ref only exists where /root/reference does")
     assert run(REF) == open(GOLDEN).read().splitlines()
+
+
+DEBUG = os.path.join(ROOT, "llm-inference-engine_b200", "shim", "_own_programs", "debug_utils_shim")
+
+
+def test_save_tensor_and_print_tensor(tmp_path):
+    """saveTensor / print_tensor of the shim (reference: src/utils/debug_utils.h:17-119, output_utils.h:9-33) on host tensors: file names,
+    the first-three-layers rule, byte counts per rank, and the two printed lines per tensor."""
+    import numpy as np
+
+    if not os.path.exists(DEBUG):
+        pytest.skip("shim/_own_programs/debug_utils_shim not built (run __graft_entry__.build())")
+    env = dict(os.environ, LLM_SAVE_TENSOR_DIR=str(tmp_path))
+    out = subprocess.run([DEBUG], stdout=subprocess.PIPE, check=True, timeout=60, env=env).stdout.decode().splitlines()
+    assert sorted(os.listdir(tmp_path)) == ["0_rank3.bin", "1_rank4.bin", "rank1.bin", "rank2.bin"]
+    want = (0.25 * np.arange(24)).astype(np.float32)
+    for name in ("rank2.bin", "0_rank3.bin", "1_rank4.bin"):
+        assert np.array_equal(np.fromfile(tmp_path / name, dtype=np.float32), want)
+    assert os.path.getsize(tmp_path / "rank1.bin") == 0
+    assert out == ["Saving intermediate tensor in rank2.bin", "Saving intermediate tensor in rank3.bin", "Saving intermediate tensor in rank4.bin",
+                   "Saving intermediate tensor in rank1.bin",
+                   "number of dimensions: 3", "2 3 4 ", "number of dimensions: 4", "1 2 3 4 ", "number of dimensions: 2", "11008 4096 "]
