@@ -48,6 +48,10 @@ template <typename T> inline int b200DType() {
 
 template <typename T> class TensorWrapper;
 
+// Untyped base of every tensor handed to a launcher or stored in a TensorMap: where the data lives, what the elements are, and the extents.
+// It carries no data pointer; callers down-cast with wrap<T>() (an unchecked static_cast, as in the reference -- the dtype field is what the
+// launchers trust).  size() multiplies the extents in int arithmetic (so a tensor is limited to 2^31-1 elements, which the [L,B,Hkv,S,d]
+// cache of the BASELINE configs respects per tensor) and is 0 for an empty shape.
 class Tensor {
 public:
     Device device;
@@ -86,6 +90,9 @@ public:
     }
 };
 
+// Typed view: Tensor + a borrowed pointer.  The constructor with data refuses a dtype that does not match T; size() is 0 while the pointer is
+// null, which is how TensorMap recognises a tensor that was declared but never given storage.  getVal() reads host tensors only (step,
+// layer_id): asking a device tensor for a value throws instead of dereferencing device memory on the host.
 template <typename T> class TensorWrapper : public Tensor {
 public:
     T *data = nullptr;
@@ -113,6 +120,8 @@ public:
     }
 };
 
+// String-keyed bundle of tensors: the argument convention of every layer's forward().  Keys are the contract (SURVEY.md 8b lists them per
+// layer); a lookup of a missing key throws and names the keys that are present.
 class TensorMap {
 public:
     std::unordered_map<std::string, Tensor *> tensor_map;
