@@ -30,6 +30,7 @@ NEEDS_EXTERNAL_FILE = {"context_decoder_example": "/home/llama2-7b-tokenizer.bin
                        "user_entry": "/home/llamaweight/model.norm.weight.bin"}  # (and user_entry is an interactive REPL)
 
 
+CMAKE_DIR = os.path.join(SHIM_DIR, "cmake.d")  # the reference's own CMake build with src/ replaced by the shim (shim/build_with_reference_cmake.sh)
 REF_LAYERS_DIR = os.path.join(SHIM_DIR, "ref_layers.d")
 REF_LAYER_EXAMPLES = ["context_attention_example", "context_decoder_example", "ffn_example", "self_attention_example", "self_decoder_example"]
 REF_LAYERS_VERIFIED_ON_GPU = False  # flip once tests/test_reference_programs.py has run on a B200 with this configuration
@@ -62,6 +63,11 @@ def test_reference_programs_were_built_when_the_reference_is_present():
     names = programs()
     assert len(names) == 22, f"expected the reference's 16 unit tests + 5 examples + user_entry compiled against the shim, got {len(names)}: {names}"
     assert not [f for f in os.listdir(SHIM_DIR) if f.endswith(".build.log")]
+    # the reference's own CMake build (its root / tests / examples CMakeLists.txt, unmodified) with src/ replaced by the shim: every target
+    # name its executables link (rmsnorm, linear, ..., llama_self_decoder) is defined by shim/src/CMakeLists.txt
+    import shutil
+    if shutil.which("cmake"):
+        assert sorted(os.listdir(CMAKE_DIR)) == [n for n in names if n != "user_entry"], sorted(os.listdir(CMAKE_DIR))
     # second configuration: the reference's own src/layers/*.cpp on the shim's launchers, with its five layer examples
     assert sorted(os.listdir(REF_LAYERS_DIR)) == sorted(REF_LAYER_EXAMPLES + ["libref_layers_on_b200.so"])
 
@@ -91,6 +97,20 @@ def test_reference_program_runs_against_the_shim(name):
                   f"shim result recorded, not asserted")
     else:
         assert not failed or ref_failed, f"{name}: failure lines with the shim but not with the reference: {failed[:3]}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["test_rmsnorm", "test_add_residual", "test_silu_and_mul", "ffn_example"])
+def test_reference_cmake_build_runs(name):
+    """Executables produced by the reference's own CMake build with src/ replaced by the shim (same sources and headers as the nvcc builds
+    above, but the reference's flags, its per-library link lines and, for the examples, the host C++ compiler)."""
+    exe = os.path.join(CMAKE_DIR, name)
+    if not os.path.exists(exe):
+        pytest.skip("shim/_ref_programs/cmake.d not built (needs /root/reference and cmake at build time)")
+    rc, out = run(exe, timeout=120)
+    assert rc == 0, f"{name} (reference CMake build on the shim) exited with {rc}:\n{out[-3000:]}"
+    if name in PASS_LINE:
+        assert PASS_LINE[name] in out and not [l for l in verdict_lines(out) if re.search(r"fail|wrong", l, re.I)], out[-3000:]
 
 
 @pytest.mark.gpu
