@@ -606,6 +606,9 @@ def main():
 
             v, sample, cores = cpu_reference_tokens_per_s(cfg, B, ctx, oracle.max_threads(), budget_s=15.0)
             cpu = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
+            # the same port on ONE thread: the reference's own CPU loops (tests/unit_tests/*.cu) are single-threaded (SURVEY.md 8d i)
+            v1, sample1, _ = cpu_reference_tokens_per_s(cfg, B, ctx, 1, budget_s=3.0)
+            cpu["single_thread"] = {"value": v1, "unit": "tokens/s", "cores": 1, "sample": sample1}
         line = {
             "metric": "decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
