@@ -100,3 +100,39 @@ def decode_step_tp(layers, hidden, attn_block, ffn_block, fold, all_reduce):
         all_reduce(z)
         pending = z
     return fold(hidden, pending)
+
+
+# ---------------------------------------------------------------- vocab-sharded LM head ("LM head vocab-sharded + allgather of
+# per-rank top-k").  Rank r owns rows [r*V/P, (r+1)*V/P) of lm_head [V, h]: it computes its slice of the logits, takes a LOCAL top-k, adds its
+# row offset to the ids and all-gathers k (value, id) pairs -- 2*k*B numbers per rank instead of V/P logits.  The global top-k is the top-k of
+# the P*k candidates under the same total order the single-GPU kernel uses (value descending, ties to the LOWER id), so ids and values are
+# bit-identical to the un-sharded result: every global winner is a local winner of the rank that owns it.
+def vocab_range(vocab, rank, world):
+    if vocab % world:
+        raise ValueError(f"tensor-parallel degree {world} must divide the vocabulary {vocab}")
+    n = vocab // world
+    return rank * n, (rank + 1) * n
+
+
+def shard_lm_head_rows(lm_head, rank, world):
+    """Rows of lm_head [V, h] owned by `rank`."""
+    lo, hi = vocab_range(lm_head.shape[0], rank, world)
+    return _contig(lm_head[lo:hi])
+
+
+def merge_topk(vals, ids, k):
+    """vals, ids: numpy [P, B, k'] -- every rank's local top-k' (ids already GLOBAL).  Returns (ids [B, k] int32, vals [B, k] float32): the k
+    best candidates per row, value descending, ties to the lower id."""
+    import numpy as np
+
+    vals, ids = np.asarray(vals, dtype=np.float32), np.asarray(ids, dtype=np.int64)
+    P, B, kk = vals.shape
+    if k > P * kk:
+        raise ValueError(f"cannot take {k} winners out of {P} x {kk} candidates")
+    v = np.transpose(vals, (1, 0, 2)).reshape(B, P * kk)
+    i = np.transpose(ids, (1, 0, 2)).reshape(B, P * kk)
+    out_i, out_v = np.empty((B, k), np.int32), np.empty((B, k), np.float32)
+    for b in range(B):
+        order = np.lexsort((i[b], -v[b].astype(np.float64)))[:k]  # primary key: value descending; secondary: id ascending
+        out_i[b], out_v[b] = i[b][order], v[b][order]
+    return out_i, out_v

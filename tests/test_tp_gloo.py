@@ -146,6 +146,77 @@ def test_two_rank_decode_equals_unsharded_oracle():
     np.testing.assert_allclose(gv, vc, rtol=2e-5, atol=2e-5)
 
 
+VOCAB, TOPK = 1000, 5
+
+
+def lm_head_inputs():
+    rng = np.random.default_rng(21)
+    hidden = rng.standard_normal((BATCH, CFG["hidden"])).astype(np.float32)
+    lm = (rng.integers(-3, 4, size=(VOCAB, CFG["hidden"])) / 8.0).astype(np.float32)  # few distinct values: exact sums, many TIED logits
+    hidden = np.round(hidden * 4) / 4
+    # identical rows on different ranks, aligned with a token's hidden state so that they ARE the largest logits of that token: an exact tie
+    # for first place between ids (10, 700) for token 0, and across the shard boundary (499, 501) for token 1 -- the lower id must come first
+    lm[10] = lm[700] = 0.5 * np.sign(hidden[0])
+    lm[499] = lm[501] = 0.375 * np.sign(hidden[1])
+    return hidden, lm
+
+
+def lm_head_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle
+
+    tp = importlib.import_module("llm-inference-engine_b200.tp")
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hidden, lm = lm_head_inputs()
+        lo, _ = tp.vocab_range(VOCAB, rank, world)
+        logits = oracle.linear(hidden, tp.shard_lm_head_rows(lm, rank, world), "nk")  # [B, V/P]
+        ids, vals = oracle.topk(logits, TOPK)
+        pack = torch.from_numpy(np.stack([vals.astype(np.float32), (ids + lo).astype(np.float32)]))  # ids < 2^24: exact in fp32
+        gathered = [torch.empty_like(pack) for _ in range(world)]
+        dist.all_gather(gathered, pack)
+        g = np.stack([t.numpy() for t in gathered])  # [P, 2, B, k]
+        ret[rank] = tp.merge_topk(g[:, 0], g[:, 1].astype(np.int64), TOPK)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_vocab_sharded_lm_head_topk_is_bit_identical():
+    """Vocab-sharded LM head (SURVEY.md 8e refinement): per-rank logits slice -> local top-k -> all-gather of k (value, id) pairs ->
+    merge reproduces the un-sharded top-k ids AND values bit for bit, ties included (world size 2, gloo)."""
+    import torch.multiprocessing as mp
+
+    from oracle import oracle
+
+    tp = importlib.import_module("llm-inference-engine_b200.tp")
+    world, port = 2, free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=lm_head_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
+    hidden, lm = lm_head_inputs()
+    logits = oracle.linear(hidden, lm, "nk")
+    want_ids, want_vals = oracle.topk(logits, TOPK)
+    assert want_ids[0, :2].tolist() == [10, 700] and want_vals[0, 0] == want_vals[0, 1]  # the fixture does contain the ties it promises
+    assert want_ids[1, :2].tolist() == [499, 501] and want_vals[1, 0] == want_vals[1, 1]
+    for r in range(world):
+        ids, vals = ret[r]
+        assert np.array_equal(ids, want_ids) and np.array_equal(vals, want_vals), f"rank {r}: {ids} {vals} vs {want_ids} {want_vals}"
+    # the merge's tie rule on its own: equal values, the lower id first, whichever rank it came from
+    i, v = tp.merge_topk(np.array([[[2.0, 1.0]], [[2.0, 2.0]]]), np.array([[[900, 5]], [[3, 40]]]), 3)
+    assert i.tolist() == [[3, 40, 900]] and v.tolist() == [[2.0, 2.0, 2.0]]
+    with pytest.raises(ValueError):
+        tp.vocab_range(1001, 0, 2)
+
+
 @pytest.mark.gpu
 def test_two_gpu_engine_matches_unsharded_oracle():
     """Needs >= 2 GPUs (gpurun --gpus 2): the sharded fused engine + NCCL all-reduce against the un-sharded oracle."""
