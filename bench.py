@@ -18,8 +18,9 @@ row-sharded O / down, head-sharded KV cache, one NCCL all-reduce per attention a
 `cpu_baseline`: the CPU restatement of the reference's path (oracle/, "port": the reference has no CPU inference path of its own,
            SURVEY.md 8d) with OpenMP on the host cores, bounded sample; `.single_thread` the same on one thread; `.reference_loops` the
            reference's own unit-test CPU loops (oracle/_ref/libref.so) composed into the layer.
---impl reference: those reference loops (kind "reference", single-threaded as written) when oracle/_ref/libref.so travelled, with the
-           all-cores port beside them; the port alone otherwise.
+--impl reference: those reference loops (kind "reference"; written single-threaded, so every linear's weight rows are cut into one block
+           per host thread, each through the same unmodified loop) when oracle/_ref/libref.so travelled, with the single-thread figure and
+           the all-cores port beside them; the port alone otherwise.
 """
 import argparse
 import importlib
@@ -208,7 +209,39 @@ def cpu_reference_tokens_per_s(cfg, batch, ctx, threads, budget_s=20.0):
     return batch / t_step, sample, threads
 
 
-def reference_loops_decoder_layer(ref, x, w, k_cache, v_cache, cfg, step):
+def reference_cpulinear(ref, a, wt, threads=1):
+    """y[M,N] = a[M,K] . wt[N,K]^T through the reference's own CPUlinear (test_linear.cu:17-33; it accumulates, so y starts at zero).  The loop
+    itself is single-threaded; with threads > 1 the weight ROWS are cut into contiguous blocks and each block is handed to the same unmodified
+    loop on its own host thread (ctypes releases the GIL): every output element is still produced by the reference's arithmetic, in its order."""
+    import ctypes as C
+
+    import numpy as np
+
+    M, K = a.shape
+    N = wt.shape[0]
+
+    def p(t):
+        return t.ctypes.data_as(C.c_void_p)
+
+    if threads <= 1 or N < 2 * threads:
+        y = np.zeros((M, N), dtype=np.float32)
+        ref.refcpu_linear(p(a), p(wt), p(y), M, K, N)
+        return y
+    from concurrent.futures import ThreadPoolExecutor
+
+    bounds = [N * t // threads for t in range(threads + 1)]
+    parts = [np.zeros((M, bounds[t + 1] - bounds[t]), dtype=np.float32) for t in range(threads)]
+
+    def run(t):
+        blk = wt[bounds[t]:bounds[t + 1]]  # a view of contiguous rows
+        ref.refcpu_linear(p(a), p(blk), p(parts[t]), M, K, blk.shape[0])
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(run, range(threads)))
+    return np.ascontiguousarray(np.concatenate(parts, axis=1))
+
+
+def reference_loops_decoder_layer(ref, x, w, k_cache, v_cache, cfg, step, threads=1):
     """One decode layer on x[B,h] (fp32, returns the new hidden state) out of the reference's OWN single-threaded unit-test CPU loops,
     compiled unmodified into oracle/_ref/libref.so (`ref`): CPUlinear test_linear.cu:17-33, CPUfusedresidandRMSNorm test_rmsnorm.cu:10-27,
     CPUresidual test_add_residual.cu:10-21, CPUSwiGLU test_silu_and_mul.cu:16-32, in the order of self_decoder.cpp:69-119.  RoPE and the
@@ -227,10 +260,8 @@ def reference_loops_decoder_layer(ref, x, w, k_cache, v_cache, cfg, step):
     def p(a):
         return a.ctypes.data_as(C.c_void_p)
 
-    def linear(a, wt):  # CPUlinear: y[M,N] += a[M,K] . wt[N,K]^T (it accumulates: y starts at zero)
-        y = np.zeros((a.shape[0], wt.shape[0]), dtype=np.float32)
-        ref.refcpu_linear(p(a), p(wt), p(y), a.shape[0], a.shape[1], wt.shape[0])
-        return y
+    def linear(a, wt):
+        return reference_cpulinear(ref, a, wt, threads)
 
     x = np.ascontiguousarray(x, dtype=np.float32).copy()
     res = x.copy()
@@ -255,16 +286,17 @@ class ReferenceLoopsSample:
     where oracle/_ref/libref.so did not travel / does not load.  measure() times ONE decoder layer and the LM head once and returns the
     extrapolated seconds per decode step."""
 
-    def __init__(self, cfg, batch, ctx):
+    def __init__(self, cfg, batch, ctx, threads=1):
         import numpy as np
 
         from oracle import oracle
 
         self.ref = oracle.ref_lib()
         self.available = self.ref is not None and hasattr(self.ref, "refcpu_linear")
+        self.threads = max(int(threads), 1)
         if not self.available:
             return
-        oracle.set_threads(1)
+        oracle.set_threads(self.threads)
         rng = np.random.default_rng(1)
         h, H, Hkv, d, I, V = (cfg[k] for k in ("hidden", "head_num", "kv_head_num", "head_size", "inter", "vocab"))
         S = ctx + 8
@@ -287,12 +319,10 @@ class ReferenceLoopsSample:
         import numpy as np
 
         t0 = time.perf_counter()
-        reference_loops_decoder_layer(self.ref, self.x, self.w, self.kc, self.vc, self.ocfg, self.ctx + 1)
+        reference_loops_decoder_layer(self.ref, self.x, self.w, self.kc, self.vc, self.ocfg, self.ctx + 1, self.threads)
         t_layer = time.perf_counter() - t0
-        y = np.zeros((self.batch, self.V), dtype=np.float32)
         t0 = time.perf_counter()
-        self.ref.refcpu_linear(self.x.ctypes.data_as(C.c_void_p), self.lm.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), self.batch,
-                               self.x.shape[1], self.V)
+        reference_cpulinear(self.ref, self.x, self.lm, self.threads)
         t_lm = time.perf_counter() - t0
         self.t_layer += t_layer
         self.t_lm += t_lm
@@ -300,22 +330,24 @@ class ReferenceLoopsSample:
         return self.cfg["layers"] * t_layer + t_lm
 
     def describe(self):
-        return (f"the reference's own unit-test CPU loops (oracle/_ref/libref.so, single-threaded as written), 1 of {self.cfg['layers']} decoder "
+        how = ("single-threaded as written" if self.threads == 1 else
+               f"CPUlinear's weight rows cut into {self.threads} blocks, one unmodified loop per host thread")
+        return (f"the reference's own unit-test CPU loops (oracle/_ref/libref.so, {how}), 1 of {self.cfg['layers']} decoder "
                 f"layers ({self.reps} reps, {self.t_layer / max(self.reps, 1) * 1e3:.1f} ms each) + LM head "
                 f"({self.t_lm / max(self.reps, 1) * 1e3:.1f} ms), fp32, batch {self.batch}, ctx {self.ctx}, extrapolated to {self.cfg['layers']} layers; "
                 f"RoPE + decode attention from the C oracle")
 
 
-def reference_loops_tokens_per_s(cfg, batch, ctx, reps=2):
+def reference_loops_tokens_per_s(cfg, batch, ctx, reps=2, threads=1):
     """cpu_baseline.reference_loops of the default arm: a bounded sample (one page-in pass + `reps` timed passes) or None."""
-    smp = ReferenceLoopsSample(cfg, batch, ctx)
+    smp = ReferenceLoopsSample(cfg, batch, ctx, threads)
     if not smp.available:
         return None
     smp.measure()  # page in
     smp.t_layer = smp.t_lm = 0.0
     smp.reps = 0
     t = sum(smp.measure() for _ in range(reps)) / reps
-    return {"value": batch / t, "unit": "tokens/s", "cores": 1, "kind": "reference", "sample": smp.describe()}
+    return {"value": batch / t, "unit": "tokens/s", "cores": smp.threads, "kind": "reference", "sample": smp.describe()}
 
 
 def run_reference(args, cfg, rank):
@@ -331,7 +363,7 @@ def run_reference(args, cfg, rank):
     threads = oracle.max_threads()
     t_all = time.perf_counter()
     n = args.warmup + args.steps
-    smp = ReferenceLoopsSample(cfg, args.batch, args.ctx)
+    smp = ReferenceLoopsSample(cfg, args.batch, args.ctx, threads)
     vals = []
     if smp.available:
         for i in range(n):
@@ -345,7 +377,8 @@ def run_reference(args, cfg, rank):
                 break
         value = sum(vals) / len(vals)
         port_v, port_sample, port_cores = cpu_reference_tokens_per_s(cfg, args.batch, args.ctx, threads, budget_s=8.0)
-        cpu = {"value": value, "unit": "tokens/s", "cores": 1, "kind": "reference", "sample": smp.describe(),
+        single = reference_loops_tokens_per_s(cfg, args.batch, args.ctx, reps=1, threads=1)
+        cpu = {"value": value, "unit": "tokens/s", "cores": smp.threads, "kind": "reference", "sample": smp.describe(), "single_thread": single,
                "port_all_cores": {"value": port_v, "unit": "tokens/s", "cores": port_cores, "kind": "port", "sample": port_sample}}
         note = ("the reference has no CPU inference path (its CUDA path is fp32/sm_86 single-GPU, SURVEY.md 8d); this arm times the CPU loops of "
                 "its own unit tests (oracle/_ref/libref.so) composed into the decoder layer; cpu_baseline.port_all_cores is the C restatement "

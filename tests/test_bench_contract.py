@@ -21,7 +21,8 @@ def test_reference_arm_prints_the_contract_line():
     cpu = d["cpu_baseline"]
     assert cpu["kind"] in ("reference", "port") and cpu["cores"] >= 1 and cpu["value"] == d["value"] and cpu["sample"]
     if cpu["kind"] == "reference":  # the reference's own unit-test loops were loadable: the all-cores port is reported beside them
-        assert cpu["cores"] == 1 and cpu["port_all_cores"]["kind"] == "port" and cpu["port_all_cores"]["value"] > cpu["value"]
+        assert cpu["port_all_cores"]["kind"] == "port" and cpu["port_all_cores"]["value"] > 0
+        assert cpu["single_thread"]["cores"] == 1 and cpu["single_thread"]["kind"] == "reference"
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
