@@ -371,7 +371,7 @@ typedef struct {
     int top_k;               /* 1..B200_TOPK_MAX_K; 1 = greedy                                               */
     int end_id;
     int max_new_tokens;      /* tokens to produce per sequence, including the one sampled from the prompt    */
-    int check_every;         /* poll the finished flags every this many steps (0: always run max_new_tokens) */
+    int check_every;         /* every this many steps, stop if every sequence has produced end_id (0: always run max_new_tokens) */
 } b200_generate_params_t;
 
 /* Device workspace b200_generate needs for this batch / prompt length (0 on a bad argument: see b200_last_error_string). */
