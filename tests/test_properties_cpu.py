@@ -119,3 +119,23 @@ def test_quantisers_round_trip_within_their_step(n, kblocks, seed):
     lo, hi = np.repeat(grp.min(axis=2), 128, axis=1), np.repeat(grp.max(axis=2), 128, axis=1)
     inside = (w >= lo + step) & (w <= hi - step)
     assert np.all(err[inside] <= 0.5 * step[inside] * 1.01 + 1e-6)
+
+
+@SET
+@given(st.sampled_from([1, 2, 4, 8]), st.integers(1, 3), st.integers(1, 6), st.integers(1, 40), st.integers(0, 2 ** 31 - 1))
+def test_vocab_sharded_topk_merge_equals_the_global_topk(world, rows, k, per_rank, seed):
+    """tp.merge_topk (vocab-sharded LM head): local top-k per vocabulary shard + merge == top-k of the whole row, ids and
+    values bit for bit, with heavily tied logits (the tie rule 'lower id first' must survive the cut into shards)."""
+    k = min(k, per_rank)
+    vocab = world * per_rank
+    rng = np.random.default_rng(seed)
+    logits = rng.integers(-3, 4, size=(rows, vocab)).astype(np.float32)
+    want_ids, want_vals = oracle.topk(logits, k)
+    vals, ids = [], []
+    for r in range(world):
+        lo, hi = tp.vocab_range(vocab, r, world)
+        i, v = oracle.topk(np.ascontiguousarray(logits[:, lo:hi]), k)
+        ids.append(i.astype(np.int64) + lo)
+        vals.append(v)
+    got_ids, got_vals = tp.merge_topk(np.stack(vals), np.stack(ids), k)
+    assert np.array_equal(got_ids, want_ids) and np.array_equal(got_vals, want_vals)
