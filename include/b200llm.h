@@ -299,14 +299,10 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
                       int step, int layer_begin, int layer_end, b200_stream_t stream);
 
 /* Diagnostic (roofline measurement): exactly the weight-streaming launches of b200_decoder_step -- the QKV / O / gate_up / down linears
- * of every layer (reference src/layers/self_attention.cpp:79-86,131-138, src/layers/ffn.cpp:105-139), chained or separate as the step
- * would run them -- without attention and without the final fold.  Call after at least one real step; outputs are meaningless.
+ * of every layer (reference src/layers/self_attention.cpp:79-86,131-138, src/layers/ffn.cpp:105-139), as the step
+ * runs them -- without attention and without the final fold.  Call after at least one real step; outputs are meaningless.
  * *n_launches (optional) receives the number of kernels launched. */
 int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b200_stream_t stream);
-
-/* Diagnostics: hand the engine a device buffer into which the chained GEMV kernels write per-CTA, per-phase %globaltimer stamps
- * (layout [num_layers][SMs][4][8] uint64); ptr == NULL switches tracing off.  Returns the number of bytes such a buffer needs. */
-size_t b200_decoder_debug_trace(b200_decoder_t *dec, void *ptr, size_t bytes);
 
 /* Prefill ("context") pass over layers [layer_begin, layer_end): LlamaContextDecoder<T>::forward
  * (src/layers/context_decoder.cpp:58-199): padding offsets -> per layer RMSNorm -> QKV linear -> split/transpose/RoPE ->

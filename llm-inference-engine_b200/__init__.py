@@ -90,7 +90,6 @@ SIGNATURES = {
     "b200_decoder_set_scratch": [_P, _P, _SZ],
     "b200_decoder_step": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200_decoder_linears_only": [_P, _I, C.POINTER(C.c_int), _P],
-    "b200_decoder_debug_trace": [_P, _P, _SZ],
     "b200_decoder_prefill_scratch_bytes": [_P, _I, _I, _I],
     "b200_decoder_prefill": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _SZ, _I, _I, _P],
     "b200_decoder_attn_block": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P],
@@ -106,7 +105,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_workspace_default_bytes": _SZ, "b200_decoder_create": _P,
              "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ, "b200_decoder_prefill_scratch_bytes": _SZ,
-             "b200_decoder_tp_buffer_bytes": _SZ, "b200_decoder_debug_trace": _SZ, "b200_generate_workspace_bytes": _SZ}
+             "b200_decoder_tp_buffer_bytes": _SZ, "b200_generate_workspace_bytes": _SZ}
 
 _lib = None
 
@@ -406,19 +405,6 @@ class Decoder:
         layer_end = self.cfg.num_layers if layer_end is None else layer_end
         check(lib().b200_decoder_step(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], step, layer_begin, layer_end,
                                       stream()))
-
-    def debug_trace(self, enable=True):
-        """Diagnostics: returns a uint64 tensor [layers, SMs, 4, 8] the chained GEMV kernels fill with %globaltimer stamps."""
-        import torch
-
-        if not enable:
-            lib().b200_decoder_debug_trace(self.handle, None, 0)
-            self._trace = None
-            return None
-        nbytes = lib().b200_decoder_debug_trace(self.handle, None, 0)
-        self._trace = torch.zeros(nbytes // 8, dtype=torch.int64, device=self.device)
-        lib().b200_decoder_debug_trace(self.handle, C.c_void_p(self._trace.data_ptr()), nbytes)
-        return self._trace
 
     def generate(self, prompt_ids, embedding, final_gamma, lm_head, k_cache, v_cache, max_new_tokens, top_k=1, end_id=2, check_every=0):
         """The generation loop (b200_generate): prompt_ids = int array [batch, prompt_len] on the HOST; returns (ids [batch, max_new_tokens],

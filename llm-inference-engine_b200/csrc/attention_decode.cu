@@ -21,10 +21,7 @@
 //     normalisation.
 #include "attention_decode.cuh"
 
-#include <cooperative_groups.h>
 #include <stdlib.h>
-
-namespace cg = cooperative_groups;
 
 namespace b200 {
 
@@ -114,16 +111,20 @@ template <typename T> __device__ __forceinline__ float round_t(float v) { return
 // final normalisation shared by the single-split path and the merge: reference decoder_self_attention.cu:145-165
 __device__ __forceinline__ float final_max(float m, int step, int head_size) { return (step < head_size && m < 0.0f) ? 0.0f : m; }
 
-template <typename T, int G>
+// GC = q heads served by one CTA (the whole GQA group, or half of it when the group has 8 heads: 8 x (q + output) slices do not
+// fit the register budget of a 288-thread CTA -- the two halves read the same K/V rows, the second read hits L2).
+template <typename T, int GC>
 __global__ void __launch_bounds__(kAttnThreads)
 decode_attn_kernel(const DecodeAttnArgs a) {
     constexpr int D = kAttnD;
+    constexpr int G = GC;
     constexpr int V = Elem<T>::kVec;                   // elements per 16-byte vector
     constexpr int LPR = D / V;                         // lanes per K/V row: 16 (16-bit) or 32 (fp32)
     constexpr int RG = kAttnWarps * 32 / LPR;          // row groups per CTA: 16 or 8
     constexpr int TP = kAttnTileBytes / (D * (int)sizeof(T));  // positions per tile: 64 or 32
     constexpr int RPG = TP / RG;                       // rows of a tile per row group: 4
     constexpr int kStageBytes = 2 * kAttnTileBytes;
+    constexpr int PS = kAttnPartStride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *ring = smem_raw;                                                   // [stages][K tile | V tile]
     float *merge = reinterpret_cast<float *>(smem_raw);                               // aliases the ring after the loop: [RG][G][D+2]
@@ -132,19 +133,18 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     float *vnew = knew + D;                                                           // [D]
     float *wts = vnew + D;                                                            // [RG][G] merge weights, then [G] max, [G] sum
     const uint32_t full0 = a_smem_u32(wts + RG * G + 2 * G + 2), empty0 = full0 + 8 * kAttnStages;
-    // cluster merge: the leader CTA's copy receives every split's (out[G][D], max, sum) -- must not alias the ring, which the
-    // leader may still be reading when a faster CTA of the cluster delivers
-    float *cl_part = wts + RG * G + 2 * G + 2 + 4 * kAttnStages;  // [nsplit <= 8][G][D+2]
     __shared__ bool is_last;
 
-    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int split = blockIdx.x, b = blockIdx.z;
     const int H = a.head_num, Hkv = a.kv_head_num;
+    const int Gtot = H / Hkv, gsplit = Gtot / G;       // CTAs per (b, kv head, split): 1, or 2 half-groups
+    const int kvh = blockIdx.y / gsplit, g0 = (blockIdx.y % gsplit) * G;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int qkv_heads = H + 2 * Hkv;
-    const int step = a.step;
-    const int p0 = split * a.chunk, p1 = min(step, p0 + a.chunk);
-    const int ntiles = (p1 - p0 + TP - 1) / TP;
-    const bool has_new = p1 == step;  // this CTA owns position step-1 (the token being appended)
+    const int step = a.step, cached = step - 1;        // positions [0, cached) are in the cache; position `cached` is the new token
+    const int p0 = split * a.chunk, p1 = min(cached, p0 + a.chunk);
+    const int ntiles = p1 > p0 ? (p1 - p0 + TP - 1) / TP : 0;
+    const bool has_new = split == a.nsplit - 1;  // the last split also serves the token being appended (from shared memory, not the cache)
     const T *qkv = reinterpret_cast<const T *>(a.qkv) + (size_t)b * qkv_heads * D;
     const T *bias = reinterpret_cast<const T *>(a.bias);
     T *kc = reinterpret_cast<T *>(a.k_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
@@ -176,11 +176,11 @@ decode_attn_kernel(const DecodeAttnArgs a) {
 
     pdl_wait();
 
-    // ---- q (all G heads of the group), and the new k / v row: RoPE at step-1, then bias (reference order)
+    // ---- q (this CTA's G heads of the group), and the new k / v row: RoPE at step-1, then bias (reference order)
     for (int i = tid; i < (G + 1) * (D / 2); i += kAttnThreads) {
         const int g = i / (D / 2), j = i % (D / 2);  // g == G: the k head
         if (g == G && !has_new) continue;
-        const int head = g < G ? kvh * G + g : H + kvh;
+        const int head = g < G ? kvh * Gtot + g0 + g : H + kvh;
         float x0 = Elem<T>::to_f(qkv[(size_t)head * D + j]), x1 = Elem<T>::to_f(qkv[(size_t)head * D + j + D / 2]);
         if (a.apply_rope && j < a.rot_dim / 2) {
             const float2 cs = a.rope_cs ? __ldg(a.rope_cs + (size_t)(step - 1) * (a.rot_dim / 2) + j)
@@ -205,7 +205,7 @@ decode_attn_kernel(const DecodeAttnArgs a) {
         }
     }
     __syncthreads();  // q / knew / vnew complete; also publishes the producer's mbarrier initialisation
-    if (has_new) {    // cache append (decoder_self_attention.cu:126,172)
+    if (has_new && g0 == 0) {  // cache append (decoder_self_attention.cu:126,172)
         for (int j = tid; j < D; j += kAttnThreads) {
             kc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(knew[j]);
             vc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(vnew[j]);
@@ -224,20 +224,6 @@ decode_attn_kernel(const DecodeAttnArgs a) {
                 if (++e_s == kAttnStages) e_s = 0, e_ph ^= 1;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue_next();
-            }
-            // (opt-in) once this CTA's last K/V tile has LANDED, HBM idles while the softmax / merge chain finishes: pull this CTA's
-            // slice of the next kernel's weights (the O projection, 33.5 MB << 126 MB of L2) into L2
-            if (a.l2_prefetch && a.l2_prefetch_bytes && ntiles > 0) {
-                const int last = ntiles - 1;
-                a_mbar_wait(full0 + 8 * (last % kAttnStages), (last / kAttnStages) & 1);
-                const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
-                const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-                const size_t per = ((a.l2_prefetch_bytes + ncta - 1) / ncta + 127) & ~(size_t)127;
-                const size_t lo = cta * per, hi = lo + per < a.l2_prefetch_bytes ? lo + per : a.l2_prefetch_bytes;
-                for (size_t o = lo; o < hi; o += 16384) {
-                    const unsigned int n = (unsigned int)((hi - o < 16384 ? hi - o : 16384) & ~(size_t)15);
-                    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)a.l2_prefetch + o), "r"(n) : "memory");
-                }
             }
         }
     } else {
@@ -269,12 +255,7 @@ decode_attn_kernel(const DecodeAttnArgs a) {
                 const int r = rg + i * RG, p = base + r;
                 ok[i] = p < p1;
                 float kf[V];
-                if (has_new && p == step - 1) {
-#pragma unroll
-                    for (int e = 0; e < V; ++e) kf[e] = knew[l * V + e];
-                } else {
-                    unpack16<T>(*reinterpret_cast<const uint4 *>(kt + (size_t)r * (D * sizeof(T)) + l * 16), kf);
-                }
+                unpack16<T>(*reinterpret_cast<const uint4 *>(kt + (size_t)r * (D * sizeof(T)) + l * 16), kf);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     float d = 0.0f;
@@ -313,12 +294,9 @@ decode_attn_kernel(const DecodeAttnArgs a) {
             // ---- P.V
 #pragma unroll
             for (int i = 0; i < RPG; ++i) {
-                const int r = rg + i * RG, p = base + r;
+                const int r = rg + i * RG;
                 float vf[V];
-                if (has_new && p == step - 1) {  // only the CTA that owns the new token holds knew / vnew
-#pragma unroll
-                    for (int e = 0; e < V; ++e) vf[e] = vnew[l * V + e];
-                } else if (ok[i]) {
+                if (ok[i]) {
                     unpack16<T>(*reinterpret_cast<const uint4 *>(vt + (size_t)r * (D * sizeof(T)) + l * 16), vf);
                 } else {
 #pragma unroll
@@ -333,6 +311,26 @@ decode_attn_kernel(const DecodeAttnArgs a) {
             if ((tid & 31) == 0) a_mbar_arrive(empty0 + 8 * s);
             if (++s == kAttnStages) s = 0, ph ^= 1;
         }
+        // ---- the token being appended: one more row, held in shared memory (never read back from the cache), row group 0 only
+        if (has_new && rg == 0) {
+            float kf[V], vf[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) kf[e] = knew[l * V + e], vf[e] = vnew[l * V + e];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float d = 0.0f;
+#pragma unroll
+                for (int e = 0; e < V; ++e) d = fmaf(qf[g][e], kf[e], d);
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(LPR == 32 ? 0xffffffffu : 0x0000ffffu, d, o);
+                const float lgn = d * scale, mt = fmaxf(m[g], lgn);
+                const float rs = expf(m[g] - mt), pn = expf(lgn - mt);  // m == -inf (no cached row in this group): rs = 0
+                sum[g] = fmaf(sum[g], rs, pn);
+                m[g] = mt;
+#pragma unroll
+                for (int e = 0; e < V; ++e) of[g][e] = fmaf(pn, vf[e], of[g][e] * rs);
+            }
+        }
         // ---- publish the row group's state (the ring is dead: every tile has been consumed by every warp after the barrier)
         asm volatile("bar.sync 1, %0;" ::"r"(kAttnWarps * 32) : "memory");
 #pragma unroll
@@ -343,28 +341,24 @@ decode_attn_kernel(const DecodeAttnArgs a) {
             if (l == 0) mp[D] = m[g], mp[D + 1] = sum[g];
         }
         asm volatile("bar.sync 1, %0;" ::"r"(kAttnWarps * 32) : "memory");
-        // merge weights exp(m_rg - M) per (rg, g); M and the merged sum per g
-        if (tid < G) {
-            const int g = tid;
-            float M = -INFINITY;
-            for (int r = 0; r < RG; ++r) M = fmaxf(M, merge[((size_t)r * G + g) * (D + 2) + D]);
-            float S = 0.0f;
-            for (int r = 0; r < RG; ++r) {
-                const float *mp = merge + ((size_t)r * G + g) * (D + 2);
-                const float w = expf(mp[D] - M);  // a row group without rows has m = -inf: weight 0
-                wts[r * G + g] = w;
-                S = fmaf(mp[D + 1], w, S);
-            }
-            wts[RG * G + g] = M;
-            wts[RG * G + G + g] = S;
+        // merge weights exp(m_rg - M) per (rg, g); M and the merged sum per g: warp g, lane = row group (fixed shuffle order)
+        if (warp < G) {
+            const int g = warp, r = tid & 31;
+            const float *mp = merge + ((size_t)(r < RG ? r : 0) * G + g) * (D + 2);
+            const float mr = r < RG ? mp[D] : -INFINITY, sr = r < RG ? mp[D + 1] : 0.0f;
+            const float M = warp_max(mr);
+            const float w = M == -INFINITY ? 0.0f : expf(mr - M);  // a row group without rows has m = -inf: weight 0
+            const float S = warp_sum(sr * w);
+            if (r < RG) wts[r * G + g] = w;
+            if (r == 0) wts[RG * G + g] = M, wts[RG * G + G + g] = S;
         }
         asm volatile("bar.sync 1, %0;" ::"r"(kAttnWarps * 32) : "memory");
     }
     __syncthreads();
 
     // ---- combine the row groups; single split: finish here, else hand the partial to the merge
-    T *out = reinterpret_cast<T *>(a.out) + ((size_t)b * H + (size_t)kvh * G) * D;
-    if (a.nsplit == 1) {
+    T *out = reinterpret_cast<T *>(a.out) + ((size_t)b * H + (size_t)kvh * Gtot + g0) * D;
+    if (a.nsplit == 1 && !a.defer_merge) {
         for (int i = tid; i < G * D; i += kAttnThreads) {
             const int g = i / D, d = i % D;
             float o = 0.0f;
@@ -375,70 +369,40 @@ decode_attn_kernel(const DecodeAttnArgs a) {
         }
         return;
     }
-    if (a.cluster) {
-        // ---- the nsplit CTAs of this (b, kv head) are one thread-block cluster: partials travel through distributed shared memory
-        cg::cluster_group cluster = cg::this_cluster();
-        float *dst = cluster.map_shared_rank(cl_part, 0) + (size_t)split * G * (D + 2);
-        for (int i = tid; i < G * D; i += kAttnThreads) {
-            const int g = i / D, d = i % D;
-            float o = 0.0f;
-#pragma unroll
-            for (int r = 0; r < RG; ++r) o = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o);
-            dst[(size_t)g * (D + 2) + d] = o;
-        }
-        if (tid < G) {
-            dst[(size_t)tid * (D + 2) + D] = wts[RG * G + tid];
-            dst[(size_t)tid * (D + 2) + D + 1] = wts[RG * G + G + tid];
-        }
-        cluster.sync();  // release / acquire: every split's partial is in the leader's shared memory
-        if (split != 0) return;
-        for (int i = tid; i < G * D; i += kAttnThreads) {
-            const int g = i / D, d = i % D;
-            float mm = -INFINITY;
-            for (int s2 = 0; s2 < a.nsplit; ++s2) mm = fmaxf(mm, cl_part[((size_t)s2 * G + g) * (D + 2) + D]);
-            mm = final_max(mm, step, D);
-            float ssum = 0.0f, o = 0.0f;
-            for (int s2 = 0; s2 < a.nsplit; ++s2) {  // split order: deterministic
-                const float *ps = cl_part + ((size_t)s2 * G + g) * (D + 2);
-                const float c = expf(ps[D] - mm);
-                ssum = fmaf(ps[D + 1], c, ssum);
-                o = fmaf(ps[d], c, o);
-            }
-            out[(size_t)g * D + d] = Elem<T>::from_f(o / (ssum + 1e-6f));
-        }
-        return;
-    }
-    // ---- no cluster: partials through global scratch, the last CTA of the (b, kv head) (self-resetting ticket) merges
-    float *part = a.partials + (((size_t)b * Hkv + kvh) * a.nsplit + split) * (size_t)G * (D + 2);
+    // ---- partials: [b, kv head][split][q head of the group][o[D], max, sum, pad, pad]
+    float *part = a.partials + ((((size_t)b * Hkv + kvh) * a.nsplit + split) * Gtot + g0) * (size_t)PS;
     for (int i = tid; i < G * D; i += kAttnThreads) {
         const int g = i / D, d = i % D;
         float o = 0.0f;
 #pragma unroll
         for (int r = 0; r < RG; ++r) o = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o);
-        part[(size_t)g * (D + 2) + d] = o;
+        part[(size_t)g * PS + d] = o;
     }
     if (tid < G) {
-        part[(size_t)tid * (D + 2) + D] = wts[RG * G + tid];
-        part[(size_t)tid * (D + 2) + D + 1] = wts[RG * G + G + tid];
+        part[(size_t)tid * PS + D] = wts[RG * G + tid];
+        part[(size_t)tid * PS + D + 1] = wts[RG * G + G + tid];
     }
+    if (a.defer_merge) return;  // the consumer (the O projection's prologue) merges: nothing else on this kernel's critical path
+    // ---- the last CTA of the (b, kv head, half group) (self-resetting ticket) merges
     __threadfence();
     __syncthreads();
-    if (tid == 0) is_last = atomicInc(&a.tickets[b * Hkv + kvh], a.nsplit - 1) == (unsigned)(a.nsplit - 1);
+    if (tid == 0) is_last = atomicInc(&a.tickets[(b * Hkv + kvh) * gsplit + (int)(blockIdx.y % gsplit)], a.nsplit - 1) == (unsigned)(a.nsplit - 1);
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const float *pbase = a.partials + ((size_t)b * Hkv + kvh) * a.nsplit * (size_t)G * (D + 2);
+    const float *pbase = a.partials + (((size_t)b * Hkv + kvh) * a.nsplit * Gtot + g0) * (size_t)PS;
+    const size_t sstride = (size_t)Gtot * PS;  // floats between the records of consecutive splits
     // Every split's (max, sum, o[d]) is requested before the first one is used: the loads are independent L2 round trips (~0.6 us each
-    // under load), and a rolled `for (s2 < nsplit)` loop serialises them -- 2 x nsplit round trips were most of this kernel's time
-    // (9 splits: ~10 us of a 12 us kernel; 32 splits: 38 us).  Same arithmetic, same split order as before: bit-identical results.
+    // under load), and a rolled `for (s2 < nsplit)` loop serialises them.  Fixed split order: deterministic.
     constexpr int kBatch = 16;
     for (int i = tid; i < G * D; i += kAttnThreads) {
         const int g = i / D, d = i % D;
+        const float *pg = pbase + (size_t)g * PS;
         float mm = -INFINITY;
         for (int s0 = 0; s0 < a.nsplit; s0 += kBatch) {
             float mv[kBatch];
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) mv[j] = s0 + j < a.nsplit ? __ldcg(pbase + ((size_t)(s0 + j) * G + g) * (D + 2) + D) : -INFINITY;
+            for (int j = 0; j < kBatch; ++j) mv[j] = s0 + j < a.nsplit ? __ldcg(pg + (size_t)(s0 + j) * sstride + D) : -INFINITY;
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) mm = fmaxf(mm, mv[j]);
         }
@@ -450,7 +414,7 @@ decode_attn_kernel(const DecodeAttnArgs a) {
             for (int j = 0; j < kBatch; ++j) {
                 mv[j] = -INFINITY, sv[j] = 0.0f, ov[j] = 0.0f;
                 if (s0 + j < a.nsplit) {
-                    const float *ps = pbase + ((size_t)(s0 + j) * G + g) * (D + 2);
+                    const float *ps = pg + (size_t)(s0 + j) * sstride;
                     mv[j] = __ldcg(ps + D), sv[j] = __ldcg(ps + D + 1), ov[j] = __ldcg(ps + d);
                 }
             }
@@ -536,30 +500,27 @@ __global__ void decode_attn_generic_kernel(const DecodeAttnArgs a) {
 }
 
 size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int head_size, int max_splits) {
-    return (size_t)batch * kv_head_num * max_splits * (head_num / kv_head_num) * (head_size + 2);
-}
-
-// Two merges of the split-KV partials exist: through global scratch + ticket (default) and through the distributed shared
-// memory of a thread-block cluster (B200_ATTN_CLUSTER=1).  Measured on B200, 7B bf16 B=1 ctx 1024: 2.585 ms/step with the
-// ticket merge (9 splits, 288 CTAs) vs 2.61 ms with clusters of 8 (256 CTAs) -- the cluster launch constrains placement
-// more than the DSMEM hop saves, so it stays opt-in.
-static bool attn_use_cluster() {
-    static const bool on = getenv("B200_ATTN_CLUSTER") != nullptr;
-    return on;
+    return (size_t)batch * kv_head_num * max_splits * (head_num / kv_head_num) * attn_part_stride(head_size);
 }
 
 int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk) {
-    // about two CTAs per SM in ONE wave (never a partial second wave), chunks of >= 32 positions; the splits of a
-    // (b, kv head) form one thread-block cluster, so at most 8 (the portable cluster size)
+    // The cached positions [0, step-1) are cut into chunks of whole 64-position tiles, about two CTAs per SM in ONE wave (never a
+    // partial second wave) and at most 16 splits (the merges request the partials in batches); the last split also serves the
+    // token being appended, which never comes from the cache.
+    const int cached = step - 1;
     int want = (2 * sm_count()) / (batch * kv_head_num);
     if (want < 1) want = 1;
-    if (attn_use_cluster() && want > 8) want = 8;
-    if (want > 16) want = 16;  // the split merge requests one batch of 16 partials at a time
-    int c = (step + want - 1) / want;
-    c = (c + 3) & ~3;
-    if (c < 32) c = 32;
+    if (want > 16) want = 16;
+    {   // TEMPORARY experiment knob (removed before commit)
+        static const int cap = getenv("B200_X_MAXSPLIT") ? atoi(getenv("B200_X_MAXSPLIT")) : 16;
+        if (want > cap) want = cap;
+    }
+    int c = (cached + want - 1) / want;
+    c = (c + 63) & ~63;
+    if (c < 64) c = 64;
     *chunk = c;
-    return (step + c - 1) / c;
+    const int n = (cached + c - 1) / c;
+    return n < 1 ? 1 : n;
 }
 
 template <typename T>
@@ -567,22 +528,33 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
     const int G = a.head_num / a.kv_head_num;
     const bool fast = a.head_size == kAttnD && (G == 1 || G == 2 || G == 4 || G == 8) && aligned16(a.k_cache) && aligned16(a.v_cache);
     if (fast) {
+        const int GC = G == 8 ? 4 : G;  // q heads per CTA
         const int RG = kAttnWarps * 32 / (kAttnD / Elem<T>::kVec);
-        a.cluster = a.nsplit > 1 && a.nsplit <= 8 && attn_use_cluster();
-        const size_t smem = (size_t)kAttnStages * 2 * kAttnTileBytes + sizeof(float) * ((size_t)G * kAttnD + 2 * kAttnD + (size_t)RG * G + 2 * G + 2) +
-                            2 * kAttnStages * 8 + (a.cluster ? sizeof(float) * (size_t)a.nsplit * G * (kAttnD + 2) : 0) + 16;
-        dim3 grid(a.nsplit, a.kv_head_num, a.batch);
-        auto go = [&](auto kern) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_pdl_cluster(kern, grid, dim3(kAttnThreads), smem, st, true, a.cluster ? (unsigned)a.nsplit : 1u, a);
+        const size_t smem = (size_t)kAttnStages * 2 * kAttnTileBytes + sizeof(float) * ((size_t)GC * kAttnD + 2 * kAttnD + (size_t)RG * GC + 2 * GC + 2) +
+                            2 * kAttnStages * 8 + 16;
+        dim3 grid(a.nsplit, a.kv_head_num * (G / GC), a.batch);
+        auto go = [&](auto kern, int slot) {
+            // the three instantiations share one function-pointer type: the opt-in to large dynamic shared memory is per kernel and device
+            static thread_local bool attr_set[3][64] = {{false}};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            dev &= 63;
+            if (!attr_set[slot][dev]) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set[slot][dev] = true;
+            }
+            launch_pdl(kern, grid, dim3(kAttnThreads), smem, st, true, a);
         };
-        switch (G) {
-            case 1: go(decode_attn_kernel<T, 1>); break;
-            case 2: go(decode_attn_kernel<T, 2>); break;
-            case 4: go(decode_attn_kernel<T, 4>); break;
-            default: go(decode_attn_kernel<T, 8>); break;
+        switch (GC) {
+            case 1: go(decode_attn_kernel<T, 1>, 0); break;
+            case 2: go(decode_attn_kernel<T, 2>, 1); break;
+            default: go(decode_attn_kernel<T, 4>, 2); break;
         }
         return cuda_status("decode_attn launch");
+    }
+    if (a.defer_merge) {
+        set_error("decode_mha: deferred merge needs head size 128");
+        return B200_ERR_STATE;
     }
     const size_t smem = sizeof(float) * ((size_t)3 * a.head_size + a.step);
     if (smem > 200 * 1024) {
@@ -592,6 +564,11 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
     cudaFuncSetAttribute(decode_attn_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_pdl(decode_attn_generic_kernel<T>, dim3(a.head_num, a.batch), dim3(128), smem, st, true, a);
     return cuda_status("decode_attn_generic launch");
+}
+
+bool decode_attn_fast_path(int head_num, int kv_head_num, int head_size) {
+    const int G = head_num / kv_head_num;
+    return head_size == kAttnD && (G == 1 || G == 2 || G == 4 || G == 8);
 }
 
 int launch_decode_attn(const DecodeAttnArgs &a, int dtype, cudaStream_t st) {
@@ -642,7 +619,7 @@ int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *
     a.nsplit = decode_attn_plan(batch, kv_head_num, step, &a.chunk);
     a.partials = reinterpret_cast<float *>(ws.scratch);
     a.tickets = ws.tickets;
-    B200_REQUIRE((size_t)batch * kv_head_num <= ws.n_tickets, "decode_mha: batch*kv_head_num exceeds the ticket pool");
+    B200_REQUIRE((size_t)batch * kv_head_num * 2 <= ws.n_tickets, "decode_mha: batch*kv_head_num exceeds the ticket pool");
     B200_REQUIRE(decode_attn_partials_floats(batch, head_num, kv_head_num, head_size, a.nsplit) * 4 <= ws.scratch_bytes,
                  "decode_mha: library workspace too small for %d splits", a.nsplit);
     return launch_decode_attn(a, dtype, as_stream(stream));

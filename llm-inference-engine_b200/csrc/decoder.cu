@@ -9,11 +9,10 @@
 //   4. gemv  Wgu    prologue: residual += attn out; (+ o bias); RMSNorm(gamma2);  epilogue: SwiGLU
 //   5. gemv  Wdown
 // For batch > 4 the same dataflow runs un-fused: norm kernel -> b200_linear (tensor-core GEMM) -> ...
-// The residual stream lives in two engine-owned ping-pong buffers so that no kernel writes a tensor another CTA of
-// the same kernel still reads.
+// The residual stream rotates over engine-owned buffers so that no kernel writes a tensor another CTA of the same kernel
+// still reads.
 #include "attention_decode.cuh"
 #include "gemv.cuh"
-#include "gemv_chain.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -32,12 +31,9 @@ struct b200_decoder {
     void *qkv = nullptr, *attn = nullptr, *y_attn = nullptr, *gu = nullptr, *act = nullptr, *y_ffn = nullptr;
     float *partials = nullptr;
     unsigned int *tickets = nullptr;
-    unsigned long long *chain_trace = nullptr;  // optional diagnostics buffer (b200_decoder_debug_trace)
     float2 *rope_cs = nullptr;  // (cos, sin) per (position, rotary pair), filled once by set_scratch
     int max_splits = 0;
     int cur = 0;  // which res[] holds the residual stream
-    char *chain_ll = nullptr;   // per-layer chained-GEMV exchange area: claim counters + LL activation buffers (zeroed every step)
-    size_t chain_ll_layer = 0;  // bytes per layer
     // fused tensor-parallel exchange (b200_decoder_tp_attach): every rank's exchange buffer as mapped in this process
     char *tp_base[b200::kTpMaxWorld] = {};
     bool tp_attached = false;
@@ -50,19 +46,13 @@ int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const v
                                   float base, int dtype, cudaStream_t st);
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
-// A kernel never writes the residual buffer other CTAs of the same launch still read: outputs go to the next buffer of the rotation
-// (three, because the chained GEMV kernel forms two successive residuals in one launch).
+// A kernel never writes the residual buffer other CTAs of the same launch still read: outputs go to the next buffer of the rotation.
 static int next_res(int cur) { return (cur + 1) % 3; }
 static size_t esize(int dtype) { return dtype == B200_F32 ? 4 : 2; }
 
 struct Carve {
-    size_t res, xn, qkv, attn, y, gu, act, partials, tickets, chain, rope, total;
+    size_t res, xn, qkv, attn, y, gu, act, partials, tickets, rope, total;
 };
-// per-layer exchange area of the chained GEMV kernel: [claim counters: 256 B][y_attn LL][act LL][y_ffn LL], 8-byte {payload, flag} words
-static size_t chain_ll_words(const b200_decoder_config_t &c, int n) { return (size_t)c.max_batch * n / (esize(c.dtype) == 2 ? 2 : 1); }
-static size_t chain_layer_bytes(const b200_decoder_config_t &c) {
-    return 256 + align_up(chain_ll_words(c, c.hidden) * 8) * 2 + align_up(chain_ll_words(c, c.inter_size) * 8);
-}
 static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     Carve k;
     const size_t e = esize(c.dtype), B = c.max_batch;
@@ -73,13 +63,12 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     k.y = align_up(B * c.hidden * e);
     k.gu = align_up(B * (size_t)2 * c.inter_size * e);
     k.act = align_up(B * (size_t)c.inter_size * e);
-    // worst case number of KV splits: chunk >= 32 positions
-    *max_splits = (c.max_seq_len + 31) / 32;
+    // worst case number of KV splits (decode_attn_plan: chunks of >= 64 positions, at most 16 splits)
+    *max_splits = (c.max_seq_len + 63) / 64 < 16 ? (c.max_seq_len + 63) / 64 : 16;
     k.partials = align_up(decode_attn_partials_floats(c.max_batch, c.head_num, c.kv_head_num, c.head_size, *max_splits) * sizeof(float));
-    k.tickets = align_up((size_t)c.max_batch * c.kv_head_num * sizeof(unsigned int));
-    k.chain = (size_t)c.num_layers * chain_layer_bytes(c);
+    k.tickets = align_up((size_t)c.max_batch * c.kv_head_num * 2 * sizeof(unsigned int));  // x 2: half-group CTAs (GQA group of 8)
     k.rope = c.rotary_dim > 0 ? align_up((size_t)c.max_seq_len * (c.rotary_dim / 2) * sizeof(float2)) : 0;
-    k.total = 3 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.chain + k.rope;
+    k.total = 3 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.rope;
     return k;
 }
 
@@ -310,9 +299,6 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     dec->partials = (float *)p, p += k.partials;
     dec->tickets = (unsigned int *)p, p += k.tickets;
     if (cudaMemset(dec->tickets, 0, k.tickets) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
-    dec->chain_ll = p, p += k.chain;
-    dec->chain_ll_layer = chain_layer_bytes(dec->cfg);
-    if (cudaMemset(dec->chain_ll, 0, k.chain) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
     dec->rope_cs = nullptr;
     if (k.rope) {
         dec->rope_cs = (float2 *)p;
@@ -324,8 +310,30 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     return B200_OK;
 }
 
-// RoPE + qkv bias + KV append + split-KV attention + merge for one layer: dec->qkv -> dec->attn
-static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache, void *v_cache, int batch, int step, cudaStream_t st) {
+// The O projection as the fused GEMV (M <= 4 dense, <= 8 quantised).  merge != 0: its prologue merges the attention's split-KV partials.
+static GemvArgs o_proj_gemv_args(const b200_decoder_t *dec, const b200_layer_weights_t &w, void *y, int batch, int step, int nsplit, bool merge) {
+    const b200_decoder_config_t &c = dec->cfg;
+    GemvArgs a = {};
+    a.w = w.o.w, a.scales = w.o.scales, a.zeros = w.o.zeros;
+    a.x = dec->attn, a.y = y;
+    a.M = batch, a.K = c.head_num * c.head_size, a.N = c.hidden, a.group = c.group;
+    if (merge) a.attn_part = dec->partials, a.attn_nsplit = nsplit, a.attn_group = c.head_num / c.kv_head_num, a.attn_step = step;
+    return a;
+}
+// Does the O projection of this engine run on the fused GEMV with the split-KV merge in its prologue?  (Otherwise the attention
+// kernel merges its own partials: tensor-core GEMM for batch > 4, head sizes other than 128.)
+static bool attn_merge_deferred(const b200_decoder_t *dec, int batch) {
+    const b200_decoder_config_t &c = dec->cfg;
+    if (batch > gemv_max_rows(c) || !decode_attn_fast_path(c.head_num, c.kv_head_num, c.head_size)) return false;
+    if (getenv("B200_X_NODEFER")) return false;  // TEMPORARY experiment knob (removed before commit)
+    GemvArgs a = o_proj_gemv_args(dec, dec->layers[0], dec->y_attn, batch, 1, 1, true);
+    a.probe = 1;
+    return launch_gemv_nk(a, c.dtype, c.w_format, false, nullptr) == B200_OK;
+}
+
+// RoPE + qkv bias + KV append + split-KV attention for one layer: dec->qkv -> dec->attn, or (deferred merge) -> dec->partials
+static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache, void *v_cache, int batch, int step, bool defer, int *nsplit,
+                                  cudaStream_t st) {
     const b200_decoder_config_t &c = dec->cfg;
     const b200_layer_weights_t &w = dec->layers[layer];
     DecodeAttnArgs a = {};
@@ -340,15 +348,8 @@ static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache,
     a.partials = dec->partials, a.tickets = dec->tickets;
     a.rope_cs = dec->rope_cs;
     a.prefetch = 1;  // the kernel in front of this one is the QKV linear: it does not touch the cache
-    {   // the O-projection weights of this layer: packed bytes the next kernel streams
-        const size_t n = (size_t)c.hidden, k = (size_t)c.head_num * c.head_size;
-        a.l2_prefetch = w.o.w;
-        a.l2_prefetch_bytes = c.w_format == B200_W_DENSE ? n * k * esize(c.dtype) : (c.w_format == B200_W_FP8E4M3 ? n * k : n * k / 2);
-        // measured on B200 (7B bf16 B=1 ctx 1024): 2.678 ms/step WITH the prefetch vs 2.619 ms without -- the extra traffic competes
-        // with the attention's own K/V loads and the O projection's ring fill already overlaps through PDL; so it is opt-in.
-        static const bool l2 = getenv("B200_L2_PREFETCH") != nullptr;
-        if (!l2) a.l2_prefetch_bytes = 0;
-    }
+    a.defer_merge = defer;
+    *nsplit = a.nsplit;
     return launch_decode_attn(a, c.dtype, st);
 }
 
@@ -370,10 +371,20 @@ static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const v
                      c.hidden, qkv_n, false, dec->qkv, batch, st, pending ? tp : nullptr);
     if (rc != B200_OK) return rc;
     dec->cur = next_res(dec->cur);
-    // 2. attention
-    rc = launch_layer_attention(dec, layer, k_cache, v_cache, batch, step, st);
+    // 2. attention (split-KV; with the O projection on the fused GEMV the merge of the splits moves into that kernel's prologue)
+    const bool defer = attn_merge_deferred(dec, batch);
+    int nsplit = 1;
+    rc = launch_layer_attention(dec, layer, k_cache, v_cache, batch, step, defer, &nsplit, st);
     if (rc != B200_OK) return rc;
     // 3. O projection (row-sharded under TP: `partial` is this rank's partial sum)
+    if (defer) {
+        GemvArgs a = o_proj_gemv_args(dec, w, partial, batch, step, nsplit, true);
+        if (push_seq > 0) {
+            a.n_push = c.tp_world;
+            for (int r = 0; r < c.tp_world; ++r) a.y_push[r] = tp_slot(dec, r, push_seq, c.tp_rank);
+        }
+        return launch_gemv_nk(a, c.dtype, c.w_format, false, st);
+    }
     return plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, partial, batch, st, push_seq);
 }
 
@@ -506,96 +517,6 @@ int b200_decoder_step_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void 
     return fold_impl(dec, hidden, tp_slot(dec, me, seq, me), batch, stream, &tlast);
 }
 
-// The chained GEMV kernel of layer l: O -> [norm] gate/up + SwiGLU -> down (-> [norm] QKV of layer l + 1 when next_qkv).
-// `cur` = which res[] holds the residual stream before the chain; returns the index after it.
-static int build_chain(b200_decoder_t *dec, int l, bool next_qkv, int batch, int cur, ChainArgs *out) {
-    const b200_decoder_config_t &c = dec->cfg;
-    const b200_layer_weights_t &w = dec->layers[l];
-    ChainArgs a = {};
-    a.M = batch, a.eps = c.rmsnorm_eps;
-    static const int poll_ns = getenv("B200_CHAIN_POLL_NS") ? atoi(getenv("B200_CHAIN_POLL_NS")) : 40;
-    a.poll_ns = poll_ns;
-    static const int l2_ahead = getenv("B200_CHAIN_L2_AHEAD") ? atoi(getenv("B200_CHAIN_L2_AHEAD")) : 0;
-    a.l2_ahead = l2_ahead;
-    char *area = dec->chain_ll + (size_t)l * dec->chain_ll_layer;
-    a.claim = reinterpret_cast<unsigned int *>(area);
-    uint2 *y_attn_ll = reinterpret_cast<uint2 *>(area + 256);
-    uint2 *y_ffn_ll = reinterpret_cast<uint2 *>(area + 256 + align_up(chain_ll_words(c, c.hidden) * 8));
-    uint2 *act_ll = reinterpret_cast<uint2 *>(area + 256 + 2 * align_up(chain_ll_words(c, c.hidden) * 8));
-    a.trace = dec->chain_trace ? dec->chain_trace + (size_t)l * sm_count() * kChainMaxPhases * 8 : nullptr;
-    const int r0 = cur, r1 = next_res(cur), r2 = next_res(r1);  // residual before the chain, after the attention block, after the FFN
-    int n = 0;
-    {   // O projection (reference self_attention.cpp:131-138)
-        ChainPhase &P = a.ph[n++];
-        P.w = w.o.w, P.x = dec->attn, P.y_ll = y_attn_ll, P.K = c.head_num * c.head_size, P.N = c.hidden;
-    }
-    {   // residual += attention output; + o bias; RMSNorm; gate/up; SwiGLU (self_decoder.cpp:92-100, ffn.cpp:105-131)
-        ChainPhase &P = a.ph[n++];
-        P.w = w.gate_up.w, P.x_ll = y_attn_ll, P.y_ll = act_ll, P.K = c.hidden, P.N = 2 * c.inter_size, P.inter = c.inter_size, P.swiglu = 1;
-        P.res_in = dec->res[r0], P.res_out = dec->res[r1], P.bias = w.o_bias, P.gamma = w.ffn_norm_gamma, P.norm = 1;
-        cur = r1;
-    }
-    {   // down projection (ffn.cpp:132-139)
-        ChainPhase &P = a.ph[n++];
-        P.w = w.down.w, P.x_ll = act_ll, P.K = c.inter_size, P.N = c.hidden;
-        if (next_qkv) P.y_ll = y_ffn_ll;
-        else P.y = dec->y_ffn;
-    }
-    if (next_qkv) {  // residual += FFN output; RMSNorm(gamma1 of layer l + 1); QKV (self_decoder.cpp:104-116 + 76-86 of the next layer)
-        const b200_layer_weights_t &wn = dec->layers[l + 1];
-        ChainPhase &P = a.ph[n++];
-        P.w = wn.qkv.w, P.x_ll = y_ffn_ll, P.y = dec->qkv, P.K = c.hidden, P.N = (c.head_num + 2 * c.kv_head_num) * c.head_size;
-        // the residual after the attention block is re-formed from its two terms: nothing another CTA wrote in this launch is read plain
-        P.res_in = dec->res[r0], P.res_ll = y_attn_ll, P.res_out = dec->res[r2], P.gamma = wn.attn_norm_gamma, P.norm = 1;
-        cur = r2;
-    }
-    a.n_phases = n;
-    *out = a;
-    return cur;
-}
-
-// batch <= 4, dense weights, one GPU: two launches per layer (attention + one chained GEMV kernel) instead of five
-static bool chain_usable(b200_decoder_t *dec, int batch, int layer_begin, int layer_end) {
-    static const bool off = getenv("B200_NO_CHAIN") != nullptr || getenv("B200_CHAIN") == nullptr;  // opt-in until it beats the separate launches
-    const b200_decoder_config_t &c = dec->cfg;
-    if (off || c.tp_world > 1 || c.w_format != B200_W_DENSE || batch > 4 || !dec->chain_ll) return false;
-    for (int l = layer_begin; l < layer_end; ++l) {
-        if (!dec->layer_set[l]) return false;
-        ChainArgs a;
-        build_chain(dec, l, l + 1 < layer_end, batch, 0, &a);
-        if (launch_gemv_chain(a, c.dtype, nullptr, true) != B200_OK) return false;
-    }
-    return true;
-}
-
-static int step_chained(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin, int layer_end,
-                        b200_stream_t stream) {
-    const b200_decoder_config_t &c = dec->cfg;
-    B200_REQUIRE(step >= 1 && step <= c.max_seq_len, "decoder: step %d outside [1, %d]", step, c.max_seq_len);
-    cudaStream_t st = as_stream(stream);
-    // claim counters and LL flags of every layer: one memset
-    if (cudaMemsetAsync(dec->chain_ll, 0, (size_t)c.num_layers * dec->chain_ll_layer, st) != cudaSuccess) return cuda_status("decoder_step memset");
-    // first layer's QKV: residual <- hidden; RMSNorm; QKV
-    const b200_layer_weights_t &w0 = dec->layers[layer_begin];
-    int rc = norm_linear(dec, hidden, nullptr, dec->res[next_res(dec->cur)], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden,
-                         (c.head_num + 2 * c.kv_head_num) * c.head_size, false, dec->qkv, batch, st);
-    if (rc != B200_OK) return rc;
-    dec->cur = next_res(dec->cur);
-    for (int l = layer_begin; l < layer_end; ++l) {
-        rc = launch_layer_attention(dec, l, k_cache, v_cache, batch, step, st);
-        if (rc != B200_OK) return rc;
-        ChainArgs a;
-        dec->cur = build_chain(dec, l, l + 1 < layer_end, batch, dec->cur, &a);
-        rc = launch_gemv_chain(a, c.dtype, st);
-        if (rc == B200_ERR_UNSUPPORTED) {
-            set_error("decoder_step: chained GEMV rejected layer %d after accepting it", l);
-            return B200_ERR_STATE;
-        }
-        if (rc != B200_OK) return rc;
-    }
-    return b200_decoder_fold(dec, hidden, dec->y_ffn, batch, stream);
-}
-
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin,
                       int layer_end, b200_stream_t stream) {
     int rc = check_ready(dec, batch);
@@ -603,7 +524,6 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
     B200_REQUIRE(dec->cfg.tp_world <= 1, "decoder_step: tensor-parallel engines drive attn_block / ffn_block themselves");
     B200_REQUIRE(hidden && k_cache && v_cache, "decoder_step: null pointer");
     B200_REQUIRE(layer_begin >= 0 && layer_end <= dec->cfg.num_layers && layer_begin < layer_end, "decoder_step: bad layer range");
-    if (chain_usable(dec, batch, layer_begin, layer_end)) return step_chained(dec, hidden, k_cache, v_cache, batch, step, layer_begin, layer_end, stream);
     const void *pending = nullptr;
     for (int l = layer_begin; l < layer_end; ++l) {
         rc = b200_decoder_attn_block(dec, l, hidden, pending, k_cache, v_cache, dec->y_attn, batch, step, stream);
@@ -615,9 +535,9 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
     return b200_decoder_fold(dec, hidden, pending, batch, stream);
 }
 
-// Diagnostic for roofline measurements: exactly the weight-streaming launches of b200_decoder_step (first QKV + per layer the chained
-// GEMV kernel, or the four separate GEMVs when the chain is not usable) without the attention kernels and the final fold.  The
-// activations are whatever the scratch buffers hold: call it after at least one real step; results are meaningless, timing is not.
+// Diagnostic for roofline measurements: exactly the weight-streaming launches of b200_decoder_step (four GEMVs per layer) without the
+// attention kernels and the final fold.  The activations are whatever the scratch buffers hold: call it after at least one real step;
+// results are meaningless, timing is not.
 int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b200_stream_t stream) {
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
@@ -627,46 +547,22 @@ int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b
     const int L = c.num_layers, qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size;
     for (int l = 0; l < L; ++l) B200_REQUIRE(dec->layer_set[l], "decoder_linears_only: layer %d not set", l);
     int launches = 0;
-    if (chain_usable(dec, batch, 0, L)) {
-        if (cudaMemsetAsync(dec->chain_ll, 0, (size_t)L * dec->chain_ll_layer, st) != cudaSuccess) return cuda_status("decoder_linears_only memset");
-        const b200_layer_weights_t &w0 = dec->layers[0];
-        rc = norm_linear(dec, dec->y_ffn, nullptr, dec->res[next_res(dec->cur)], nullptr, w0.attn_norm_gamma, w0.qkv, c.hidden, qkv_n, false, dec->qkv,
-                         batch, st);
+    for (int l = 0; l < L; ++l) {
+        const b200_layer_weights_t &w = dec->layers[l];
+        rc = norm_linear(dec, dec->y_ffn, dec->res[dec->cur], dec->res[next_res(dec->cur)], nullptr, w.attn_norm_gamma, w.qkv, c.hidden, qkv_n, false,
+                         dec->qkv, batch, st);
         if (rc != B200_OK) return rc;
-        dec->cur = next_res(dec->cur), ++launches;
-        for (int l = 0; l < L; ++l) {
-            ChainArgs a;
-            dec->cur = build_chain(dec, l, l + 1 < L, batch, dec->cur, &a);
-            if ((rc = launch_gemv_chain(a, c.dtype, st)) != B200_OK) return rc;
-            ++launches;
-        }
-    } else {
-        for (int l = 0; l < L; ++l) {
-            const b200_layer_weights_t &w = dec->layers[l];
-            rc = norm_linear(dec, dec->y_ffn, dec->res[dec->cur], dec->res[next_res(dec->cur)], nullptr, w.attn_norm_gamma, w.qkv, c.hidden, qkv_n, false,
-                             dec->qkv, batch, st);
-            if (rc != B200_OK) return rc;
-            dec->cur = next_res(dec->cur);
-            if ((rc = plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, dec->y_attn, batch, st)) != B200_OK) return rc;
-            rc = norm_linear(dec, dec->y_attn, dec->res[dec->cur], dec->res[next_res(dec->cur)], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
-                             2 * c.inter_size, true, dec->act, batch, st);
-            if (rc != B200_OK) return rc;
-            dec->cur = next_res(dec->cur);
-            if ((rc = plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, dec->y_ffn, batch, st)) != B200_OK) return rc;
-            launches += 4;
-        }
+        dec->cur = next_res(dec->cur);
+        if ((rc = plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, dec->y_attn, batch, st)) != B200_OK) return rc;
+        rc = norm_linear(dec, dec->y_attn, dec->res[dec->cur], dec->res[next_res(dec->cur)], w.o_bias, w.ffn_norm_gamma, w.gate_up, c.hidden,
+                         2 * c.inter_size, true, dec->act, batch, st);
+        if (rc != B200_OK) return rc;
+        dec->cur = next_res(dec->cur);
+        if ((rc = plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, dec->y_ffn, batch, st)) != B200_OK) return rc;
+        launches += 4;
     }
     if (n_launches) *n_launches = launches;
     return B200_OK;
-}
-
-// Diagnostics: device buffer of num_layers * SMs * 4 phases * 8 uint64 globaltimer stamps written by the chained GEMV kernels
-// (NULL switches tracing off).  Returns the bytes such a buffer needs when ptr == NULL and bytes == 0.
-size_t b200_decoder_debug_trace(b200_decoder_t *dec, void *ptr, size_t bytes) {
-    if (!dec) return 0;
-    const size_t need = (size_t)dec->cfg.num_layers * sm_count() * kChainMaxPhases * 8 * sizeof(unsigned long long);
-    dec->chain_trace = (ptr && bytes >= need) ? (unsigned long long *)ptr : nullptr;
-    return need;
 }
 
 static size_t prefill_carve(const b200_decoder_config_t &c, int batch, int mq, int T, size_t *off /*[11]*/) {

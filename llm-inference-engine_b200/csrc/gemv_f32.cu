@@ -13,8 +13,7 @@ int launch_gemv_nk(const GemvArgs &a, int dtype, int fmt, bool swiglu, cudaStrea
         return B200_ERR_INVALID_ARG;
     }
     // weight-only quantised, 16-bit activations, M <= 8: dequant into tensor-core fragments (gemv_q.cuh)
-    static const bool no_q = getenv("B200_GEMV_Q_SIMT") != nullptr;  // A/B knob: force the SIMT dequant path
-    if (fmt != WF_DENSE && !no_q && (dtype == B200_BF16 || dtype == B200_F16)) {
+    if (fmt != WF_DENSE && (dtype == B200_BF16 || dtype == B200_F16)) {
         const int rc = dtype == B200_BF16 ? launch_gemv_q_bf16(a, fmt, swiglu, st) : launch_gemv_q_f16(a, fmt, swiglu, st);
         if (rc != B200_ERR_UNSUPPORTED) return rc;
     }

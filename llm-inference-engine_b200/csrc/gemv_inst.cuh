@@ -9,16 +9,23 @@ namespace b200 {
 
 template <typename T, int FMT, int MB, bool SW, int XV>
 static int launch_gemv_geom(const GemvArgs &a, const GemvGeom &g, size_t smem, cudaStream_t st) {
-    auto kern = gemv_nk_kernel<T, FMT, MB, SW, XV>;
-    static thread_local size_t cached_smem[64] = {0};  // per device, per instantiation: opt in to large dynamic smem once
+    // the merging variant (O projection behind the split-KV decode attention) exists for the plain epilogue only
+    const bool merge = a.attn_part != nullptr;
+    if (merge && SW) return B200_ERR_UNSUPPORTED;
+    auto kern = gemv_nk_kernel<T, FMT, MB, SW, XV, false>;
+    if constexpr (!SW) {
+        if (merge) kern = gemv_nk_kernel<T, FMT, MB, SW, XV, true>;
+    }
+    static thread_local size_t cached_smem[2][64] = {{0}};  // per device, per instantiation: opt in to large dynamic smem once
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (cached_smem[dev] < smem) {
+    if (cached_smem[merge][dev] < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return cuda_status("gemv cudaFuncSetAttribute");
-        cached_smem[dev] = smem;
+        cached_smem[merge][dev] = smem;
     }
+    if (a.probe) return B200_OK;
     const int units = SW ? a.inter : (a.N + 1) / 2;
     int grid = sm_count();
     const int need = (units + g.groups - 1) / g.groups;
@@ -39,16 +46,13 @@ static int launch_gemv_inst(const GemvArgs &a, cudaStream_t st) {
     g.pieces = (int)((row_bytes + g.piece_bytes - 1) / g.piece_bytes);
     g.stage_bytes = kGemvRows * ((g.piece_bytes + 127) / 128 * 128);
     g.cw = ((g.piece_bytes / 16 + 31) / 32 + kGemvGW - 1) / kGemvGW;
-    // B200_GEMV_HALF=1: half-size CTAs (one group of 8 compute warps, half the ring) so that two DIFFERENT kernels' CTAs fit on an
-    // SM and kernel i+1 prefetches its weights under kernel i (experiment)
-    static const bool half = getenv("B200_GEMV_HALF") != nullptr;
-    g.groups = half ? 1 : kGemvGroups;
+    g.groups = kGemvGroups;
     // shared memory: activations + rings + barriers + per-lane partial sums
     const int Kp = (a.K + WT::kBlock - 1) / WT::kBlock * WT::kBlock;
     size_t fixed = ((size_t)MB * Kp * sizeof(typename WT::XS) + 127) & ~(size_t)127;
     fixed += (size_t)g.groups * (2 * kGemvMaxStages + 4) * 8;
     fixed += (size_t)g.groups * kGemvGW * 2 * kGemvRows * MB * 32 * sizeof(float);
-    const size_t budget = half ? 111 * 1024 : 224 * 1024;
+    const size_t budget = 224 * 1024;
     const size_t per_stage = (size_t)g.groups * g.stage_bytes;
     if (fixed + 3 * per_stage > budget) return B200_ERR_UNSUPPORTED;
     g.stages = (int)((budget - fixed) / per_stage);

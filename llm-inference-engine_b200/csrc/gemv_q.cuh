@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint32_t two_bytes) {
 }
 
 // smem: [ xs : M * xs_stride halves | rings : groups * stages * stage_bytes | barriers | partials : groups * 2 * GW * 16*8 floats ]
-template <typename T, int FMT, bool kSwiGLU>
+template <typename T, int FMT, bool kSwiGLU, bool kMerge>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
     static_assert(FMT == WF_FP8 || FMT == WF_INT4, "quantised formats only");
@@ -170,8 +170,8 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
             *reinterpret_cast<uint4 *>(xs + (size_t)m * geo.xs_stride + (size_t)i * V) = pk;
         };
         static_assert(V == 8, "gemv_q_kernel: 16-bit activation types only");
-        if (a.M == 1) gemv_stage_activations<T, 1>(a, n_threads, red, store);  // single-trip instantiation: no spills in the B = 1 prologue
-        else gemv_stage_activations<T, 0>(a, n_threads, red, store);
+        if (a.M == 1) gemv_stage_activations<T, 1, kMerge>(a, n_threads, red, store);  // single-trip instantiation: no spills in the B = 1 prologue
+        else gemv_stage_activations<T, 0, kMerge>(a, n_threads, red, store);
         __syncthreads();
     }
     pdl_launch_dependents();
@@ -378,15 +378,21 @@ static int launch_gemv_q_inst(const GemvArgs &a, cudaStream_t st) {
     g.stages = (int)((budget - fixed) / per_stage);
     if (g.stages > kGemvMaxStages) g.stages = kGemvMaxStages;
     const size_t smem = fixed + (size_t)g.stages * per_stage;
-    auto kern = gemv_q_kernel<T, FMT, SW>;
-    static thread_local size_t cached_smem[64] = {0};
+    const bool merge = a.attn_part != nullptr;
+    if (merge && SW) return B200_ERR_UNSUPPORTED;
+    auto kern = gemv_q_kernel<T, FMT, SW, false>;
+    if constexpr (!SW) {
+        if (merge) kern = gemv_q_kernel<T, FMT, SW, true>;
+    }
+    static thread_local size_t cached_smem[2][64] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (cached_smem[dev] < smem) {
+    if (cached_smem[merge][dev] < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cuda_status("gemv_q cudaFuncSetAttribute");
-        cached_smem[dev] = smem;
+        cached_smem[merge][dev] = smem;
     }
+    if (a.probe) return B200_OK;
     const int units = SW ? (a.inter + 7) / 8 : (a.N + kQRows - 1) / kQRows;
     int grid = sm_count();
     const int need = (units + kGemvGroups - 1) / kGemvGroups;

@@ -300,9 +300,8 @@ int b200_linear(const void *x, const void *w, const void *scales, const void *ze
     // ---- decode-shaped: weight-streaming GEMV
     if (w_layout == B200_LAYOUT_NK) {
         int done = 0, rc = B200_OK;
-        static const bool force_tc = getenv("B200_FORCE_TC") != nullptr;  // benchmarking aid: tensor-core path for every M
         // dense 16-bit, M > 4: tcgen05 GEMM (swap-AB + split-K for M <= 128, 128x256 tiles above)
-        if ((M > 4 || force_tc) && dtype != B200_F32 && w_format == B200_W_DENSE) {
+        if (M > 4 && dtype != B200_F32 && w_format == B200_W_DENSE) {
             rc = launch_gemm_tc(x, w, y, M, N, K, dtype, st);
             if (rc == B200_OK) done = 1;
             else if (rc != B200_ERR_UNSUPPORTED) return rc;

@@ -476,8 +476,7 @@ int b200_context_attention(const void *q, const void *k_cache, const void *v_cac
     const size_t eb = dtype == B200_F32 ? 4 : 2;
     const size_t loff = (size_t)layer * batch * kv_head_num * max_seq_len * head_size * eb;
     // head size 128, 16-bit: tcgen05 / TMEM flash attention (context_attn_tc.cu); everything else: the SIMT tiles below
-    static const bool force_simt = getenv("B200_CTX_ATTN_SIMT") != nullptr;
-    if (!force_simt) {
+    {
         const int rc = launch_context_attention_tc(q, (const char *)k_cache + loff, (const char *)v_cache + loff, out, seq_off, input_len,
                                                    context_len, batch, head_num, kv_head_num, max_q_len, max_seq_len, head_size, scale, dtype, st);
         if (rc != B200_ERR_UNSUPPORTED) return rc;

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <unistd.h>
+#include <string>
 #include <vector>
 #include <cuda_runtime.h>
 #include "src/layers/includes/self_decoder.h"
@@ -103,33 +104,116 @@ int main(int argc, char **argv) {
         decoder->forward(in, layer_weights, out, &dp);
     };
 
+    // The same work without the layer classes: the reference's launch functions called in LlamaSelfDecoder::forward's order
+    // (self_decoder.cpp:69-119, self_attention.cpp:79-139, ffn.cpp:105-140) on buffers allocated once.  `syncs`: keep the
+    // cudaDeviceSynchronize the reference does after every launcher (DeviceSyncAndCheckCudaError) -- its actual behaviour -- or not
+    // (its kernels + cuBLAS at their best).  Used when forward() itself does not survive on this GPU / driver (recorded in the JSON).
+    float *d_res = device_fill((size_t)batch * hidden, 0.0f, 13), *d_qkv = device_fill((size_t)batch * qkv_cols, 0.0f, 14);
+    float *d_mha = device_fill((size_t)batch * hidden, 0.0f, 15), *d_gu = device_fill((size_t)batch * 2 * inter, 0.0f, 16);
+    float *d_act = device_fill((size_t)batch * inter, 0.0f, 17);
+    auto launchers_once = [&](bool syncs) {
+        auto sync = [&]() { if (syncs) cudaDeviceSynchronize(); };
+        auto *x = new TensorWrapper<float>(Device::GPU, f, {batch, hidden}, d_out);
+        auto *res = new TensorWrapper<float>(Device::GPU, f, {batch, hidden}, d_res);
+        auto *qkv = new TensorWrapper<float>(Device::GPU, f, {batch, head_num + 2 * kv_head_num, head_size}, d_qkv);
+        auto *mha = new TensorWrapper<float>(Device::GPU, f, {batch, hidden}, d_mha);
+        auto *gu = new TensorWrapper<float>(Device::GPU, f, {batch, 2, inter}, d_gu);
+        auto *act = new TensorWrapper<float>(Device::GPU, f, {batch, inter}, d_act);
+        auto *kc = new TensorWrapper<float>(Device::GPU, f, {layers, batch, kv_head_num, max_seq, head_size}, d_k);
+        auto *vc = new TensorWrapper<float>(Device::GPU, f, {layers, batch, kv_head_num, max_seq, head_size}, d_v);
+        auto *fin = new TensorWrapper<bool>(Device::GPU, b8, {batch}, d_finished);
+        auto *stp = new TensorWrapper<int>(Device::CPU, i32, {1}, h_step);
+        cudaMemcpyAsync(d_out, d_in, sizeof(float) * batch * hidden, cudaMemcpyDeviceToDevice, 0);
+        for (int l = 0; l < layers; ++l) {
+            int *h_l = new int(l);
+            auto *lid = new TensorWrapper<int>(Device::CPU, i32, {1}, h_l);
+            LlamaLayerWeight<float> *w = layer_weights->at(l);
+            launchRMSNorm(x, res, &w->attention_norm_weight, 1e-6f);
+            sync();
+            launchLinearGemm(x, &w->self_attention_weight.qkv, qkv, wrapper, false, w->self_attention_weight.qkv.is_transposed);
+            sync();
+            launchRope(qkv, stp, &sp);
+            sync();
+            launchDecoderMaskedMultiHeadAttention<float>(qkv, &w->self_attention_weight.qkv, lid, kc, vc, fin, stp, mha, &sp);
+            sync();
+            launchLinearGemm(mha, &w->self_attention_weight.output, x, wrapper, false, w->self_attention_weight.output.is_transposed);
+            sync();
+            launchFusedAddBiasResidualAndRMSNorm(res, x, &w->self_attention_weight.output, w->ffn_norm_weight.gamma, 1e-6f);
+            sync();
+            launchLinearGemm(x, &w->ffn_weight.gate_and_up, gu, wrapper, false, w->ffn_weight.gate_and_up.is_transposed);
+            sync();
+            launchSiluAndMul(gu, act);
+            sync();
+            launchLinearGemm(act, &w->ffn_weight.down, x, wrapper, false, w->ffn_weight.down.is_transposed);
+            sync();
+            launchAddResidual(res, x, false);
+            sync();
+        }
+    };
+
     // the reference prints from inside its launchers: keep stdout for the JSON line only
     fflush(stdout);
     const int saved = dup(1);
     FILE *devnull = fopen("/dev/null", "w");
     dup2(fileno(devnull), 1);
-    for (int i = 0; i < warmup; ++i) forward_once();
-    cudaDeviceSynchronize();
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
-    cudaEventRecord(e0, 0);
-    for (int i = 0; i < iters; ++i) forward_once();
-    cudaEventRecord(e1, 0);
-    cudaEventSynchronize(e1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    std::string forward_error;
+    float ms = -1.f;
+    try {
+        for (int i = 0; i < warmup; ++i) forward_once();
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters; ++i) forward_once();
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    } catch (const std::exception &ex) {
+        forward_error = ex.what();
+        ms = -1.f;
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+    }
+    float ms_l[2] = {-1.f, -1.f};  // launcher sequence: [0] with the reference's per-launcher device syncs, [1] without
+    std::string launcher_error;
+    for (int v = 0; v < 2; ++v) {
+        try {
+            for (int i = 0; i < warmup; ++i) launchers_once(v == 0);
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0, 0);
+            for (int i = 0; i < iters; ++i) launchers_once(v == 0);
+            cudaEventRecord(e1, 0);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms_l[v], e0, e1);
+        } catch (const std::exception &ex) {
+            launcher_error = ex.what();
+            cudaDeviceSynchronize();
+            cudaGetLastError();
+        }
+    }
     const cudaError_t err = cudaGetLastError();
     fflush(stdout);
     dup2(saved, 1);
+    auto clean = [](std::string t) {
+        for (char &ch : t)
+            if (ch == '"' || ch == '\\' || ch == '\n') ch = ' ';
+        return t;
+    };
 
-    const double per = ms / iters;
     const double weight_bytes = (double)layers * 4.0 * ((double)hidden * qkv_cols + (double)hidden * hidden + 3.0 * hidden * (double)inter);
-    printf("{\"impl\": \"reference-cuda\", \"what\": \"LlamaSelfDecoder<float>::forward, the reference's kernels + cuBLAS, fp32, batch 1\", "
-           "\"layers\": %d, \"step\": %d, \"hidden\": %d, \"inter\": %d, \"iters\": %d, \"warmup\": %d, \"ms_per_step\": %.4f, "
-           "\"tokens_per_s\": %.3f, \"weight_bytes_per_step\": %.0f, \"weight_gb_per_s\": %.1f, \"cuda_status\": \"%s\", "
+    auto per = [&](float t) { return t > 0 ? (double)t / iters : -1.0; };
+    auto tps = [&](float t) { return t > 0 ? 1000.0 / ((double)t / iters) : 0.0; };
+    auto gbs = [&](float t) { return t > 0 ? weight_bytes / ((double)t / iters * 1e-3) / 1e9 : 0.0; };
+    printf("{\"impl\": \"reference-cuda\", \"what\": \"the reference's kernels + cuBLAS SGEMM, fp32, batch 1\", "
+           "\"layers\": %d, \"step\": %d, \"hidden\": %d, \"inter\": %d, \"iters\": %d, \"warmup\": %d, "
+           "\"forward\": {\"what\": \"LlamaSelfDecoder<float>::forward\", \"ms_per_step\": %.4f, \"tokens_per_s\": %.3f, \"weight_gb_per_s\": %.1f, \"error\": \"%s\"}, "
+           "\"launchers_with_syncs\": {\"what\": \"the reference's launch functions in forward()'s order, device sync after each as the reference does\", "
+           "\"ms_per_step\": %.4f, \"tokens_per_s\": %.3f, \"weight_gb_per_s\": %.1f}, "
+           "\"launchers_no_syncs\": {\"what\": \"same without the syncs\", \"ms_per_step\": %.4f, \"tokens_per_s\": %.3f, \"weight_gb_per_s\": %.1f}, "
+           "\"launcher_error\": \"%s\", \"weight_bytes_per_step\": %.0f, \"cuda_status\": \"%s\", "
            "\"note\": \"decoder layers only (no LM head / sampling: dead code in the reference); one layer's weights shared by all layers\"}\n",
-           layers, step_arg, hidden, inter, iters, warmup, per, 1000.0 / per, weight_bytes, weight_bytes / (per * 1e-3) / 1e9,
-           cudaGetErrorString(err));
+           layers, step_arg, hidden, inter, iters, warmup, per(ms), tps(ms), gbs(ms), clean(forward_error).c_str(), per(ms_l[0]), tps(ms_l[0]),
+           gbs(ms_l[0]), per(ms_l[1]), tps(ms_l[1]), gbs(ms_l[1]), clean(launcher_error).c_str(), weight_bytes, cudaGetErrorString(err));
     fflush(stdout);
-    _exit(err == cudaSuccess ? 0 : 1);  // no destructors: the reference's wrappers would free buffers they do not own
+    _exit((ms_l[0] > 0 || ms > 0) ? 0 : 1);  // no destructors: the reference's wrappers would free buffers they do not own
 }

@@ -304,9 +304,8 @@ def test_prefill_engine_matches_oracle(dtype):
 
 
 @pytest.mark.gpu
-def test_linears_only_and_trace_diagnostics():
-    """b200_decoder_linears_only launches exactly the step's weight-streaming kernels (4 per layer un-chained); b200_decoder_debug_trace
-    hands out a buffer of the documented size and can be switched off again."""
+def test_linears_only_diagnostic():
+    """b200_decoder_linears_only launches exactly the step's weight-streaming kernels (4 per layer)."""
     import torch
 
     model = make_model(SMALL, seed=2)
@@ -316,24 +315,4 @@ def test_linears_only_and_trace_diagnostics():
     dec.step(xd, kcd, vcd, 5)
     n = dec.linears_only(1)
     torch.cuda.synchronize()
-    assert n in (4 * SMALL["layers"], 1 + SMALL["layers"])  # separate launches, or first QKV + one chained kernel per layer
-    tr = dec.debug_trace(True)
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    assert tr.numel() == SMALL["layers"] * sms * 4 * 8
-    assert dec.debug_trace(False) is None
-
-
-@pytest.mark.gpu
-def test_chained_gemv_experiment_still_matches_the_oracle():
-    """The opt-in chained GEMV kernel (B200_CHAIN=1) is read once per process: run the engine parity cases in a child."""
-    import os
-    import subprocess
-    import sys
-
-    env = dict(os.environ, B200_CHAIN="1")
-    here = os.path.dirname(os.path.abspath(__file__))
-    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_decoder_engine.py"), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-                        "-k", "test_engine_matches_oracle or graph_replay"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600,
-                       cwd=os.path.dirname(here))
-    out = p.stdout.decode(errors="replace")
-    assert p.returncode == 0, out[-3000:]
+    assert n == 4 * SMALL["layers"]

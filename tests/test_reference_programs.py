@@ -33,7 +33,7 @@ NEEDS_EXTERNAL_FILE = {"context_decoder_example": "/home/llama2-7b-tokenizer.bin
 CMAKE_DIR = os.path.join(SHIM_DIR, "cmake.d")  # the reference's own CMake build with src/ replaced by the shim (shim/build_with_reference_cmake.sh)
 REF_LAYERS_DIR = os.path.join(SHIM_DIR, "ref_layers.d")
 REF_LAYER_EXAMPLES = ["context_attention_example", "context_decoder_example", "ffn_example", "self_attention_example", "self_decoder_example"]
-REF_LAYERS_VERIFIED_ON_GPU = False  # flip once tests/test_reference_programs.py has run on a B200 with this configuration
+REF_LAYERS_VERIFIED_ON_GPU = True  # run on a B200 in round 2: profiles/r2_reference_layers_on_shim.txt
 
 
 def programs():
