@@ -358,7 +358,7 @@ decode_attn_kernel(const DecodeAttnArgs a) {
 
     // ---- combine the row groups; single split: finish here, else hand the partial to the merge
     T *out = reinterpret_cast<T *>(a.out) + ((size_t)b * H + (size_t)kvh * Gtot + g0) * D;
-    if (a.nsplit == 1 && !a.defer_merge) {
+    if (a.nsplit == 1) {
         for (int i = tid; i < G * D; i += kAttnThreads) {
             const int g = i / D, d = i % D;
             float o = 0.0f;
@@ -382,7 +382,6 @@ decode_attn_kernel(const DecodeAttnArgs a) {
         part[(size_t)tid * PS + D] = wts[RG * G + tid];
         part[(size_t)tid * PS + D + 1] = wts[RG * G + G + tid];
     }
-    if (a.defer_merge) return;  // the consumer (the O projection's prologue) merges: nothing else on this kernel's critical path
     // ---- the last CTA of the (b, kv head, half group) (self-resetting ticket) merges
     __threadfence();
     __syncthreads();
@@ -504,17 +503,15 @@ size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int
 }
 
 int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk) {
-    // The cached positions [0, step-1) are cut into chunks of whole 64-position tiles, about two CTAs per SM in ONE wave (never a
-    // partial second wave) and at most 16 splits (the merges request the partials in batches); the last split also serves the
-    // token being appended, which never comes from the cache.
+    // The cached positions [0, step-1) are cut into chunks of whole 64-position tiles, about ONE CTA per SM (measured on the 7B
+    // step, ctx 1024: 4 splits x 32 heads = 128 CTAs 2.535 / 2.616 ms, 8 splits = 256 CTAs 2.550 / 2.625 ms on two boxes -- a CTA with
+    // a 3-stage ring streams its share of the cache as fast as two, and the merge reads half as many partials) and at most 16 splits
+    // (the merge requests the partials in one batch); the last split also serves the token being appended, which never comes from
+    // the cache.
     const int cached = step - 1;
-    int want = (2 * sm_count()) / (batch * kv_head_num);
+    int want = sm_count() / (batch * kv_head_num);
     if (want < 1) want = 1;
     if (want > 16) want = 16;
-    {   // TEMPORARY experiment knob (removed before commit)
-        static const int cap = getenv("B200_X_MAXSPLIT") ? atoi(getenv("B200_X_MAXSPLIT")) : 16;
-        if (want > cap) want = cap;
-    }
     int c = (cached + want - 1) / want;
     c = (c + 63) & ~63;
     if (c < 64) c = 64;
@@ -552,10 +549,6 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
         }
         return cuda_status("decode_attn launch");
     }
-    if (a.defer_merge) {
-        set_error("decode_mha: deferred merge needs head size 128");
-        return B200_ERR_STATE;
-    }
     const size_t smem = sizeof(float) * ((size_t)3 * a.head_size + a.step);
     if (smem > 200 * 1024) {
         set_error("decode_mha: step %d too long for the generic head-size path", a.step);
@@ -564,11 +557,6 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
     cudaFuncSetAttribute(decode_attn_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_pdl(decode_attn_generic_kernel<T>, dim3(a.head_num, a.batch), dim3(128), smem, st, true, a);
     return cuda_status("decode_attn_generic launch");
-}
-
-bool decode_attn_fast_path(int head_num, int kv_head_num, int head_size) {
-    const int G = head_num / kv_head_num;
-    return head_size == kAttnD && (G == 1 || G == 2 || G == 4 || G == 8);
 }
 
 int launch_decode_attn(const DecodeAttnArgs &a, int dtype, cudaStream_t st) {

@@ -11,15 +11,12 @@ struct DecodeAttnArgs {
     void *v_cache;
     void *out;         // [B, H*d]
     float *partials;   // [B*Hkv][nsplit][G][kAttnPartStride]: per split and q head the un-normalised output o[d], then (max, sum)
-    unsigned int *tickets;  // [B*Hkv], zero-initialised, self-resetting (unused when defer_merge)
+    unsigned int *tickets;  // [B*Hkv], zero-initialised, self-resetting
     const float2 *rope_cs;  // optional (cos, sin) table [max_seq_len][rot_dim/2] made by launch_rope_table(); NULL: compute
     int batch, head_num, kv_head_num, head_size, max_seq_len, step;
     int apply_rope, rot_dim;
     float rot_base;
     int nsplit, chunk;
-    int defer_merge;  // 1 (fused engine, O projection on the GEMV): leave the per-split partials in `partials`; the O projection's
-                      // prologue merges them while it stages its activations (AttnMerge in gemv.cuh) -- no fence, no ticket, no
-                      // last-arriver reload on this kernel's critical path
     int prefetch;  // 1: cached K/V rows may be requested before griddepcontrol.wait (fused engine only: the kernel in front
                    // of this one does not write the cache)
 };
@@ -31,8 +28,7 @@ inline int attn_part_stride(int head_size) { return head_size + 4; }
 int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk);
 size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int head_size, int max_splits);
 int launch_decode_attn(const DecodeAttnArgs &a, int dtype, cudaStream_t st);
-// true when the split-KV kernel (head size 128, GQA group 1/2/4/8) serves this shape: only it can defer its merge
-bool decode_attn_fast_path(int head_num, int kv_head_num, int head_size);
+
 // (cos, sin) of pos / base^(2j / rot_dim) for pos < positions, j < rot_dim / 2 -- the values the kernels compute on the fly
 int launch_rope_table(float2 *table, int positions, int rot_dim, float rot_base, cudaStream_t st);
 

@@ -41,22 +41,31 @@ struct Workspace {
 bool get_workspace(Workspace *ws);
 
 // ------------------------------------------------------------------ tensor-parallel exchange over NVLink peer memory
-// One-shot all-reduce fused into the producer AND the consumer of a row-sharded linear.  Every rank owns an exchange buffer that
-// all other ranks of the node map through CUDA IPC.  PUSH: the producing linear's epilogue stores this rank's partial sum [B,h]
-// straight into EVERY rank's buffer (slot [source rank]; posted NVLink writes, no round trip).  The first kernel of the next block
-// then signals "my partial is complete" into every peer's flag word, waits for every peer's signal, reads the P partials from its
-// OWN memory and adds them in rank order (identical on every rank, deterministic).  No NCCL call, no extra launch, no remote read.
-// (A first version pulled the partials with peer loads from every CTA: 148 CTAs x (P-1) peers x 8 KB per exchange and one NVLink
-// round trip per peer made TP-8 slower than one GPU.)
-// Flag values grow monotonically: epoch (bumped once per decode step by a one-thread kernel) * 4096 + block sequence number.
+// One-shot all-reduce fused into the producer AND the consumer of a row-sharded linear, with no handshake at all.  Every rank owns an
+// exchange buffer that all other ranks of the node map through CUDA IPC.  PUSH: the producing linear's epilogue stores this rank's
+// partial sum [B,h] straight into EVERY rank's buffer (slot [source rank]; posted NVLink writes, no round trip) as 8-byte words
+// {payload: 32 bits of the tensor, flag: 32 bits} -- the "LL" layout: an aligned 8-byte store is never torn, so a word whose flag holds
+// the expected value carries valid data.  The first kernel of the next block polls the P partials in its OWN memory until every word
+// shows the flag of this block, and adds them in rank order (identical on every rank, deterministic).  No NCCL call, no extra launch,
+// no remote read, no fence, no signal: the data is its own arrival notice, so the exchange costs one NVLink one-way latency behind
+// the producer's last store.  (Round 1 signalled with per-rank flag words AFTER the consumer's griddepcontrol.wait: producer drained
+// -> st.release.sys to 7 peers -> every CTA polled ld.acquire.sys -> only then the data was read: 8-18 us per exchange, and TP-8 ran
+// slower than TP-4.)
+// Flag values grow monotonically and are never zero (the buffers start zeroed): epoch (bumped once per decode step by a one-thread
+// kernel) * 4096 + block sequence number.  Two slots alternate; a slot is rewritten by block seq + 2, which a rank can only produce after
+// it has consumed block seq + 1 from everybody, i.e. after every rank has finished reading block seq.
 constexpr int kTpMaxWorld = 8;
 struct TpExchange {
-    const void *peer_x[kTpMaxWorld];        // the P partials of this slot, one per source rank, all in THIS rank's exchange buffer
-    unsigned int *peer_flags[kTpMaxWorld];  // in every rank's buffer: the flag word (this slot, written by THIS rank)
-    const unsigned int *my_flags;           // this rank's flag words of this slot: [world], one per writer
-    const unsigned int *epoch;              // this rank's step counter (device memory)
-    unsigned int *error;                    // set to 1 if a peer never signalled (time-out instead of a hang)
-    int world, rank, seq;                   // world <= 1: exchange disabled
+    const void *peer_x[kTpMaxWorld];  // the P partials of this slot (LL words), one per source rank, all in THIS rank's exchange buffer
+    const unsigned int *epoch;        // this rank's step counter (device memory)
+    unsigned int *error;              // set to 1 if a peer's data never arrived (time-out instead of a hang); sticky
+    int world, rank, seq;             // world <= 1: exchange disabled
+};
+// producer side of the same protocol: where this rank's partial of block `seq` goes in every rank's buffer
+struct TpPush {
+    void *dst[kTpMaxWorld];
+    const unsigned int *epoch;
+    int n, seq;                       // n == 0: plain store into y
 };
 
 // out = gamma * (o + bias) * rsqrt(mean((o+bias)^2)+eps), o = in (+ rin); rout <- o.  in == NULL: in place on out.
@@ -106,38 +115,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
-// ------------------------------------------------------------------ tensor-parallel exchange (device)
-// Called by EVERY thread of EVERY CTA of the consuming kernel, after griddepcontrol.wait (so this rank's producer is complete).
-__device__ __forceinline__ void tp_exchange_sync(const TpExchange &t) {
-    if (t.world <= 1) return;
-    const unsigned int want = *t.epoch * 4096u + (unsigned int)t.seq;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < t.world) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flags[threadIdx.x]), "r"(want) : "memory");
-    }
-    if ((int)threadIdx.x < t.world) {
-        const unsigned int *f = t.my_flags + threadIdx.x;
-        const long long t0 = clock64();
-        for (;;) {
-            unsigned int v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if ((int)(v - want) >= 0) break;
-            if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died; leave a mark instead of hanging the GPU
-                atomicExch(t.error, 1u);
-                break;
-            }
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
-}
-// 16 bytes of every rank's partial at byte offset `off`; peer memory is read uncached (it changes between kernels)
-__device__ __forceinline__ uint4 tp_ld_v4(const void *base, size_t off) {
-    uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"((const char *)base + off));
-    return r;
 }
 
 // ------------------------------------------------------------------ element traits
@@ -244,6 +221,90 @@ template <> __device__ __forceinline__ uint4 pack16<__half>(const float *f) {
     r.z = *reinterpret_cast<uint32_t *>(&c);
     r.w = *reinterpret_cast<uint32_t *>(&d);
     return r;
+}
+
+// ------------------------------------------------------------------ tensor-parallel exchange (device)
+__device__ __forceinline__ unsigned int tp_flag(const unsigned int *epoch, int seq) {
+    unsigned int e;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(epoch));
+    return e * 4096u + (unsigned int)seq;
+}
+__device__ __forceinline__ uint4 tp_ld_v4(const void *p) {  // uncached: the words change under this kernel's feet
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void tp_st_v2(void *p, unsigned int payload, unsigned int flag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(payload), "r"(flag) : "memory");
+}
+__device__ __forceinline__ void tp_st_v4(void *p, unsigned int p0, unsigned int p1, unsigned int flag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%2};" ::"l"(p), "r"(p0), "r"(flag), "r"(p1) : "memory");
+}
+// LL words are indexed by 32-bit payload word: element e of a tensor of T lives in word e * sizeof(T) / 4.
+// PUSH two consecutive elements (e0 even) of this rank's partial to every rank.
+template <typename T>
+__device__ __forceinline__ void tp_push_pair(const TpPush &p, unsigned int flag, size_t e0, float v0, float v1) {
+    if constexpr (sizeof(T) == 2) {
+        const T a = Elem<T>::from_f(v0), b = Elem<T>::from_f(v1);
+        const unsigned int w = (unsigned int)*reinterpret_cast<const unsigned short *>(&a) | ((unsigned int)*reinterpret_cast<const unsigned short *>(&b) << 16);
+        for (int r = 0; r < p.n; ++r) tp_st_v2(reinterpret_cast<char *>(p.dst[r]) + (e0 / 2) * 8, w, flag);
+    } else {
+        for (int r = 0; r < p.n; ++r) tp_st_v4(reinterpret_cast<char *>(p.dst[r]) + e0 * 8, __float_as_uint(v0), __float_as_uint(v1), flag);
+    }
+}
+// PUSH one 16-byte vector of T (4 payload words, first element e0 a multiple of the vector length)
+__device__ __forceinline__ void tp_push_vec(const TpPush &p, unsigned int flag, size_t word0, const uint4 &v) {
+    for (int r = 0; r < p.n; ++r) {
+        char *d = reinterpret_cast<char *>(p.dst[r]) + word0 * 8;
+        tp_st_v4(d, v.x, v.y, flag);
+        tp_st_v4(d + 16, v.z, v.w, flag);
+    }
+}
+// CONSUME one 16-byte vector of T (payload words [word0, word0 + 4)) of every rank's partial: f[j] = round_T(sum over ranks in rank
+// order).  Polls until all flags show `want`; a peer that never delivers trips the (sticky) error word after ~2 s and the result is NaN.
+template <typename T>
+__device__ __forceinline__ void tp_reduce_vec(const TpExchange &t, unsigned int want, size_t word0, float *f) {
+    constexpr int V = Elem<T>::kVec;
+#pragma unroll
+    for (int j = 0; j < V; ++j) f[j] = 0.0f;
+    bool poisoned = false;
+#pragma unroll
+    for (int r0 = 0; r0 < kTpMaxWorld; r0 += 4) {  // four ranks' loads in flight at a time (register budget of the fused prologues)
+        if (r0 >= t.world) break;
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (r0 + j < t.world) {
+                const char *src = reinterpret_cast<const char *>(t.peer_x[r0 + j]) + word0 * 8;
+                a[j] = tp_ld_v4(src), b[j] = tp_ld_v4(src + 16);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (r0 + j < t.world) {
+                if (a[j].y != want || a[j].w != want || b[j].y != want || b[j].w != want) {
+                    const char *src = reinterpret_cast<const char *>(t.peer_x[r0 + j]) + word0 * 8;
+                    const long long t0 = clock64();
+                    for (;;) {
+                        a[j] = tp_ld_v4(src), b[j] = tp_ld_v4(src + 16);
+                        if (a[j].y == want && a[j].w == want && b[j].y == want && b[j].w == want) break;
+                        unsigned int err;
+                        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(err) : "l"(t.error));
+                        if (err || clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died; leave a mark instead of hanging the GPU
+                            atomicExch(t.error, 1u);
+                            poisoned = true;
+                            break;
+                        }
+                        __nanosleep(32);
+                    }
+                }
+                float g[V];
+                unpack16<T>(make_uint4(a[j].x, a[j].z, b[j].x, b[j].z), g);
+#pragma unroll
+                for (int k = 0; k < V; ++k) f[k] += g[k];
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) f[j] = poisoned ? __int_as_float(0x7fc00000) : Elem<T>::to_f(Elem<T>::from_f(f[j]));
 }
 
 // ------------------------------------------------------------------ reductions

@@ -41,9 +41,9 @@ struct b200_decoder {
 
 namespace b200 {
 
-int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const int *padding_offset, const int *history_len,
-                                  int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size, int max_seq_len, int rot_dim,
-                                  float base, int dtype, cudaStream_t st);
+int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const void *bias, const int *padding_offset,
+                                  const int *history_len, int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size,
+                                  int max_seq_len, int rot_dim, float base, int dtype, cudaStream_t st);
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 // A kernel never writes the residual buffer other CTAs of the same launch still read: outputs go to the next buffer of the rotation.
@@ -73,38 +73,40 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
 }
 
 // ---- exchange buffer of the fused tensor-parallel path (one per rank, peer-mapped everywhere):
-//      [0, 256)    flag words: [2 slots][kTpMaxWorld writers]
 //      [256, 512)  this rank's step counter (epoch) and error word
-//      [512, ...)  partial sums: [2 slots][world source ranks][max_batch * hidden elements]
-constexpr size_t kTpFlagsOff = 0, kTpEpochOff = 256, kTpErrorOff = 260, kTpDataOff = 512;
-static size_t tp_slot_bytes(const b200_decoder_config_t &c) { return align_up((size_t)c.max_batch * c.hidden * esize(c.dtype)); }
+//      [512, ...)  partial sums as LL words {payload, flag} (common.cuh): [2 slots][world source ranks][max_batch * hidden elements]
+constexpr size_t kTpEpochOff = 256, kTpErrorOff = 260, kTpDataOff = 512;
+static size_t tp_slot_bytes(const b200_decoder_config_t &c) { return align_up(2 * (size_t)c.max_batch * c.hidden * esize(c.dtype)); }
 // where the partial of block `seq` produced by rank `src` lives inside rank `owner`'s buffer
 static void *tp_slot(const b200_decoder *d, int owner, int seq, int src) {
     return d->tp_base[owner] + kTpDataOff + ((size_t)(seq & 1) * d->cfg.tp_world + src) * tp_slot_bytes(d->cfg);
 }
-// descriptor for the consumer of block `seq` (seq >= 1): P local partials + the flag words
+// descriptor for the consumer of block `seq` (seq >= 1): the P partials, all in this rank's own buffer
 static TpExchange tp_consume(const b200_decoder *d, int seq) {
     TpExchange t = {};
     const b200_decoder_config_t &c = d->cfg;
     t.world = c.tp_world, t.rank = c.tp_rank, t.seq = seq;
-    for (int r = 0; r < c.tp_world; ++r) {
-        t.peer_x[r] = tp_slot(d, c.tp_rank, seq, r);
-        t.peer_flags[r] = reinterpret_cast<unsigned int *>(d->tp_base[r] + kTpFlagsOff) + (seq & 1) * kTpMaxWorld + c.tp_rank;
-    }
-    t.my_flags = reinterpret_cast<const unsigned int *>(d->tp_base[c.tp_rank] + kTpFlagsOff) + (seq & 1) * kTpMaxWorld;
+    for (int r = 0; r < c.tp_world; ++r) t.peer_x[r] = tp_slot(d, c.tp_rank, seq, r);
     t.epoch = reinterpret_cast<const unsigned int *>(d->tp_base[c.tp_rank] + kTpEpochOff);
     t.error = reinterpret_cast<unsigned int *>(d->tp_base[c.tp_rank] + kTpErrorOff);
     return t;
 }
-// batched (M > 4) path: the tensor-core GEMM wrote this rank's partial into its own buffer; copy it to every peer's
+// descriptor for the producer of block `seq`: this rank's slot in every rank's buffer
+static TpPush tp_produce(const b200_decoder *d, int seq) {
+    TpPush p = {};
+    const b200_decoder_config_t &c = d->cfg;
+    p.n = c.tp_world, p.seq = seq;
+    for (int r = 0; r < c.tp_world; ++r) p.dst[r] = tp_slot(d, r, seq, c.tp_rank);
+    p.epoch = reinterpret_cast<const unsigned int *>(d->tp_base[c.tp_rank] + kTpEpochOff);
+    return p;
+}
+// batched (M > 4) path: the tensor-core GEMM wrote this rank's partial as a plain tensor; re-emit it as LL words into every rank's buffer
 template <typename T>
-__global__ void tp_push_kernel(const T *src, TpExchange dsts, size_t n_vec) {
+__global__ void tp_push_kernel(const T *src, TpPush push, size_t n_vec) {
     pdl_wait();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 v = ld_v4(reinterpret_cast<const char *>(src) + i * 16);
-        for (int r = 0; r < dsts.world; ++r)
-            if (r != dsts.rank) st_v4(reinterpret_cast<char *>(const_cast<void *>(dsts.peer_x[r])) + i * 16, v);
-    }
+    const unsigned int flag = tp_flag(push.epoch, push.seq);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x)
+        tp_push_vec(push, flag, i * 4, ld_v4(reinterpret_cast<const char *>(src) + i * 16));
 }
 __global__ void tp_begin_step_kernel(unsigned int *epoch) {
     pdl_wait();
@@ -146,50 +148,44 @@ static int plain_linear(b200_decoder *d, const void *x, const b200_linear_weight
         a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
         a.x = x, a.y = y;
         a.M = M, a.K = K, a.N = N, a.group = c.group;
-        if (push_seq > 0) {
-            a.n_push = c.tp_world;
-            for (int r = 0; r < c.tp_world; ++r) a.y_push[r] = tp_slot(d, r, push_seq, c.tp_rank);
-        }
+        if (push_seq > 0) a.push = tp_produce(d, push_seq);
         const int rc = launch_gemv_nk(a, c.dtype, c.w_format, false, st);
         if (rc != B200_ERR_UNSUPPORTED) return rc;
     }
     int rc = b200_linear(x, w.w, w.scales, w.zeros, y, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
     if (rc != B200_OK || push_seq <= 0) return rc;
-    TpExchange dsts = {};
-    dsts.world = c.tp_world, dsts.rank = c.tp_rank;
-    for (int r = 0; r < c.tp_world; ++r) dsts.peer_x[r] = tp_slot(d, r, push_seq, c.tp_rank);
+    const TpPush push = tp_produce(d, push_seq);
     const size_t n_vec = (size_t)M * N * esize(c.dtype) / 16;
     const int grid = (int)((n_vec + 255) / 256 < 64 ? (n_vec + 255) / 256 : 64);
-    B200_DISPATCH_DTYPE(c.dtype, launch_pdl(tp_push_kernel<T>, dim3(grid), dim3(256), 0, st, true, (const T *)y, dsts, n_vec));
+    B200_DISPATCH_DTYPE(c.dtype, launch_pdl(tp_push_kernel<T>, dim3(grid), dim3(256), 0, st, true, (const T *)y, push, n_vec));
     return cuda_status("tp_push launch");
 }
 
+// hidden <- residual + last FFN output (n_vec 16-byte vectors); under tensor parallelism the FFN output is the fused all-reduce of
+// every rank's partial (LL words, rank order, rounded to T)
 template <typename T>
-__global__ void fold_kernel(T *out, const T *a, const T *b, size_t n, const TpExchange tp) {
+__global__ void fold_kernel(T *out, const T *a, const T *b, size_t n_vec, size_t n_tail, const TpExchange tp) {
+    constexpr int V = Elem<T>::kVec;
     pdl_wait();
-    tp_exchange_sync(tp);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float add = 0.0f;
-        if (tp.world > 1) {  // fused all-reduce of the last FFN partial, rank order, rounded to T
-            for (int r = 0; r < tp.world; ++r) {
-                unsigned short u;
-                asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(u) : "l"(reinterpret_cast<const char *>(tp.peer_x[r]) + i * sizeof(T)));
-                if constexpr (sizeof(T) == 2) {
-                    T v;
-                    *reinterpret_cast<unsigned short *>(&v) = u;
-                    add += Elem<T>::to_f(v);
-                } else {
-                    unsigned int w32;
-                    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w32) : "l"(reinterpret_cast<const char *>(tp.peer_x[r]) + i * sizeof(T)));
-                    add += __uint_as_float(w32);
-                }
-            }
-            add = round_to<T>(add);
+    const unsigned int want = tp.world > 1 ? tp_flag(tp.epoch, tp.seq) : 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        float add[V], res[V];
+        if (tp.world > 1) {
+            tp_reduce_vec<T>(tp, want, i * 4, add);
         } else if (b) {
-            add = Elem<T>::to_f(b[i]);
+            unpack16<T>(ld_v4(b + i * V), add);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) add[j] = 0.0f;
         }
-        out[i] = Elem<T>::from_f(Elem<T>::to_f(a[i]) + add);
+        unpack16<T>(ld_v4(a + i * V), res);
+#pragma unroll
+        for (int j = 0; j < V; ++j) res[j] += add[j];
+        st_v4(out + i * V, pack16<T>(res));
     }
+    // elements past the last whole vector (hidden sizes that are not a multiple of the vector length: single-GPU only)
+    for (size_t i = n_vec * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec * V + n_tail; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = Elem<T>::from_f(Elem<T>::to_f(a[i]) + (b ? Elem<T>::to_f(b[i]) : 0.0f));
 }
 
 static int check_ready(const b200_decoder *d, int batch) {
@@ -310,30 +306,8 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     return B200_OK;
 }
 
-// The O projection as the fused GEMV (M <= 4 dense, <= 8 quantised).  merge != 0: its prologue merges the attention's split-KV partials.
-static GemvArgs o_proj_gemv_args(const b200_decoder_t *dec, const b200_layer_weights_t &w, void *y, int batch, int step, int nsplit, bool merge) {
-    const b200_decoder_config_t &c = dec->cfg;
-    GemvArgs a = {};
-    a.w = w.o.w, a.scales = w.o.scales, a.zeros = w.o.zeros;
-    a.x = dec->attn, a.y = y;
-    a.M = batch, a.K = c.head_num * c.head_size, a.N = c.hidden, a.group = c.group;
-    if (merge) a.attn_part = dec->partials, a.attn_nsplit = nsplit, a.attn_group = c.head_num / c.kv_head_num, a.attn_step = step;
-    return a;
-}
-// Does the O projection of this engine run on the fused GEMV with the split-KV merge in its prologue?  (Otherwise the attention
-// kernel merges its own partials: tensor-core GEMM for batch > 4, head sizes other than 128.)
-static bool attn_merge_deferred(const b200_decoder_t *dec, int batch) {
-    const b200_decoder_config_t &c = dec->cfg;
-    if (batch > gemv_max_rows(c) || !decode_attn_fast_path(c.head_num, c.kv_head_num, c.head_size)) return false;
-    if (getenv("B200_X_NODEFER")) return false;  // TEMPORARY experiment knob (removed before commit)
-    GemvArgs a = o_proj_gemv_args(dec, dec->layers[0], dec->y_attn, batch, 1, 1, true);
-    a.probe = 1;
-    return launch_gemv_nk(a, c.dtype, c.w_format, false, nullptr) == B200_OK;
-}
-
-// RoPE + qkv bias + KV append + split-KV attention for one layer: dec->qkv -> dec->attn, or (deferred merge) -> dec->partials
-static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache, void *v_cache, int batch, int step, bool defer, int *nsplit,
-                                  cudaStream_t st) {
+// RoPE + qkv bias + KV append + split-KV attention + merge for one layer: dec->qkv -> dec->attn
+static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache, void *v_cache, int batch, int step, cudaStream_t st) {
     const b200_decoder_config_t &c = dec->cfg;
     const b200_layer_weights_t &w = dec->layers[layer];
     DecodeAttnArgs a = {};
@@ -348,8 +322,6 @@ static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache,
     a.partials = dec->partials, a.tickets = dec->tickets;
     a.rope_cs = dec->rope_cs;
     a.prefetch = 1;  // the kernel in front of this one is the QKV linear: it does not touch the cache
-    a.defer_merge = defer;
-    *nsplit = a.nsplit;
     return launch_decode_attn(a, c.dtype, st);
 }
 
@@ -371,20 +343,10 @@ static int attn_block_impl(b200_decoder_t *dec, int layer, void *hidden, const v
                      c.hidden, qkv_n, false, dec->qkv, batch, st, pending ? tp : nullptr);
     if (rc != B200_OK) return rc;
     dec->cur = next_res(dec->cur);
-    // 2. attention (split-KV; with the O projection on the fused GEMV the merge of the splits moves into that kernel's prologue)
-    const bool defer = attn_merge_deferred(dec, batch);
-    int nsplit = 1;
-    rc = launch_layer_attention(dec, layer, k_cache, v_cache, batch, step, defer, &nsplit, st);
+    // 2. attention
+    rc = launch_layer_attention(dec, layer, k_cache, v_cache, batch, step, st);
     if (rc != B200_OK) return rc;
     // 3. O projection (row-sharded under TP: `partial` is this rank's partial sum)
-    if (defer) {
-        GemvArgs a = o_proj_gemv_args(dec, w, partial, batch, step, nsplit, true);
-        if (push_seq > 0) {
-            a.n_push = c.tp_world;
-            for (int r = 0; r < c.tp_world; ++r) a.y_push[r] = tp_slot(dec, r, push_seq, c.tp_rank);
-        }
-        return launch_gemv_nk(a, c.dtype, c.w_format, false, st);
-    }
     return plain_linear(dec, dec->attn, w.o, c.head_num * c.head_size, c.hidden, partial, batch, st, push_seq);
 }
 
@@ -422,12 +384,17 @@ static int fold_impl(b200_decoder_t *dec, void *hidden, const void *pending, int
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
     B200_REQUIRE(hidden, "decoder_fold: null pointer");
-    const size_t n = (size_t)batch * dec->cfg.hidden;
-    const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    const size_t n = (size_t)batch * dec->cfg.hidden, vec = 16 / esize(dec->cfg.dtype);
+    // whole rows must be vectors for the vector path (row starts stay 16-byte aligned); otherwise everything goes through the scalar tail
+    const bool vec_ok = dec->cfg.hidden % vec == 0 && aligned16(hidden) && (!pending || aligned16(pending));
+    B200_REQUIRE(vec_ok || !tpx, "decoder_fold: tensor-parallel fold needs 16-byte rows");
+    const size_t n_vec = vec_ok ? n / vec : 0, n_tail = n - n_vec * vec;
+    const size_t work = n_vec + n_tail;
+    const int grid = (int)((work + 255) / 256 < 1024 ? (work + 255) / 256 : 1024);
     TpExchange tp = {};
     if (tpx) tp = *tpx;
-    B200_DISPATCH_DTYPE(dec->cfg.dtype, launch_pdl(fold_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), true, (T *)hidden,
-                                                   (const T *)dec->res[dec->cur], (const T *)pending, n, tp));
+    B200_DISPATCH_DTYPE(dec->cfg.dtype, launch_pdl(fold_kernel<T>, dim3(grid ? grid : 1), dim3(256), 0, as_stream(stream), true, (T *)hidden,
+                                                   (const T *)dec->res[dec->cur], (const T *)pending, n_vec, n_tail, tp));
     return cuda_status("decoder_fold launch");
 }
 
@@ -500,21 +467,21 @@ int b200_decoder_step_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void 
     launch_pdl(tp_begin_step_kernel, dim3(1), dim3(32), 0, st, true, reinterpret_cast<unsigned int *>(dec->tp_base[c.tp_rank] + kTpEpochOff));
     if ((rc = cuda_status("tp_begin_step launch")) != B200_OK) return rc;
     int seq = 0;  // sequence number of the last partial produced in this step
-    const int me = c.tp_rank;
+    // `partial` / `pending` below are plain staging tensors: the batched (tensor-core) linears write their partial there before it is
+    // re-emitted as LL words; the fused GEMVs push straight from their epilogue and never touch them
     for (int l = 0; l < c.num_layers; ++l) {
         // attention block: consumes the previous layer's FFN partials (seq), pushes its O-projection partial as block seq + 1
         TpExchange tin = seq ? tp_consume(dec, seq) : TpExchange{};
-        rc = attn_block_impl(dec, l, hidden, seq ? tp_slot(dec, me, seq, me) : nullptr, k_cache, v_cache, tp_slot(dec, me, seq + 1, me), batch, step,
-                             stream, seq ? &tin : nullptr, seq + 1);
+        rc = attn_block_impl(dec, l, hidden, seq ? dec->y_ffn : nullptr, k_cache, v_cache, dec->y_attn, batch, step, stream, seq ? &tin : nullptr, seq + 1);
         if (rc != B200_OK) return rc;
         ++seq;
         TpExchange tmid = tp_consume(dec, seq);
-        rc = ffn_block_impl(dec, l, tp_slot(dec, me, seq, me), tp_slot(dec, me, seq + 1, me), batch, stream, &tmid, seq + 1);
+        rc = ffn_block_impl(dec, l, dec->y_attn, dec->y_ffn, batch, stream, &tmid, seq + 1);
         if (rc != B200_OK) return rc;
         ++seq;
     }
     TpExchange tlast = tp_consume(dec, seq);
-    return fold_impl(dec, hidden, tp_slot(dec, me, seq, me), batch, stream, &tlast);
+    return fold_impl(dec, hidden, dec->y_ffn, batch, stream, &tlast);
 }
 
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, int step, int layer_begin,
@@ -536,13 +503,13 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
 }
 
 // Diagnostic for roofline measurements: exactly the weight-streaming launches of b200_decoder_step (four GEMVs per layer) without the
-// attention kernels and the final fold.  The activations are whatever the scratch buffers hold: call it after at least one real step;
+// attention kernels and the final fold (a tensor-parallel engine runs them on its shard, without the exchange).  The activations are
+// whatever the scratch buffers hold: call it after at least one real step;
 // results are meaningless, timing is not.
 int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b200_stream_t stream) {
     int rc = check_ready(dec, batch);
     if (rc != B200_OK) return rc;
     const b200_decoder_config_t &c = dec->cfg;
-    B200_REQUIRE(c.tp_world <= 1, "decoder_linears_only: single-GPU engines only");
     cudaStream_t st = as_stream(stream);
     const int L = c.num_layers, qkv_n = (c.head_num + 2 * c.kv_head_num) * c.head_size;
     for (int l = 0; l < L; ++l) B200_REQUIRE(dec->layer_set[l], "decoder_linears_only: layer %d not set", l);
@@ -605,6 +572,7 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
     B200_REQUIRE(batch >= 1 && batch <= c.max_batch && max_q_len >= 1 && num_tokens >= 1 && num_tokens <= batch * max_q_len,
                  "decoder_prefill: bad shape (batch %d, max_q_len %d, num_tokens %d)", batch, max_q_len, num_tokens);
     B200_REQUIRE(batch == c.max_batch, "decoder_prefill: batch %d must equal the cache's batch dimension (max_batch %d)", batch, c.max_batch);
+    B200_REQUIRE(max_q_len <= c.max_seq_len, "decoder_prefill: max_q_len %d exceeds the cache length %d", max_q_len, c.max_seq_len);
     B200_REQUIRE(layer_begin >= 0 && layer_end <= c.num_layers && layer_begin < layer_end, "decoder_prefill: bad layer range");
     B200_REQUIRE(((uintptr_t)scratch & 255) == 0, "decoder_prefill: scratch must be 256-byte aligned");
     size_t off[11];
@@ -632,9 +600,12 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
         if ((rc = linear(xn, w.qkv, qkv, h, qkv_n)) != B200_OK) return rc;
         // split + RoPE + KV append: one fused pass (k / v go straight into the cache); un-vectorisable shapes take the two launchers
         const size_t layer_off = (size_t)l * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
-        rc = launch_prefill_qkv_rope_cache(qp, (char *)k_cache + layer_off, (char *)v_cache + layer_off, qkv, padding_offset, history_len, max_q_len, T,
-                                           c.head_num, c.kv_head_num, c.head_size, c.max_seq_len, c.rotary_dim, c.rotary_base, c.dtype, st);
+        rc = launch_prefill_qkv_rope_cache(qp, (char *)k_cache + layer_off, (char *)v_cache + layer_off, qkv, w.qkv_bias, padding_offset, history_len,
+                                           max_q_len, T, c.head_num, c.kv_head_num, c.head_size, c.max_seq_len, c.rotary_dim, c.rotary_base, c.dtype, st);
         if (rc == B200_ERR_UNSUPPORTED) {
+            // un-vectorisable head sizes take the reference's two launchers, whose prefill kernel has no bias term
+            B200_REQUIRE(!w.qkv_bias, "decoder_prefill: qkv bias needs a head size the fused prefill kernel supports (multiple of %d)",
+                         c.dtype == B200_F32 ? 8 : 16);
             rc = b200_qkv_bias_transpose_rope(qp, kp, vp, qkv, w.qkv_bias, padding_offset, history_len, input_len, batch, max_q_len, T, c.head_num,
                                               c.kv_head_num, c.head_size, c.rotary_dim, c.rotary_base, c.dtype, stream);
             if (rc != B200_OK) return rc;

@@ -67,16 +67,9 @@ struct GemvArgs {
     int inter;  // SwiGLU: rows (i, inter + i) form a unit, n_out = inter
     int y_f32;
     TpExchange tp;  // world > 1: x is the sum over ranks of tp.peer_x[*] (fused one-shot all-reduce), `x` itself is ignored
-    // n_push > 0: y is this rank's PARTIAL sum of a row-sharded linear; the reducer stores it into every rank's exchange buffer
-    // (y_push[p], peer-mapped memory: posted NVLink writes) instead of `y`, so that the consumers read only local memory
-    void *y_push[kTpMaxWorld];
-    int n_push;
-    // attn_part != NULL: x is the merge of the decode attention's split-KV partials (decode_attn_kernel with defer_merge;
-    // reference decoder_self_attention.cu:145-186 final normalisation), formed while the activations are staged; `x` is ignored.
-    // Records [M * kv heads][attn_nsplit][attn_group][kAttnPartStride floats: o[128], max, sum, pad, pad]; K = heads * 128.
-    const float *attn_part;
-    int attn_nsplit, attn_group, attn_step;
-    int probe;  // host only: 1 = answer whether this launch is supported (B200_OK / B200_ERR_UNSUPPORTED) without launching
+    // push.n > 0: y is this rank's PARTIAL sum of a row-sharded linear; the reducer stores it into every rank's exchange buffer
+    // (peer-mapped memory: posted NVLink writes of LL words, common.cuh) instead of `y`, so that the consumers read only local memory
+    TpPush push;
 };
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy PTX
@@ -244,72 +237,13 @@ __device__ __forceinline__ void dot_rows(const uint4 (&wv)[kGemvRows], const boo
     }
 }
 
-// ------------------------------------------------------------------ merge of the decode attention's split-KV partials
-// V consecutive output elements (one 16-byte vector of T) of token m, starting at element i*V of the [heads * 128] attention output.
-// Same arithmetic and split order as the merging CTA of decode_attn_kernel: M = max_s m_s (clamped at 0 when step < head size, the
-// reference's quirk), c_s = exp(m_s - M), out = sum_s c_s o_s / (sum_s c_s sum_s + 1e-6).  All loads of a batch of 8 splits are
-// independent and issued together (one L2 round trip); the records are L2-resident (written by the kernel in front of this one).
-constexpr int kAttnMergeD = 128, kAttnMergeStride = 132, kAttnMergeBatch = 4;
-template <int V>
-__device__ __forceinline__ void attn_merge_vec(const GemvArgs &a, int m, int i, float *f) {
-    constexpr int D = kAttnMergeD, PS = kAttnMergeStride, NB = kAttnMergeBatch;
-    const int k0 = i * V, head = k0 / D, d0 = k0 % D;
-    const int G = a.attn_group, kvh = head / G, g = head % G, Hkv = (a.K / D) / G, ns = a.attn_nsplit;
-    const float *pg = a.attn_part + ((((size_t)m * Hkv + kvh) * ns) * G + g) * (size_t)PS;
-    const size_t sstride = (size_t)G * PS;
-    float2 ms[NB];             // (max, sum) of the batch's splits
-    float4 ov[NB][V / 4];      // their o[d0 .. d0 + V)
-    auto load_batch = [&](int s0) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-            if (s0 + j < ns) {
-                const float *ps = pg + (size_t)(s0 + j) * sstride;
-                ms[j] = __ldcg(reinterpret_cast<const float2 *>(ps + D));
-#pragma unroll
-                for (int q = 0; q < V / 4; ++q) ov[j][q] = __ldcg(reinterpret_cast<const float4 *>(ps + d0) + q);
-            }
-    };
-    load_batch(0);  // in flight while the maxima of all splits are fetched (register budget: 4 splits at a time)
-    float mm = -INFINITY;
-    for (int s0 = 0; s0 < ns; s0 += 8) {
-        float mv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mv[j] = s0 + j < ns ? __ldcg(pg + (size_t)(s0 + j) * sstride + D) : -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mm = fmaxf(mm, mv[j]);
-    }
-    if (a.attn_step < D && mm < 0.0f) mm = 0.0f;
-    float ssum = 0.0f;
-#pragma unroll
-    for (int e = 0; e < V; ++e) f[e] = 0.0f;
-    for (int s0 = 0; s0 < ns; s0 += NB) {
-        if (s0 > 0) load_batch(s0);
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-            if (s0 + j < ns) {  // split order: deterministic, identical to the merging CTA of decode_attn_kernel
-                const float c = expf(ms[j].x - mm);
-                ssum = fmaf(ms[j].y, c, ssum);
-#pragma unroll
-                for (int q = 0; q < V / 4; ++q) {
-                    f[4 * q + 0] = fmaf(ov[j][q].x, c, f[4 * q + 0]);
-                    f[4 * q + 1] = fmaf(ov[j][q].y, c, f[4 * q + 1]);
-                    f[4 * q + 2] = fmaf(ov[j][q].z, c, f[4 * q + 2]);
-                    f[4 * q + 3] = fmaf(ov[j][q].w, c, f[4 * q + 3]);
-                }
-            }
-    }
-    const float den = ssum + 1e-6f;
-#pragma unroll
-    for (int e = 0; e < V; ++e) f[e] = f[e] / den;
-}
-
 // ------------------------------------------------------------------ activation staging shared by the GEMV kernels
 // For every token row m < a.M and every 16-byte vector i of the row: x (or, under tensor parallelism, the fused all-reduce of every
 // rank's partial -- TpExchange) (+ residual) -> T; residual_out <- that (CTA 0 only); (+ bias) -> T; RMSNorm with gamma when given
 // (reference src/kernels/rmsnorm.cu:35-80, add_residual_and_rmsnorm.cu:43-121).  The V fp32 values of each vector are handed to
 // store(m, i, f).  One global read pass when the row fits the per-thread register cache.  Every thread of the CTA must call;
 // `red` = shared float[33].  The caller synchronises afterwards.
-template <typename T, int MB, bool kMerge, typename Store>
+template <typename T, int MB, typename Store>
 __device__ __forceinline__ void gemv_stage_activations(const GemvArgs &a, int n_threads, float *red, Store store) {
     constexpr int V = Elem<T>::kVec;
     const int K = a.K;
@@ -319,32 +253,12 @@ __device__ __forceinline__ void gemv_stage_activations(const GemvArgs &a, int n_
     const T *bias = a.norm ? reinterpret_cast<const T *>(a.bias) : nullptr;
     const T *gamma = a.norm ? reinterpret_cast<const T *>(a.gamma) : nullptr;
     const int nv = K / V;
-    tp_exchange_sync(a.tp);
+    const unsigned int tp_want = a.tp.world > 1 ? tp_flag(a.tp.epoch, a.tp.seq) : 0u;
     // pre-norm value of vector i of row m
     auto prenorm = [&](int m, int i, float *f, bool write_res) {
-        if (kMerge) {
-            attn_merge_vec<V>(a, m, i, f);
-#pragma unroll
-            for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);  // the un-fused attention kernel stores a tensor of T
-        } else if (a.tp.world > 1) {
+        if (a.tp.world > 1) {
             // one-shot all-reduce: add every rank's partial in rank order, round to T as an all-reduced tensor of T would be
-            const size_t off = ((size_t)m * K + (size_t)i * V) * sizeof(T);
-#pragma unroll
-            for (int j = 0; j < V; ++j) f[j] = 0.0f;
-            uint4 raw[kTpMaxWorld];
-#pragma unroll
-            for (int r2 = 0; r2 < kTpMaxWorld; ++r2)  // all loads in flight before the first add
-                if (r2 < a.tp.world) raw[r2] = tp_ld_v4(a.tp.peer_x[r2], off);
-#pragma unroll
-            for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
-                if (r2 < a.tp.world) {
-                    float g[V];
-                    unpack16<T>(raw[r2], g);
-#pragma unroll
-                    for (int j = 0; j < V; ++j) f[j] += g[j];
-                }
-#pragma unroll
-            for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
+            tp_reduce_vec<T>(a.tp, tp_want, ((size_t)m * K + (size_t)i * V) * sizeof(T) / 4, f);
         } else {
             unpack16<T>(ld_v4(xin + (size_t)m * K + (size_t)i * V), f);
         }
@@ -425,8 +339,7 @@ __device__ __forceinline__ void gemv_stage_activations(const GemvArgs &a, int n_
 // smem: [ xs : MB * Kp * sizeof(XS) | rings : groups * stages * stage_bytes | barriers : groups * (2 * kGemvMaxStages + 4) * 8 |
 //         partial sums : groups * 2 * GW * R*MB * 32 floats ]
 // XV > 0: every compute warp keeps its XV = pieces * cw activation vectors per token in registers (dense formats only).
-// kMerge: the activations are the merge of the decode attention's split-KV partials (the O projection; GemvArgs::attn_part).
-template <typename T, int FMT, int MB, bool kSwiGLU, int XV, bool kMerge>
+template <typename T, int FMT, int MB, bool kSwiGLU, int XV>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
     using WT = WTraits<T, FMT>;
@@ -516,7 +429,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
         }
         for (int m = a.M; m < MB; ++m)  // padding rows of the batch tile
             for (int i = threadIdx.x; i < Kp; i += n_threads) xs[(size_t)m * Kp + i] = XS(0.0f);
-        gemv_stage_activations<T, MB, kMerge>(a, n_threads, red, [&](int m, int i, const float *f) {
+        gemv_stage_activations<T, MB>(a, n_threads, red, [&](int m, int i, const float *f) {
             if constexpr (FMT == WF_DENSE) {
                 *reinterpret_cast<uint4 *>(xs + (size_t)m * Kp + (size_t)i * V) = pack16<T>(f);
             } else {
@@ -543,6 +456,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
         }
     } else if (!is_compute) {
         // ================================================= reducer: add the group's per-lane partials in a fixed order
+        const unsigned int push_flag = a.push.n > 0 ? tp_flag(a.push.epoch, a.push.seq) : 0u;
         for (int un = 0; un < my_units; ++un) {
             const int u = gid + un * total_groups;
             const int b = un & 1;
@@ -583,6 +497,11 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
                             if (a.y_f32) reinterpret_cast<float *>(a.y)[(size_t)m * a.inter + u] = v;
                             else reinterpret_cast<T *>(a.y)[(size_t)m * a.inter + u] = Elem<T>::from_f(v);
                         }
+                } else if (a.push.n > 0) {
+                    // rows (2u, 2u + 1) of every token: one LL word (16-bit T) or two (fp32) per token and peer; N is even here
+#pragma unroll
+                    for (int m = 0; m < MB; ++m)
+                        if (m < a.M) tp_push_pair<T>(a.push, push_flag, (size_t)m * N + 2 * u, out[0][m], out[1][m]);
                 } else {
 #pragma unroll
                     for (int r = 0; r < R; ++r)
@@ -591,10 +510,7 @@ gemv_nk_kernel(const GemvArgs a, const GemvGeom geo) {
 #pragma unroll
                             for (int m = 0; m < MB; ++m)
                                 if (m < a.M) {
-                                    if (a.n_push > 0) {
-                                        const T v = Elem<T>::from_f(out[r][m]);
-                                        for (int pp = 0; pp < a.n_push; ++pp) reinterpret_cast<T *>(a.y_push[pp])[(size_t)m * N + row] = v;
-                                    } else if (a.y_f32) {
+                                    if (a.y_f32) {
                                         reinterpret_cast<float *>(a.y)[(size_t)m * N + row] = out[r][m];
                                     } else {
                                         reinterpret_cast<T *>(a.y)[(size_t)m * N + row] = Elem<T>::from_f(out[r][m]);

@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint32_t two_bytes) {
 }
 
 // smem: [ xs : M * xs_stride halves | rings : groups * stages * stage_bytes | barriers | partials : groups * 2 * GW * 16*8 floats ]
-template <typename T, int FMT, bool kSwiGLU, bool kMerge>
+template <typename T, int FMT, bool kSwiGLU>
 __global__ void __launch_bounds__(kGemvThreads, 1)
 gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
     static_assert(FMT == WF_FP8 || FMT == WF_INT4, "quantised formats only");
@@ -170,8 +170,8 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
             *reinterpret_cast<uint4 *>(xs + (size_t)m * geo.xs_stride + (size_t)i * V) = pk;
         };
         static_assert(V == 8, "gemv_q_kernel: 16-bit activation types only");
-        if (a.M == 1) gemv_stage_activations<T, 1, kMerge>(a, n_threads, red, store);  // single-trip instantiation: no spills in the B = 1 prologue
-        else gemv_stage_activations<T, 0, kMerge>(a, n_threads, red, store);
+        if (a.M == 1) gemv_stage_activations<T, 1>(a, n_threads, red, store);  // single-trip instantiation: no spills in the B = 1 prologue
+        else gemv_stage_activations<T, 0>(a, n_threads, red, store);
         __syncthreads();
     }
     pdl_launch_dependents();
@@ -187,6 +187,7 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
     } else if (!is_compute) {
         // ================================================= reducer: lane (g, t) finishes rows g, g+8 x tokens 2t, 2t+1
         const int g = lane >> 2, t = lane & 3;
+        const unsigned int push_flag = a.push.n > 0 ? tp_flag(a.push.epoch, a.push.seq) : 0u;
         for (int un = 0; un < my_units; ++un) {
             const int u = gid + un * total_groups;
             const int b = un & 1;
@@ -209,6 +210,23 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
                         o[h][0] *= s8, o[h][1] *= s8;
                     }
             }
+            if (!kSwiGLU && a.push.n > 0) {
+                // tensor-parallel partial: LL words hold two consecutive rows.  Lanes g and g ^ 1 (lane ^ 4) swap one value each: the even
+                // lane ends up with rows (g, g + 1), the odd one with rows (g + 7, g + 8); N is a multiple of 16 rows per unit here
+                const bool odd = g & 1;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float give = odd ? o[0][e] : o[1][e];
+                    const float got = __shfl_xor_sync(0xffffffffu, give, 4);
+                    const int m = 2 * t + e;
+                    if (m < a.M) {
+                        const int r0 = odd ? g + 7 : g;  // first row of the pair inside the unit
+                        if (row_ok(u, r0 + 1))
+                            tp_push_pair<T>(a.push, push_flag, (size_t)m * N + unit_row(u, r0), odd ? got : o[0][e], odd ? o[1][e] : got);
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int m = 2 * t + e;
@@ -227,10 +245,7 @@ gemv_q_kernel(const GemvArgs a, const GemvQGeom geo) {
                     for (int h = 0; h < 2; ++h)
                         if (row_ok(u, g + 8 * h)) {
                             const size_t idx = (size_t)m * N + unit_row(u, g + 8 * h);
-                            if (a.n_push > 0) {
-                                const T v = Elem<T>::from_f(o[h][e]);
-                                for (int pp = 0; pp < a.n_push; ++pp) reinterpret_cast<T *>(a.y_push[pp])[idx] = v;
-                            } else if (a.y_f32) {
+                            if (a.y_f32) {
                                 reinterpret_cast<float *>(a.y)[idx] = o[h][e];
                             } else {
                                 reinterpret_cast<T *>(a.y)[idx] = Elem<T>::from_f(o[h][e]);
@@ -378,21 +393,15 @@ static int launch_gemv_q_inst(const GemvArgs &a, cudaStream_t st) {
     g.stages = (int)((budget - fixed) / per_stage);
     if (g.stages > kGemvMaxStages) g.stages = kGemvMaxStages;
     const size_t smem = fixed + (size_t)g.stages * per_stage;
-    const bool merge = a.attn_part != nullptr;
-    if (merge && SW) return B200_ERR_UNSUPPORTED;
-    auto kern = gemv_q_kernel<T, FMT, SW, false>;
-    if constexpr (!SW) {
-        if (merge) kern = gemv_q_kernel<T, FMT, SW, true>;
-    }
-    static thread_local size_t cached_smem[2][64] = {{0}};
+    auto kern = gemv_q_kernel<T, FMT, SW>;
+    static thread_local size_t cached_smem[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (cached_smem[merge][dev] < smem) {
+    if (cached_smem[dev] < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cuda_status("gemv_q cudaFuncSetAttribute");
-        cached_smem[merge][dev] = smem;
+        cached_smem[dev] = smem;
     }
-    if (a.probe) return B200_OK;
     const int units = SW ? (a.inter + 7) / 8 : (a.N + kQRows - 1) / kQRows;
     int grid = sm_count();
     const int need = (units + kGemvGroups - 1) / kGemvGroups;

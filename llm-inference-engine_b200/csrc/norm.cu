@@ -27,28 +27,12 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
     T *rout = residual_out ? residual_out + (size_t)row * hidden : nullptr;
 
     pdl_wait();
-    tp_exchange_sync(tp);
+    const unsigned int tp_want = tp.world > 1 ? tp_flag(tp.epoch, tp.seq) : 0u;
     // pre-norm value of vector i: o (+ residual); residual_out <- that; (+ bias)
     auto prenorm = [&](int i, float *f) {
         if constexpr (kVec) {
-            if (tp.world > 1) {  // fused one-shot all-reduce of the row-sharded linear's partial sums (rank order)
-                const size_t off = ((size_t)row * hidden + (size_t)i * V) * sizeof(T);
-#pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = 0.0f;
-                uint4 raw[kTpMaxWorld];
-#pragma unroll
-                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
-                    if (r2 < tp.world) raw[r2] = tp_ld_v4(tp.peer_x[r2], off);
-#pragma unroll
-                for (int r2 = 0; r2 < kTpMaxWorld; ++r2)
-                    if (r2 < tp.world) {
-                        float g[V];
-                        unpack16<T>(raw[r2], g);
-#pragma unroll
-                        for (int j = 0; j < V; ++j) f[j] += g[j];
-                    }
-#pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j]);
+            if (tp.world > 1) {  // fused one-shot all-reduce of the row-sharded linear's partial sums (rank order), LL words
+                tp_reduce_vec<T>(tp, tp_want, ((size_t)row * hidden + (size_t)i * V) * sizeof(T) / 4, f);
             } else {
                 unpack16<T>(ld_v4(x + (size_t)i * V), f);
             }

@@ -96,9 +96,9 @@ __global__ void qkv_rope_kernel(T *q, T *k, T *v, const T *__restrict__ qkv, con
 // the second pass over them disappear).  cos/sin of the token's position are evaluated once per CTA (same expressions as above).
 template <typename T>
 __global__ void __launch_bounds__(256)
-prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict__ qkv, const int *__restrict__ padding_offset,
-                              const int *__restrict__ history_len, int seq_len, int head_num, int kv_head_num, int head_size, int max_seq_len,
-                              int rot_dim, float base) {
+prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict__ qkv, const T *__restrict__ bias,
+                              const int *__restrict__ padding_offset, const int *__restrict__ history_len, int seq_len, int head_num,
+                              int kv_head_num, int head_size, int max_seq_len, int rot_dim, float base) {
     constexpr int V = Elem<T>::kVec;
     extern __shared__ float2 cs[];  // [head_size / 2] (cos, sin); identity past rot_dim / 2
     const int t = blockIdx.x;
@@ -132,6 +132,7 @@ prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict_
         } else {
             d = v_cache + (((size_t)b * kv_head_num + (head - head_num - kv_head_num)) * max_seq_len + pos_i) * head_size;
         }
+        if (head >= head_num && pos_i >= max_seq_len) continue;  // a prompt longer than the cache: never write past the layer's slab
         if (head < head_num + kv_head_num) {
 #pragma unroll
             for (int e = 0; e < V; ++e) {
@@ -141,21 +142,35 @@ prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict_
                 hi[e] = bb * c.x + a * c.y;
             }
         }
+        if (bias) {
+            // same convention as the decode step (decoder_self_attention.cu:93-127): RoPE result stored in T, then + bias in T -- the
+            // K / V rows a prompt leaves in the cache are the ones the decode kernel would have appended token by token.  (The
+            // reference's prefill launcher drops the bias, qkv_bias_and_rope.cu:28-78; b200_qkv_bias_transpose_rope keeps that.)
+            float blo[V], bhi[V];
+            unpack16<T>(ld_v4(bias + (size_t)head * head_size + i0), blo);
+            unpack16<T>(ld_v4(bias + (size_t)head * head_size + i0 + half), bhi);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                lo[e] = round_to<T>(round_to<T>(lo[e]) + blo[e]);
+                hi[e] = round_to<T>(round_to<T>(hi[e]) + bhi[e]);
+            }
+        }
         st_v4(d + i0, pack16<T>(lo));
         st_v4(d + i0 + half, pack16<T>(hi));
     }
 }
 
 // q [B,H,max_q,d]; k_cache / v_cache: LAYER base [B,Hkv,S,d].  B200_ERR_UNSUPPORTED when the shape cannot be vectorised.
-int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const int *padding_offset, const int *history_len,
-                                  int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size, int max_seq_len, int rot_dim,
-                                  float base, int dtype, cudaStream_t st) {
+int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const void *bias, const int *padding_offset,
+                                  const int *history_len, int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size,
+                                  int max_seq_len, int rot_dim, float base, int dtype, cudaStream_t st) {
     const int vec = dtype == B200_F32 ? 4 : 8;
-    if (head_size % (2 * vec) != 0 || !aligned16(q) || !aligned16(k_layer) || !aligned16(v_layer) || !aligned16(qkv)) return B200_ERR_UNSUPPORTED;
+    if (head_size % (2 * vec) != 0 || !aligned16(q) || !aligned16(k_layer) || !aligned16(v_layer) || !aligned16(qkv) || (bias && !aligned16(bias)))
+        return B200_ERR_UNSUPPORTED;
     const size_t smem = sizeof(float2) * (size_t)(head_size / 2);
     B200_DISPATCH_DTYPE(dtype, launch_pdl(prefill_qkv_rope_cache_kernel<T>, dim3(num_tokens), dim3(256), smem, st, true, (T *)q, (T *)k_layer,
-                                          (T *)v_layer, (const T *)qkv, padding_offset, history_len, seq_len, head_num, kv_head_num, head_size,
-                                          max_seq_len, rot_dim, base));
+                                          (T *)v_layer, (const T *)qkv, (const T *)bias, padding_offset, history_len, seq_len, head_num, kv_head_num,
+                                          head_size, max_seq_len, rot_dim, base));
     return cuda_status("prefill_qkv_rope_cache launch");
 }
 
@@ -168,7 +183,7 @@ __global__ void concat_kv_kernel(const T *__restrict__ k_src, const T *__restric
     const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z >> 1;
     const bool is_v = blockIdx.z & 1;
     pdl_wait();
-    if (t >= cur_len[b]) return;
+    if (t >= cur_len[b] || history_len[b] + t >= max_seq_len) return;  // never write past the layer's cache slab
     const T *src = (is_v ? v_src : k_src) + (((size_t)b * kv_head_num + h) * max_q_len + t) * head_size;
     T *dst = (is_v ? v_cache : k_cache) + (((size_t)b * kv_head_num + h) * max_seq_len + history_len[b] + t) * head_size;
     for (int i = threadIdx.x; i < head_size; i += blockDim.x) dst[i] = src[i];

@@ -130,14 +130,18 @@ __global__ void sampling_kernel(const int *__restrict__ topk_id, T *topk_val, in
     curandState_t state;
     curand_init((unsigned long long)step, (unsigned long long)b, 0ull, &state);
     float thr = curand_uniform(&state) * sum;
-    int chosen = id[0] % vocab;
+    int chosen = id[0];
     for (int i = 0; i < k; ++i) {
         thr -= Elem<T>::to_f(val[i]);
         if (thr < 0.0f) {
-            chosen = id[i] % vocab;
+            chosen = id[i];
             break;
         }
     }
+    // an empty top-k slot (id -1 / INT_MAX: every candidate NaN or -inf, or vocab < k) must never reach the embedding gather of the next
+    // step: the row ends instead (end_id when it is a valid token, else token 0)
+    if (chosen < 0 || chosen == INT_MAX) chosen = (end_id >= 0 && end_id < vocab) ? end_id : 0;
+    else chosen %= vocab;
     output_id[b] = chosen;
     if (!finished[b]) ++seq_len[b];
     finished[b] = (uint8_t)(chosen == end_id);
