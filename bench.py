@@ -43,7 +43,7 @@ CONFIGS = {
 WBYTES = {"bf16": 2.0, "fp8": 1.0, "int4": 0.5}
 
 
-def algorithmic_bytes(cfg, batch, ctx, wformat, tp=1, group=128):
+def algorithmic_bytes(cfg, batch, ctx, wformat, tp=1, group=128, head_sharded=False):
     """Bytes one decode step must read from HBM on ONE rank: packed layer weights (+ quantisation
     scales / zero points) + the KV rows of [0, ctx) + the bf16 LM head.  Activations, gammas, the appended KV row and the
     embedding row (< 0.01 %) are excluded."""
@@ -55,7 +55,8 @@ def algorithmic_bytes(cfg, batch, ctx, wformat, tp=1, group=128):
     if wformat == "int4":
         wb += params / group * 3 / tp
     kv = batch * 2 * (Hkv // tp if Hkv >= tp else 1) * d * ctx * 2
-    return L * (wb + kv) + V * h * 2, L * wb + V * h * 2
+    head = V * h * 2 / (tp if head_sharded else 1)
+    return L * (wb + kv) + head, L * wb + head
 
 
 class ClockSampler:
@@ -556,16 +557,15 @@ def tp_parity_check(args, mod, tpmod, dist, dev, rank, world, fused):
 
 
 def dominant_linear_kernel(batch, wformat):
-    """Name of the kernel the weight-streaming linears of a decode step dispatch to (decoder.cu norm_linear / plain_linear, linear.cu)."""
+    """Name of the kernel the weight-streaming linears of a decode step dispatch to (decoder.cu norm_linear / plain_linear, gemv_f32.cu,
+    linear.cu)."""
+    if batch == 1:
+        return "gemv_nk_kernel" if wformat == "bf16" else "gemv_q_kernel"
+    if batch <= 16:
+        return "gemv_mma_kernel"
     if wformat == "bf16":
-        if batch <= 4:
-            return "gemv_nk_kernel"
         return "gemm_tc_kernel (tcgen05, swap-AB + stream-K)" if batch <= 128 else "gemm_tc_kernel (tcgen05)"
-    if batch <= 8:
-        return "gemv_q_kernel"
-    if batch <= 32:
-        return "gemv_q_kernel (passes of <= 8 tokens)"
-    return "generic SIMT fallback"
+    return "gemv_mma_kernel (passes of <= 16 tokens)" if batch <= 64 else "generic SIMT fallback"
 
 
 def run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank):
@@ -733,7 +733,9 @@ def main():
                 tmp_vals=torch.empty((B, 8, K_TOP), dtype=torch.float32, device=dev), topk_ids=torch.empty((B, K_TOP), dtype=torch.int32, device=dev),
                 topk_vals=torch.empty((B, K_TOP), dtype=torch.float32, device=dev), seq_len=torch.full((B,), ctx, dtype=torch.int32, device=dev),
                 finished=torch.zeros(B, dtype=torch.uint8, device=dev), output_id=torch.zeros(B, dtype=torch.int32, device=dev))
-    launches_per_step = 1 + L * 5 + 1 + (B + 3) // 4 + 2 + 1
+    # embedding, per layer [norm,] QKV, attention, O, [norm,] gate/up, down (the two norms are fused into the GEMVs at batch 1), fold,
+    # [final norm,] LM head (16 tokens per pass), top-k x 2, sampling
+    launches_per_step = 1 + L * (5 if B == 1 else 7) + 1 + ((1 if B == 1 else 1 + (B + 15) // 16)) + 2 + 1
     tp_mode = "none"
     if tp > 1:
         tp_mode = "nccl all-reduce"
@@ -750,6 +752,11 @@ def main():
         tp_parity = tp_parity_check(args, mod, tpmod, dist, dev, rank, tp, tp_mode.startswith("fused"))
         if rank == 0 and not tp_parity["ok"]:
             print(f"[bench] tensor-parallel parity leg FAILED: {json.dumps(tp_parity)[:1500]}", file=sys.stderr)
+
+    sharded_head = None
+    if tp > 1 and V % tp == 0 and not os.environ.get("B200_TP_REPLICATED_HEAD"):
+        sharded_head = tpmod.VocabShardedHead(mod, dec, tpmod.shard_lm_head_rows(lm_head, rank, tp), V, rank, tp, B, K_TOP, dev)
+        launches_per_step += 8  # local top-k x 2, pack x 2, candidate copies x 2, index widen + gather (torch), merge top-k x 2 - replaced tail
 
     if args.mode == "prefill":
         run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank)
@@ -790,7 +797,10 @@ def main():
                 return y_ffn
 
             tpmod.decode_step_tp(L, hidden, attn_block, ffn_block, lambda h, pending: dec.fold(h, pending), dist.all_reduce)
-        dec.lm_head_topk_sample(hidden, final_gamma, lm_head, bufs, K_TOP, step, END_ID)
+        if sharded_head is not None:  # vocab-sharded LM head: local top-k, one all-gather of k (value, id) pairs, merge, sampling
+            sharded_head.run(dist, hidden, final_gamma, bufs["seq_len"], bufs["finished"], bufs["output_id"], step, END_ID)
+        else:
+            dec.lm_head_topk_sample(hidden, final_gamma, lm_head, bufs, K_TOP, step, END_ID)
 
     stream = torch.cuda.Stream(device=dev)
     graph = None
@@ -897,7 +907,7 @@ def main():
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        step_bytes, gemv_bytes = algorithmic_bytes(cfg, B, ctx, args.wformat, tp)
+        step_bytes, gemv_bytes = algorithmic_bytes(cfg, B, ctx, args.wformat, tp, head_sharded=sharded_head is not None)
         xin = torch.randn(B, h, device=dev).to(dt)
         xin_i = torch.randn(B, Il, device=dev).to(dt)
         xin_a = torch.randn(B, Hl * d, device=dev).to(dt)
@@ -931,8 +941,9 @@ def main():
         stream.synchronize()
         gemv_ms = r0.elapsed_time(r1) / reps
         achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
-        kernel_name = "%s (all %d weight-streaming linears of one step, back to back%s) + gemv_nk_kernel (LM head)" % (
-            dominant_linear_kernel(B, args.wformat), n_gemv - 1, ", this rank's shard, no exchange" if tp > 1 else "")
+        kernel_name = "%s (the %d weight-streaming linears of one step%s, back to back%s) + LM head" % (
+            dominant_linear_kernel(B, args.wformat), 4 * L, "" if B == 1 else " with their %d norm kernels" % (2 * L),
+            ", this rank's shard, no exchange" if tp > 1 else "")
         # DRAM traffic of the same launches: a STATIC figure from the committed ncu capture of this command (read + write bytes over
         # algorithmic bytes), not measured in this run -- only quoted for the configuration that was captured
         traffic, traffic_src = None, None
@@ -962,6 +973,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "launch_mode": "cuda-graph replay" if graph is not None else "eager", "preheat_steps": preheat_steps,
             "tp_exchange": tp_mode, "tp_parity": tp_parity,
+            "lm_head": ("vocab-sharded: local top-k + one NCCL all-gather of k (value, id) pairs per rank + merge" if sharded_head is not None else
+                        "replicated" if tp > 1 else "single GPU"),
             "timed_regions": {"count": len(region_ms), "steps_each": args.steps, "ms": region_ms, "reported": "median", "e2e_ms": e2e_regions},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "launches": n_gemv, "avg_launch_us": gemv_ms * 1e3 / n_gemv,
                          "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,

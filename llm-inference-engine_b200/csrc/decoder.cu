@@ -113,15 +113,17 @@ __global__ void tp_begin_step_kernel(unsigned int *epoch) {
     if (threadIdx.x == 0) *epoch += 1;
 }
 
-// rows one fused GEMV launch can take: 4 (SIMT kernels), 8 for weight-only quantised 16-bit models (tensor-core dequant kernel)
-static int gemv_max_rows(const b200_decoder_config_t &c) { return (c.w_format != B200_W_DENSE && c.dtype != B200_F32) ? 8 : 4; }
+// rows one fused GEMV launch can take: 16 for 16-bit models (tensor-core GEMV, gemv_mma.cuh), 4 for fp32 (SIMT GEMV)
+static int gemv_max_rows(const b200_decoder_config_t &c) { return c.dtype != B200_F32 ? 16 : 4; }
 
 // prologue (add residual / bias / RMSNorm) + linear (+ SwiGLU): fused GEMV for M <= 4 (8 quantised), un-fused otherwise.
 // tp (optional): x is the fused all-reduce of every rank's partial (TpExchange) instead of a local tensor.
 static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void *res_out, const void *bias, const void *gamma,
                        const b200_linear_weight_t &w, int K, int N, bool swiglu, void *y, int M, cudaStream_t st, const TpExchange *tp = nullptr) {
     const b200_decoder_config_t &c = d->cfg;
-    if (M <= gemv_max_rows(c)) {
+    const bool b16 = c.dtype != B200_F32;
+    // one token (any dtype) and fp32 up to 4: the prologue runs inside the GEMV (SIMT kernels / round-1 quantised kernel)
+    if (M == 1 || (!b16 && M <= 4)) {
         GemvArgs a = {};
         a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
         a.x = x, a.y = y;
@@ -131,8 +133,18 @@ static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void 
         const int rc = launch_gemv_nk(a, c.dtype, c.w_format, swiglu, st);
         if (rc != B200_ERR_UNSUPPORTED) return rc;
     }
+    // more tokens: the prologue (tensor-parallel reduce, + residual, + bias, RMSNorm) runs ONCE in a small kernel; fused into the GEMV every
+    // CTA would redo it for every token (gemv_mma.cuh)
     int rc = launch_norm_tp(c.dtype, x, d->xn, res_in, res_out, bias, gamma, c.rmsnorm_eps, M, K, tp, st);
     if (rc != B200_OK) return rc;
+    if (b16 && M <= gemv_max_rows(c)) {  // tensor-core GEMV, SwiGLU in its epilogue
+        GemvArgs a = {};
+        a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
+        a.x = d->xn, a.y = y;
+        a.M = M, a.K = K, a.N = N, a.group = c.group, a.inter = swiglu ? N / 2 : 0;
+        rc = launch_gemv_nk(a, c.dtype, c.w_format, swiglu, st);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
     if (!swiglu) return b200_linear(d->xn, w.w, w.scales, w.zeros, y, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
     rc = b200_linear(d->xn, w.w, w.scales, w.zeros, d->gu, M, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, st);
     if (rc != B200_OK) return rc;
@@ -526,7 +538,8 @@ int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b
         if (rc != B200_OK) return rc;
         dec->cur = next_res(dec->cur);
         if ((rc = plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, dec->y_ffn, batch, st)) != B200_OK) return rc;
-        launches += 4;
+        // 4 linears; for 2+ tokens of a 16-bit model (5+ in fp32) each of the two prologues is its own small kernel (norm_linear)
+        launches += (batch == 1 || (c.dtype == B200_F32 && batch <= 4)) ? 4 : 6;
     }
     if (n_launches) *n_launches = launches;
     return B200_OK;
@@ -640,15 +653,33 @@ int b200_lm_head_topk_sample(b200_decoder_t *dec, const void *hidden, const void
     const b200_decoder_config_t &c = dec->cfg;
     cudaStream_t st = as_stream(stream);
     // final RMSNorm (reference llama.cpp:247-253) fused into the LM-head GEMV; logits in fp32
-    for (int m0 = 0; m0 < batch; m0 += 4) {
+    const bool b16 = c.dtype != B200_F32;
+    const int pass = b16 ? 16 : 4;  // tokens per read of the LM head (tensor-core GEMV / SIMT GEMV)
+    const void *xh = hidden;
+    bool normed = false;
+    if (b16 && batch >= 2) {  // final RMSNorm once, in front (see norm_linear)
+        rc = launch_norm_tp(c.dtype, hidden, dec->xn, nullptr, nullptr, nullptr, final_gamma, c.rmsnorm_eps, batch, c.hidden, nullptr, st);
+        if (rc != B200_OK) return rc;
+        xh = dec->xn, normed = true;
+    }
+    for (int m0 = 0; m0 < batch; m0 += pass) {
         GemvArgs a = {};
         a.w = lm_head;
-        a.x = (const char *)hidden + (size_t)m0 * c.hidden * esize(c.dtype);
+        a.x = (const char *)xh + (size_t)m0 * c.hidden * esize(c.dtype);
         a.y = logits + (size_t)m0 * vocab;
         a.y_f32 = 1;
-        a.gamma = final_gamma, a.eps = c.rmsnorm_eps, a.norm = 1;
-        a.M = batch - m0 < 4 ? batch - m0 : 4, a.K = c.hidden, a.N = vocab;
+        if (!normed) a.gamma = final_gamma, a.eps = c.rmsnorm_eps, a.norm = 1;
+        a.M = batch - m0 < pass ? batch - m0 : pass, a.K = c.hidden, a.N = vocab;
         rc = launch_gemv_nk(a, c.dtype, WF_DENSE, false, st);
+        if (rc == B200_ERR_UNSUPPORTED && pass > 4) {  // shapes the tensor-core GEMV cannot split: the SIMT GEMV, 4 tokens at a time
+            for (int m1 = m0; m1 < m0 + a.M; m1 += 4) {
+                GemvArgs b = a;
+                b.x = (const char *)xh + (size_t)m1 * c.hidden * esize(c.dtype);
+                b.y = logits + (size_t)m1 * vocab;
+                b.M = m0 + a.M - m1 < 4 ? m0 + a.M - m1 : 4;
+                if ((rc = launch_gemv_nk(b, c.dtype, WF_DENSE, false, st)) != B200_OK) break;
+            }
+        }
         if (rc == B200_ERR_UNSUPPORTED) set_error("lm_head_topk_sample: hidden size %d not supported by the GEMV", c.hidden);
         if (rc != B200_OK) return rc;
     }

@@ -237,6 +237,38 @@ __device__ __forceinline__ void dot_rows(const uint4 (&wv)[kGemvRows], const boo
     }
 }
 
+// ------------------------------------------------------------------ pre-norm value of one activation vector
+// Vector i (V = 16 bytes of T) of token row m before the RMSNorm: x (or, under tensor parallelism, the fused all-reduce of every rank's
+// partial -- TpExchange) (+ residual) -> T; residual_out <- that (CTA 0 only, when write_res); (+ bias) -> T.  The reference's kernels
+// form these sums in T (add_residual_and_rmsnorm.cu:71-92): rounded at the same points.
+template <typename T>
+__device__ __forceinline__ void gemv_prenorm_vec(const GemvArgs &a, unsigned int tp_want, int m, int i, float *f, bool write_res) {
+    constexpr int V = Elem<T>::kVec;
+    const int K = a.K;
+    const T *rin = a.norm ? reinterpret_cast<const T *>(a.res_in) : nullptr;
+    T *rout = a.norm ? reinterpret_cast<T *>(a.res_out) : nullptr;
+    const T *bias = a.norm ? reinterpret_cast<const T *>(a.bias) : nullptr;
+    if (a.tp.world > 1) {
+        // one-shot all-reduce: add every rank's partial in rank order, round to T as an all-reduced tensor of T would be
+        tp_reduce_vec<T>(a.tp, tp_want, ((size_t)m * K + (size_t)i * V) * sizeof(T) / 4, f);
+    } else {
+        unpack16<T>(ld_v4(reinterpret_cast<const T *>(a.x) + (size_t)m * K + (size_t)i * V), f);
+    }
+    if (rin) {
+        float r[V];
+        unpack16<T>(ld_v4(rin + (size_t)m * K + (size_t)i * V), r);
+#pragma unroll
+        for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
+    }
+    if (write_res && rout && blockIdx.x == 0) st_v4(rout + (size_t)m * K + (size_t)i * V, pack16<T>(f));
+    if (bias) {
+        float b[V];
+        unpack16<T>(ld_v4(bias + (size_t)i * V), b);
+#pragma unroll
+        for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + b[j]);
+    }
+}
+
 // ------------------------------------------------------------------ activation staging shared by the GEMV kernels
 // For every token row m < a.M and every 16-byte vector i of the row: x (or, under tensor parallelism, the fused all-reduce of every
 // rank's partial -- TpExchange) (+ residual) -> T; residual_out <- that (CTA 0 only); (+ bias) -> T; RMSNorm with gamma when given
@@ -247,35 +279,11 @@ template <typename T, int MB, typename Store>
 __device__ __forceinline__ void gemv_stage_activations(const GemvArgs &a, int n_threads, float *red, Store store) {
     constexpr int V = Elem<T>::kVec;
     const int K = a.K;
-    const T *xin = reinterpret_cast<const T *>(a.x);
-    const T *rin = a.norm ? reinterpret_cast<const T *>(a.res_in) : nullptr;
-    T *rout = a.norm ? reinterpret_cast<T *>(a.res_out) : nullptr;
-    const T *bias = a.norm ? reinterpret_cast<const T *>(a.bias) : nullptr;
     const T *gamma = a.norm ? reinterpret_cast<const T *>(a.gamma) : nullptr;
     const int nv = K / V;
     const unsigned int tp_want = a.tp.world > 1 ? tp_flag(a.tp.epoch, a.tp.seq) : 0u;
     // pre-norm value of vector i of row m
-    auto prenorm = [&](int m, int i, float *f, bool write_res) {
-        if (a.tp.world > 1) {
-            // one-shot all-reduce: add every rank's partial in rank order, round to T as an all-reduced tensor of T would be
-            tp_reduce_vec<T>(a.tp, tp_want, ((size_t)m * K + (size_t)i * V) * sizeof(T) / 4, f);
-        } else {
-            unpack16<T>(ld_v4(xin + (size_t)m * K + (size_t)i * V), f);
-        }
-        if (rin) {
-            float r[V];
-            unpack16<T>(ld_v4(rin + (size_t)m * K + (size_t)i * V), r);
-#pragma unroll
-            for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
-        }
-        if (write_res && rout && blockIdx.x == 0) st_v4(rout + (size_t)m * K + (size_t)i * V, pack16<T>(f));
-        if (bias) {
-            float b[V];
-            unpack16<T>(ld_v4(bias + (size_t)i * V), b);
-#pragma unroll
-            for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + b[j]);
-        }
-    };
+    auto prenorm = [&](int m, int i, float *f, bool write_res) { gemv_prenorm_vec<T>(a, tp_want, m, i, f, write_res); };
     const bool cached = nv <= kGemvXCache * n_threads;  // the row fits the per-thread register cache: one global pass
     // MB == 1: a single trip known at compile time (keeps the B = 1 instantiation spill-free); otherwise a rolled run-time loop
 #pragma unroll 1

@@ -5,6 +5,8 @@ namespace b200 {
 int launch_gemv_nk_f32(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st) { return launch_gemv_t<float, false>(a, fmt, swiglu, st); }
 int launch_gemv_nk_bf16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
 int launch_gemv_nk_f16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
+int launch_gemv_mma_bf16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
+int launch_gemv_mma_f16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
 int launch_gemv_q_bf16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
 int launch_gemv_q_f16(const GemvArgs &a, int fmt, bool swiglu, cudaStream_t st);
 int launch_gemv_nk(const GemvArgs &a, int dtype, int fmt, bool swiglu, cudaStream_t st) {
@@ -12,8 +14,16 @@ int launch_gemv_nk(const GemvArgs &a, int dtype, int fmt, bool swiglu, cudaStrea
         set_error("gemv: SwiGLU epilogue needs N == 2*inter");
         return B200_ERR_INVALID_ARG;
     }
-    // weight-only quantised, 16-bit activations, M <= 8: dequant into tensor-core fragments (gemv_q.cuh)
-    if (fmt != WF_DENSE && (dtype == B200_BF16 || dtype == B200_F16)) {
+    const bool b16 = dtype == B200_BF16 || dtype == B200_F16;
+    // 16-bit activations, 2..16 tokens, plain activations (no fused prologue): the tensor-core GEMV (gemv_mma.cuh), one pass over the
+    // weights whatever the batch and the format
+    if (b16 && a.M >= 2 && a.M <= 16) {
+        const int rc = dtype == B200_BF16 ? launch_gemv_mma_bf16(a, fmt, swiglu, st) : launch_gemv_mma_f16(a, fmt, swiglu, st);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+    // weight-only quantised, 16-bit activations, M <= 8 (a single token, or shapes / fused prologues the kernel above does not take):
+    // dequant into mma fragments with the SIMT GEMV's fused prologue (gemv_q.cuh)
+    if (b16 && fmt != WF_DENSE && a.M <= 8) {
         const int rc = dtype == B200_BF16 ? launch_gemv_q_bf16(a, fmt, swiglu, st) : launch_gemv_q_f16(a, fmt, swiglu, st);
         if (rc != B200_ERR_UNSUPPORTED) return rc;
     }

@@ -300,30 +300,40 @@ int b200_linear(const void *x, const void *w, const void *scales, const void *ze
     // ---- decode-shaped: weight-streaming GEMV
     if (w_layout == B200_LAYOUT_NK) {
         int done = 0, rc = B200_OK;
-        // dense 16-bit, M > 4: tcgen05 GEMM (swap-AB + split-K for M <= 128, 128x256 tiles above)
-        if (M > 4 && dtype != B200_F32 && w_format == B200_W_DENSE) {
+        const bool b16 = dtype != B200_F32;
+        // weight-streaming GEMV in passes of `step` tokens (one pass = one read of the weights): 16-bit activations take 16 tokens per pass on
+        // the tensor-core GEMV (gemv_mma.cuh: dense, FP8, INT4), fp32 4 on the SIMT GEMV
+        auto gemv_passes = [&](int step) -> int {
+            for (int m0 = 0; m0 < M; m0 += step) {
+                GemvArgs a = {};
+                a.w = w, a.scales = scales, a.zeros = zeros;
+                a.x = (const char *)x + (size_t)m0 * K * elem_bytes(dtype);
+                a.y = (char *)y + (size_t)m0 * N * elem_bytes(dtype);
+                a.M = M - m0 < step ? M - m0 : step, a.K = K, a.N = N, a.group = group;
+                const int r = launch_gemv_nk(a, dtype, w_format, false, st);
+                if (r != B200_OK) return r;
+            }
+            return B200_OK;
+        };
+        // decode batches: one pass
+        if (M <= (b16 ? 16 : 4)) {
+            rc = gemv_passes(b16 ? 16 : 4);
+            if (rc == B200_OK) done = 1;
+            else if (rc != B200_ERR_UNSUPPORTED) return rc;
+        }
+        // dense 16-bit beyond that (and shapes the GEMV cannot take): tcgen05 GEMM (swap-AB + stream-K for M <= 128, 128x256 tiles above)
+        if (!done && M > 4 && b16 && w_format == B200_W_DENSE) {
             rc = launch_gemm_tc(x, w, y, M, N, K, dtype, st);
             if (rc == B200_OK) done = 1;
             else if (rc != B200_ERR_UNSUPPORTED) return rc;
         }
-        if (!done && M <= 32) {
-            // weight-streaming GEMV in passes: quantised weights take up to 8 rows per pass (tensor-core dequant kernel, gemv_q.cuh;
-            // 4 passes over packed weights still move fewer bytes than one pass over bf16), the SIMT kernels 4 rows
-            for (int step = (w_format != B200_W_DENSE && dtype != B200_F32) ? 8 : 4; step >= 4 && !done; step -= 4) {
-                if (M > 4 * step) continue;
-                rc = B200_OK;
-                for (int m0 = 0; m0 < M; m0 += step) {
-                    GemvArgs a = {};
-                    a.w = w, a.scales = scales, a.zeros = zeros;
-                    a.x = (const char *)x + (size_t)m0 * K * elem_bytes(dtype);
-                    a.y = (char *)y + (size_t)m0 * N * elem_bytes(dtype);
-                    a.M = M - m0 < step ? M - m0 : step, a.K = K, a.N = N, a.group = group;
-                    rc = launch_gemv_nk(a, dtype, w_format, false, st);
-                    if (rc != B200_OK) break;
-                }
-                if (rc == B200_OK) done = 1;
-                else if (rc != B200_ERR_UNSUPPORTED) return rc;
-            }
+        // quantised weights up to 64 tokens: passes of 16 (4 passes over packed INT4 move what one pass over bf16 moves); smaller steps
+        // for the shapes only the older kernels take
+        for (int step = b16 ? 16 : 4; !done && step >= 4 && M <= 64; step = step == 16 ? 8 : step - 4) {
+            if (M > 4 * step) continue;
+            rc = gemv_passes(step);
+            if (rc == B200_OK) done = 1;
+            else if (rc != B200_ERR_UNSUPPORTED) return rc;
         }
         if (done) return B200_OK;
     } else if (M <= 4 && N % (16 / elem_bytes(dtype)) == 0 && aligned16(w)) {

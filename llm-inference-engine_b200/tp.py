@@ -136,3 +136,48 @@ def merge_topk(vals, ids, k):
         order = np.lexsort((i[b], -v[b].astype(np.float64)))[:k]  # primary key: value descending; secondary: id ascending
         out_i[b], out_v[b] = i[b][order], v[b][order]
     return out_i, out_v
+
+
+class VocabShardedHead:
+    """The sampling tail of a tensor-parallel decode step with the LM head vocab-sharded (reference src/models/llama/llama.cpp:247-311 on
+    one GPU): final RMSNorm + this rank's rows of lm_head (b200_lm_head_topk_sample on the shard, local top-k) -> ids made global ->
+    ONE NCCL all-gather of k (value, id) pairs per row and rank -> b200_topk over the P*k candidates (value descending, ties to the
+    lower candidate index = the lower global id: shards are ascending id ranges and a local top-k lists equal values by ascending id)
+    -> b200_sampling.  Every buffer is allocated once, so the whole tail can be captured in a CUDA graph.  Bit-identical to the
+    un-sharded tail given the same hidden state (tests/tp_engine_check.py)."""
+
+    def __init__(self, mod, dec, lm_head_shard, vocab, rank, world, batch, k, device):
+        import torch
+
+        self.mod, self.dec, self.lm, self.vocab, self.rank, self.world, self.k = mod, dec, lm_head_shard, vocab, rank, world, k
+        self.lo, _ = vocab_range(vocab, rank, world)
+        vl, nb = lm_head_shard.shape[0], mod.TOPK_BLOCKS
+        i32, f32 = torch.int32, torch.float32
+        self.local = dict(logits=torch.empty((batch, vl), dtype=f32, device=device), tmp_ids=torch.empty((batch, nb, k), dtype=i32, device=device),
+                          tmp_vals=torch.empty((batch, nb, k), dtype=f32, device=device), topk_ids=torch.empty((batch, k), dtype=i32, device=device),
+                          topk_vals=torch.empty((batch, k), dtype=f32, device=device))
+        self.mine = torch.empty((batch, 2 * k), dtype=i32, device=device)            # [vals as int32 bits | global ids]
+        self.all = torch.empty((world, batch, 2 * k), dtype=i32, device=device)
+        self.cand_vals = torch.empty((batch, world * k), dtype=f32, device=device)
+        self.cand_ids = torch.empty((batch, world * k), dtype=i32, device=device)
+        self.tmp_i = torch.empty((batch, nb, k), dtype=i32, device=device)
+        self.tmp_v = torch.empty((batch, nb, k), dtype=f32, device=device)
+        self.idx = torch.empty((batch, k), dtype=i32, device=device)
+        self.topk_vals = torch.empty((batch, k), dtype=f32, device=device)
+        self.topk_ids = torch.empty((batch, k), dtype=i32, device=device)
+
+    def run(self, dist, hidden, final_gamma, seq_len, finished, output_id, step, end_id):
+        import torch
+
+        mod, k, B, P = self.mod, self.k, hidden.shape[0], self.world
+        self.dec.lm_head_topk_sample(hidden, final_gamma, self.lm, self.local, k, step, end_id)  # no output_id: logits + local top-k only
+        self.mine[:, :k].copy_(self.local["topk_vals"].view(torch.int32))
+        torch.add(self.local["topk_ids"], self.lo, out=self.mine[:, k:])
+        dist.all_gather_into_tensor(self.all, self.mine)
+        self.cand_vals.view(torch.int32).view(B, P, k).copy_(self.all[:, :, :k].permute(1, 0, 2))  # bit copy: values stay float32
+        self.cand_ids.view(B, P, k).copy_(self.all[:, :, k:].permute(1, 0, 2))
+        p = mod.ptr
+        mod.check(mod.lib().b200_topk(p(self.cand_vals), p(self.tmp_i), p(self.tmp_v), p(self.idx), p(self.topk_vals), B, P * k, k, mod.F32, mod.stream()))
+        torch.gather(self.cand_ids, 1, self.idx.long(), out=self.topk_ids)
+        mod.check(mod.lib().b200_sampling(p(self.topk_ids), p(self.topk_vals), p(seq_len), p(finished), p(output_id), B, k, step, end_id, self.vocab,
+                                          mod.F32, mod.stream()))

@@ -7,6 +7,7 @@ usage: python scripts/dispatch_plan.py > profiles/<tag>_dispatch_plan.txt"""
 BUDGET = 224 * 1024
 GROUPS, GW, MAX_STAGES, ROWS, PIECE = 2, 8, 8, 2, 8192
 Q_ROWS, Q_TOK = 16, 8
+MMA_WARPS, MMA_ROWS = 16, 8
 WARPS = GROUPS * GW
 
 
@@ -44,9 +45,56 @@ def gemv_q_plan(M, K, fmt):
     return None
 
 
+def gemv_mma_plan(M, K, fmt, max_units=8):
+    """gemv_mma.cuh gemv_mma_geometry (16-bit activations, 1..16 tokens): None when unsupported."""
+    if M < 1 or M > 16 or K % 128:
+        return None
+    dense = fmt == "dense"
+    tok = 8 if M <= 8 else 16
+    xs_rows = tok if M == tok else M + 1
+    k_round = -(-K // 512) * 512
+    best, best_score = None, -1
+    piece_bytes0 = 2048 if fmt == "int4" else 4096
+    while piece_bytes0 >= 1024:
+        piece_bytes = piece_bytes0
+        piece_bytes0 //= 2
+        piece_k = piece_bytes // 2 if dense else (piece_bytes if fmt == "fp8" else piece_bytes * 2)
+        if piece_k > k_round:
+            piece_k = k_round
+            piece_bytes = piece_k * 2 if dense else (piece_k if fmt == "fp8" else piece_k // 2)
+        if fmt == "int4" and (piece_k // MMA_WARPS) % 128:
+            continue
+        row_stride = piece_bytes + (64 if dense else (32 if fmt == "fp8" else 16))
+        stage_bytes = MMA_ROWS * row_stride
+        pieces_total = -(-K // piece_k)
+        for parts in range(1, pieces_total + 1):
+            ppp = -(-pieces_total // parts)
+            if -(-pieces_total // ppp) != parts:
+                continue
+            part_k = ppp * piece_k
+            fixed = (xs_rows * (part_k + 32) * 2 + 127) // 128 * 128 + (2 * MAX_STAGES + 4) * 8 + 2 * MMA_WARPS * 128 * 4 + (max_units * 128 * 4 if parts > 1 else 0) + 128
+            if fixed + 3 * stage_bytes > 226 * 1024:
+                continue
+            stages = min((226 * 1024 - fixed) // stage_bytes, MAX_STAGES)
+            score = min(stages * stage_bytes, 196608) + (49152 if piece_bytes >= 4096 else (0 if piece_bytes >= 2048 else -49152)) - 8192 * (parts - 1)
+            if best is None or score > best_score:
+                best_score = score
+                best = dict(kernel="gemv_mma", pieces=pieces_total, piece_bytes=piece_bytes, stages=stages, parts=parts, part_k=part_k)
+    return best
+
+
 def gemv_any(M, K, fmt):
-    """gemv_f32.cu launch_gemv_nk for a 16-bit model: tensor-core dequant kernel first, then the SIMT kernel (M <= 4)."""
-    return gemv_q_plan(M, K, fmt) or gemv_nk_plan(M, K, fmt)
+    """gemv_f32.cu launch_gemv_nk for a 16-bit model: the tensor-core GEMV for 2..16 dense tokens and 1..16 quantised ones, then the round-1
+    quantised kernel (M <= 8), then the SIMT kernel (M <= 4)."""
+    if M <= 16 and (fmt != "dense" or M >= 2):
+        g = gemv_mma_plan(M, K, fmt)
+        if g:
+            return g
+        if fmt != "dense" and M <= 8:
+            g = gemv_q_plan(M, K, fmt)
+            if g:
+                return g
+    return gemv_nk_plan(M, K, fmt)
 
 
 def linear_plan(M, K, fmt, fused_rows):
@@ -55,25 +103,29 @@ def linear_plan(M, K, fmt, fused_rows):
         g = gemv_any(M, K, fmt)
         if g:
             return ("fused " + g["kernel"], 1, g)
-    if fmt == "dense" and M > 4:  # linear.cu:305
+    if M <= 16:  # linear.cu: one GEMV pass for decode batches
+        g = gemv_any(M, K, fmt)
+        if g:
+            return ("un-fused " + g["kernel"], 1, g)
+    if fmt == "dense" and M > 4:
         return ("un-fused gemm_tc (tcgen05, swap-AB stream-K)" if M <= 128 else "un-fused gemm_tc", 1, None)
-    for step in ((8, 4) if fmt != "dense" else (4,)):  # linear.cu:311-327
-        if M > 4 * step:
+    for step in (16, 8, 4):  # linear.cu: quantised weights up to 64 tokens in passes
+        if M > 4 * step or M > 64:
             continue
         plans = [gemv_any(min(step, M - m0), K, fmt) for m0 in range(0, M, step)]
         if all(plans):
             return (f"un-fused {plans[0]['kernel']} x {len(plans)} passes of <= {step} tokens", len(plans), plans[0])
-    return ("un-fused generic SIMT fallback (launch_simt, linear.cu:359-372)", 1, None)
+    return ("un-fused generic SIMT fallback (launch_simt, linear.cu)", 1, None)
 
 
 def step_plan(name, hidden, heads, kv_heads, d, inter, tp, batch, fmt):
-    fused_rows = 8 if fmt != "dense" else 4  # decoder.cu gemv_max_rows (16-bit models)
+    fused_rows = 16  # decoder.cu gemv_max_rows (16-bit models)
     shapes = [("qkv", hidden, (heads + 2 * kv_heads) * d // tp), ("o", heads * d // tp, hidden), ("gate_up", hidden, 2 * inter // tp),
               ("down", inter // tp, hidden)]
     lines = [f"{name}, batch {batch}, weights {fmt}" + (f", TP-{tp} (one rank)" if tp > 1 else "")]
     for lin, K, N in shapes:
         path, passes, g = linear_plan(batch, K, fmt, fused_rows)
-        geo = f"pieces {g['pieces']} x {g['piece_bytes']} B, {g['stages']} stages" if g else "-"
+        geo = (f"pieces {g['pieces']} x {g['piece_bytes']} B, {g['stages']} stages" + (f", {g['parts']} activation parts of {g['part_k']} k" if g.get("parts") else "")) if g else "-"
         wbytes = K * N * {"dense": 2, "fp8": 1, "int4": 0.5}[fmt]
         lines.append(f"  {lin:8s} K={K:6d} N={N:6d}  {path:58s} weights read {passes} x {wbytes / 1e6:7.1f} MB   {geo}")
     return lines

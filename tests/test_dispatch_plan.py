@@ -17,18 +17,29 @@ def test_dense_batch1_geometry_matches_the_design_document():
     assert g["pieces"] == 3 and g["piece_bytes"] % 512 == 0 and g["pieces"] * g["piece_bytes"] >= 11008 * 2
 
 
-def test_quantised_geometry_and_the_down_projection_limit():
+def test_quantised_round1_kernel_geometry_is_still_modelled():
     assert dp.gemv_q_plan(1, 4096, "int4") == dict(kernel="gemv_q", pieces=1, piece_bytes=2048, stages=3)
-    assert dp.gemv_q_plan(8, 4096, "fp8")["piece_bytes"] == 1024            # eight staged tokens leave room for 1-KiB pieces only
     assert dp.gemv_q_plan(8, 11008, "fp8") is None and dp.gemv_q_plan(8, 11008, "int4") is None  # 176 KB of activations: no ring fits
-    assert dp.gemv_q_plan(4, 11008, "fp8")["stages"] >= 3
-    path, passes, _ = dp.linear_plan(16, 11008, "fp8", fused_rows=8)
-    assert passes == 4 and "4 tokens" in path                               # batch 16: the down weights are streamed four times
-    path, passes, _ = dp.linear_plan(16, 4096, "fp8", fused_rows=8)
-    assert passes == 2
 
 
-def test_dense_batched_decode_goes_to_the_tensor_core_gemm():
-    for m in (5, 8, 32, 128):
-        assert dp.linear_plan(m, 4096, "dense", fused_rows=4)[0].startswith("un-fused gemm_tc")
-    assert dp.linear_plan(4, 4096, "dense", fused_rows=4)[0] == "fused gemv_nk"
+def test_tensor_core_gemv_reads_the_weights_once_up_to_16_tokens():
+    """gemv_mma.cuh: activations staged in K parts of 64 KiB, so K = 8192 and K = 11008 keep a >= 4-stage ring at 8 and at 16 tokens; every
+    decode batch up to 16 is ONE pass over the weights, in every format (round 1: 2 passes at batch 16, 4 for the K = 11008 down projection)."""
+    for m, k in ((2, 4096), (8, 4096), (16, 4096), (8, 8192), (8, 11008), (16, 11008)):  # incl. the 70B-shaped hidden size and the 7B down projection
+        g = dp.gemv_mma_plan(m, k, "dense")
+        assert g and g["piece_bytes"] == 4096 and g["stages"] >= 4 and g["parts"] * g["part_k"] >= k, (m, k, g)
+        assert (8 if m <= 8 else 16) * g["part_k"] * 2 <= 66 * 1024 or m < 8  # a staged part stays <= 64 KiB (+ padding) at full token tiles
+    for fmt in ("dense", "fp8", "int4"):
+        for m in (2, 8, 16):
+            for k in (4096, 11008):
+                path, passes, geo = dp.linear_plan(m, k, fmt, fused_rows=16)
+                assert passes == 1 and path == "fused gemv_mma", (fmt, m, k, path)
+    assert dp.linear_plan(1, 4096, "dense", fused_rows=16)[0] == "fused gemv_nk"  # a single dense token stays on the SIMT kernel
+    assert dp.linear_plan(1, 4096, "int4", fused_rows=16)[0] == "fused gemv_mma"
+    path, passes, _ = dp.linear_plan(32, 4096, "fp8", fused_rows=16)
+    assert passes == 2 and "16 tokens" in path
+
+
+def test_dense_batches_beyond_16_go_to_the_tensor_core_gemm():
+    for m in (17, 32, 128):
+        assert dp.linear_plan(m, 4096, "dense", fused_rows=16)[0].startswith("un-fused gemm_tc")

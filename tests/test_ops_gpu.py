@@ -567,8 +567,20 @@ def test_gemv_full_size_properties():
         y1 = mod.linear(x1, w)
         assert torch.equal(y1, mod.linear(x1, w))  # deterministic
         y2 = mod.linear(torch.cat([x1, x1 * 2]), w)  # exact scaling by 2 in every format
-        assert torch.equal(y2[0], y1[0]) and torch.equal(y2[1].float(), y1[0].float() * 2)
+        assert torch.equal(y2[1].float(), y2[0].float() * 2)
+        # batch invariance inside a kernel family: a token's result does not depend on how many other tokens share the launch (2..16 tokens
+        # run on the tensor-core GEMV, one token on the SIMT GEMV: across the two only the summation order differs)
+        xs = torch.cat([x1, x1 * 2, torch.randn(5, K, device=dev).bfloat16()])
+        y7 = mod.linear(xs, w)
+        y16 = mod.linear(torch.cat([xs, torch.randn(9, K, device=dev).bfloat16()]), w)
+        assert torch.equal(y7, mod.linear(xs, w))  # deterministic
+        # across batch sizes the kernel geometry (activation K parts, ring depth) may differ: same values up to the fp32 summation order
+        assert_close(y7[:2].float().cpu().numpy(), y2.float().cpu().numpy(), "bf16", "7-token launch vs 2-token launch")
+        assert_close(y16[:7].float().cpu().numpy(), y7.float().cpu().numpy(), "bf16", "16-token launch vs 7-token launch")
+        assert_close(y2[0].float().cpu().numpy(), y1[0].float().cpu().numpy(), "bf16", "one token: tensor-core GEMV vs SIMT GEMV")
         sub = mod.linear(x1, w[1000:1256].contiguous())
         assert torch.equal(sub[0], y1[0, 1000:1256])
+        sub2 = mod.linear(xs, w[1000:1256].contiguous())
+        assert torch.equal(sub2, y7[:, 1000:1256])
         ref = (x1.double() @ w.double().T).float()
         assert_close(y1.float().cpu().numpy(), ref.cpu().numpy(), "bf16", "7B gemv vs fp64 matmul")

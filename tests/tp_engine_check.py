@@ -80,6 +80,33 @@ def main():
         except AssertionError as e:
             ok = False
             print(f"[rank {rank}] {mode} {dtype} batch {batch} FAILED: {e}", flush=True)
+    # ---- vocab-sharded LM head + top-k + sampling: bit-identical to the un-sharded tail on the same hidden state
+    try:
+        V, hsz, B, K = 32000, cfg["hidden"], 3, 5
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)  # same on every rank
+        lm = torch.empty((V, hsz), dtype=torch.bfloat16, device=dev).normal_(0.0, 0.02, generator=g)
+        hid = torch.randn((B, hsz), device=dev, generator=g).to(torch.bfloat16)
+        gam = (1 + 0.1 * torch.randn(hsz, device=dev, generator=g)).to(torch.bfloat16)
+        dcfg = mod.DecoderConfig(cfg["hidden"], 8 // world, 8 // world, 128, cfg["inter"] // world, 1, 64, B, 2, 0, 128, 1e-6, 128, 10000.0, world, rank)
+        d2 = mod.Decoder(dcfg, dev)
+        i32, f32 = torch.int32, torch.float32
+        full = dict(logits=torch.empty((B, V), dtype=f32, device=dev), tmp_ids=torch.empty((B, 8, K), dtype=i32, device=dev),
+                    tmp_vals=torch.empty((B, 8, K), dtype=f32, device=dev), topk_ids=torch.empty((B, K), dtype=i32, device=dev),
+                    topk_vals=torch.empty((B, K), dtype=f32, device=dev), seq_len=torch.full((B,), 9, dtype=i32, device=dev),
+                    finished=torch.zeros(B, dtype=torch.uint8, device=dev), output_id=torch.zeros(B, dtype=i32, device=dev))
+        d2.lm_head_topk_sample(hid, gam, lm, full, K, 7, 2)
+        head = tp.VocabShardedHead(mod, d2, tp.shard_lm_head_rows(lm, rank, world), V, rank, world, B, K, dev)
+        seq2, fin2, out2 = torch.full((B,), 9, dtype=i32, device=dev), torch.zeros(B, dtype=torch.uint8, device=dev), torch.zeros(B, dtype=i32, device=dev)
+        head.run(dist, hid, gam, seq2, fin2, out2, 7, 2)
+        torch.cuda.synchronize()
+        same = (torch.equal(head.topk_ids, full["topk_ids"]) and torch.equal(head.topk_vals, full["topk_vals"]) and torch.equal(out2, full["output_id"])
+                and torch.equal(seq2, full["seq_len"]) and torch.equal(fin2, full["finished"]))
+        assert same, f"sharded ids {head.topk_ids.tolist()} vs {full['topk_ids'].tolist()}"
+        print(f"[rank {rank}] TP-{world} vocab-sharded LM head: top-k ids / values / sampled ids bit-identical to the un-sharded tail: OK", flush=True)
+    except AssertionError as e:
+        ok = False
+        print(f"[rank {rank}] vocab-sharded LM head FAILED: {e}", flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     code = 1 if int(flag.item()) else 0
