@@ -559,7 +559,7 @@ def tp_parity_check(args, mod, tpmod, dist, dev, rank, world, fused):
 def dominant_linear_kernel(batch, wformat):
     """Name of the kernel the weight-streaming linears of a decode step dispatch to (decoder.cu norm_linear / plain_linear, gemv_f32.cu,
     linear.cu)."""
-    if batch == 1:
+    if batch == 1 or (wformat != "bf16" and batch <= 4):
         return "gemv_nk_kernel" if wformat == "bf16" else "gemv_q_kernel"
     if batch <= 16:
         return "gemv_mma_kernel"
@@ -735,7 +735,8 @@ def main():
                 finished=torch.zeros(B, dtype=torch.uint8, device=dev), output_id=torch.zeros(B, dtype=torch.int32, device=dev))
     # embedding, per layer [norm,] QKV, attention, O, [norm,] gate/up, down (the two norms are fused into the GEMVs at batch 1), fold,
     # [final norm,] LM head (16 tokens per pass), top-k x 2, sampling
-    launches_per_step = 1 + L * (5 if B == 1 else 7) + 1 + ((1 if B == 1 else 1 + (B + 15) // 16)) + 2 + 1
+    fused_norm = B == 1 or (args.wformat != "bf16" and B <= 4)
+    launches_per_step = 1 + L * (5 if fused_norm else 7) + 1 + ((1 if B == 1 else 1 + (B + 15) // 16)) + 2 + 1
     tp_mode = "none"
     if tp > 1:
         tp_mode = "nccl all-reduce"
@@ -942,7 +943,7 @@ def main():
         gemv_ms = r0.elapsed_time(r1) / reps
         achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
         kernel_name = "%s (the %d weight-streaming linears of one step%s, back to back%s) + LM head" % (
-            dominant_linear_kernel(B, args.wformat), 4 * L, "" if B == 1 else " with their %d norm kernels" % (2 * L),
+            dominant_linear_kernel(B, args.wformat), 4 * L, "" if fused_norm else " with their %d norm kernels" % (2 * L),
             ", this rank's shard, no exchange" if tp > 1 else "")
         # DRAM traffic of the same launches: a STATIC figure from the committed ncu capture of this command (read + write bytes over
         # algorithmic bytes), not measured in this run -- only quoted for the configuration that was captured

@@ -122,8 +122,8 @@ static int norm_linear(b200_decoder *d, const void *x, const void *res_in, void 
                        const b200_linear_weight_t &w, int K, int N, bool swiglu, void *y, int M, cudaStream_t st, const TpExchange *tp = nullptr) {
     const b200_decoder_config_t &c = d->cfg;
     const bool b16 = c.dtype != B200_F32;
-    // one token (any dtype) and fp32 up to 4: the prologue runs inside the GEMV (SIMT kernels / round-1 quantised kernel)
-    if (M == 1 || (!b16 && M <= 4)) {
+    // one token (any dtype), fp32 up to 4, quantised weights up to 4: the prologue runs inside the GEMV (SIMT kernels / gemv_q.cuh)
+    if (M == 1 || (!b16 && M <= 4) || (c.w_format != B200_W_DENSE && M <= 4)) {
         GemvArgs a = {};
         a.w = w.w, a.scales = w.scales, a.zeros = w.zeros;
         a.x = x, a.y = y;
@@ -539,7 +539,7 @@ int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b
         dec->cur = next_res(dec->cur);
         if ((rc = plain_linear(dec, dec->act, w.down, c.inter_size, c.hidden, dec->y_ffn, batch, st)) != B200_OK) return rc;
         // 4 linears; for 2+ tokens of a 16-bit model (5+ in fp32) each of the two prologues is its own small kernel (norm_linear)
-        launches += (batch == 1 || (c.dtype == B200_F32 && batch <= 4)) ? 4 : 6;
+        launches += (batch == 1 || ((c.dtype == B200_F32 || c.w_format != B200_W_DENSE) && batch <= 4)) ? 4 : 6;
     }
     if (n_launches) *n_launches = launches;
     return B200_OK;

@@ -4,8 +4,9 @@
 //
 // HBM-bound by construction: every weight byte crosses HBM once per call WHATEVER the batch (<= 16), and the arithmetic runs on
 // mma.sync.m16n8k16 (the SIMT GEMV of gemv.cuh is ALU-bound from 4 tokens on: 46 % of HBM at batch 4).  Orientation: the TOKENS are
-// the mma M dimension (16 slots: batch 9..16 costs what batch 1..8 costs), a work unit is 8 WEIGHT ROWS (the mma N dimension), so small
-// linears (N = 4096: 512 units) still spread over all SMs.  Structure:
+// the mma M dimension (16 slots: batch 9..16 costs what batch 1..8 costs), a work unit is 8 WEIGHT ROWS (the mma N dimension; 16 for the
+// quantised formats, whose activation fragments are then loaded once per two row groups), so small linears (N = 4096: 512 / 256 units)
+// still spread over all SMs.  Structure:
 //   * one persistent CTA per SM: 16 compute warps, one TMA-producer warp, one reducer warp.  Units are dealt round-robin over CTAs; the
 //     16 warps split the k range of every ring stage (a stage = <= 4 KiB of each of the unit's 8 rows, one 1-D bulk copy per row), so
 //     a unit is done by the whole CTA and the tail of a launch is one stage, not one unit;
@@ -33,9 +34,8 @@ namespace b200 {
 
 constexpr int kMmaWarps = 16;                        // compute warps
 constexpr int kMmaThreads = (kMmaWarps + 2) * 32;    // + producer warp + reducer warp
-constexpr int kMmaRows = 8;                          // weight rows per unit = mma N
+constexpr int kMmaRows = 8;                          // weight rows per row group = mma N; a unit is RG row groups
 constexpr int kMmaMaxStages = 8;
-constexpr int kMmaTile = 16 * kMmaRows;              // fp32 values of one 16-token x 8-row tile
 
 struct MmaGeom {
     int piece_bytes;  // bytes of one weight row per ring stage (one bulk copy)
@@ -49,6 +49,7 @@ struct MmaGeom {
     int tok;          // token slots of the mma tile in use: 8 or 16
     int xs_rows;      // token rows staged: M (+ one zero row that every slot past the batch reads)
     int max_units;    // units of the busiest CTA (size of the cross-part accumulator)
+    int rg;           // row groups of 8 weight rows per unit (the A fragments of a k block are loaded once and used rg times)
 };
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -70,17 +71,23 @@ __device__ __forceinline__ uint32_t mma_e4m3x2_to_f16x2(uint32_t two_bytes) {
 //   i even: ((w' & 0x000f000f) | 0x64006400) = {1024 + n, 1024 + n} minus {1024 + z};
 //   i odd : ((w' & 0x00f000f0) | 0x64006400) = {1024 + 16 n, ...}: one HFMA2 with 1/16 and -(64 + z) (exact: 64 + n is an f16 integer);
 //   w' = w for i = 0, 1 and w >> 8 for i = 2, 3.
-__device__ __forceinline__ void mma_deq_int4(uint32_t w, uint32_t zq, uint32_t (&d)[4]) {
-    const uint32_t m_lo = 0x000f000fu, m_hi = 0x00f000f0u, magic = 0x64006400u;
+// zpk = f16x2 {1024 + z, 1024 + z}, nz = f16x2 {-(64 + z), -(64 + z)}: prepared once per quantisation group (mma_int4_consts)
+__device__ __forceinline__ void mma_int4_consts(uint32_t zq, uint32_t &zpk, uint32_t &nz) {
+    const uint32_t z16 = 0x6400u | zq;
+    zpk = z16 | (z16 << 16);
+    const __half2 n2 = __float2half2_rn(-(64.0f + (float)zq));
+    nz = *reinterpret_cast<const uint32_t *>(&n2);
+}
+__device__ __forceinline__ void mma_deq_int4(uint32_t w, uint32_t zpk, uint32_t nz32, uint32_t (&d)[4]) {
+    const uint32_t m_lo = 0x000f000fu, m_hi = 0x00f000f0u, magic = 0x64006400u, sixteenth = 0x2c002c00u;  // f16 1/16 = 0x2c00
     const uint32_t w8 = w >> 8;
     uint32_t h0, h1, h2, h3;
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(h0) : "r"(w), "r"(m_lo), "r"(magic));
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(h1) : "r"(w), "r"(m_hi), "r"(magic));
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(h2) : "r"(w8), "r"(m_lo), "r"(magic));
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(h3) : "r"(w8), "r"(m_hi), "r"(magic));
-    const uint32_t z16 = 0x6400u | zq, zpk = z16 | (z16 << 16);  // f16x2 {1024 + z, 1024 + z}
-    const __half2 z = *reinterpret_cast<const __half2 *>(&zpk);
-    const __half2 nz = __float2half2_rn(-(64.0f + (float)zq)), s16 = __float2half2_rn(0.0625f);
+    const __half2 z = *reinterpret_cast<const __half2 *>(&zpk), nz = *reinterpret_cast<const __half2 *>(&nz32);
+    const __half2 s16 = *reinterpret_cast<const __half2 *>(&sixteenth);
     const __half2 r0 = __hsub2(*reinterpret_cast<const __half2 *>(&h0), z), r2 = __hsub2(*reinterpret_cast<const __half2 *>(&h2), z);
     const __half2 r1 = __hfma2(*reinterpret_cast<const __half2 *>(&h1), s16, nz), r3 = __hfma2(*reinterpret_cast<const __half2 *>(&h3), s16, nz);
     d[0] = *reinterpret_cast<const uint32_t *>(&r0), d[1] = *reinterpret_cast<const uint32_t *>(&r1);
@@ -90,13 +97,17 @@ __device__ __forceinline__ void mma_deq_int4(uint32_t w, uint32_t zq, uint32_t (
 // smem: [ xs : tok * xs_stride * 2 B | ring : stages * stage_bytes | barriers : (2 * kMmaMaxStages + 4) * 8 | tiles : 2 * 16 warps * 128
 //         floats | cross-part accumulator : max_units * 128 floats (parts > 1) ]
 // NT = 1: M <= 8 (token slots 8..15 are zero A fragments), NT = 2: M <= 16.
-template <typename T, int FMT, bool kSwiGLU, int NT>
+// RG = row groups (of 8 weight rows) per unit: 2 for FP8, whose k per weight byte is twice the dense one -- with one row group the
+// activation fragments re-read from shared memory for every 8 rows load the shared-memory pipe as much as the weights do.
+template <typename T, int FMT, bool kSwiGLU, int NT, int RG>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
     constexpr int V = Elem<T>::kVec;
     static_assert(V == 8, "gemv_mma_kernel: 16-bit activation types only");
     constexpr bool kDense = FMT == WF_DENSE;
-    constexpr int R = kMmaRows;
+    constexpr int R = kMmaRows * RG;  // weight rows per unit
+    constexpr int kMmaTile = 16 * R;  // fp32 values of one warp's 16-token x R-row tile
+    static_assert(R <= 16, "one producer lane per row of a unit");
     using XT = typename std::conditional<kDense, T, __half>::type;  // staged activation type (quantised weights dequantise to f16)
     extern __shared__ __align__(128) unsigned char smem[];
 
@@ -104,7 +115,7 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const size_t row_bytes = kDense ? (size_t)K * 2 : (FMT == WF_FP8 ? (size_t)K : (size_t)K / 2);
-    const int units = kSwiGLU ? (a.inter + 3) / 4 : (N + R - 1) / R;
+    const int units = kSwiGLU ? (a.inter + R / 2 - 1) / (R / 2) : (N + R - 1) / R;
     const int stages = geo.stages, parts = geo.parts;
     const bool is_compute = warp < kMmaWarps, is_producer = warp == kMmaWarps;
     const int gid = blockIdx.x, total = gridDim.x;
@@ -126,11 +137,11 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
     off += parts > 1 ? (size_t)geo.max_units * kMmaTile * sizeof(float) : 0;
     const uint32_t ring_u32 = smem_u32(ring);
 
-    // row r (0..7) of unit u: plain 8u + r; SwiGLU: gate row 4u + r/2 (r even) and its up row inter + 4u + r/2 (r odd)
-    auto unit_row = [&](int u, int r) -> int { return kSwiGLU ? ((r & 1) ? a.inter : 0) + 4 * u + (r >> 1) : R * u + r; };
-    auto row_ok = [&](int u, int r) -> bool { return kSwiGLU ? (4 * u + (r >> 1) < a.inter) : (R * u + r < N); };
+    // row r (0 .. R-1) of unit u: plain R u + r; SwiGLU: gate row j = (R/2) u + r/2 (r even) and its up row inter + j (r odd)
+    auto unit_row = [&](int u, int r) -> int { return kSwiGLU ? ((r & 1) ? a.inter : 0) + (R / 2) * u + (r >> 1) : R * u + r; };
+    auto row_ok = [&](int u, int r) -> bool { return kSwiGLU ? ((R / 2) * u + (r >> 1) < a.inter) : (R * u + r < N); };
 
-    // ---- producer WARP: order (part, unit, piece); lane 0 arms the stage barrier, lanes 0..7 issue one bulk copy per row
+    // ---- producer WARP: order (part, unit, piece); lane 0 arms the stage barrier, lanes 0 .. R-1 issue one bulk copy per row
     int p_part = 0, p_un = 0, p_pc = 0, p_item = 0, p_s = 0;
     auto issue_next = [&]() {  // all 32 lanes of the producer warp
         const int u = gid + p_un * total;
@@ -180,74 +191,83 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
             issue_next();
         }
     } else if (!is_compute) {
-        // ================================================= reducer: lane l finishes token l/2, rows 4(l%2) .. +3 of every tile
-        const int m = lane >> 1, r0 = (lane & 1) * 4;
+        // ================================================= reducer: per pass, lane l finishes 4 consecutive rows of one token of the tile
         const unsigned int push_flag = a.push.n > 0 ? tp_flag(a.push.epoch, a.push.seq) : 0u;
         int h = 0;  // hand-off counter: order (part, unit)
         for (int p = 0; p < parts; ++p) {
             for (int un = 0; un < my_units; ++un, ++h) {
                 const int u = gid + un * total;
                 const int b = h & 1;
-                float s8[4] = {1.f, 1.f, 1.f, 1.f};
+                float s8[RG][4];
                 if constexpr (FMT == WF_FP8) {  // requested before the wait: the L2 latency hides behind the compute warps
-                    if (p + 1 == parts) {
+#pragma unroll
+                    for (int ps = 0; ps < RG; ++ps) {
+                        const int r0 = (ps * 128 + lane * 4) % R;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (row_ok(u, r0 + i)) s8[i] = __ldg(reinterpret_cast<const float *>(a.scales) + unit_row(u, r0 + i));
+                            s8[ps][i] = (p + 1 == parts && row_ok(u, r0 + i)) ? __ldg(reinterpret_cast<const float *>(a.scales) + unit_row(u, r0 + i)) : 1.0f;
                     }
                 }
                 mbar_wait(ready0 + b * 8, (h >> 1) & 1);
-                const float *slot = tiles + (size_t)b * kMmaWarps * kMmaTile + lane * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v[RG];
 #pragma unroll
-                for (int w2 = 0; w2 < kMmaWarps; ++w2) {  // fixed order: deterministic
-                    const float4 q = *reinterpret_cast<const float4 *>(slot + (size_t)w2 * kMmaTile);
-                    v.x += q.x, v.y += q.y, v.z += q.z, v.w += q.w;
+                for (int ps = 0; ps < RG; ++ps) {
+                    const float *slot = tiles + (size_t)b * kMmaWarps * kMmaTile + ps * 128 + lane * 4;
+                    v[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int w2 = 0; w2 < kMmaWarps; ++w2) {  // fixed order: deterministic
+                        const float4 q = *reinterpret_cast<const float4 *>(slot + (size_t)w2 * kMmaTile);
+                        v[ps].x += q.x, v[ps].y += q.y, v[ps].z += q.z, v[ps].w += q.w;
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(free0 + b * 8);
-                if (parts > 1) {  // accumulate across K parts (part order: deterministic)
-                    float4 *acc = reinterpret_cast<float4 *>(outacc + (size_t)un * kMmaTile) + lane;
-                    if (p > 0) {
-                        const float4 o = *acc;
-                        v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
-                    }
-                    if (p + 1 < parts) {
-                        *acc = v;
-                        continue;
-                    }
-                }
-                if (m >= a.M) continue;
-                float o[4] = {v.x, v.y, v.z, v.w};
-                if constexpr (FMT == WF_FP8) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) o[i] *= s8[i];
-                }
-                if constexpr (kSwiGLU) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int j = 4 * u + (r0 >> 1) + i;  // rows (r0 + 2i, r0 + 2i + 1) = (gate_j, up_j)
-                        if (j < a.inter) {
-                            // the un-fused reference stores gate / up in T before SiLU reads them
-                            const float gt = round_to<T>(o[2 * i]), up = round_to<T>(o[2 * i + 1]);
-                            const float sv = (gt / (1.0f + expf(-gt))) * up;
-                            if (a.y_f32) reinterpret_cast<float *>(a.y)[(size_t)m * a.inter + j] = sv;
-                            else reinterpret_cast<T *>(a.y)[(size_t)m * a.inter + j] = Elem<T>::from_f(sv);
+                for (int ps = 0; ps < RG; ++ps) {
+                    const int e0 = ps * 128 + lane * 4, m = e0 / R, r0 = e0 % R;  // token, first of this lane's 4 rows
+                    if (parts > 1) {  // accumulate across K parts (part order: deterministic)
+                        float4 *acc = reinterpret_cast<float4 *>(outacc + (size_t)un * kMmaTile + e0);
+                        if (p > 0) {
+                            const float4 o = *acc;
+                            v[ps].x += o.x, v[ps].y += o.y, v[ps].z += o.z, v[ps].w += o.w;
+                        }
+                        if (p + 1 < parts) {
+                            *acc = v[ps];
+                            continue;
                         }
                     }
-                } else if (a.push.n > 0) {
-                    // tensor-parallel partial: LL words hold two consecutive rows (N is even)
+                    if (m >= a.M) continue;
+                    float o[4] = {v[ps].x, v[ps].y, v[ps].z, v[ps].w};
+                    if constexpr (FMT == WF_FP8) {
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        if (row_ok(u, r0 + 2 * i + 1)) tp_push_pair<T>(a.push, push_flag, (size_t)m * N + R * u + r0 + 2 * i, o[2 * i], o[2 * i + 1]);
-                } else {
+                        for (int i = 0; i < 4; ++i) o[i] *= s8[ps][i];
+                    }
+                    if constexpr (kSwiGLU) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (row_ok(u, r0 + i)) {
-                            const size_t idx = (size_t)m * N + R * u + r0 + i;
-                            if (a.y_f32) reinterpret_cast<float *>(a.y)[idx] = o[i];
-                            else reinterpret_cast<T *>(a.y)[idx] = Elem<T>::from_f(o[i]);
+                        for (int i = 0; i < 2; ++i) {
+                            const int j = (R / 2) * u + (r0 >> 1) + i;  // rows (r0 + 2i, r0 + 2i + 1) = (gate_j, up_j)
+                            if (j < a.inter) {
+                                // the un-fused reference stores gate / up in T before SiLU reads them
+                                const float gt = round_to<T>(o[2 * i]), up = round_to<T>(o[2 * i + 1]);
+                                const float sv = (gt / (1.0f + expf(-gt))) * up;
+                                if (a.y_f32) reinterpret_cast<float *>(a.y)[(size_t)m * a.inter + j] = sv;
+                                else reinterpret_cast<T *>(a.y)[(size_t)m * a.inter + j] = Elem<T>::from_f(sv);
+                            }
                         }
+                    } else if (a.push.n > 0) {
+                        // tensor-parallel partial: LL words hold two consecutive rows (N is even)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            if (row_ok(u, r0 + 2 * i + 1)) tp_push_pair<T>(a.push, push_flag, (size_t)m * N + R * u + r0 + 2 * i, o[2 * i], o[2 * i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (row_ok(u, r0 + i)) {
+                                const size_t idx = (size_t)m * N + R * u + r0 + i;
+                                if (a.y_f32) reinterpret_cast<float *>(a.y)[idx] = o[i];
+                                else reinterpret_cast<T *>(a.y)[idx] = Elem<T>::from_f(o[i]);
+                            }
+                    }
                 }
             }
         }
@@ -289,24 +309,27 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
                 // one sweep: thread (column c) takes vector c of every token row, all loads in flight before the first conversion
                 const int nvp = (pk1 - pk0) / V;
                 for (int c = tid; c < nvp; c += NC) {
-                    uint4 raw[16];
+#pragma unroll 1
+                    for (int m0 = 0; m0 < a.M; m0 += 8) {  // eight rows' loads in flight at a time
+                        uint4 raw[8];
 #pragma unroll
-                    for (int m = 0; m < 16; ++m)
-                        if (m < a.M) raw[m] = ld_v4(xin + (size_t)m * K + pk0 + (size_t)c * V);
+                        for (int m = 0; m < 8; ++m)
+                            if (m0 + m < a.M) raw[m] = ld_v4(xin + (size_t)(m0 + m) * K + pk0 + (size_t)c * V);
 #pragma unroll
-                    for (int m = 0; m < 16; ++m)
-                        if (m < a.M) {
-                            float q[V], o[V];
-                            unpack16<T>(raw[m], q);
+                        for (int m = 0; m < 8; ++m)
+                            if (m0 + m < a.M) {
+                                float q[V], o[V];
+                                unpack16<T>(raw[m], q);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[FMT == WF_INT4 ? ((j & 3) * 2 + (j >> 2)) : j] = q[j];  // INT4: [k0 k4 k1 k5 k2 k6 k3 k7]
-                            const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
-                            const __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<const uint32_t *>(&h0), pk.y = *reinterpret_cast<const uint32_t *>(&h1);
-                            pk.z = *reinterpret_cast<const uint32_t *>(&h2), pk.w = *reinterpret_cast<const uint32_t *>(&h3);
-                            *reinterpret_cast<uint4 *>(xs + (size_t)m * geo.xs_stride + (size_t)c * V) = pk;
-                        }
+                                for (int j = 0; j < 8; ++j) o[FMT == WF_INT4 ? ((j & 3) * 2 + (j >> 2)) : j] = q[j];  // INT4: [k0 k4 k1 k5 k2 k6 k3 k7]
+                                const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+                                const __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
+                                uint4 pk;
+                                pk.x = *reinterpret_cast<const uint32_t *>(&h0), pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+                                pk.z = *reinterpret_cast<const uint32_t *>(&h2), pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+                                *reinterpret_cast<uint4 *>(xs + (size_t)(m0 + m) * geo.xs_stride + (size_t)c * V) = pk;
+                            }
+                    }
                 }
                 cbar();
             }
@@ -315,11 +338,11 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
             const XT *x0 = xs + (size_t)min(g, a.M) * geo.xs_stride + 8 * t;
             const XT *x1 = xs + (size_t)min(g + 8, a.M) * geo.xs_stride + 8 * t;
             const int npc = part_pieces(p);
-            // INT4: zero points of row g and scales of rows 2t, 2t+1 for the (<= 4) groups of this warp's slice of a stage.  They are
-            // requested ONE STAGE AHEAD (a stage is 16 KiB = 0.4 us of this SM's share of HBM, an L2 round trip is longer)
+            // INT4: zero points of rows g + 8 rg and scales of rows 2t, 2t+1 (+ 8 rg) for the (<= 2) quantisation groups of this warp's
+            // slice of a stage.  They are requested ONE STAGE AHEAD (a stage is 0.4-0.7 us of this SM's share of HBM, an L2 round trip is longer)
             struct QParams {
-                uint32_t z;
-                float s0[4], s1[4];
+                uint32_t z;         // byte [2 rg + q]
+                float s0[RG][2], s1[RG][2];
             };
             auto load_qparams = [&](int un_, int pc_) -> QParams {
                 QParams q = {};
@@ -327,21 +350,29 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
                     const int u_ = gid + un_ * total;
                     const int kw_ = pk0 + pc_ * geo.piece_k + warp * wk, kend_ = min(kw_ + wk, pk1);
                     const int ng = kend_ > kw_ ? (kend_ - kw_ + a.group - 1) / a.group : 0;
-                    const int zrow = min(unit_row(u_, g), N - 1), srow0 = min(unit_row(u_, 2 * t), N - 1), srow1 = min(unit_row(u_, 2 * t + 1), N - 1);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < ng) {
-                            const size_t gi = (size_t)(kw_ / a.group + j);
-                            q.z |= (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(a.zeros) + (size_t)zrow * ngroups_k + gi) << (8 * j);
-                            q.s0[j] = Elem<T>::to_f(__ldg(reinterpret_cast<const T *>(a.scales) + (size_t)srow0 * ngroups_k + gi));
-                            q.s1[j] = Elem<T>::to_f(__ldg(reinterpret_cast<const T *>(a.scales) + (size_t)srow1 * ngroups_k + gi));
-                        }
+                    for (int rg = 0; rg < RG; ++rg) {
+                        const int zrow = min(unit_row(u_, 8 * rg + g), N - 1), srow0 = min(unit_row(u_, 8 * rg + 2 * t), N - 1),
+                                  srow1 = min(unit_row(u_, 8 * rg + 2 * t + 1), N - 1);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            if (j < ng) {
+                                const size_t gi = (size_t)(kw_ / a.group + j);
+                                q.z |= (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(a.zeros) + (size_t)zrow * ngroups_k + gi) << (8 * (2 * rg + j));
+                                q.s0[rg][j] = Elem<T>::to_f(__ldg(reinterpret_cast<const T *>(a.scales) + (size_t)srow0 * ngroups_k + gi));
+                                q.s1[rg][j] = Elem<T>::to_f(__ldg(reinterpret_cast<const T *>(a.scales) + (size_t)srow1 * ngroups_k + gi));
+                            }
+                    }
                 }
                 return q;
             };
             QParams qcur = my_units > 0 ? load_qparams(0, 0) : QParams{};
             for (int un = 0; un < my_units; ++un, ++h) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                float acc[RG][4], acc2[RG][4];
+#pragma unroll
+                for (int rg = 0; rg < RG; ++rg)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[rg][i] = acc2[rg][i] = 0.0f;
                 for (int pc = 0; pc < npc; ++pc) {
                     const int kw = pk0 + pc * geo.piece_k + warp * wk;  // first k of this warp's slice of the stage
                     const int kend = min(kw + wk, pk1);
@@ -351,61 +382,103 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
                         const int pc2 = pc + 1 < npc ? pc + 1 : 0, un2 = pc + 1 < npc ? un : un + 1;
                         if (un2 < my_units) qnxt = load_qparams(un2, pc2);
                     }
+                    // row g of row group rg, this warp's bytes of the stage row
                     const unsigned char *wrow = ring + (size_t)s * geo.stage_bytes + (size_t)g * geo.row_stride + (size_t)warp * wbytes;
+                    const size_t rg_stride = (size_t)8 * geo.row_stride;
                     const XT *xa = x0 + (kw - pk0), *xb = x1 + (kw - pk0);
                     if constexpr (FMT == WF_INT4) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {  // 128-k quantisation groups of the slice (unrolled: the parameters stay in registers)
+                        for (int q = 0; q < 2; ++q) {  // 128-k quantisation groups of the slice (unrolled: the parameters stay in registers)
                             if (kw + q * 128 >= kend) continue;
-                            float ag[4] = {0.f, 0.f, 0.f, 0.f};
-                            const uint32_t zq = (qcur.z >> (8 * q)) & 0xffu;
+                            float ag[RG][4];
+                            uint32_t zpk[RG], nz[RG];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {  // 32-k blocks of the group
+                            for (int rg = 0; rg < RG; ++rg) {
+                                ag[rg][0] = ag[rg][1] = ag[rg][2] = ag[rg][3] = 0.0f;
+                                mma_int4_consts((qcur.z >> (8 * (2 * rg + q))) & 0xffu, zpk[rg], nz[rg]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {  // 32-k blocks of the group: the A fragments are loaded once for all row groups
                                 const int kk = q * 128 + j * 32;
-                                const uint32_t wv = *reinterpret_cast<const uint32_t *>(wrow + (kk + 8 * t) / 2);
-                                uint32_t d[4];
-                                mma_deq_int4(wv, zq, d);
                                 const uint4 av = *reinterpret_cast<const uint4 *>(xa + kk);
                                 uint4 bv = make_uint4(0u, 0u, 0u, 0u);
                                 if constexpr (NT == 2) bv = *reinterpret_cast<const uint4 *>(xb + kk);
-                                mma_f16f16(ag, av.x, bv.x, av.y, bv.y, d[0], d[1]);
-                                mma_f16f16(ag, av.z, bv.z, av.w, bv.w, d[2], d[3]);
+#pragma unroll
+                                for (int rg = 0; rg < RG; ++rg) {
+                                    const uint32_t wv = *reinterpret_cast<const uint32_t *>(wrow + rg * rg_stride + (kk + 8 * t) / 2);
+                                    uint32_t d[4];
+                                    mma_deq_int4(wv, zpk[rg], nz[rg], d);
+                                    mma_f16f16(ag[rg], av.x, bv.x, av.y, bv.y, d[0], d[1]);
+                                    mma_f16f16(ag[rg], av.z, bv.z, av.w, bv.w, d[2], d[3]);
+                                }
                             }
-                            acc[0] = fmaf(qcur.s0[q], ag[0], acc[0]), acc[1] = fmaf(qcur.s1[q], ag[1], acc[1]);
-                            acc[2] = fmaf(qcur.s0[q], ag[2], acc[2]), acc[3] = fmaf(qcur.s1[q], ag[3], acc[3]);
+#pragma unroll
+                            for (int rg = 0; rg < RG; ++rg) {
+                                acc[rg][0] = fmaf(qcur.s0[rg][q], ag[rg][0], acc[rg][0]), acc[rg][1] = fmaf(qcur.s1[rg][q], ag[rg][1], acc[rg][1]);
+                                acc[rg][2] = fmaf(qcur.s0[rg][q], ag[rg][2], acc[rg][2]), acc[rg][3] = fmaf(qcur.s1[rg][q], ag[rg][3], acc[rg][3]);
+                            }
                         }
                         qcur = qnxt;
                     } else {
-                        for (int kk = 0; kw + kk < kend; kk += 32) {  // 32-k blocks: two mma k-steps
+                        // 32-k blocks (two mma k-steps each), four at a time: all fragment loads first, then two independent accumulator
+                        // chains per row group (a rolled loop serialised load -> mma -> mma per block: 4 x ~110 cycles per stage and warp)
+                        using WQ = typename std::conditional<kDense, uint4, uint2>::type;  // the 8 weights of (a row, this lane's 8 k)
+                        auto block = [&](float (&c)[4], const uint4 &av, const uint4 &bv, const WQ &wq) {
+                            if constexpr (kDense) {
+                                if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                                    mma_bf16(c, av.x, bv.x, av.y, bv.y, wq.x, wq.y);
+                                    mma_bf16(c, av.z, bv.z, av.w, bv.w, wq.z, wq.w);
+                                } else {
+                                    mma_f16f16(c, av.x, bv.x, av.y, bv.y, wq.x, wq.y);
+                                    mma_f16f16(c, av.z, bv.z, av.w, bv.w, wq.z, wq.w);
+                                }
+                            } else {  // FP8: wq.x / wq.y hold the 8 bytes of the block
+                                mma_f16f16(c, av.x, bv.x, av.y, bv.y, mma_e4m3x2_to_f16x2(wq.x), mma_e4m3x2_to_f16x2(wq.x >> 16));
+                                mma_f16f16(c, av.z, bv.z, av.w, bv.w, mma_e4m3x2_to_f16x2(wq.y), mma_e4m3x2_to_f16x2(wq.y >> 16));
+                            }
+                        };
+                        auto load_w = [&](int rg, int kk) -> WQ {
+                            if constexpr (kDense) return *reinterpret_cast<const uint4 *>(wrow + rg * rg_stride + (size_t)(kk + 8 * t) * 2);
+                            else return *reinterpret_cast<const uint2 *>(wrow + rg * rg_stride + (kk + 8 * t));
+                        };
+                        int kk = 0;
+                        for (; kw + kk + 128 <= kend; kk += 128) {
+                            WQ wq[RG][4];
+                            uint4 av[4], bv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                                for (int rg = 0; rg < RG; ++rg) wq[rg][j] = load_w(rg, kk + 32 * j);
+                                av[j] = *reinterpret_cast<const uint4 *>(xa + kk + 32 * j);
+                                bv[j] = make_uint4(0u, 0u, 0u, 0u);
+                                if constexpr (NT == 2) bv[j] = *reinterpret_cast<const uint4 *>(xb + kk + 32 * j);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int rg = 0; rg < RG; ++rg) block((j & 1) ? acc2[rg] : acc[rg], av[j], bv[j], wq[rg][j]);
+                        }
+                        for (; kw + kk < kend; kk += 32) {  // short slices (K not a multiple of the stage width)
                             const uint4 av = *reinterpret_cast<const uint4 *>(xa + kk);
                             uint4 bv = make_uint4(0u, 0u, 0u, 0u);
                             if constexpr (NT == 2) bv = *reinterpret_cast<const uint4 *>(xb + kk);
-                            if constexpr (kDense) {
-                                const uint4 wv = *reinterpret_cast<const uint4 *>(wrow + (size_t)(kk + 8 * t) * 2);
-                                if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
-                                    mma_bf16(acc, av.x, bv.x, av.y, bv.y, wv.x, wv.y);
-                                    mma_bf16(acc, av.z, bv.z, av.w, bv.w, wv.z, wv.w);
-                                } else {
-                                    mma_f16f16(acc, av.x, bv.x, av.y, bv.y, wv.x, wv.y);
-                                    mma_f16f16(acc, av.z, bv.z, av.w, bv.w, wv.z, wv.w);
-                                }
-                            } else {
-                                const uint2 wv = *reinterpret_cast<const uint2 *>(wrow + (kk + 8 * t));
-                                mma_f16f16(acc, av.x, bv.x, av.y, bv.y, mma_e4m3x2_to_f16x2(wv.x), mma_e4m3x2_to_f16x2(wv.x >> 16));
-                                mma_f16f16(acc, av.z, bv.z, av.w, bv.w, mma_e4m3x2_to_f16x2(wv.y), mma_e4m3x2_to_f16x2(wv.y >> 16));
-                            }
+#pragma unroll
+                            for (int rg = 0; rg < RG; ++rg) block(acc[rg], av, bv, load_w(rg, kk));
                         }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty0 + s * 8);  // this warp has left the stage
                     if (++s == stages) s = 0, ph ^= 1;
                 }
-                // ---- hand this warp's 16 x 8 tile of the (part, unit) to the reducer (double-buffered slot)
+                // ---- hand this warp's 16 x R tile of the (part, unit) to the reducer (double-buffered slot)
                 const int b = h & 1;
                 if (h >= 2) mbar_wait(free0 + b * 8, ((h >> 1) - 1) & 1);
                 float *slot = tiles + ((size_t)b * kMmaWarps + warp) * kMmaTile;
-                *reinterpret_cast<float2 *>(slot + g * R + 2 * t) = make_float2(acc[0], acc[1]);
-                *reinterpret_cast<float2 *>(slot + (g + 8) * R + 2 * t) = make_float2(acc[2], acc[3]);
+#pragma unroll
+                for (int rg = 0; rg < RG; ++rg) {
+                    *reinterpret_cast<float2 *>(slot + g * R + 8 * rg + 2 * t) = make_float2(acc[rg][0] + acc2[rg][0], acc[rg][1] + acc2[rg][1]);
+                    *reinterpret_cast<float2 *>(slot + (g + 8) * R + 8 * rg + 2 * t) = make_float2(acc[rg][2] + acc2[rg][2], acc[rg][3] + acc2[rg][3]);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ready0 + b * 8);
             }
@@ -417,12 +490,16 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
 // Geometry for (M, K, format): false when the shape cannot use this kernel.
 inline size_t gemv_mma_fixed_smem(const MmaGeom &g) {
     size_t fixed = ((size_t)g.xs_rows * g.xs_stride * 2 + 127) & ~(size_t)127;
-    return fixed + (size_t)(2 * kMmaMaxStages + 6) * 8 + (size_t)2 * kMmaWarps * kMmaTile * 4 + (g.parts > 1 ? (size_t)g.max_units * kMmaTile * 4 : 0);
+    const size_t tile = (size_t)16 * kMmaRows * g.rg * 4;  // bytes of one warp's fp32 tile
+    return fixed + (size_t)(2 * kMmaMaxStages + 6) * 8 + (size_t)2 * kMmaWarps * tile + (g.parts > 1 ? (size_t)g.max_units * tile : 0);
 }
 inline size_t gemv_mma_smem(const MmaGeom &g) { return gemv_mma_fixed_smem(g) + (size_t)g.stages * g.stage_bytes; }
 
 // Geometry for (M, K, format): false when the shape cannot use this kernel.  Among the (bytes per stage row, number of activation parts)
 // that leave a ring of >= 3 stages, the best-scoring one wins (see the score below).
+// row groups per unit: 2 for FP8 (measured at batch 16: 5.32 -> 4.98 ms per 7B step); INT4 stays at 1 (with 2 its dequantisation
+// registers spill: 6.06 -> 8.15 ms)
+inline int gemv_mma_row_groups(int fmt) { return fmt == WF_FP8 ? 2 : 1; }
 inline bool gemv_mma_geometry(int M, int K, int N_units_max, int fmt, MmaGeom *out) {
     if (M < 1 || M > 16 || K % 128 != 0) return false;
     const bool dense = fmt == WF_DENSE;
@@ -435,16 +512,18 @@ inline bool gemv_mma_geometry(int M, int K, int N_units_max, int fmt, MmaGeom *o
         g.tok = M <= 8 ? 8 : 16;
         g.xs_rows = M == g.tok ? g.tok : M + 1;  // token slots past the batch all read ONE zero row
         g.max_units = N_units_max;
+        g.rg = gemv_mma_row_groups(fmt);
         g.piece_bytes = piece_bytes;
         g.piece_k = dense ? g.piece_bytes / 2 : (fmt == WF_FP8 ? g.piece_bytes : g.piece_bytes * 2);
         if (g.piece_k > k_round) {  // short rows: one piece
             g.piece_k = k_round;
             g.piece_bytes = dense ? g.piece_k * 2 : (fmt == WF_FP8 ? g.piece_k : g.piece_k / 2);
         }
-        if (fmt == WF_INT4 && (g.piece_k / kMmaWarps) % 128 != 0) continue;  // a warp's slice must hold whole quantisation groups
+        // a warp's slice of a stage must hold whole quantisation groups, and at most two of them (their parameters live in registers)
+        if (fmt == WF_INT4 && ((g.piece_k / kMmaWarps) % 128 != 0 || g.piece_k / kMmaWarps > 256)) continue;
         // pad so that the per-lane fragment loads of 8 rows fall on different banks: 16 B (dense) / 8 B (FP8) / 4 B (INT4) per lane, 4 lanes per row
         g.row_stride = g.piece_bytes + (dense ? 64 : (fmt == WF_FP8 ? 32 : 16));
-        g.stage_bytes = kMmaRows * g.row_stride;
+        g.stage_bytes = kMmaRows * g.rg * g.row_stride;
         const int pieces_total = (K + g.piece_k - 1) / g.piece_k;
         for (g.parts = 1; g.parts <= pieces_total; ++g.parts) {
             const int ppp = (pieces_total + g.parts - 1) / g.parts;  // pieces per part
@@ -457,10 +536,10 @@ inline bool gemv_mma_geometry(int M, int K, int N_units_max, int fmt, MmaGeom *o
             if (g.stages > kMmaMaxStages) g.stages = kMmaMaxStages;
             // bytes in flight (what keeps HBM busy; beyond ~190 KiB nothing is gained), 4 KiB bulk copies preferred over 2 KiB ones (the
             // copy engine is request-rate bound: round 1 measured 1 KiB copies capping a kernel near 3.3 TB/s), a part boundary (one
-            // named barrier + one re-staging, hidden under the ring) counted as 8 KiB
+            // named barrier + one re-staging + one more hand-off per unit) counted as 48 KiB
             const long inflight = (long)g.stages * g.stage_bytes;
             const long score = (inflight < 196608 ? inflight : 196608) + (g.piece_bytes >= 4096 ? 49152 : (g.piece_bytes >= 2048 ? 0 : -49152)) -
-                               8192L * (g.parts - 1);
+                               49152L * (g.parts - 1);
             if (!found || score > best) best = score, *out = g, found = true;
         }
     }
@@ -469,7 +548,7 @@ inline bool gemv_mma_geometry(int M, int K, int N_units_max, int fmt, MmaGeom *o
 
 template <typename T, int FMT, bool SW, int NT>
 static int launch_gemv_mma_inst(const GemvArgs &a, const MmaGeom &g, int grid, cudaStream_t st) {
-    auto kern = gemv_mma_kernel<T, FMT, SW, NT>;
+    auto kern = gemv_mma_kernel<T, FMT, SW, NT, FMT == WF_FP8 ? 2 : 1>;
     const size_t smem = gemv_mma_smem(g);
     static thread_local size_t cached_smem[64] = {0};  // per device, per instantiation
     int dev = 0;
@@ -489,11 +568,12 @@ static int launch_gemv_mma_t(const GemvArgs &a, int fmt, bool swiglu, cudaStream
     if (a.M < 1 || a.M > 16 || a.K % 128 != 0 || !aligned16(a.w) || !aligned16(a.x)) return B200_ERR_UNSUPPORTED;
     if (a.norm || a.tp.world > 1) return B200_ERR_UNSUPPORTED;  // plain activations only (see the header: the prologue work runs once, in front)
     if (fmt == WF_INT4 && a.group != 128) return B200_ERR_UNSUPPORTED;
-    if (swiglu && a.inter % 4 != 0) return B200_ERR_UNSUPPORTED;
+    if (swiglu && a.inter % 8 != 0) return B200_ERR_UNSUPPORTED;
     if (a.push.n > 0 && a.N % 2 != 0) return B200_ERR_UNSUPPORTED;
     const size_t row_bytes = fmt == WF_DENSE ? (size_t)a.K * 2 : (fmt == WF_FP8 ? (size_t)a.K : (size_t)a.K / 2);
     if (row_bytes % 16 != 0) return B200_ERR_UNSUPPORTED;
-    const int units = swiglu ? (a.inter + 3) / 4 : (a.N + kMmaRows - 1) / kMmaRows;
+    const int R = kMmaRows * gemv_mma_row_groups(fmt);  // weight rows per unit
+    const int units = swiglu ? (a.inter + R / 2 - 1) / (R / 2) : (a.N + R - 1) / R;
     int grid = sm_count();
     if (grid > units) grid = units;
     if (grid < 1) grid = 1;

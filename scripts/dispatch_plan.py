@@ -64,19 +64,23 @@ def gemv_mma_plan(M, K, fmt, max_units=8):
             piece_bytes = piece_k * 2 if dense else (piece_k if fmt == "fp8" else piece_k // 2)
         if fmt == "int4" and (piece_k // MMA_WARPS) % 128:
             continue
+        if fmt == "int4" and piece_k // MMA_WARPS > 256:
+            continue
+        rg = 2 if fmt == "fp8" else 1  # row groups of 8 weight rows per unit
         row_stride = piece_bytes + (64 if dense else (32 if fmt == "fp8" else 16))
-        stage_bytes = MMA_ROWS * row_stride
+        stage_bytes = MMA_ROWS * rg * row_stride
         pieces_total = -(-K // piece_k)
         for parts in range(1, pieces_total + 1):
             ppp = -(-pieces_total // parts)
             if -(-pieces_total // ppp) != parts:
                 continue
             part_k = ppp * piece_k
-            fixed = (xs_rows * (part_k + 32) * 2 + 127) // 128 * 128 + (2 * MAX_STAGES + 4) * 8 + 2 * MMA_WARPS * 128 * 4 + (max_units * 128 * 4 if parts > 1 else 0) + 128
+            tile = 16 * MMA_ROWS * rg * 4
+            fixed = (xs_rows * (part_k + 32) * 2 + 127) // 128 * 128 + (2 * MAX_STAGES + 6) * 8 + 2 * MMA_WARPS * tile + (max_units * tile if parts > 1 else 0)
             if fixed + 3 * stage_bytes > 226 * 1024:
                 continue
             stages = min((226 * 1024 - fixed) // stage_bytes, MAX_STAGES)
-            score = min(stages * stage_bytes, 196608) + (49152 if piece_bytes >= 4096 else (0 if piece_bytes >= 2048 else -49152)) - 8192 * (parts - 1)
+            score = min(stages * stage_bytes, 196608) + (49152 if piece_bytes >= 4096 else (0 if piece_bytes >= 2048 else -49152)) - 49152 * (parts - 1)
             if best is None or score > best_score:
                 best_score = score
                 best = dict(kernel="gemv_mma", pieces=pieces_total, piece_bytes=piece_bytes, stages=stages, parts=parts, part_k=part_k)
@@ -84,16 +88,16 @@ def gemv_mma_plan(M, K, fmt, max_units=8):
 
 
 def gemv_any(M, K, fmt):
-    """gemv_f32.cu launch_gemv_nk for a 16-bit model: the tensor-core GEMV for 2..16 dense tokens and 1..16 quantised ones, then the round-1
-    quantised kernel (M <= 8), then the SIMT kernel (M <= 4)."""
-    if M <= 16 and (fmt != "dense" or M >= 2):
+    """gemv_f32.cu launch_gemv_nk for a 16-bit model: the tensor-core GEMV for 2..16 dense tokens and 5..16 quantised ones, the round-1
+    quantised kernel for 1..4 quantised tokens (fused prologue), the SIMT kernel for one dense token."""
+    if 2 <= M <= 16 and (fmt == "dense" or M > 4):
         g = gemv_mma_plan(M, K, fmt)
         if g:
             return g
-        if fmt != "dense" and M <= 8:
-            g = gemv_q_plan(M, K, fmt)
-            if g:
-                return g
+    if fmt != "dense" and M <= 8:
+        g = gemv_q_plan(M, K, fmt)
+        if g:
+            return g
     return gemv_nk_plan(M, K, fmt)
 
 

@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out
+timeout -k 5 600 python -m pytest tests/test_ops_gpu.py tests/test_decoder_engine.py tests/test_fullsize_gpu.py -x -q -m gpu --timeout 900 -p no:cacheprovider -k "linear or gemv or engine or quantised" > gpurun_out/r2l_tests.log 2>&1; tail -3 gpurun_out/r2l_tests.log | cut -c1-300
+run() { tag=$1; shift; timeout 300 python bench.py --no-cpu-baseline --steps 128 --regions 3 "$@" > gpurun_out/r2l_$tag.log 2>&1; echo "$tag: $(grep -o '"value": [0-9.]*, "unit": "tokens/s", "n_gpus"\|"ms_per_step": [0-9.]*\|"frac": [0-9.]*' gpurun_out/r2l_$tag.log | head -4 | tr '\n' ' ')"; }
+run b2 --batch 2
+run b4 --batch 4
+run b8 --batch 8
+run b16 --batch 16
+run fp8_b16 --wformat fp8 --batch 16
+run int4_b16 --wformat int4 --batch 16
+run 70b_rank_b8 --config 70b-tp8-rank --batch 8

@@ -27,15 +27,18 @@ def test_tensor_core_gemv_reads_the_weights_once_up_to_16_tokens():
     decode batch up to 16 is ONE pass over the weights, in every format (round 1: 2 passes at batch 16, 4 for the K = 11008 down projection)."""
     for m, k in ((2, 4096), (8, 4096), (16, 4096), (8, 8192), (8, 11008), (16, 11008)):  # incl. the 70B-shaped hidden size and the 7B down projection
         g = dp.gemv_mma_plan(m, k, "dense")
-        assert g and g["piece_bytes"] == 4096 and g["stages"] >= 4 and g["parts"] * g["part_k"] >= k, (m, k, g)
-        assert (8 if m <= 8 else 16) * g["part_k"] * 2 <= 66 * 1024 or m < 8  # a staged part stays <= 64 KiB (+ padding) at full token tiles
+        assert g and g["stages"] >= 3 and g["parts"] * g["part_k"] >= k, (m, k, g)
+        assert (m + 1) * (g["part_k"] + 32) * 2 + g["stages"] * 8 * (g["piece_bytes"] + 64) <= 226 * 1024  # the staged part and the ring share the SM
+    assert dp.gemv_mma_plan(8, 4096, "dense")["parts"] == 1 and dp.gemv_mma_plan(16, 4096, "dense")["parts"] == 2
+    assert dp.gemv_mma_plan(8, 8192, "dense")["parts"] == 2  # 8 tokens x 8192 k do not fit beside a ring: two parts of 4096
     for fmt in ("dense", "fp8", "int4"):
         for m in (2, 8, 16):
             for k in (4096, 11008):
                 path, passes, geo = dp.linear_plan(m, k, fmt, fused_rows=16)
-                assert passes == 1 and path == "fused gemv_mma", (fmt, m, k, path)
+                want = "fused gemv_q" if (fmt != "dense" and m <= 4) else "fused gemv_mma"
+                assert passes == 1 and path == want, (fmt, m, k, path)
     assert dp.linear_plan(1, 4096, "dense", fused_rows=16)[0] == "fused gemv_nk"  # a single dense token stays on the SIMT kernel
-    assert dp.linear_plan(1, 4096, "int4", fused_rows=16)[0] == "fused gemv_mma"
+    assert dp.linear_plan(1, 4096, "int4", fused_rows=16)[0] == "fused gemv_q"  # up to 4 quantised tokens: the kernel with the fused prologue
     path, passes, _ = dp.linear_plan(32, 4096, "fp8", fused_rows=16)
     assert passes == 2 and "16 tokens" in path
 
