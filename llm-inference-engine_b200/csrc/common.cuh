@@ -252,6 +252,16 @@ __device__ __forceinline__ void tp_push_pair(const TpPush &p, unsigned int flag,
         for (int r = 0; r < p.n; ++r) tp_st_v4(reinterpret_cast<char *>(p.dst[r]) + e0 * 8, __float_as_uint(v0), __float_as_uint(v1), flag);
     }
 }
+// PUSH four consecutive elements (e0 a multiple of 4) of a 16-bit tensor: two LL words in ONE 16-byte store per peer (NVLink moves a
+// 16-byte store for the price of an 8-byte one: the packet overhead dominates at these sizes)
+template <typename T>
+__device__ __forceinline__ void tp_push_quad(const TpPush &p, unsigned int flag, size_t e0, const float (&v)[4]) {
+    static_assert(sizeof(T) == 2, "tp_push_quad: 16-bit element types");
+    const T a = Elem<T>::from_f(v[0]), b = Elem<T>::from_f(v[1]), c = Elem<T>::from_f(v[2]), d = Elem<T>::from_f(v[3]);
+    const unsigned int w0 = (unsigned int)*reinterpret_cast<const unsigned short *>(&a) | ((unsigned int)*reinterpret_cast<const unsigned short *>(&b) << 16);
+    const unsigned int w1 = (unsigned int)*reinterpret_cast<const unsigned short *>(&c) | ((unsigned int)*reinterpret_cast<const unsigned short *>(&d) << 16);
+    for (int r = 0; r < p.n; ++r) tp_st_v4(reinterpret_cast<char *>(p.dst[r]) + (e0 / 2) * 8, w0, w1, flag);
+}
 // PUSH one 16-byte vector of T (4 payload words, first element e0 a multiple of the vector length)
 __device__ __forceinline__ void tp_push_vec(const TpPush &p, unsigned int flag, size_t word0, const uint4 &v) {
     for (int r = 0; r < p.n; ++r) {
@@ -262,24 +272,25 @@ __device__ __forceinline__ void tp_push_vec(const TpPush &p, unsigned int flag, 
 }
 // CONSUME one 16-byte vector of T (payload words [word0, word0 + 4)) of every rank's partial: f[j] = round_T(sum over ranks in rank
 // order).  Polls until all flags show `want`; a peer that never delivers trips the (sticky) error word after ~2 s and the result is NaN.
-template <typename T>
+// RB = ranks whose loads are in flight together: 4 inside the fused GEMV prologues (register budget), 8 where registers are free.
+template <typename T, int RB = 4>
 __device__ __forceinline__ void tp_reduce_vec(const TpExchange &t, unsigned int want, size_t word0, float *f) {
     constexpr int V = Elem<T>::kVec;
 #pragma unroll
     for (int j = 0; j < V; ++j) f[j] = 0.0f;
     bool poisoned = false;
 #pragma unroll
-    for (int r0 = 0; r0 < kTpMaxWorld; r0 += 4) {  // four ranks' loads in flight at a time (register budget of the fused prologues)
+    for (int r0 = 0; r0 < kTpMaxWorld; r0 += RB) {  // RB ranks' loads in flight at a time
         if (r0 >= t.world) break;
-        uint4 a[4], b[4];
+        uint4 a[RB], b[RB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < RB; ++j)
             if (r0 + j < t.world) {
                 const char *src = reinterpret_cast<const char *>(t.peer_x[r0 + j]) + word0 * 8;
                 a[j] = tp_ld_v4(src), b[j] = tp_ld_v4(src + 16);
             }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < RB; ++j)
             if (r0 + j < t.world) {
                 if (a[j].y != want || a[j].w != want || b[j].y != want || b[j].w != want) {
                     const char *src = reinterpret_cast<const char *>(t.peer_x[r0 + j]) + word0 * 8;

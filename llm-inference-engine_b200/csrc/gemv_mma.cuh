@@ -255,10 +255,14 @@ gemv_mma_kernel(const GemvArgs a, const MmaGeom geo) {
                             }
                         }
                     } else if (a.push.n > 0) {
-                        // tensor-parallel partial: LL words hold two consecutive rows (N is even)
+                        // tensor-parallel partial: this lane's four consecutive rows are two LL words = one 16-byte store per peer
+                        if (row_ok(u, r0 + 3) && (N & 3) == 0) {
+                            tp_push_quad<T>(a.push, push_flag, (size_t)m * N + R * u + r0, o);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 2; ++i)
-                            if (row_ok(u, r0 + 2 * i + 1)) tp_push_pair<T>(a.push, push_flag, (size_t)m * N + R * u + r0 + 2 * i, o[2 * i], o[2 * i + 1]);
+                            for (int i = 0; i < 2; ++i)
+                                if (row_ok(u, r0 + 2 * i + 1)) tp_push_pair<T>(a.push, push_flag, (size_t)m * N + R * u + r0 + 2 * i, o[2 * i], o[2 * i + 1]);
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)

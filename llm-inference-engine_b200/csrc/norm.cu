@@ -13,8 +13,10 @@ constexpr int kNormMaxVec = 8;  // 16-byte vectors cached per thread
 
 // residual_out <- o (pre-bias), out <- gamma * (o + bias) * rsqrt(mean((o+bias)^2) + eps), o = in (+ residual_in).
 // kCopyOnly (launchRMSNorm): residual_out <- x, no add.
-template <typename T, bool kVec>
-__global__ void __launch_bounds__(kNormThreads)
+// kThreads x kMaxVec: 256 x 8 for many rows (prefill); 512 x 4 for the few rows of a decode batch, where a row is ONE dependent chain of
+// loads (under tensor parallelism 2 x world polled loads per vector) and more threads mean fewer of them per thread.
+template <typename T, bool kVec, int kThreads, int kMaxVec>
+__global__ void __launch_bounds__(kThreads)
 norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T *__restrict__ bias,
             const T *__restrict__ gamma, float eps, int hidden, const TpExchange tp) {
     constexpr int V = kVec ? Elem<T>::kVec : 1;
@@ -32,7 +34,7 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
     auto prenorm = [&](int i, float *f) {
         if constexpr (kVec) {
             if (tp.world > 1) {  // fused one-shot all-reduce of the row-sharded linear's partial sums (rank order), LL words
-                tp_reduce_vec<T>(tp, tp_want, ((size_t)row * hidden + (size_t)i * V) * sizeof(T) / 4, f);
+                tp_reduce_vec<T, kTpMaxWorld>(tp, tp_want, ((size_t)row * hidden + (size_t)i * V) * sizeof(T) / 4, f);
             } else {
                 unpack16<T>(ld_v4(x + (size_t)i * V), f);
             }
@@ -68,11 +70,11 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
         else o[i] = Elem<T>::from_f(f[0]);
     };
 
-    float cache[kNormMaxVec][V];
+    float cache[kMaxVec][V];
     float ss = 0.0f;
 #pragma unroll
-    for (int c = 0; c < kNormMaxVec; ++c) {
-        const int i = threadIdx.x + c * kNormThreads;
+    for (int c = 0; c < kMaxVec; ++c) {
+        const int i = threadIdx.x + c * kThreads;
         if (i < nvec) {
             prenorm(i, cache[c]);
 #pragma unroll
@@ -80,7 +82,7 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
         }
     }
     // rows longer than the register cache: park the pre-norm value in `out` and re-read it below
-    for (int i = threadIdx.x + kNormMaxVec * kNormThreads; i < nvec; i += kNormThreads) {
+    for (int i = threadIdx.x + kMaxVec * kThreads; i < nvec; i += kThreads) {
         float f[V];
         prenorm(i, f);
 #pragma unroll
@@ -92,11 +94,11 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
     ss = block_sum(ss, red);
     const float r = rsqrtf(ss / (float)hidden + eps);
 #pragma unroll
-    for (int c = 0; c < kNormMaxVec; ++c) {
-        const int i = threadIdx.x + c * kNormThreads;
+    for (int c = 0; c < kMaxVec; ++c) {
+        const int i = threadIdx.x + c * kThreads;
         if (i < nvec) finish(i, cache[c], r);
     }
-    for (int i = threadIdx.x + kNormMaxVec * kNormThreads; i < nvec; i += kNormThreads) {
+    for (int i = threadIdx.x + kMaxVec * kThreads; i < nvec; i += kThreads) {
         float f[V];
         if constexpr (kVec) unpack16<T>(ld_v4(o + (size_t)i * V), f);
         else f[0] = Elem<T>::to_f(o[i]);
@@ -135,8 +137,11 @@ static int launch_norm(const T *in, T *out, const T *rin, T *rout, const T *bias
         return B200_ERR_UNSUPPORTED;
     }
     cudaError_t e;
-    if (vec) e = launch_pdl(norm_kernel<T, true>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
-    else e = launch_pdl(norm_kernel<T, false>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
+    // a decode batch (<= 16 rows): 512 threads per row, one to four vectors each -- (nearly) every load of the row in flight at once
+    const bool wide = vec && tokens <= 16 && hidden / (16 / (int)sizeof(T)) <= 4 * 512;
+    if (wide) e = launch_pdl(norm_kernel<T, true, 512, 4>, dim3(tokens), dim3(512), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
+    else if (vec) e = launch_pdl(norm_kernel<T, true, kNormThreads, kNormMaxVec>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
+    else e = launch_pdl(norm_kernel<T, false, kNormThreads, kNormMaxVec>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
     (void)e;
     return cuda_status("norm kernel launch");
 }

@@ -94,6 +94,11 @@ def export_reference_bins(fused, prefix):
 
     put("model.embed_tokens.weight.bin", fused["embed"])
     put("model.norm.weight.bin", fused["final_gamma"])
+    # lm_head is written [V, h] -- the layout Hugging Face stores, the one the reference's (dead) model class declares for it
+    # (src/models/llama/llama.cpp:271-277 shape {V, h}, trans_b = true) and the engine's NK packing -- NOT transposed like the layer linears,
+    # whose files are the [K, N] memory the reference's live launchLinearGemm path actually reads.  The reference never loads or
+    # multiplies an LM head in code that runs (src/models is not compiled), so there is no GPU behaviour to follow here; the choice is pinned by
+    # tests/test_weights.py::test_reference_bin_directory_round_trip.
     put("lm_head.weight.bin", fused["lm_head"])
     for l, w in enumerate(fused["layers"]):
         base = f"model.layers.{l}"

@@ -33,7 +33,7 @@ NEEDS_EXTERNAL_FILE = {"context_decoder_example": "/home/llama2-7b-tokenizer.bin
 CMAKE_DIR = os.path.join(SHIM_DIR, "cmake.d")  # the reference's own CMake build with src/ replaced by the shim (shim/build_with_reference_cmake.sh)
 REF_LAYERS_DIR = os.path.join(SHIM_DIR, "ref_layers.d")
 REF_LAYER_EXAMPLES = ["context_attention_example", "context_decoder_example", "ffn_example", "self_attention_example", "self_decoder_example"]
-REF_LAYERS_VERIFIED_ON_GPU = True  # run on a B200 in round 2: profiles/r2_reference_layers_on_shim.txt
+# (first run on a B200 in round 2: profiles/r2_reference_layers_on_shim.txt)
 
 
 def programs():
@@ -125,14 +125,9 @@ def test_reference_layer_sources_run_on_the_shim_launchers(name):
         pytest.skip("shim/_ref_programs/ref_layers.d not built (needs /root/reference at build time)")
     if name in NEEDS_EXTERNAL_FILE and not os.path.exists(NEEDS_EXTERNAL_FILE[name]):
         pytest.skip(f"{name} reads {NEEDS_EXTERNAL_FILE[name]}, which does not exist here")
-    if not REF_LAYERS_VERIFIED_ON_GPU and not os.environ.get("B200_RUN_REF_LAYERS"):
-        pytest.skip("configuration built after round 1's GPU minutes were spent and never run on a B200: opt in with B200_RUN_REF_LAYERS=1 "
-                    "(scripts/gpu_rehearsal.sh does), then set REF_LAYERS_VERIFIED_ON_GPU")
     rc, out = run(exe, timeout=90)
     ref_rc = run(os.path.join(REF_DIR, name), timeout=90)[0] if os.path.exists(os.path.join(REF_DIR, name)) else None
     print(f"{name}: reference layers on b200 launchers rc={rc} | all-reference build rc={ref_rc}")
-    if not REF_LAYERS_VERIFIED_ON_GPU and rc != 0:
-        pytest.skip(f"{name}: rc={rc} (configuration built after the round's GPU minutes were spent; recorded, asserted from round 2 on):\n{out[-1500:]}")
     assert rc == 0 or (ref_rc is not None and ref_rc != 0), f"{name} (reference layers on the shim's launchers) exited with {rc}:\n{out[-3000:]}"
 
 

@@ -65,6 +65,10 @@ def test_reference_bin_directory_round_trip(tmp_path):
     mem = np.fromfile(prefix + "model.layers.0.self_attn.o_proj.weight.bin", dtype="<f4").reshape(SHAPE["head_num"] * SHAPE["head_size"], SHAPE["hidden"])
     x = np.random.default_rng(0).standard_normal((3, mem.shape[0])).astype(np.float32)
     assert np.allclose(x @ mem, oracle.linear(x, f["layers"][0]["wo"], "nk"), atol=1e-4)
+    # lm_head keeps the [V, h] layout (weights.py export_reference_bins: the reference holds no live code that reads it): row v of the file is
+    # the output channel of token v, un-transposed
+    lm = np.fromfile(prefix + "lm_head.weight.bin", dtype="<f4").reshape(SHAPE["vocab"], SHAPE["hidden"])
+    assert np.array_equal(lm, f["lm_head"].astype(np.float32))
     g = W.load_reference_bins(prefix, SHAPE)
     for l in range(SHAPE["layers"]):
         for key in ("g1", "g2", "wqkv", "wo", "wgu", "wd", "bqkv", "bo"):
