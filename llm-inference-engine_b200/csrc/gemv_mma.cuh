@@ -511,6 +511,10 @@ inline bool gemv_mma_geometry(int M, int K, int N_units_max, int fmt, MmaGeom *o
     const int k_round = (K + 511) / 512 * 512;  // what 16 warps x 32 k can split
     long best = 0;
     bool found = false;
+    // a part boundary (one named barrier + one re-staging + one more hand-off per unit) is worth 48 KiB of ring at <= 8 tokens and 8 KiB at
+    // 9..16, where the alternative to more parts is 2 KiB copies (measured, 7B step: batch 8 3.78 ms with 1 part against 3.90 with 2;
+    // batch 16 4.82 ms with 2 / 6 parts of 4 KiB pieces against 5.16 with 2 / 3 parts and 2 KiB pieces for the down projection)
+    const long part_penalty = M <= 8 ? 49152L : 8192L;
     for (int piece_bytes = fmt == WF_INT4 ? 2048 : 4096; piece_bytes >= 1024; piece_bytes /= 2) {
         MmaGeom g = {};
         g.tok = M <= 8 ? 8 : 16;
@@ -539,11 +543,10 @@ inline bool gemv_mma_geometry(int M, int K, int N_units_max, int fmt, MmaGeom *o
             g.stages = (int)((budget - fixed) / g.stage_bytes);
             if (g.stages > kMmaMaxStages) g.stages = kMmaMaxStages;
             // bytes in flight (what keeps HBM busy; beyond ~190 KiB nothing is gained), 4 KiB bulk copies preferred over 2 KiB ones (the
-            // copy engine is request-rate bound: round 1 measured 1 KiB copies capping a kernel near 3.3 TB/s), a part boundary (one
-            // named barrier + one re-staging + one more hand-off per unit) counted as 48 KiB
+            // copy engine is request-rate bound: round 1 measured 1 KiB copies capping a kernel near 3.3 TB/s), minus the part penalty
             const long inflight = (long)g.stages * g.stage_bytes;
             const long score = (inflight < 196608 ? inflight : 196608) + (g.piece_bytes >= 4096 ? 49152 : (g.piece_bytes >= 2048 ? 0 : -49152)) -
-                               49152L * (g.parts - 1);
+                               part_penalty * (g.parts - 1);
             if (!found || score > best) best = score, *out = g, found = true;
         }
     }

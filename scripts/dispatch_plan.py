@@ -80,7 +80,7 @@ def gemv_mma_plan(M, K, fmt, max_units=8):
             if fixed + 3 * stage_bytes > 226 * 1024:
                 continue
             stages = min((226 * 1024 - fixed) // stage_bytes, MAX_STAGES)
-            score = min(stages * stage_bytes, 196608) + (49152 if piece_bytes >= 4096 else (0 if piece_bytes >= 2048 else -49152)) - 49152 * (parts - 1)
+            score = min(stages * stage_bytes, 196608) + (49152 if piece_bytes >= 4096 else (0 if piece_bytes >= 2048 else -49152)) - (49152 if M <= 8 else 8192) * (parts - 1)
             if best is None or score > best_score:
                 best_score = score
                 best = dict(kernel="gemv_mma", pieces=pieces_total, piece_bytes=piece_bytes, stages=stages, parts=parts, part_k=part_k)
@@ -105,8 +105,8 @@ def linear_plan(M, K, fmt, fused_rows):
     """One linear of the decode step: (path, passes over the weights, geometry)."""
     if M <= fused_rows:
         g = gemv_any(M, K, fmt)
-        if g:
-            return ("fused " + g["kernel"], 1, g)
+        if g:  # gemv_nk / gemv_q run the norm / residual / TP-reduce prologue themselves; gemv_mma takes plain activations (norm_kernel in front)
+            return (("norm_kernel + " if g["kernel"] == "gemv_mma" else "fused ") + g["kernel"], 1, g)
     if M <= 16:  # linear.cu: one GEMV pass for decode batches
         g = gemv_any(M, K, fmt)
         if g:

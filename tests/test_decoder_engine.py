@@ -256,6 +256,12 @@ def oracle_prefill(model, cfg, dtype, x, kc, vc, input_len, hist):
         oracle.rmsnorm(xn, None, w["g1"], cfg["eps"])
         qkv = oracle.linear(xn, w["wqkv"], "nk").reshape(T, H + 2 * Hkv, d)
         q, k, v = oracle.qkv_bias_transpose_rope(qkv, po, hist, B, mq, H, Hkv, d, cfg["base"])
+        if w.get("bqkv") is not None:
+            # the engine's prefill adds the qkv bias with the DECODE step's convention (decoder_self_attention.cu:93-127: RoPE result stored in
+            # T, then + bias in T), so that a prompt leaves in the cache the rows the decode kernel would have appended; the reference's own
+            # prefill launcher drops the bias (qkv_bias_and_rope.cu:28-78), which the stand-alone b200_qkv_bias_transpose_rope keeps
+            bq, bk, bv = w["bqkv"][:H * d].reshape(1, H, 1, d), w["bqkv"][H * d:(H + Hkv) * d].reshape(1, Hkv, 1, d), w["bqkv"][(H + Hkv) * d:].reshape(1, Hkv, 1, d)
+            q, k, v = rounded(rounded(q, dtype) + bq, dtype), rounded(rounded(k, dtype) + bk, dtype), rounded(rounded(v, dtype) + bv, dtype)
         oracle.concat_kv_cache(k, kc, input_len, hist, l)
         oracle.concat_kv_cache(v, vc, input_len, hist, l)
         attn = oracle.context_attention(q, kc, vc, po, input_len, ctx, l, T, mk, 1.0 / np.sqrt(d))
@@ -268,14 +274,16 @@ def oracle_prefill(model, cfg, dtype, x, kc, vc, input_len, hist):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bias", [False, True])
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_prefill_engine_matches_oracle(dtype):
+def test_prefill_engine_matches_oracle(dtype, bias):
     """b200_decoder_prefill (tensor-core linears + tcgen05 context attention for 16-bit) against the oracle composition, ragged batch
-    with history; then one decode step on top of the prefilled cache against the oracle's decode layer."""
+    with history; then one decode step on top of the prefilled cache against the oracle's decode layer.  bias = True: models with qkv / o
+    biases -- the prefill must leave in the cache exactly the rows (RoPE, then + bias) the decode step reads and appends."""
     import torch
 
     cfg = dict(hidden=512, head_num=4, kv_head_num=2, head_size=128, inter=768, layers=2, max_seq=400, eps=1e-6, base=10000.0)
-    model = make_model(cfg, seed=31, bias=False)
+    model = make_model(cfg, seed=31, bias=bias)
     oracle.set_threads(oracle.max_threads())
     rng = np.random.default_rng(5)
     input_len, hist = np.array([150, 37, 129], np.int32), np.array([40, 0, 130], np.int32)

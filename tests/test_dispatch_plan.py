@@ -35,7 +35,7 @@ def test_tensor_core_gemv_reads_the_weights_once_up_to_16_tokens():
         for m in (2, 8, 16):
             for k in (4096, 11008):
                 path, passes, geo = dp.linear_plan(m, k, fmt, fused_rows=16)
-                want = "fused gemv_q" if (fmt != "dense" and m <= 4) else "fused gemv_mma"
+                want = "fused gemv_q" if (fmt != "dense" and m <= 4) else "norm_kernel + gemv_mma"
                 assert passes == 1 and path == want, (fmt, m, k, path)
     assert dp.linear_plan(1, 4096, "dense", fused_rows=16)[0] == "fused gemv_nk"  # a single dense token stays on the SIMT kernel
     assert dp.linear_plan(1, 4096, "int4", fused_rows=16)[0] == "fused gemv_q"  # up to 4 quantised tokens: the kernel with the fused prologue
