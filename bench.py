@@ -4,23 +4,29 @@
 A "step" is one decode step over one batch of synthetic input: embedding gather -> 32 fused decoder layers over the KV cache ->
 final RMSNorm + LM head -> top-k -> sampling.  Default workload (N=1): BASELINE.json configs[1], Llama-2-7B, 32 layers, bf16,
 batch 1, 1024-token context.  With --gpus N > 1 the same model runs tensor-parallel over N ranks (column-sharded QKV / gate-up,
-row-sharded O / down, head-sharded KV cache, one NCCL all-reduce per attention and per MLP block): total work is fixed, so
-"scaling" is "strong".
+row-sharded O / down, head-sharded KV cache, one all-reduce per attention and per MLP block -- fused into the neighbouring kernels over NVLink
+peer memory by default, NCCL with B200_TP_NCCL=1): total work is fixed, so "scaling" is "strong".
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 7b|70b] [--batch B] [--ctx C]
                   [--wformat bf16|fp8|int4]
 
-`value`  : device-resident decode tokens/s (inputs in HBM, CUDA-graph replay, timed with CUDA events, max over ranks).
+`value`  : device-resident decode tokens/s (inputs in HBM, CUDA-graph replay, timed with CUDA events, max over ranks); the MEDIAN of
+           `--regions` (5) timed regions of exactly --steps steps each, all listed in `timed_regions`.
 `e2e`    : the same through the C ABI with HOST buffers: token ids copied H2D from pinned memory and sampled ids copied D2H
-           inside the timed region, every step.
-`roofline`: the weight-streaming GEMV (the dominant kernel: >96 % of a step's bytes) timed live with CUDA events over one step's
-           worth of launches; algorithmic bytes = the packed weight bytes it must read.
+           inside the timed region, every step (median of 3 regions).
+`roofline`: the weight-streaming linears of one step (the dominant kernels: >96 % of a step's bytes at batch 1), issued by ONE C call
+           (b200_decoder_linears_only: exactly the engine's launches minus attention; on this rank's shard under tensor parallelism) and
+           timed live with CUDA events; algorithmic bytes = the packed weight bytes.  `roofline.kernel` names the kernel
+           this configuration dispatches to; `traffic` is a STATIC figure from the committed ncu capture, labelled as such.
 `cpu_baseline`: the CPU restatement of the reference's path (oracle/, "port": the reference has no CPU inference path of its own,
-           SURVEY.md 8d) with OpenMP on the host cores, bounded sample; `.single_thread` the same on one thread; `.reference_loops` the
-           reference's own unit-test CPU loops (oracle/_ref/libref.so) composed into the layer.
+           SURVEY.md 8d) with OpenMP on the host cores, bounded sample, extrapolated from one layer; `.single_thread` the same on one thread;
+           `.reference_loops` the reference's own unit-test CPU loops (oracle/_ref/libref.so) composed into the layer.  Runs in a CHILD
+           process: the process that loads and times libb200llm.so never loads oracle/*.so.
+`tp_parity` (--gpus N > 1): before the timed region the sharded engine runs a small Llama-shaped model through the same exchange and every
+           rank compares its output with the un-sharded CPU oracle (child process of rank 0); `lm_head`: vocab-sharded under TP.
 --impl reference: those reference loops (kind "reference"; written single-threaded, so every linear's weight rows are cut into one block
            per host thread, each through the same unmodified loop) when oracle/_ref/libref.so travelled, with the single-thread figure and
-           the all-cores port beside them; the port alone otherwise.
+           the all-cores port beside them; the port alone otherwise.  `"extrapolated": true` (one layer + LM head per step, scaled).
 """
 import argparse
 import importlib
@@ -949,10 +955,10 @@ def main():
         # algorithmic bytes), not measured in this run -- only quoted for the configuration that was captured
         traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             if args.config == "7b" and args.wformat == "bf16" and B == 1 and tp == 1:
                 traffic = gemv_bytes * float(tr["traffic_over_algorithmic"])
-                traffic_src = ("static: profiles/r1c_traffic.json (ncu --set full capture of this command: dram__bytes_read+write of the QKV / O / "
+                traffic_src = ("static: profiles/r2_traffic.json (ncu --set full capture of this command: dram__bytes_read+write of the QKV / O / "
                                "gate_up / down launches over their algorithmic bytes, scaled to the step); not measured in this run")
         except Exception:
             pass

@@ -294,13 +294,16 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes);
 
 /* One decode step over layers [layer_begin, layer_end): hidden[B,h] in/out (the residual stream),
  * k_cache/v_cache [L,B,Hkv,S,d], step = 1-based count of tokens including the current one.
+ * LlamaSelfDecoder<T>::forward, src/layers/self_decoder.cpp:24-122.  One token: 5 launches per layer (the norms run inside the
+ * GEMVs); 2..16 tokens of a 16-bit model: 7 (norm kernel + tensor-core GEMV, every batch reads the weights once); more: tcgen05 GEMM.
  * tp_world == 1 only. */
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch,
                       int step, int layer_begin, int layer_end, b200_stream_t stream);
 
 /* Diagnostic (roofline measurement): exactly the weight-streaming launches of b200_decoder_step -- the QKV / O / gate_up / down linears
  * of every layer (reference src/layers/self_attention.cpp:79-86,131-138, src/layers/ffn.cpp:105-139), as the step
- * runs them -- without attention and without the final fold.  Call after at least one real step; outputs are meaningless.
+ * runs them (with their norm kernels where the step has them: 2+ tokens) -- without attention and without the final fold; a
+ * tensor-parallel engine runs them on its shard, without the exchange.  Call after at least one real step; outputs are meaningless.
  * *n_launches (optional) receives the number of kernels launched. */
 int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b200_stream_t stream);
 
@@ -309,8 +312,11 @@ int b200_decoder_linears_only(b200_decoder_t *dec, int batch, int *n_launches, b
  * KV append at history_len -> causal attention over context_len keys -> O linear -> add-bias-residual-RMSNorm -> gate/up ->
  * SwiGLU -> down -> add-residual.  hidden[num_tokens, h] in/out (un-padded tokens, sequences back to back);
  * input_len / history_len / context_len: device int[batch] (context = history + input); max_q_len >= max(input_len).
- * The cache batch dimension is the engine's max_batch.  `scratch`: caller-owned device memory of at least
- * b200_decoder_prefill_scratch_bytes(); linears run on the tensor-core GEMM (library workspace must be set). */
+ * The cache batch dimension is the engine's max_batch; max_q_len <= max_seq_len (rows past the cache slab are never written).  A qkv bias is
+ * added with the decode step's convention (RoPE result stored, then + bias: the rows a prompt leaves in the cache are those the decode
+ * kernel would have appended; the reference's own prefill launcher drops the bias, which b200_qkv_bias_transpose_rope keeps).  `scratch`:
+ * caller-owned device memory of at least b200_decoder_prefill_scratch_bytes(); linears run on the tensor-core GEMM (library workspace
+ * must be set). */
 size_t b200_decoder_prefill_scratch_bytes(const b200_decoder_t *dec, int batch, int max_q_len, int num_tokens);
 int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len,
                          const int *history_len, const int *context_len, int batch, int max_q_len, int num_tokens,
@@ -332,10 +338,13 @@ int b200_decoder_fold(b200_decoder_t *dec, void *hidden, const void *pending, in
 /* Fused tensor-parallel decode step: no NCCL on the path.  Every rank owns one EXCHANGE BUFFER (b200_decoder_tp_buffer_bytes) that all
  * other ranks of the node map through CUDA IPC (b200_tp_alloc_exported on the owner, b200_tp_open on the peers; the 64-byte handles
  * travel over any host channel, e.g. torch.distributed.all_gather_object).  The row-sharded O / down linears PUSH their partial sums
- * into every rank's buffer from their epilogue (posted NVLink stores); the first kernel of the next block signals completion into
- * every peer's flag word, waits for every peer (bounded: ~2 s, then b200_decoder_tp_error() reads non-zero), and adds the P partials
- * -- now all in local memory -- in rank order: a one-shot all-reduce fused into the producing linear's epilogue and the
- * residual-add + RMSNorm prologue of the consuming one.  bases[r] = rank r's buffer as mapped in THIS process. */
+ * into every rank's buffer from their epilogue as 8-byte {payload, flag} words (posted NVLink stores; an aligned 8-byte store is never
+ * torn, so a word whose flag shows the block's sequence number carries valid data).  The first kernel of the next block POLLS those words
+ * in its own memory -- no flag exchange, no fence -- and adds the P partials in rank order: a one-shot all-reduce fused into the
+ * producing linear's epilogue and the residual-add + RMSNorm of the consuming one (inside the GEMV at one token, in the norm kernel for
+ * more).  A peer that never delivers trips a sticky error word after ~2 s: b200_decoder_tp_error() then reads non-zero and the affected
+ * results are NaN, not plausible numbers -- check it at every synchronisation point.  bases[r] = rank r's buffer as mapped in THIS
+ * process.  Replaces nothing in the reference (single GPU); semantics = src/layers/self_decoder.cpp:69-119 under Megatron sharding. */
 size_t b200_decoder_tp_buffer_bytes(const b200_decoder_t *dec);
 int b200_tp_alloc_exported(size_t bytes, void **ptr, void *handle64);
 int b200_tp_open(const void *handle64, void **ptr);

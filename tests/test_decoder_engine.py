@@ -311,6 +311,60 @@ def test_prefill_engine_matches_oracle(dtype, bias):
         assert rel_fro(a, r_) <= (1e-5 if dtype == "f32" else 1e-2)
 
 
+def dequantised_model(mod, dec, model, cfg, w_format):
+    """The oracle's view of a quantised engine: fp32 weights exactly dequantised from the bytes the device holds."""
+    deq = dict(layers=[], seed=model["seed"], exact=("wqkv", "wo", "wgu", "wd"))
+    for l, w in enumerate(model["layers"]):
+        kept = dec._keep[l]
+
+        def dq(t, K):
+            q, sc, z = (list(t) + [None])[:3]
+            if w_format == mod.W_FP8:
+                return oracle.dequantize_fp8(to_np(q).reshape(-1, K), to_np(sc).astype(np.float32))
+            G = K // 128
+            return oracle.dequantize_int4(to_np(q).reshape(-1, K // 2), to_np(sc).astype(np.float32).reshape(-1, G), to_np(z).reshape(-1, G), 128)
+
+        deq["layers"].append(dict(w, wqkv=dq(kept["qkv"], cfg["hidden"]), wo=dq(kept["o"], cfg["head_num"] * cfg["head_size"]),
+                                  wgu=dq(kept["gate_up"], cfg["hidden"]), wd=dq(kept["down"], cfg["inter"])))
+    return deq
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["fp8", "int4"])
+def test_prefill_engine_quantised_weights_run_on_the_tensor_core_gemm(fmt):
+    """FP8 / INT4 weights at prefill sizes (316 tokens > 128): every linear is dequantised into scratch and multiplied by the tcgen05 GEMM
+    (round 1: SIMT fallback).  Oracle on the exactly dequantised weights; the bf16 rounding of the dequantised weights (2^-9 relative,
+    independent per weight) is inside the 1e-2 bar."""
+    import torch
+
+    mod = b200()
+    cfg = dict(hidden=512, head_num=4, kv_head_num=2, head_size=128, inter=768, layers=2, max_seq=400, eps=1e-6, base=10000.0)
+    model = make_model(cfg, seed=33, bias=False)
+    w_format = mod.W_FP8 if fmt == "fp8" else mod.W_INT4
+    oracle.set_threads(oracle.max_threads())
+    rng = np.random.default_rng(6)
+    input_len, hist = np.array([150, 37, 129], np.int32), np.array([40, 0, 130], np.int32)
+    B, T = len(input_len), int(input_len.sum())
+    x = rounded(rng.standard_normal((T, cfg["hidden"])), "bf16")
+    kc = rounded(0.5 * rng.standard_normal((cfg["layers"], B, cfg["kv_head_num"], cfg["max_seq"], cfg["head_size"])), "bf16")
+    vc = rounded(0.5 * rng.standard_normal(kc.shape), "bf16")
+    dec = build_decoder(model, cfg, "bf16", B, w_format=w_format, group=128)
+    xd, kcd, vcd = to_dev(x, "bf16"), to_dev(kc, "bf16"), to_dev(vc, "bf16")
+    ctx = input_len + hist
+    dec.prefill(xd, kcd, vcd, to_dev(input_len), to_dev(hist), to_dev(ctx), int(input_len.max()))
+    torch.cuda.synchronize()
+    deq = dequantised_model(mod, dec, model, cfg, w_format)
+    # oracle_prefill rounds the weights it is given to the dtype: hand it the dequantised ones as they are
+    ref, rkc, _ = oracle_prefill(deq, cfg, "f32", x, kc.copy(), vc.copy(), input_len, hist)
+    got = to_np(xd)
+    assert np.isfinite(got).all()
+    assert rel_fro(got, ref) <= 1e-2, f"quantised ({fmt}) prefill vs oracle on the dequantised weights: {rel_fro(got, ref):.3e}"
+    gk = to_np(kcd)
+    for b in range(B):
+        lo, hi = int(hist[b]), int(ctx[b])
+        assert rel_fro(gk[:, b, :, lo:hi], rkc[:, b, :, lo:hi]) <= 1e-2
+
+
 @pytest.mark.gpu
 def test_linears_only_diagnostic():
     """b200_decoder_linears_only launches exactly the step's weight-streaming kernels (4 per layer)."""
