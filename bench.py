@@ -615,7 +615,7 @@ def run_prefill(args, cfg, mod, dec, dev, dt, kc, vc, rank):
         print(json.dumps({
             "metric": "prefill tokens/s", "value": T * 1e3 / ms, "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']} {L}-layer bf16 prefill, batch {B} x {Tq} tokens", "batch": B, "prompt_tokens": Tq,
+            "config": {"workload": f"{cfg['name']} {L}-layer {args.wformat} prefill, batch {B} x {Tq} tokens", "batch": B, "prompt_tokens": Tq, "weights": args.wformat,
                        "cache_policy": "weights (13 GB) larger than L2"},
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel + context_attn_tc_kernel (whole prefill pass)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,

@@ -145,6 +145,13 @@ int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *
                     const uint8_t *finished, int batch, int head_num, int kv_head_num, int head_size,
                     int max_seq_len, int step, int layer, int apply_rope, int rotary_dim,
                     float rotary_base, int dtype, b200_stream_t stream);
+/* The same over a RAGGED batch (an extension: the reference shares one step across the batch, self_decoder.cpp:33-39 "step" is a CPU
+ * int[1]): row b sits at its own 1-based position steps[b] (DEVICE int[batch], clamped to [1, max_step]); max_step >= max(steps) plans
+ * the KV splits.  Row b's result is what b200_decode_mha returns for that row at step = steps[b]. */
+int b200_decode_mha_ragged(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out,
+                           const int *steps, int batch, int head_num, int kv_head_num, int head_size,
+                           int max_seq_len, int max_step, int layer, int apply_rope, int rotary_dim,
+                           float rotary_base, int dtype, b200_stream_t stream);
 
 /* launchFusedQKVAddBiasAndTransposeAndRope, src/kernels/includes/qkv_bias_and_rope.cuh:12-23
  * (kernel src/kernels/qkv_bias_and_rope.cu:5-79): QKV[T, H+2Hkv, d] -> q[B,H,Sq,d], k,v[B,Hkv,Sq,d]
@@ -300,6 +307,11 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes);
 int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch,
                       int step, int layer_begin, int layer_end, b200_stream_t stream);
 
+/* b200_decoder_step over a ragged batch: row b decodes at its own position steps[b] (DEVICE int[batch]; max_step >= max(steps)).  Only
+ * the attention kernel depends on positions; see b200_decode_mha_ragged. */
+int b200_decoder_step_ragged(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch,
+                             const int *steps, int max_step, int layer_begin, int layer_end, b200_stream_t stream);
+
 /* Diagnostic (roofline measurement): exactly the weight-streaming launches of b200_decoder_step -- the QKV / O / gate_up / down linears
  * of every layer (reference src/layers/self_attention.cpp:79-86,131-138, src/layers/ffn.cpp:105-139), as the step
  * runs them (with their norm kernels where the step has them: 2+ tokens) -- without attention and without the final fold; a
@@ -382,13 +394,24 @@ typedef struct {
 /* Device workspace b200_generate needs for this batch / prompt length (0 on a bad argument: see b200_last_error_string). */
 size_t b200_generate_workspace_bytes(const b200_decoder_t *dec, const b200_generate_params_t *p, int batch, int prompt_len);
 
-/* prompt_ids: HOST int[batch, prompt_len] (every sequence the same length; batch must equal the engine's max_batch, which is the
- * cache's batch dimension).  k_cache / v_cache: caller-owned [L, batch, Hkv, max_seq_len, d], overwritten from position 0.
+/* prompt_ids: HOST int[batch, prompt_len] (every sequence the same length -- b200_generate_ragged takes prompts of different lengths;
+ * batch must equal the engine's max_batch, which is the cache's batch dimension).  k_cache / v_cache: caller-owned [L, batch, Hkv, max_seq_len, d], overwritten from position 0.
  * out_ids: HOST int[batch, max_new_tokens]: the sampled ids; everything from a sequence's first end_id on is end_id.
  * n_generated (optional): HOST int[batch], tokens before the first end_id.  Synchronises the stream before returning. */
 int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const int *prompt_ids, int batch, int prompt_len,
                   void *k_cache, void *v_cache, void *workspace, size_t workspace_bytes, int *out_ids, int *n_generated,
                   b200_stream_t stream);
+
+/* The same loop over prompts of DIFFERENT lengths (the "dynamic prompt length" of SURVEY.md 8f rank 2; the reference hard-codes one
+ * 13-token prompt, llama.cpp:327-341).  prompt_ids: HOST int[batch, prompt_len], row b holds prompt_lens[b] ids followed by padding that
+ * is never read; prompt_lens: HOST int[batch], 1 <= prompt_lens[b] <= prompt_len (NULL: all rows prompt_len long = b200_generate).
+ * The prompts run through the context decoder packed back to back (no padded token is computed); every decode step then runs the whole
+ * batch with row b at position prompt_lens[b] + i (b200_decoder_step_ragged).  Row b's greedy ids are those of the same prompt
+ * generated alone.  The sampling seed `step` stays shared by the batch as in the reference (sampling.cu:44-52 seeds with (step, row)):
+ * it starts at the LONGEST prompt length.  Workspace: b200_generate_workspace_bytes(dec, p, batch, prompt_len). */
+int b200_generate_ragged(b200_decoder_t *dec, const b200_generate_params_t *p, const int *prompt_ids, const int *prompt_lens,
+                         int batch, int prompt_len, void *k_cache, void *v_cache, void *workspace, size_t workspace_bytes,
+                         int *out_ids, int *n_generated, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,7 @@ SIGNATURES = {
     "b200_transpose2d": [_P, _P, _I, _I, _I, _P],
     "b200_rope_decode": [_P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_decode_mha": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_decode_mha_ragged": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_qkv_bias_transpose_rope": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_concat_kv_cache": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "b200_repeat_kv_cache": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -85,10 +86,12 @@ SIGNATURES = {
     "b200_decoder_get_config": [_P, C.POINTER(DecoderConfig)],
     "b200_generate_workspace_bytes": [_P, C.POINTER(GenerateParams), _I, _I],
     "b200_generate": [_P, C.POINTER(GenerateParams), _P, _I, _I, _P, _P, _P, _SZ, _P, _P, _P],
+    "b200_generate_ragged": [_P, C.POINTER(GenerateParams), _P, _P, _I, _I, _P, _P, _P, _SZ, _P, _P, _P],
     "b200_decoder_set_layer": [_P, _I, C.POINTER(LayerWeights)],
     "b200_decoder_scratch_bytes": [_P],
     "b200_decoder_set_scratch": [_P, _P, _SZ],
     "b200_decoder_step": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_decoder_step_ragged": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     "b200_decoder_linears_only": [_P, _I, C.POINTER(C.c_int), _P],
     "b200_decoder_prefill_scratch_bytes": [_P, _I, _I, _I],
     "b200_decoder_prefill": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _SZ, _I, _I, _P],
@@ -242,12 +245,17 @@ def rope_decode(qkv, head_num, kv_head_num, step, rot_dim, base):
     check(lib().b200_rope_decode(ptr(qkv), B, head_num, kv_head_num, d, step, rot_dim, base, dtype_code(qkv), stream()))
 
 
-def decode_mha(qkv, bias, k_cache, v_cache, head_num, kv_head_num, step, layer, apply_rope=False, rot_dim=0, base=10000.0):
+def decode_mha(qkv, bias, k_cache, v_cache, head_num, kv_head_num, step, layer, apply_rope=False, rot_dim=0, base=10000.0, steps=None):
+    """steps (optional): int32 device tensor [B] of per-row positions (ragged batch); `step` must then be >= their maximum."""
     torch = _torch()
     ensure_workspace()
     B, _, d = qkv.shape
     S = k_cache.shape[3]
     out = torch.empty((B, head_num * d), dtype=qkv.dtype, device=qkv.device)
+    if steps is not None:
+        check(lib().b200_decode_mha_ragged(ptr(qkv), ptr(bias), ptr(k_cache), ptr(v_cache), ptr(out), ptr(steps), B, head_num, kv_head_num, d,
+                                           S, step, layer, int(apply_rope), rot_dim, base, dtype_code(qkv), stream()))
+        return out
     check(lib().b200_decode_mha(ptr(qkv), ptr(bias), ptr(k_cache), ptr(v_cache), ptr(out), None, B, head_num, kv_head_num, d, S, step,
                                 layer, int(apply_rope), rot_dim, base, dtype_code(qkv), stream()))
     return out
@@ -406,9 +414,17 @@ class Decoder:
         check(lib().b200_decoder_step(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], step, layer_begin, layer_end,
                                       stream()))
 
-    def generate(self, prompt_ids, embedding, final_gamma, lm_head, k_cache, v_cache, max_new_tokens, top_k=1, end_id=2, check_every=0):
-        """The generation loop (b200_generate): prompt_ids = int array [batch, prompt_len] on the HOST; returns (ids [batch, max_new_tokens],
-        n_generated [batch]) as numpy arrays.  embedding / lm_head: [vocab, hidden] tensors of the engine's dtype."""
+    def step_ragged(self, hidden, k_cache, v_cache, steps, max_step, layer_begin=0, layer_end=None):
+        """steps: int32 device tensor [batch] of per-row 1-based positions; max_step >= max(steps)."""
+        layer_end = self.cfg.num_layers if layer_end is None else layer_end
+        check(lib().b200_decoder_step_ragged(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], ptr(steps), max_step,
+                                             layer_begin, layer_end, stream()))
+
+    def generate(self, prompt_ids, embedding, final_gamma, lm_head, k_cache, v_cache, max_new_tokens, top_k=1, end_id=2, check_every=0,
+                 prompt_lens=None):
+        """The generation loop (b200_generate / b200_generate_ragged): prompt_ids = int array [batch, prompt_len] on the HOST, prompt_lens
+        (optional) = the real length of every row (the rest of a row is padding); returns (ids [batch, max_new_tokens], n_generated [batch])
+        as numpy arrays.  embedding / lm_head: [vocab, hidden] tensors of the engine's dtype."""
         import numpy as np
 
         torch = _torch()
@@ -423,6 +439,13 @@ class Decoder:
         base = (ws.data_ptr() + 255) // 256 * 256
         out = np.empty((B, max_new_tokens), dtype=np.int32)
         ngen = np.empty(B, dtype=np.int32)
+        if prompt_lens is not None:
+            lens = np.ascontiguousarray(np.asarray(prompt_lens, dtype=np.int32))
+            assert lens.shape == (B,)
+            check(lib().b200_generate_ragged(self.handle, C.byref(gp), prompt.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), B, T,
+                                             ptr(k_cache), ptr(v_cache), C.c_void_p(base), nbytes, out.ctypes.data_as(C.c_void_p),
+                                             ngen.ctypes.data_as(C.c_void_p), stream()))
+            return out, ngen
         check(lib().b200_generate(self.handle, C.byref(gp), prompt.ctypes.data_as(C.c_void_p), B, T, ptr(k_cache), ptr(v_cache),
                                   C.c_void_p(base), nbytes, out.ctypes.data_as(C.c_void_p), ngen.ctypes.data_as(C.c_void_p), stream()))
         return out, ngen

@@ -141,10 +141,15 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     const int kvh = blockIdx.y / gsplit, g0 = (blockIdx.y % gsplit) * G;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int qkv_heads = H + 2 * Hkv;
-    const int step = a.step, cached = step - 1;        // positions [0, cached) are in the cache; position `cached` is the new token
+    // ragged batches: every row has its own step (read from device memory: written several kernels ago, visible before griddepcontrol.wait)
+    const int step = a.steps ? min(max(__ldg(a.steps + b), 1), a.step) : a.step;
+    const int cached = step - 1;                       // positions [0, cached) are in the cache; position `cached` is the new token
     const int p0 = split * a.chunk, p1 = min(cached, p0 + a.chunk);
     const int ntiles = p1 > p0 ? (p1 - p0 + TP - 1) / TP : 0;
-    const bool has_new = split == a.nsplit - 1;  // the last split also serves the token being appended (from shared memory, not the cache)
+    // the row's last split also serves the token being appended (from shared memory, not the cache); the grid is planned for the longest
+    // row: splits past a shorter row's end contribute an empty partial (max = -inf, sum = 0)
+    const int nsplit_b = cached > 0 ? (cached + a.chunk - 1) / a.chunk : 1;
+    const bool has_new = split == nsplit_b - 1;
     const T *qkv = reinterpret_cast<const T *>(a.qkv) + (size_t)b * qkv_heads * D;
     const T *bias = reinterpret_cast<const T *>(a.bias);
     T *kc = reinterpret_cast<T *>(a.k_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
@@ -440,7 +445,7 @@ __global__ void decode_attn_generic_kernel(const DecodeAttnArgs a) {
     __shared__ float red[33];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int H = a.head_num, Hkv = a.kv_head_num, rep = H / Hkv, kvh = h / rep;
-    const int step = a.step;
+    const int step = a.steps ? min(max(__ldg(a.steps + b), 1), a.step) : a.step;
     const T *qkv = reinterpret_cast<const T *>(a.qkv) + (size_t)b * (H + 2 * Hkv) * D;
     const T *bias = reinterpret_cast<const T *>(a.bias);
     T *kc = reinterpret_cast<T *>(a.k_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
@@ -582,10 +587,9 @@ int b200_rope_decode(void *qkv, int batch, int head_num, int kv_head_num, int he
     return cuda_status("rope_decode launch");
 }
 
-int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const uint8_t *finished,
-                    int batch, int head_num, int kv_head_num, int head_size, int max_seq_len, int step, int layer,
-                    int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
-    (void)finished;  // unused by the reference kernel as well
+static int decode_mha_impl(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const int *steps,
+                           int batch, int head_num, int kv_head_num, int head_size, int max_seq_len, int step, int layer,
+                           int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
     B200_REQUIRE(qkv && k_cache && v_cache && out, "decode_mha: null pointer");
     B200_REQUIRE(batch >= 0 && head_num > 0 && kv_head_num > 0 && head_size > 0, "decode_mha: bad shape");
     B200_REQUIRE(head_num % kv_head_num == 0, "decode_mha: head_num %d not a multiple of kv_head_num %d", head_num, kv_head_num);
@@ -602,7 +606,7 @@ int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *
     a.k_cache = (char *)k_cache + layer_off, a.v_cache = (char *)v_cache + layer_off;
     a.out = out;
     a.batch = batch, a.head_num = head_num, a.kv_head_num = kv_head_num, a.head_size = head_size;
-    a.max_seq_len = max_seq_len, a.step = step;
+    a.max_seq_len = max_seq_len, a.step = step, a.steps = steps;
     a.apply_rope = apply_rope, a.rot_dim = rotary_dim, a.rot_base = rotary_base;
     a.nsplit = decode_attn_plan(batch, kv_head_num, step, &a.chunk);
     a.partials = reinterpret_cast<float *>(ws.scratch);
@@ -611,6 +615,23 @@ int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *
     B200_REQUIRE(decode_attn_partials_floats(batch, head_num, kv_head_num, head_size, a.nsplit) * 4 <= ws.scratch_bytes,
                  "decode_mha: library workspace too small for %d splits", a.nsplit);
     return launch_decode_attn(a, dtype, as_stream(stream));
+}
+
+
+int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const uint8_t *finished,
+                    int batch, int head_num, int kv_head_num, int head_size, int max_seq_len, int step, int layer,
+                    int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
+    (void)finished;  // unused by the reference kernel as well
+    return decode_mha_impl(qkv, qkv_bias, k_cache, v_cache, out, nullptr, batch, head_num, kv_head_num, head_size, max_seq_len, step, layer,
+                           apply_rope, rotary_dim, rotary_base, dtype, stream);
+}
+
+int b200_decode_mha_ragged(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const int *steps, int batch,
+                           int head_num, int kv_head_num, int head_size, int max_seq_len, int max_step, int layer, int apply_rope,
+                           int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
+    B200_REQUIRE(steps, "decode_mha_ragged: null steps");
+    return decode_mha_impl(qkv, qkv_bias, k_cache, v_cache, out, steps, batch, head_num, kv_head_num, head_size, max_seq_len, max_step, layer,
+                           apply_rope, rotary_dim, rotary_base, dtype, stream);
 }
 
 }  // extern "C"

@@ -14,6 +14,7 @@ struct DecodeAttnArgs {
     unsigned int *tickets;  // [B*Hkv], zero-initialised, self-resetting
     const float2 *rope_cs;  // optional (cos, sin) table [max_seq_len][rot_dim/2] made by launch_rope_table(); NULL: compute
     int batch, head_num, kv_head_num, head_size, max_seq_len, step;
+    const int *steps;  // optional device int[batch]: per-row step (ragged batches), clamped to [1, step]; `step` is then their maximum (the split plan)
     int apply_rope, rot_dim;
     float rot_base;
     int nsplit, chunk;

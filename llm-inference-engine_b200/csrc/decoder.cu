@@ -34,6 +34,7 @@ struct b200_decoder {
     float2 *rope_cs = nullptr;  // (cos, sin) per (position, rotary pair), filled once by set_scratch
     int max_splits = 0;
     int cur = 0;  // which res[] holds the residual stream
+    const int *steps_dev = nullptr;  // per-row steps of a ragged batch (device int[batch]); set only inside b200_decoder_step_ragged
     // fused tensor-parallel exchange (b200_decoder_tp_attach): every rank's exchange buffer as mapped in this process
     char *tp_base[b200::kTpMaxWorld] = {};
     bool tp_attached = false;
@@ -332,7 +333,7 @@ static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache,
     a.k_cache = (char *)k_cache + layer_off, a.v_cache = (char *)v_cache + layer_off;
     a.out = dec->attn;
     a.batch = batch, a.head_num = c.head_num, a.kv_head_num = c.kv_head_num, a.head_size = c.head_size;
-    a.max_seq_len = c.max_seq_len, a.step = step;
+    a.max_seq_len = c.max_seq_len, a.step = step, a.steps = dec->steps_dev;
     a.apply_rope = c.rotary_dim > 0, a.rot_dim = c.rotary_dim, a.rot_base = c.rotary_base;
     a.nsplit = decode_attn_plan(batch, c.kv_head_num, step, &a.chunk);
     a.partials = dec->partials, a.tickets = dec->tickets;
@@ -516,6 +517,18 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
         pending = dec->y_ffn;
     }
     return b200_decoder_fold(dec, hidden, pending, batch, stream);
+}
+
+// Ragged batch: row b sits at its own 1-based position steps[b] (device memory; rows of different prompt lengths decoding together).
+// Only the attention kernel looks at positions (RoPE angle, cache row appended, number of cached rows read); its split plan is made for
+// max_step and rows that end earlier leave empty partials.  Everything else in the step is position-free.
+int b200_decoder_step_ragged(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch, const int *steps, int max_step,
+                             int layer_begin, int layer_end, b200_stream_t stream) {
+    B200_REQUIRE(dec && steps, "decoder_step_ragged: null argument");
+    dec->steps_dev = steps;
+    const int rc = b200_decoder_step(dec, hidden, k_cache, v_cache, batch, max_step, layer_begin, layer_end, stream);
+    dec->steps_dev = nullptr;
+    return rc;
 }
 
 // Diagnostic for roofline measurements: exactly the weight-streaming launches of b200_decoder_step (four GEMVs per layer) without the

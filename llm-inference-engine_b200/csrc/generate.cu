@@ -22,7 +22,7 @@ namespace b200 {
 static size_t g_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct GenCarve {
-    size_t ids, lens, hidden_prompt, prefill, hidden, logits, tmp_ids, tmp_vals, topk_ids, topk_vals, seq_len, finished, output_id, out_ids, total;
+    size_t ids, lens, hidden_prompt, prefill, hidden, logits, tmp_ids, tmp_vals, topk_ids, topk_vals, seq_len, finished, output_id, out_ids, steps, total;
 };
 
 static GenCarve gen_carve(const b200_decoder_t *dec, const b200_generate_params_t *p, int batch, int prompt_len) {
@@ -37,7 +37,7 @@ static GenCarve gen_carve(const b200_decoder_t *dec, const b200_generate_params_
         return at;
     };
     k.ids = take(T * sizeof(int));
-    k.lens = take((size_t)3 * batch * sizeof(int));
+    k.lens = take((size_t)4 * batch * sizeof(int));  // input / history / context lengths + the packed row of every sequence's last prompt token
     k.hidden_prompt = take(T * c.hidden * e);
     k.prefill = take(b200_decoder_prefill_scratch_bytes(dec, batch, prompt_len, (int)T));
     k.hidden = take((size_t)batch * c.hidden * e);
@@ -50,6 +50,7 @@ static GenCarve gen_carve(const b200_decoder_t *dec, const b200_generate_params_
     k.finished = take((size_t)batch);
     k.output_id = take((size_t)batch * sizeof(int));
     k.out_ids = take((size_t)batch * p->max_new_tokens * sizeof(int));
+    k.steps = take((size_t)batch * p->max_new_tokens * sizeof(int));  // ragged prompts: per-row positions of every decode step
     k.total = o;
     return k;
 }
@@ -80,8 +81,9 @@ size_t b200_generate_workspace_bytes(const b200_decoder_t *dec, const b200_gener
     return gen_carve(dec, p, batch, prompt_len).total;
 }
 
-int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const int *prompt_ids, int batch, int prompt_len, void *k_cache,
-                  void *v_cache, void *workspace, size_t workspace_bytes, int *out_ids, int *n_generated, b200_stream_t stream) {
+int b200_generate_ragged(b200_decoder_t *dec, const b200_generate_params_t *p, const int *prompt_ids, const int *prompt_lens, int batch,
+                         int prompt_len, void *k_cache, void *v_cache, void *workspace, size_t workspace_bytes, int *out_ids, int *n_generated,
+                         b200_stream_t stream) {
     int rc = gen_check(dec, p, batch, prompt_len);
     if (rc != B200_OK) return rc;
     B200_REQUIRE(prompt_ids && k_cache && v_cache && workspace && out_ids, "generate: null pointer");
@@ -90,40 +92,60 @@ int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const in
     B200_REQUIRE(workspace_bytes >= k.total, "generate: need %zu bytes of workspace, got %zu", k.total, workspace_bytes);
     b200_decoder_config_t c;
     b200_decoder_get_config(dec, &c);
-    const size_t e = c.dtype == B200_F32 ? 4 : 2;
-    const int T = batch * prompt_len, V = p->vocab, K = p->top_k, N = p->max_new_tokens;
-    for (int i = 0; i < T; ++i) B200_REQUIRE(prompt_ids[i] >= 0 && prompt_ids[i] < V, "generate: prompt id %d at %d outside the vocabulary", prompt_ids[i], i);
+    const int V = p->vocab, K = p->top_k, N = p->max_new_tokens;
+    // ---- the prompts, packed back to back (the context decoder's un-padded token layout); prompt_lens == NULL: all of length prompt_len
+    std::vector<int> len(batch, prompt_len), packed;
+    bool ragged = false;
+    int max_len = 0;
+    for (int b = 0; b < batch; ++b) {
+        if (prompt_lens) len[b] = prompt_lens[b];
+        B200_REQUIRE(len[b] >= 1 && len[b] <= prompt_len, "generate: prompt length %d of sequence %d outside [1, %d]", len[b], b, prompt_len);
+        ragged = ragged || len[b] != len[0];
+        max_len = len[b] > max_len ? len[b] : max_len;
+        for (int t = 0; t < len[b]; ++t) {
+            const int id = prompt_ids[(size_t)b * prompt_len + t];
+            B200_REQUIRE(id >= 0 && id < V, "generate: prompt id %d at (%d, %d) outside the vocabulary", id, b, t);
+            packed.push_back(id);
+        }
+    }
+    const int T = (int)packed.size();
     char *w = (char *)workspace;
     int *ids = (int *)(w + k.ids), *lens = (int *)(w + k.lens);
     void *hidden_prompt = w + k.hidden_prompt, *hidden = w + k.hidden;
     float *logits = (float *)(w + k.logits), *tmp_vals = (float *)(w + k.tmp_vals), *topk_vals = (float *)(w + k.topk_vals);
     int *tmp_ids = (int *)(w + k.tmp_ids), *topk_ids = (int *)(w + k.topk_ids), *seq_len = (int *)(w + k.seq_len);
     uint8_t *finished = (uint8_t *)(w + k.finished);
-    int *output_id = (int *)(w + k.output_id), *out_dev = (int *)(w + k.out_ids);
+    int *output_id = (int *)(w + k.output_id), *out_dev = (int *)(w + k.out_ids), *steps_dev = (int *)(w + k.steps);
     cudaStream_t st = as_stream(stream);
 
-    // ---- host -> device: the prompt and the three length vectors of the context decoder (input = context = prompt_len, history 0)
-    std::vector<int> hl((size_t)3 * batch);
-    for (int b = 0; b < batch; ++b) hl[b] = prompt_len, hl[batch + b] = 0, hl[2 * batch + b] = prompt_len;
-    if (cudaMemcpyAsync(ids, prompt_ids, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+    // ---- host -> device: the prompt, the three length vectors of the context decoder (input = context = prompt length, history 0), the
+    //      packed row of every sequence's last prompt token, and (ragged only) the position of every row at every decode step
+    std::vector<int> hl((size_t)4 * batch), steps_host;
+    for (int b = 0, cum = 0; b < batch; ++b) {
+        hl[b] = len[b], hl[batch + b] = 0, hl[2 * batch + b] = len[b];
+        cum += len[b];
+        hl[3 * batch + b] = cum - 1;
+    }
+    if (ragged) {
+        steps_host.resize((size_t)N * batch);
+        for (int i = 0; i < N; ++i)
+            for (int b = 0; b < batch; ++b) steps_host[(size_t)i * batch + b] = len[b] + i;
+    }
+    if (cudaMemcpyAsync(ids, packed.data(), (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(lens, hl.data(), hl.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(seq_len, len.data(), (size_t)batch * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||  // llama.cpp: sequence_lengths
+        (ragged && cudaMemcpyAsync(steps_dev, steps_host.data(), steps_host.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) ||
         cudaMemsetAsync(finished, 0, (size_t)batch, st) != cudaSuccess)
         return cuda_status("generate H2D");
-    if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_status("generate H2D sync");  // `hl` is about to go out of scope
-    {   // sequence lengths start at the prompt length (llama.cpp: sequence_lengths)
-        std::vector<int> sl(batch, prompt_len);
-        if (cudaMemcpy(seq_len, sl.data(), (size_t)batch * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return cuda_status("generate H2D");
-    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_status("generate H2D sync");  // pageable host vectors: done with them here
 
-    // ---- first token: embedding -> context decoder -> last prompt token of every sequence -> sampling tail
+    // ---- first token: embedding -> context decoder -> last prompt token of every sequence (a row gather) -> sampling tail
     if ((rc = b200_input_embedding(ids, p->embedding, hidden_prompt, T, c.hidden, c.dtype, stream)) != B200_OK) return rc;
-    rc = b200_decoder_prefill(dec, hidden_prompt, k_cache, v_cache, lens, lens + batch, lens + 2 * batch, batch, prompt_len, T, w + k.prefill,
-                              b200_decoder_prefill_scratch_bytes(dec, batch, prompt_len, T), 0, c.num_layers, stream);
+    rc = b200_decoder_prefill(dec, hidden_prompt, k_cache, v_cache, lens, lens + batch, lens + 2 * batch, batch, max_len, T, w + k.prefill,
+                              b200_decoder_prefill_scratch_bytes(dec, batch, max_len, T), 0, c.num_layers, stream);
     if (rc != B200_OK) return rc;
-    if (cudaMemcpy2DAsync(hidden, (size_t)c.hidden * e, (const char *)hidden_prompt + (size_t)(prompt_len - 1) * c.hidden * e,
-                          (size_t)prompt_len * c.hidden * e, (size_t)c.hidden * e, batch, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        return cuda_status("generate gather");
-    int step = prompt_len;  // llama.cpp:353: step->data = &context_length
+    if ((rc = b200_input_embedding(lens + 3 * batch, hidden_prompt, hidden, batch, c.hidden, c.dtype, stream)) != B200_OK) return rc;
+    int step = max_len;  // llama.cpp:353: step->data = &context_length (ragged: the longest prompt -- the sampling seed is shared by the batch)
     rc = b200_lm_head_topk_sample(dec, hidden, p->final_gamma, p->lm_head, V, logits, tmp_ids, tmp_vals, topk_ids, topk_vals, seq_len, finished,
                                   output_id, batch, K, step, p->end_id, stream);
     if (rc != B200_OK) return rc;
@@ -153,7 +175,9 @@ int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const in
         }
         ++step;  // llama.cpp:372
         if ((rc = b200_input_embedding(output_id, p->embedding, hidden, batch, c.hidden, c.dtype, stream)) != B200_OK) return rc;
-        if ((rc = b200_decoder_step(dec, hidden, k_cache, v_cache, batch, step, 0, c.num_layers, stream)) != B200_OK) return rc;
+        rc = ragged ? b200_decoder_step_ragged(dec, hidden, k_cache, v_cache, batch, steps_dev + (size_t)i * batch, step, 0, c.num_layers, stream)
+                    : b200_decoder_step(dec, hidden, k_cache, v_cache, batch, step, 0, c.num_layers, stream);
+        if (rc != B200_OK) return rc;
         rc = b200_lm_head_topk_sample(dec, hidden, p->final_gamma, p->lm_head, V, logits, tmp_ids, tmp_vals, topk_ids, topk_vals, seq_len, finished,
                                       output_id, batch, K, step, p->end_id, stream);
         if (rc != B200_OK) return rc;
@@ -173,6 +197,12 @@ int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const in
         if (n_generated) n_generated[b] = n;
     }
     return B200_OK;
+}
+
+int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const int *prompt_ids, int batch, int prompt_len, void *k_cache,
+                  void *v_cache, void *workspace, size_t workspace_bytes, int *out_ids, int *n_generated, b200_stream_t stream) {
+    return b200_generate_ragged(dec, p, prompt_ids, nullptr, batch, prompt_len, k_cache, v_cache, workspace, workspace_bytes, out_ids, n_generated,
+                                stream);
 }
 
 }  // extern "C"
