@@ -8,14 +8,23 @@
 // without materialising [B,H,Sq,Sk] scores or the GQA-repeated K/V, output already un-padded [T, H, d].
 //
 // One CTA = 128 query rows of one (b, h).  576 threads, warp-specialised:
-//   warp 16  TMA producer: Q tile once, then K and V tiles of 128 keys (cp.async.bulk.tensor.2d, 128-byte swizzle) in a 2-stage ring
+//   warp 16  TMA producer: Q tile once, then K and V tiles of 128 keys (cp.async.bulk.tensor.2d, 128-byte swizzle); K and V have their
+//            own 2-stage rings and barriers, requested in the order the MMAs consume them (K0 K1 V0 K2 V1 ...): a K slot is free as
+//            soon as ITS S = Q.K^T has been computed, a whole tile step before the V slot of the same tile
 //   warp 17  MMA issuer:  S = Q.K^T (128x128x128, tcgen05.mma kind::f16, fp32 in TMEM, two S buffers so the logits of tile j+1 are
-//            computed while the softmax threads work on tile j) and O_j = P_j.V_j (V is the MN-major B operand)
+//            computed while the softmax threads work on tile j) and O += P_j.V_j (V is the MN-major B operand); the output
+//            accumulator STAYS in TMEM for the whole key loop
 //   warps 0-15 softmax + epilogue: warp w owns TMEM lanes 32*(w%4).. (query rows) and columns 32*(w/4).. : four threads share a
 //            row, 32 keys / 32 output dims each (16 warps keep the SM's four schedulers busy; with one thread per row the softmax
-//            ran at one warp per scheduler and took 6x longer than the MMAs).  tcgen05.ld the logits once into registers, mask,
-//            exchange the row max through shared memory, p = ex2(s - max) -> shared memory (bf16/fp16, the 128-byte-swizzled
-//            K-major layout the second MMA reads), then tcgen05.ld the tile's P.V slice and accumulate the rescaled output.
+//            ran at one warp per scheduler and took 6x longer than the MMAs).  tcgen05.ld the logits once into registers, mask
+//            (diagonal / last tile only), exchange the row max through shared memory (named barrier of the row's 4 warps),
+//            p = ex2(s - m) -> shared memory (bf16/fp16, the 128-byte-swizzled K-major layout the second MMA reads).
+//            LAZY RESCALE: m is the max the row's accumulator was last scaled to, not the running max; only when the running max
+//            has grown by more than 2^8 is the accumulator pulled out of TMEM, scaled and put back (tcgen05.ld / .st) -- after the
+//            first tiles that almost never happens, so no thread waits for a P.V product inside the loop (round 1 read every
+//            tile's product back into registers: the softmax threads sat behind the MMA they had just fed, 4.5 us per tile step).
+//            The final output is O * c / (l * c + 1e-6) with c = 2^(m - running max): the reference's +1e-6 is relative to the
+//            sum taken at the true max.
 // Causal structure: q tiles visit only the key tiles up to their diagonal; heavy (late) q tiles are scheduled first.
 #include "common.cuh"
 
@@ -95,6 +104,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -127,6 +151,9 @@ __device__ __forceinline__ uint32_t idesc_f16(bool bf16, int m, int n, bool b_mn
     return d;
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleStep = 8.0f;  // log2 domain: the accumulator is rescaled when the running max has grown by more than 2^8
+
 // smem: [Q 32K][K ring 2x32K][V ring 2x32K][P 32K][barriers][tmem slot][row-max / row-sum exchange 2x128x4 floats]
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -136,11 +163,11 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sQ = smem, *sK = sQ + kTileBytes, *sV = sK + kKvStages * kTileBytes, *sP = sV + kKvStages * kTileBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kTileBytes);
-    // barriers: q_full, kv_full[2], kv_empty[2], s_full[2], p_ready, o_full, o_taken
-    const uint32_t q_full = s_u32(bars), kv_full0 = q_full + 8, kv_empty0 = kv_full0 + 16, s_full0 = kv_empty0 + 16, p_ready = s_full0 + 16,
-                   o_full = p_ready + 8, o_taken = o_full + 8, s_free0 = o_taken + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
-    float *red = reinterpret_cast<float *>(bars + 14);  // [2][128][4]
+    // barriers: q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_free[2], p_ready, pv_done
+    const uint32_t q_full = s_u32(bars), k_full0 = q_full + 8, k_empty0 = k_full0 + 16, v_full0 = k_empty0 + 16, v_empty0 = v_full0 + 16,
+                   s_full0 = v_empty0 + 16, s_free0 = s_full0 + 16, p_ready = s_free0 + 16, pv_done = p_ready + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    float *red = reinterpret_cast<float *>(bars + 18);  // [2][128][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) tiles first
@@ -153,14 +180,15 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
         bar_init(q_full, 1);
         for (int s = 0; s < kKvStages; ++s) {
-            bar_init(kv_full0 + 8 * s, 1);
-            bar_init(kv_empty0 + 8 * s, 1);   // released by tcgen05.commit of the P.V MMA
+            bar_init(k_full0 + 8 * s, 1);
+            bar_init(k_empty0 + 8 * s, 1);   // released by tcgen05.commit of the Q.K^T MMA
+            bar_init(v_full0 + 8 * s, 1);
+            bar_init(v_empty0 + 8 * s, 1);   // released by tcgen05.commit of the P.V MMA
             bar_init(s_full0 + 8 * s, 1);
             bar_init(s_free0 + 8 * s, kSoftmaxThreads);   // all softmax threads have read S[s]
         }
         bar_init(p_ready, kSoftmaxThreads);
-        bar_init(o_full, 1);
-        bar_init(o_taken, kSoftmaxThreads);
+        bar_init(pv_done, 1);                // tcgen05.commit of the P.V MMA: P may be overwritten, O holds tiles 0..j
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kSoftmaxWarps + 1) {
@@ -170,7 +198,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;  // columns: S0 [0,128) S1 [128,256) O_tile [256,384)
+    const uint32_t tmem = *tmem_slot;  // columns: S0 [0,128) S1 [128,256) O [256,384)
 
     pdl_wait();
     pdl_launch_dependents();
@@ -186,20 +214,28 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int kv_row0 = (b * p.kv_head_num + kvh) * p.max_seq_len;
 
     if (warp == kSoftmaxWarps) {
-        // ================================================= TMA producer
+        // ================================================= TMA producer: Q, then K0 | K1 V0 | K2 V1 | ... | V(n-1)
         if (ntiles > 0 && elect_one()) {
             bar_expect_tx(q_full, kTileBytes);
             tma_load_2d(s_u32(sQ), &tmQ, 0, q_row0, q_full);
             tma_load_2d(s_u32(sQ) + kHalfBytes, &tmQ, 64, q_row0, q_full);
-            for (int j = 0; j < ntiles; ++j) {
-                const int s = j % kKvStages;
-                bar_wait(kv_empty0 + 8 * s, ((j / kKvStages) & 1) ^ 1);
-                bar_expect_tx(kv_full0 + 8 * s, 2 * kTileBytes);
-                const uint32_t dk = s_u32(sK + s * kTileBytes), dv = s_u32(sV + s * kTileBytes);
-                tma_load_2d(dk, &tmK, 0, kv_row0 + j * kKeys, kv_full0 + 8 * s);
-                tma_load_2d(dk + kHalfBytes, &tmK, 64, kv_row0 + j * kKeys, kv_full0 + 8 * s);
-                tma_load_2d(dv, &tmV, 0, kv_row0 + j * kKeys, kv_full0 + 8 * s);
-                tma_load_2d(dv + kHalfBytes, &tmV, 64, kv_row0 + j * kKeys, kv_full0 + 8 * s);
+            for (int j = 0; j <= ntiles; ++j) {
+                if (j < ntiles) {
+                    const int s = j % kKvStages;
+                    bar_wait(k_empty0 + 8 * s, ((j / kKvStages) & 1) ^ 1);
+                    bar_expect_tx(k_full0 + 8 * s, kTileBytes);
+                    const uint32_t dk = s_u32(sK + s * kTileBytes);
+                    tma_load_2d(dk, &tmK, 0, kv_row0 + j * kKeys, k_full0 + 8 * s);
+                    tma_load_2d(dk + kHalfBytes, &tmK, 64, kv_row0 + j * kKeys, k_full0 + 8 * s);
+                }
+                if (j >= 1) {
+                    const int jv = j - 1, s = jv % kKvStages;
+                    bar_wait(v_empty0 + 8 * s, ((jv / kKvStages) & 1) ^ 1);
+                    bar_expect_tx(v_full0 + 8 * s, kTileBytes);
+                    const uint32_t dv = s_u32(sV + s * kTileBytes);
+                    tma_load_2d(dv, &tmV, 0, kv_row0 + jv * kKeys, v_full0 + 8 * s);
+                    tma_load_2d(dv + kHalfBytes, &tmV, 64, kv_row0 + jv * kKeys, v_full0 + 8 * s);
+                }
             }
         }
     } else if (warp == kSoftmaxWarps + 1) {
@@ -209,7 +245,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const uint32_t id_pv = idesc_f16(p.is_bf16 != 0, kRows, kD, true);
             auto issue_qk = [&](int j) {  // S[j % 2] = Q . K_j^T
                 const int s = j % kKvStages, sb = j & 1;
-                bar_wait(kv_full0 + 8 * s, (j / kKvStages) & 1);
+                bar_wait(k_full0 + 8 * s, (j / kKvStages) & 1);
                 bar_wait(s_free0 + 8 * sb, ((j >> 1) & 1) ^ 1);  // the softmax threads are done with what S[sb] held (tile j - 2)
                 tc_fence_after();
                 if (elect_one()) {
@@ -220,6 +256,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                         tc_mma_f16(tmem + (uint32_t)(sb * kKeys), desc_kmajor(aq + off), desc_kmajor(bk + off), id_qk, k > 0 ? 1u : 0u);
                     }
                     tc_commit(s_full0 + 8 * sb);
+                    tc_commit(k_empty0 + 8 * s);  // K_j may be overwritten
                 }
                 __syncwarp();
             };
@@ -228,8 +265,8 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             for (int j = 0; j < ntiles; ++j) {
                 if (j + 1 < ntiles) issue_qk(j + 1);  // next tile's logits while the softmax threads work on tile j
                 const int s = j % kKvStages;
-                bar_wait(p_ready, j & 1);                       // P_j is in shared memory (and V_j has landed: waited in issue_qk(j))
-                bar_wait(o_taken, (j & 1) ^ 1);                 // the previous tile's P.V has been read out of TMEM
+                bar_wait(v_full0 + 8 * s, (j / kKvStages) & 1);
+                bar_wait(p_ready, j & 1);                       // P_j is in shared memory, O has been rescaled if it had to be
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t ap = s_u32(sP), bv = s_u32(sV + s * kTileBytes);
@@ -237,10 +274,10 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     for (int k = 0; k < kKeys / 16; ++k) {
                         const uint32_t aoff = (uint32_t)(k / 4) * kHalfBytes + (uint32_t)(k % 4) * 32;  // P: K-major over keys
                         const uint32_t boff = (uint32_t)k * 16 * 128;                                    // V: 16 keys = 2048 bytes further
-                        tc_mma_f16(tmem + 2 * kKeys, desc_kmajor(ap + aoff), desc_mnmajor(bv + boff), id_pv, k > 0 ? 1u : 0u);
+                        tc_mma_f16(tmem + 2 * kKeys, desc_kmajor(ap + aoff), desc_mnmajor(bv + boff), id_pv, (j > 0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(kv_empty0 + 8 * s);  // K_j / V_j (and P_j) may be overwritten
-                    tc_commit(o_full);
+                    tc_commit(v_empty0 + 8 * s);  // V_j may be overwritten
+                    tc_commit(pv_done);           // P_j may be overwritten; O holds tiles 0..j
                 }
                 __syncwarp();
             }
@@ -252,48 +289,72 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int qi = q0 + row;
         const int lim = qi + (klen - qlen);    // keys <= lim are visible to this row
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cg * 32);
-        const float sl2 = p.scale * 1.4426950408889634f;  // logits in the log2 domain: exp(x) = ex2(x * log2 e)
+        const uint32_t o_addr = lane_addr + (uint32_t)(2 * kKeys);
+        const float sl2 = p.scale * kLog2e;  // logits in the log2 domain: exp(x) = ex2(x * log2 e)
         // the reference's running max starts at FLT_MIN (scale_and_mask_and_softmax.cu:86-126)
-        float m_run = FLT_MIN * 1.4426950408889634f, l_part = 0.0f;
-        float o[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[e] = 0.0f;
+        float m_run = FLT_MIN * kLog2e;  // running max of the row (log2 domain)
+        float m_use = m_run;             // the max the accumulator and the partial sum are scaled to (m_use <= m_run <= m_use + 8)
+        float l_part = 0.0f;
+        uint32_t r[32];
         for (int j = 0; j < ntiles; ++j) {
             const int sb = j & 1, k0 = j * kKeys + cg * 32;
             bar_wait(s_full0 + 8 * sb, (j >> 1) & 1);
             tc_fence_after();
-            uint32_t r[32];
             tc_ld32(lane_addr + (uint32_t)(sb * kKeys), r);
             tc_wait_ld();
             tc_fence_before();
             bar_arrive(s_free0 + 8 * sb);  // the logits are in registers: S[sb] may be overwritten by tile j + 2
-            float sv[32], mloc = -INFINITY;
+            // tiles entirely below the diagonal and inside the context need no mask (CTA-uniform: row 0 of the tile sees the fewest keys)
+            const bool edge = j * kKeys + kKeys - 1 > q0 + (klen - qlen) || j * kKeys + kKeys > klen;
+            float mloc = -INFINITY;
+            if (edge) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int kg = k0 + e;
-                sv[e] = (kg < klen && kg <= lim) ? sl2 * __uint_as_float(r[e]) : -INFINITY;
-                mloc = fmaxf(mloc, sv[e]);
+                for (int e = 0; e < 32; ++e) {
+                    const int kg = k0 + e;
+                    if (!(kg < klen && kg <= lim)) r[e] = 0xff800000u;  // -inf
+                    mloc = fmaxf(mloc, __uint_as_float(r[e]));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) mloc = fmaxf(mloc, __uint_as_float(r[e]));
             }
             float *rx = red + ((size_t)(j & 1) * kRows + row) * 4;
-            rx[cg] = mloc;
-            asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxThreads) : "memory");
+            rx[cg] = mloc * sl2;  // scale > 0: the max commutes with the scaling
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(128) : "memory");  // the 4 warps that share these 32 rows
             const float4 m4 = *reinterpret_cast<const float4 *>(rx);
-            const float mx = fmaxf(fmaxf(m_run, fmaxf(m4.x, m4.y)), fmaxf(m4.z, m4.w));
-            float corr;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"(m_run - mx));
-            // p = ex2(s - max): masked keys are -inf -> 0.  Rounded to T for the MMA (the reference's probabilities are a T tensor);
+            m_run = fmaxf(fmaxf(m_run, fmaxf(m4.x, m4.y)), fmaxf(m4.z, m4.w));
+            // ---- lazy rescale (identical decision in the row's 4 threads: they see the same m_run and m_use)
+            const bool need = m_run - m_use > kRescaleStep;
+            if (__any_sync(0xffffffffu, need)) {
+                const float corr = need ? ex2f(m_use - m_run) : 1.0f;
+                if (need) m_use = m_run;
+                l_part *= corr;
+                if (j > 0) {  // tile 0 overwrites the accumulator: nothing to rescale
+                    uint32_t acc[32];
+                    bar_wait(pv_done, (j - 1) & 1);  // every P.V issued so far has landed in O
+                    tc_fence_after();
+                    tc_ld32(o_addr, acc);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc[e] = __float_as_uint(__uint_as_float(acc[e]) * corr);
+                    tc_st32(o_addr, acc);
+                    tc_wait_st();
+                    tc_fence_before();
+                }
+            }
+            // p = ex2(s - m_use): masked keys are -inf -> 0.  Rounded to T for the MMA (the reference's probabilities are a T tensor);
             // the row sum uses the unrounded values.  Shared memory: K-major, 128-byte swizzle (16-byte chunk index XOR (row % 8)).
             float psum = 0.0f;
             uint32_t packed[16];
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
-                float p0, p1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(sv[e] - mx));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(sv[e + 1] - mx));
+                const float p0 = ex2f(fmaf(__uint_as_float(r[e]), sl2, -m_use)), p1 = ex2f(fmaf(__uint_as_float(r[e + 1]), sl2, -m_use));
                 psum += p0 + p1;
                 const T a0 = Elem<T>::from_f(p0), a1 = Elem<T>::from_f(p1);
                 packed[e / 2] = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
             }
+            l_part += psum;
+            if (j > 0) bar_wait(pv_done, (j - 1) & 1);  // the previous P.V has read P out of shared memory
             unsigned char *prow = sP + (cg >> 1) * kHalfBytes + row * 128;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -304,42 +365,36 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             // context_len is not initialised by anybody).  Row r of the tile is key j*128 + r; each of the row's 4 threads clears
             // its quarter of the 256 bytes.
             if (j * kKeys + row >= klen) {
-                bar_wait(kv_full0 + 8 * (j % kKvStages), (j / kKvStages) & 1);
+                bar_wait(v_full0 + 8 * (j % kKvStages), (j / kKvStages) & 1);
                 unsigned char *vrow = sV + (j % kKvStages) * kTileBytes + (cg >> 1) * kHalfBytes + row * 128 + (cg & 1) * 64;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4 *>(vrow + q * 16) = make_uint4(0, 0, 0, 0);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of P / V visible to the MMA (async proxy)
             bar_arrive(p_ready);
-            l_part = fmaf(l_part, corr, psum);
-            m_run = mx;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] *= corr;
-            // ---- this tile's P.V, this thread's 32 output dims
-            bar_wait(o_full, j & 1);
-            tc_fence_after();
-            tc_ld32(lane_addr + (uint32_t)(2 * kKeys), r);
-            tc_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] += __uint_as_float(r[e]);
-            tc_fence_before();
-            bar_arrive(o_taken);
         }
-        // row sum across the row's 4 threads
+        // row sum across the row's 4 threads; the accumulator comes out of TMEM once
         float *rx = red + ((size_t)(ntiles & 1) * kRows + row) * 4;
         rx[cg] = l_part;
-        asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxThreads) : "memory");
-        if (active && qi < qlen) {
-            const float4 l4 = *reinterpret_cast<const float4 *>(rx);
-            const float inv = 1.0f / (((l4.x + l4.y) + (l4.z + l4.w)) + 1e-6f);
-            const int t = b * p.max_q_len + qi - p.seq_off[b];  // un-padded token index
-            T *dst = reinterpret_cast<T *>(p.out) + ((size_t)t * p.head_num + h) * kD + cg * 32;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(128) : "memory");
+        if (ntiles > 0) {  // CTA-uniform
+            bar_wait(pv_done, (ntiles - 1) & 1);
+            tc_fence_after();
+            tc_ld32(o_addr, r);
+            tc_wait_ld();
+            if (qi < qlen) {
+                const float4 l4 = *reinterpret_cast<const float4 *>(rx);
+                const float c = ex2f(m_use - m_run);  // the sum and the accumulator are relative to m_use; the reference's are relative to the max
+                const float inv = c / (((l4.x + l4.y) + (l4.z + l4.w)) * c + 1e-6f);
+                const int t = b * p.max_q_len + qi - p.seq_off[b];  // un-padded token index
+                T *dst = reinterpret_cast<T *>(p.out) + ((size_t)t * p.head_num + h) * kD + cg * 32;
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-                float f[8];
+                for (int e = 0; e < 32; e += 8) {
+                    float f[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) f[u] = o[e + u] * inv;
-                st_v4(dst + e, pack16<T>(f));
+                    for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(r[e + u]) * inv;
+                    st_v4(dst + e, pack16<T>(f));
+                }
             }
         }
     }
@@ -402,7 +457,7 @@ int launch_context_attention_tc(const void *q, const void *k_layer, const void *
     p.out = out, p.seq_off = seq_off, p.input_len = input_len, p.context_len = context_len;
     p.head_num = head_num, p.kv_head_num = kv_head_num, p.max_q_len = max_q_len, p.max_seq_len = max_seq_len;
     p.scale = scale, p.is_bf16 = bf16 ? 1 : 0;
-    const size_t smem = (size_t)(2 + 2 * kKvStages) * kTileBytes + 1024 + 16 * 8 + 16 + 2 * kRows * 4 * sizeof(float);
+    const size_t smem = (size_t)(2 + 2 * kKvStages) * kTileBytes + 1024 + 18 * 8 + 16 + 2 * kRows * 4 * sizeof(float);
     dim3 grid((max_q_len + kRows - 1) / kRows, head_num, batch);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

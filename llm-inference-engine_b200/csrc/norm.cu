@@ -15,7 +15,8 @@ constexpr int kNormMaxVec = 8;  // 16-byte vectors cached per thread
 // kCopyOnly (launchRMSNorm): residual_out <- x, no add.
 // kThreads x kMaxVec: 256 x 8 for many rows (prefill); 512 x 4 for the few rows of a decode batch, where a row is ONE dependent chain of
 // loads (under tensor parallelism 2 x world polled loads per vector) and more threads mean fewer of them per thread.
-template <typename T, bool kVec, int kThreads, int kMaxVec>
+// kTp: the row comes from the tensor-parallel exchange (a separate instance: the polled 2 x world loads per vector cost ~100 registers)
+template <typename T, bool kVec, int kThreads, int kMaxVec, bool kTp>
 __global__ void __launch_bounds__(kThreads)
 norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T *__restrict__ bias,
             const T *__restrict__ gamma, float eps, int hidden, const TpExchange tp) {
@@ -29,11 +30,11 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
     T *rout = residual_out ? residual_out + (size_t)row * hidden : nullptr;
 
     pdl_wait();
-    const unsigned int tp_want = tp.world > 1 ? tp_flag(tp.epoch, tp.seq) : 0u;
+    const unsigned int tp_want = kTp ? tp_flag(tp.epoch, tp.seq) : 0u;
     // pre-norm value of vector i: o (+ residual); residual_out <- that; (+ bias)
     auto prenorm = [&](int i, float *f) {
         if constexpr (kVec) {
-            if (tp.world > 1) {  // fused one-shot all-reduce of the row-sharded linear's partial sums (rank order), LL words
+            if constexpr (kTp) {  // fused one-shot all-reduce of the row-sharded linear's partial sums (rank order), LL words
                 tp_reduce_vec<T, kTpMaxWorld>(tp, tp_want, ((size_t)row * hidden + (size_t)i * V) * sizeof(T) / 4, f);
             } else {
                 unpack16<T>(ld_v4(x + (size_t)i * V), f);
@@ -137,11 +138,27 @@ static int launch_norm(const T *in, T *out, const T *rin, T *rout, const T *bias
         return B200_ERR_UNSUPPORTED;
     }
     cudaError_t e;
+    const int nvec = hidden / (16 / (int)sizeof(T));
     // a decode batch (<= 16 rows): 512 threads per row, one to four vectors each -- (nearly) every load of the row in flight at once
-    const bool wide = vec && tokens <= 16 && hidden / (16 / (int)sizeof(T)) <= 4 * 512;
-    if (wide) e = launch_pdl(norm_kernel<T, true, 512, 4>, dim3(tokens), dim3(512), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
-    else if (vec) e = launch_pdl(norm_kernel<T, true, kNormThreads, kNormMaxVec>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
-    else e = launch_pdl(norm_kernel<T, false, kNormThreads, kNormMaxVec>, dim3(tokens), dim3(kNormThreads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp);
+    const bool wide = vec && tokens <= 16 && nvec <= 4 * 512;
+    auto go = [&](auto kern, int threads) { return launch_pdl(kern, dim3(tokens), dim3(threads), 0, st, true, in, out, rin, rout, bias, gamma, eps, hidden, tp); };
+    if (tp.world > 1) {
+        if (wide) e = go(norm_kernel<T, true, 512, 4, true>, 512);
+        else e = go(norm_kernel<T, true, kNormThreads, kNormMaxVec, true>, kNormThreads);
+    } else if (wide) {
+        e = go(norm_kernel<T, true, 512, 4, false>, 512);
+    } else if (vec && nvec <= 2 * kNormThreads) {
+        // many rows (prefill): the register cache is sized to the row (2 vectors per thread at hidden 4096, 16-bit) so that several CTAs
+        // fit an SM -- one HBM pass needs loads in flight, and round 1's single 152-register instance ran ONE CTA per SM (27 us for
+        // 2048 x 4096 where the bytes take 10)
+        e = go(norm_kernel<T, true, kNormThreads, 2, false>, kNormThreads);
+    } else if (vec && nvec <= 4 * kNormThreads) {
+        e = go(norm_kernel<T, true, kNormThreads, 4, false>, kNormThreads);
+    } else if (vec) {
+        e = go(norm_kernel<T, true, kNormThreads, kNormMaxVec, false>, kNormThreads);
+    } else {
+        e = go(norm_kernel<T, false, kNormThreads, kNormMaxVec, false>, kNormThreads);
+    }
     (void)e;
     return cuda_status("norm kernel launch");
 }

@@ -495,14 +495,18 @@ def test_prefill_chain(dtype):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("ramp", [0.0, 0.007, 0.05])
 @pytest.mark.parametrize("B,H,Hkv,S,input_len,hist", [
     (2, 8, 2, 700, [300, 129], [290, 0]),       # 3 query tiles, 5 key tiles, GQA 4:1, ragged batch, history
     (1, 4, 4, 256, [256], [0]),                 # exact tiles, pure causal prefill
     (3, 2, 1, 130, [1, 128, 2], [0, 2, 127]),   # single-row prompts, tile-edge lengths
+    (1, 2, 2, 1100, [1024], [60]),              # 8 query tiles, up to 9 key tiles: the accumulator lives in TMEM across all of them
 ])
-def test_context_attention_tensor_core(B, H, Hkv, S, input_len, hist, dtype):
+def test_context_attention_tensor_core(B, H, Hkv, S, input_len, hist, dtype, ramp):
     """The tcgen05 / TMEM context attention (head size 128, 16-bit) against the oracle chain; cache rows past context_len hold NaN
-    bit patterns (nobody initialises them): they must not leak into the result."""
+    bit patterns (nobody initialises them): they must not leak into the result.  ramp > 0: the logits grow with the key position
+    (by ~15 / ~100 in the log2 domain per 128-key tile), so the row max moves at every tile and the kernel's lazy rescale of the
+    TMEM accumulator (tcgen05.ld -> scale -> tcgen05.st) runs at every tile instead of never."""
     import torch
 
     mod = b200()
@@ -517,7 +521,11 @@ def test_context_attention_tensor_core(B, H, Hkv, S, input_len, hist, dtype):
     for b in range(B):
         q[b, :, :input_len[b]] = r.standard_normal((H, input_len[b], d))
     q = rounded(q, dtype)
-    kc = rounded(0.5 * r.standard_normal((L, B, Hkv, S, d)), dtype)
+    kc = 0.5 * r.standard_normal((L, B, Hkv, S, d))
+    if ramp:
+        q = rounded(q + (q != 0), dtype)  # every real query row gets +1 in every dimension: q.k grows by 128 * ramp per position
+        kc = kc + ramp * np.arange(S, dtype=np.float64)[:, None]
+    kc = rounded(kc, dtype)
     vc = rounded(0.5 * r.standard_normal((L, B, Hkv, S, d)), dtype)
     kcd, vcd = to_dev(kc, dtype), to_dev(vc, dtype)
     for b in range(B):  # poison what lies beyond the context
