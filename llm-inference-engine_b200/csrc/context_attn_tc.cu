@@ -185,9 +185,9 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             bar_init(v_full0 + 8 * s, 1);
             bar_init(v_empty0 + 8 * s, 1);   // released by tcgen05.commit of the P.V MMA
             bar_init(s_full0 + 8 * s, 1);
-            bar_init(s_free0 + 8 * s, kSoftmaxThreads);   // all softmax threads have read S[s]
+            bar_init(s_free0 + 8 * s, kSoftmaxWarps);     // all softmax warps have read S[s] (one arrival per warp)
         }
-        bar_init(p_ready, kSoftmaxThreads);
+        bar_init(p_ready, kSoftmaxWarps);    // one arrival per softmax warp: 512 arrivals on one mbarrier serialise (measured)
         bar_init(pv_done, 1);                // tcgen05.commit of the P.V MMA: P may be overwritten, O holds tiles 0..j
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -303,7 +303,8 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             tc_ld32(lane_addr + (uint32_t)(sb * kKeys), r);
             tc_wait_ld();
             tc_fence_before();
-            bar_arrive(s_free0 + 8 * sb);  // the logits are in registers: S[sb] may be overwritten by tile j + 2
+            __syncwarp();
+            if (lane == 0) bar_arrive(s_free0 + 8 * sb);  // the warp's logits are in registers: S[sb] may be overwritten by tile j + 2
             // tiles entirely below the diagonal and inside the context need no mask (CTA-uniform: row 0 of the tile sees the fewest keys)
             const bool edge = j * kKeys + kKeys - 1 > q0 + (klen - qlen) || j * kKeys + kKeys > klen;
             float mloc = -INFINITY;
@@ -371,7 +372,8 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4 *>(vrow + q * 16) = make_uint4(0, 0, 0, 0);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of P / V visible to the MMA (async proxy)
-            bar_arrive(p_ready);
+            __syncwarp();
+            if (lane == 0) bar_arrive(p_ready);
         }
         // row sum across the row's 4 threads; the accumulator comes out of TMEM once
         float *rx = red + ((size_t)(ntiles & 1) * kRows + row) * 4;

@@ -42,8 +42,14 @@ def test_decode_mha_ragged_rows_equal_the_oracle_row_by_row(H, Hkv, d, S, steps,
         rk, rv = kc[:, b:b + 1].copy(), vc[:, b:b + 1].copy()
         ref = oracle.decode_mha(q1, bias, rk, rv, H, Hkv, step, layer)
         assert_close(out[b:b + 1], ref, dtype, f"ragged decode mha row {b} at step {step}")
-        # cache: exactly one row appended, at THIS row's position; everything else untouched
-        assert np.array_equal(gk[:, b:b + 1], rounded(rk, dtype)) and np.array_equal(gv[:, b:b + 1], rounded(rv, dtype)), f"cache of row {b}"
+        # cache: exactly one row appended, at THIS row's position (KV-cache indices: bit-exact); everything else untouched.  The appended
+        # K row went through the device's cos / sin (RoPE at step-1): equal to the oracle's within the dtype's tolerance, V bit for bit.
+        touched = np.zeros(kc.shape[3], bool)
+        touched[step - 1] = True
+        assert np.array_equal(gk[:, b:b + 1][:, :, :, ~touched], kc[:, b:b + 1][:, :, :, ~touched]), f"K cache of row {b} outside position {step - 1}"
+        assert np.array_equal(gk[1 - layer, b], kc[1 - layer, b]), "other layer untouched"
+        assert_close(gk[layer, b:b + 1, :, step - 1], rk[layer, :, :, step - 1], dtype, f"appended K row of batch row {b}")
+        assert np.array_equal(gv[:, b:b + 1], rounded(rv, dtype)), f"V cache of row {b}"
 
 
 @pytest.mark.gpu
