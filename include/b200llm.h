@@ -107,6 +107,14 @@ int b200_linear(const void *x, const void *w, const void *scales, const void *ze
                 int M, int K, int N, int dtype, int w_format, int w_layout, int group,
                 b200_stream_t stream);
 
+/* launchLinearGemm (gate_up) + launchSiluAndMul in ONE kernel for prefill-sized token counts (src/layers/ffn.cpp:105-129,
+ * src/kernels/silu_and_mul.cu:6-41): act[M, inter] = silu(x . Wgate^T) * (x . Wup^T), w_gate_up dense `dtype` [2*inter, K] (gate rows
+ * first, the engine's packed layout).  Bit-identical to b200_linear followed by b200_silu_and_mul (gate and up are rounded to `dtype`
+ * before the activation, as the two-launcher path stores them); the [M, 2*inter] intermediate is never written.  16-bit dtypes, M > 128,
+ * K % 8 == 0, inter >= 128; B200_ERR_UNSUPPORTED otherwise. */
+int b200_linear_swiglu(const void *x, const void *w_gate_up, void *act, int M, int K, int inter_size, int dtype,
+                       b200_stream_t stream);
+
 /* launchLinearStridedBatchGemm, src/kernels/includes/linear.cuh:22-29 (src/kernels/linear.cu:89-158):
  * for each of `batch` matrices C[M,N] = A[M,K] * op(B); trans_b=0: B is [K,N]; trans_b=1: B is [N,K]
  * and the product is the true A*B^T (the reference's QK^T defect D4 is NOT reproduced). */

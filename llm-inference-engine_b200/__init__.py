@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200_fused_add_bias_residual_rmsnorm": [_P, _P, _P, _P, _F, _I, _I, _I, _P],
     "b200_add_residual": [_P, _P, _I, _I, _I, _P],
     "b200_linear": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b200_linear_swiglu": [_P, _P, _P, _I, _I, _I, _I, _P],
     "b200_batched_gemm": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_quantize_fp8": [_P, _P, _P, _I, _I, _I, _P],
     "b200_quantize_int4": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -194,6 +195,17 @@ def linear(x, w, layout=LAYOUT_NK, w_format=W_DENSE, scales=None, zeros=None, gr
         ensure_workspace()  # split-K partials
     check(lib().b200_linear(ptr(x), ptr(w), ptr(scales), ptr(zeros), ptr(y), M, K, N, dtype_code(x), w_format, layout, group, stream()))
     return y
+
+
+def linear_swiglu(x, w_gate_up):
+    """act[M, I] = silu(x . Wgate^T) * (x . Wup^T) in one tensor-core kernel (b200_linear_swiglu): w_gate_up [2I, K] dense, gate rows first."""
+    torch = _torch()
+    M, K = x.shape
+    inter = w_gate_up.shape[0] // 2
+    act = torch.empty((M, inter), dtype=x.dtype, device=x.device)
+    ensure_workspace()
+    check(lib().b200_linear_swiglu(ptr(x), ptr(w_gate_up), ptr(act), M, K, inter, dtype_code(x), stream()))
+    return act
 
 
 def batched_gemm(a, b, trans_b):

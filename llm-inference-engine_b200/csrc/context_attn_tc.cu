@@ -325,12 +325,14 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const float4 m4 = *reinterpret_cast<const float4 *>(rx);
             m_run = fmaxf(fmaxf(m_run, fmaxf(m4.x, m4.y)), fmaxf(m4.z, m4.w));
             // ---- lazy rescale (identical decision in the row's 4 threads: they see the same m_run and m_use)
-            const bool need = m_run - m_use > kRescaleStep;
-            if (__any_sync(0xffffffffu, need)) {
-                const float corr = need ? ex2f(m_use - m_run) : 1.0f;
-                if (need) m_use = m_run;
-                l_part *= corr;
-                if (j > 0) {  // tile 0 overwrites the accumulator: nothing to rescale
+            if (j == 0) {
+                m_use = m_run;  // tile 0 overwrites the accumulator and the sum is still 0: adopting the first tile's max is free
+            } else {
+                const bool need = m_run - m_use > kRescaleStep;
+                if (__any_sync(0xffffffffu, need)) {
+                    const float corr = need ? ex2f(m_use - m_run) : 1.0f;
+                    if (need) m_use = m_run;
+                    l_part *= corr;
                     uint32_t acc[32];
                     bar_wait(pv_done, (j - 1) & 1);  // every P.V issued so far has landed in O
                     tc_fence_after();
@@ -344,15 +346,20 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 }
             }
             // p = ex2(s - m_use): masked keys are -inf -> 0.  Rounded to T for the MMA (the reference's probabilities are a T tensor);
-            // the row sum uses the unrounded values.  Shared memory: K-major, 128-byte swizzle (16-byte chunk index XOR (row % 8)).
+            // the row sum uses the unrounded values.  Packed two at a time (F2FP on the ALU pipe: a scalar cvt to bf16 is an XU
+            // instruction like ex2 itself and doubled the load on the pipe this loop is bound by).
+            // Shared memory: K-major, 128-byte swizzle (16-byte chunk index XOR (row % 8)).
             float psum = 0.0f;
-            uint32_t packed[16];
+            uint4 packed[4];
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-                const float p0 = ex2f(fmaf(__uint_as_float(r[e]), sl2, -m_use)), p1 = ex2f(fmaf(__uint_as_float(r[e + 1]), sl2, -m_use));
-                psum += p0 + p1;
-                const T a0 = Elem<T>::from_f(p0), a1 = Elem<T>::from_f(p1);
-                packed[e / 2] = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+            for (int q = 0; q < 4; ++q) {
+                float pf[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    pf[u] = ex2f(fmaf(__uint_as_float(r[8 * q + u]), sl2, -m_use));
+                    psum += pf[u];
+                }
+                packed[q] = pack16<T>(pf);
             }
             l_part += psum;
             if (j > 0) bar_wait(pv_done, (j - 1) & 1);  // the previous P.V has read P out of shared memory
@@ -360,7 +367,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int chunk = ((cg & 1) * 4 + q) ^ (row & 7);
-                *reinterpret_cast<uint4 *>(prow + chunk * 16) = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                *reinterpret_cast<uint4 *>(prow + chunk * 16) = packed[q];
             }
             // rows of V past the context must not reach the tensor core: 0 * NaN would poison the output (the cache beyond
             // context_len is not initialised by anybody).  Row r of the tile is key j*128 + r; each of the row's 4 threads clears

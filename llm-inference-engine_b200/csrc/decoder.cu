@@ -49,6 +49,7 @@ int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const v
 int launch_dequant_vec(const void *w, const void *scales, const void *zeros, void *dst, int N, int K, int w_format, int group, int dtype,
                        cudaStream_t st);  // linear.cu
 int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, int dtype, cudaStream_t st);  // gemm_tc.cu
+int launch_gemm_tc_swiglu(const void *x, const void *w, void *act, int M, int inter, int K, int dtype, cudaStream_t st);  // gemm_tc.cu
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 // A kernel never writes the residual buffer other CTAs of the same launch still read: outputs go to the next buffer of the rotation.
@@ -667,8 +668,24 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
         // residual += attention output; (+ o bias); xn = RMSNorm
         rc = launch_norm_any(c.dtype, y, xn, res, res, w.o_bias, w.ffn_norm_gamma, c.rmsnorm_eps, T, h, st);
         if (rc != B200_OK) return rc;
-        if ((rc = linear(xn, w.gate_up, gu, h, 2 * c.inter_size)) != B200_OK) return rc;
-        if ((rc = b200_silu_and_mul(gu, act, T, c.inter_size, c.dtype, stream)) != B200_OK) return rc;
+        // gate_up + SwiGLU: one tensor-core GEMM whose epilogue applies the activation (16-bit, T > 128; quantised weights: dequantised
+        // into scratch first); otherwise the two launchers
+        rc = B200_ERR_UNSUPPORTED;
+        if (c.dtype != B200_F32 && T > 128) {
+            const void *wgu = w.gate_up.w;
+            if (c.w_format != B200_W_DENSE) {
+                rc = launch_dequant_vec(w.gate_up.w, w.gate_up.scales, w.gate_up.zeros, wdq, 2 * c.inter_size, h, c.w_format, c.group, c.dtype, st);
+                if (rc != B200_OK && rc != B200_ERR_UNSUPPORTED) return rc;
+                wgu = rc == B200_OK ? wdq : nullptr;
+                rc = B200_ERR_UNSUPPORTED;
+            }
+            if (wgu) rc = launch_gemm_tc_swiglu(xn, wgu, act, T, c.inter_size, h, c.dtype, st);
+        }
+        if (rc == B200_ERR_UNSUPPORTED) {
+            if ((rc = linear(xn, w.gate_up, gu, h, 2 * c.inter_size)) != B200_OK) return rc;
+            rc = b200_silu_and_mul(gu, act, T, c.inter_size, c.dtype, stream);
+        }
+        if (rc != B200_OK) return rc;
         if ((rc = linear(act, w.down, y, c.inter_size, h)) != B200_OK) return rc;
         pending = y;
     }

@@ -43,6 +43,10 @@ struct GemmTcParams {
     int is_bf16;
     int acc_bufs;  // TMEM accumulators (2 when 2*bn <= 512)
     unsigned int tmem_cols;
+    // SwiGLU epilogue (gate_up linear of the prefill path, launchLinearGemm + launchSiluAndMul in one kernel): B = W [2I, K] with the gate
+    // rows first; tile tb multiplies gate rows [128 tb, +128) AND up rows [I + 128 tb, +128) as one N = 256 tile (two TMA boxes into one
+    // B stage), the epilogue reads both halves of the accumulator and writes silu(gate) * up: C [rowsA, I], rowsB = I.  0: plain GEMM.
+    int swiglu_inter;
 };
 
 // One contiguous piece of work of a CTA: k-blocks [kb0, kb1) of one output tile.  nslots > 1: the tile is shared with
@@ -235,7 +239,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
                     bar_expect_tx(full0 + 8 * s, (uint32_t)stage_bytes);
                     tma_load_2d(sa, &tmA, kb * kBK, ta * kBM, full0 + 8 * s);
-                    tma_load_2d(sa + kATileBytes, &tmB, kb * kBK, tb * p.bn, full0 + 8 * s);
+                    if (p.swiglu_inter) {  // box = 128 rows: the gate rows, then the up rows of the same columns
+                        tma_load_2d(sa + kATileBytes, &tmB, kb * kBK, tb * 128, full0 + 8 * s);
+                        tma_load_2d(sa + kATileBytes + 128 * kBK * 2, &tmB, kb * kBK, p.swiglu_inter + tb * 128, full0 + 8 * s);
+                    } else {
+                        tma_load_2d(sa + kATileBytes, &tmB, kb * kBK, tb * p.bn, full0 + 8 * s);
+                    }
                 }
             }
         }
@@ -284,7 +293,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn);
             const int i = ta * kBM + q * 32 + lane;  // row of A this thread owns
             const int j0 = tb * p.bn;
-            if (sg.nslots == 1) {
+            if (p.swiglu_inter) {
+                // gate in accumulator columns [0, 128), up in [128, 256): both rounded to T first (the reference's linear writes a T
+                // tensor that launchSiluAndMul reads back, src/kernels/silu_and_mul.cu:6-41), same expression as silu_and_mul_kernel
+                for (int c = 0; c < 128; c += 16) {
+                    uint32_t g[16], u[16];
+                    tc_ld16(taddr + c, g);
+                    tc_ld16(taddr + 128 + c, u);
+                    tc_wait_ld();
+                    const int valid = min(16, p.rowsB - (tb * 128 + c));
+                    if (i < p.rowsA && valid > 0) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float gf = round_to<T>(__uint_as_float(g[e])), uf = round_to<T>(__uint_as_float(u[e]));
+                            g[e] = __float_as_uint((gf / (1.0f + expf(-gf))) * uf);
+                        }
+                        store_row16<T>(C + (size_t)i * p.ldc + tb * 128 + c, g, valid);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(tempty0 + 8 * acc);
+            } else if (sg.nslots == 1) {
                 for (int c = 0; c < p.bn; c += 16) {
                     uint32_t r[16];
                     tc_ld16(taddr + c, r);
@@ -422,28 +452,38 @@ static unsigned int pow2_cols(int c) {
     return v;
 }
 
-int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, int dtype, cudaStream_t st) {
+static int launch_gemm_tc_impl(const void *x, const void *w, void *y, int M, int N, int K, int dtype, int swiglu_inter, cudaStream_t st) {
     if (dtype != B200_BF16 && dtype != B200_F16) return B200_ERR_UNSUPPORTED;
     if (M < 1 || K % 8 != 0 || K < kBK || !aligned16(x) || !aligned16(w) || !y) return B200_ERR_UNSUPPORTED;
     const bool bf16 = dtype == B200_BF16;
     const bool swap = M <= 128;
+    if (swiglu_inter && (swap || swiglu_inter < 128)) return B200_ERR_UNSUPPORTED;  // the fused epilogue exists for prefill-sized token counts
     GemmTcParams p = {};
     p.C = y, p.ldc = N, p.K = K, p.swap = swap ? 1 : 0, p.is_bf16 = bf16 ? 1 : 0;
+    p.swiglu_inter = swiglu_inter;
     p.kb_total = (K + kBK - 1) / kBK;
     const void *a_ptr, *b_ptr;
+    int rows_b_map;  // rows of the B tensor as the TMA sees it
     if (swap) {
         a_ptr = w, b_ptr = x;
         p.rowsA = N, p.rowsB = M;
         p.bn = (M + 15) / 16 * 16;
+        rows_b_map = M;
     } else {
         a_ptr = x, b_ptr = w;
         p.rowsA = M, p.rowsB = N;
         p.bn = N >= 256 ? 256 : (N + 15) / 16 * 16;
+        rows_b_map = N;
     }
     const int sms = sm_count();
-    if (!swap && p.bn == 256 && ((M + kBM - 1) / kBM) * ((N + 255) / 256) * 2 <= sms) p.bn = 128;  // under half a wave: more, smaller tiles
+    if (swiglu_inter) {
+        p.bn = 256, p.rowsB = swiglu_inter, p.ldc = swiglu_inter;  // N = I output columns; the MMA tile is 128 gate + 128 up rows
+        rows_b_map = 2 * swiglu_inter;
+    } else if (!swap && p.bn == 256 && ((M + kBM - 1) / kBM) * ((N + 255) / 256) * 2 <= sms) {
+        p.bn = 128;  // under half a wave: more, smaller tiles
+    }
     p.tilesA = (p.rowsA + kBM - 1) / kBM;
-    const int tilesB = (p.rowsB + p.bn - 1) / p.bn;
+    const int tilesB = swiglu_inter ? (swiglu_inter + 127) / 128 : (p.rowsB + p.bn - 1) / p.bn;
     p.tiles = p.tilesA * tilesB;
     const long long total = (long long)p.tiles * p.kb_total;
     int grid = p.tiles < sms ? p.tiles : sms;
@@ -473,7 +513,7 @@ int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, i
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + (2 * kMaxStages + 4) * 8 + 16;
 
     CUtensorMap tmA, tmB;
-    if (!make_map(&tmA, a_ptr, p.rowsA, K, kBM, bf16) || !make_map(&tmB, b_ptr, p.rowsB, K, p.bn, bf16)) {
+    if (!make_map(&tmA, a_ptr, p.rowsA, K, kBM, bf16) || !make_map(&tmB, b_ptr, rows_b_map, K, swiglu_inter ? 128 : p.bn, bf16)) {
         set_error("gemm_tc: cuTensorMapEncodeTiled failed (rows %d/%d, K %d)", p.rowsA, p.rowsB, K);
         return B200_ERR_CUDA;
     }
@@ -484,6 +524,16 @@ int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, i
     if (bf16) launch(gemm_tc_kernel<__nv_bfloat16>);
     else launch(gemm_tc_kernel<__half>);
     return cuda_status("gemm_tc launch");
+}
+
+int launch_gemm_tc(const void *x, const void *w, void *y, int M, int N, int K, int dtype, cudaStream_t st) {
+    return launch_gemm_tc_impl(x, w, y, M, N, K, dtype, 0, st);
+}
+
+// act[M, inter] = silu(x . Wgate^T) * (x . Wup^T), w = [2 * inter, K] (gate rows, then up rows): the gate_up linear and launchSiluAndMul in one
+// kernel (prefill sizes, M > 128); the [M, 2 * inter] intermediate is never written.  B200_ERR_UNSUPPORTED: use the two launchers.
+int launch_gemm_tc_swiglu(const void *x, const void *w, void *act, int M, int inter, int K, int dtype, cudaStream_t st) {
+    return launch_gemm_tc_impl(x, w, act, M, inter, K, dtype, inter, st);
 }
 
 }  // namespace b200

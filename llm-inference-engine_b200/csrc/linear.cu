@@ -492,4 +492,14 @@ int b200_transpose2d(const void *src, void *dst, int rows, int cols, int dtype, 
     return cuda_status("transpose2d launch");
 }
 
+int b200_linear_swiglu(const void *x, const void *w_gate_up, void *act, int M, int K, int inter_size, int dtype, b200_stream_t stream) {
+    B200_REQUIRE(x && w_gate_up && act, "linear_swiglu: null pointer");
+    B200_REQUIRE(M >= 0 && K > 0 && inter_size > 0, "linear_swiglu: bad shape M=%d K=%d inter=%d", M, K, inter_size);
+    B200_REQUIRE(dtype == B200_F16 || dtype == B200_BF16, "linear_swiglu: 16-bit activations only (dtype %d)", dtype);
+    if (M == 0) return B200_OK;
+    const int rc = launch_gemm_tc_swiglu(x, w_gate_up, act, M, inter_size, K, dtype, as_stream(stream));
+    if (rc == B200_ERR_UNSUPPORTED) set_error("linear_swiglu: shape M=%d K=%d inter=%d not served by the fused tensor-core kernel (M > 128, K %% 8 == 0, inter >= 128)", M, K, inter_size);
+    return rc;
+}
+
 }  // extern "C"

@@ -303,6 +303,27 @@ def test_decode_mha_vs_reference_kernel():
 
 
 # ------------------------------------------------------------------ MLP / embedding / sampling tail
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,K,inter", [(2048, 4096, 11008), (316, 512, 768), (129, 64, 128), (300, 256, 200), (1000, 1024, 1300)])
+def test_linear_swiglu_fused_epilogue_is_linear_then_silu_and_mul_bit_for_bit(M, K, inter, dtype):
+    """The prefill path's gate_up GEMM with the SwiGLU epilogue (one tcgen05 kernel: gate and up rows of the same columns multiplied as
+    one N = 256 tile) against the two launchers it replaces (launchLinearGemm -> launchSiluAndMul, src/layers/ffn.cpp:105-129): same
+    accumulation, same rounding points -> bit-identical; and against the oracle within the dtype's tolerance.  inter = 200 / 1300: the last
+    tile's gate half runs into the up rows and its up half past the tensor (masked / zero-filled)."""
+    mod = b200()
+    r = rng(41)
+    x = rounded(r.standard_normal((M, K)), dtype)
+    w = rounded(r.standard_normal((2 * inter, K)) / np.sqrt(K), dtype)
+    xd, wd = to_dev(x, dtype), to_dev(w, dtype)
+    fused = to_np(mod.linear_swiglu(xd, wd))
+    gu = mod.linear(xd, wd)
+    two = to_np(mod.silu_and_mul(gu.view(M, 2, inter)))
+    assert np.array_equal(fused, two), f"fused epilogue differs from the two launchers: max {np.abs(fused - two).max():.3e}"
+    if M * K * inter <= 316 * 512 * 768 * 8:
+        ref = oracle.silu_and_mul(rounded(oracle.linear(x, w, "nk"), dtype).reshape(M, 2, inter))
+        assert_close(fused, ref, dtype, "fused gate_up + swiglu")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_silu_and_mul(dtype):
     mod = b200()
