@@ -195,6 +195,29 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // ---- the producer does not wait for the TMEM allocation: Q and the first two K tiles are requested before the CTA-wide barrier
+    //      (its own thread initialised the mbarriers), so their latency overlaps the rest of the prologue
+    int ntiles_early = 0;
+    if (warp == kSoftmaxWarps && lane == 0) {
+        pdl_wait();  // q and the cache rows come from the kernel in front of this one
+        const int qlen = p.input_len[b], klen = p.context_len[b];
+        const int q_hi = min(q0 + kRows, qlen) - 1;
+        const int k_hi = q0 < qlen ? min(klen, q_hi + (klen - qlen) + 1) : 0;
+        ntiles_early = (k_hi + kKeys - 1) / kKeys;
+        if (ntiles_early > 0) {
+            const int kvh = h / (p.head_num / p.kv_head_num);
+            const int q_row0 = (b * p.head_num + h) * p.max_q_len + q0, kv_row0 = (b * p.kv_head_num + kvh) * p.max_seq_len;
+            bar_expect_tx(q_full, kTileBytes);
+            tma_load_2d(s_u32(sQ), &tmQ, 0, q_row0, q_full);
+            tma_load_2d(s_u32(sQ) + kHalfBytes, &tmQ, 64, q_row0, q_full);
+            for (int j = 0; j < min(ntiles_early, kKvStages); ++j) {
+                bar_expect_tx(k_full0 + 8 * j, kTileBytes);
+                const uint32_t dk = s_u32(sK + j * kTileBytes);
+                tma_load_2d(dk, &tmK, 0, kv_row0 + j * kKeys, k_full0 + 8 * j);
+                tma_load_2d(dk + kHalfBytes, &tmK, 64, kv_row0 + j * kKeys, k_full0 + 8 * j);
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -210,17 +233,13 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int k_hi = active ? min(klen, q_hi + (klen - qlen) + 1) : 0;
     const int ntiles = (k_hi + kKeys - 1) / kKeys;
     const int kvh = h / (p.head_num / p.kv_head_num);
-    const int q_row0 = (b * p.head_num + h) * p.max_q_len + q0;
     const int kv_row0 = (b * p.kv_head_num + kvh) * p.max_seq_len;
 
     if (warp == kSoftmaxWarps) {
-        // ================================================= TMA producer: Q, then K0 | K1 V0 | K2 V1 | ... | V(n-1)
-        if (ntiles > 0 && elect_one()) {
-            bar_expect_tx(q_full, kTileBytes);
-            tma_load_2d(s_u32(sQ), &tmQ, 0, q_row0, q_full);
-            tma_load_2d(s_u32(sQ) + kHalfBytes, &tmQ, 64, q_row0, q_full);
-            for (int j = 0; j <= ntiles; ++j) {
-                if (j < ntiles) {
+        // ================================================= TMA producer (K0, K1 are on their way): V0 | K2 V1 | K3 V2 | ... | V(n-1)
+        if (lane == 0) {
+            for (int j = 1; j <= ntiles; ++j) {
+                if (j >= kKvStages && j < ntiles) {
                     const int s = j % kKvStages;
                     bar_wait(k_empty0 + 8 * s, ((j / kKvStages) & 1) ^ 1);
                     bar_expect_tx(k_full0 + 8 * s, kTileBytes);
@@ -228,14 +247,12 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     tma_load_2d(dk, &tmK, 0, kv_row0 + j * kKeys, k_full0 + 8 * s);
                     tma_load_2d(dk + kHalfBytes, &tmK, 64, kv_row0 + j * kKeys, k_full0 + 8 * s);
                 }
-                if (j >= 1) {
-                    const int jv = j - 1, s = jv % kKvStages;
-                    bar_wait(v_empty0 + 8 * s, ((jv / kKvStages) & 1) ^ 1);
-                    bar_expect_tx(v_full0 + 8 * s, kTileBytes);
-                    const uint32_t dv = s_u32(sV + s * kTileBytes);
-                    tma_load_2d(dv, &tmV, 0, kv_row0 + jv * kKeys, v_full0 + 8 * s);
-                    tma_load_2d(dv + kHalfBytes, &tmV, 64, kv_row0 + jv * kKeys, v_full0 + 8 * s);
-                }
+                const int jv = j - 1, s = jv % kKvStages;
+                bar_wait(v_empty0 + 8 * s, ((jv / kKvStages) & 1) ^ 1);
+                bar_expect_tx(v_full0 + 8 * s, kTileBytes);
+                const uint32_t dv = s_u32(sV + s * kTileBytes);
+                tma_load_2d(dv, &tmV, 0, kv_row0 + jv * kKeys, v_full0 + 8 * s);
+                tma_load_2d(dv + kHalfBytes, &tmV, 64, kv_row0 + jv * kKeys, v_full0 + 8 * s);
             }
         }
     } else if (warp == kSoftmaxWarps + 1) {
