@@ -160,6 +160,16 @@ int b200_decode_mha_ragged(const void *qkv, const void *qkv_bias, void *k_cache,
                            const int *steps, int batch, int head_num, int kv_head_num, int head_size,
                            int max_seq_len, int max_step, int layer, int apply_rope, int rotary_dim,
                            float rotary_base, int dtype, b200_stream_t stream);
+/* The same over a PAGED cache (the reference's cache is one static [L,B,Hkv,S,d] tensor, src/models/llama/llama.cpp:47-48):
+ * k_pool / v_pool [L, num_pages, Hkv, B200_KV_PAGE_SIZE, d]; position p of batch row b lives in page
+ * block_table[b * max_pages_per_seq + p / B200_KV_PAGE_SIZE] (DEVICE int32), row p % B200_KV_PAGE_SIZE.  One page of one kv head is
+ * exactly one 16 KiB stage of the kernel's K / V ring (16-bit), so paging costs no extra copies -- only the table look-up, made one tile
+ * ahead.  steps as in b200_decode_mha_ragged.  Head size 128 only.  Results are bit-identical to the contiguous kernel on the same rows. */
+#define B200_KV_PAGE_SIZE 64
+int b200_decode_mha_paged(const void *qkv, const void *qkv_bias, void *k_pool, void *v_pool, void *out,
+                          const int *block_table, const int *steps, int batch, int head_num, int kv_head_num,
+                          int head_size, int num_pages, int max_pages_per_seq, int max_step, int layer,
+                          int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream);
 
 /* launchFusedQKVAddBiasAndTransposeAndRope, src/kernels/includes/qkv_bias_and_rope.cuh:12-23
  * (kernel src/kernels/qkv_bias_and_rope.cu:5-79): QKV[T, H+2Hkv, d] -> q[B,H,Sq,d], k,v[B,Hkv,Sq,d]
@@ -219,6 +229,12 @@ int b200_context_attention(const void *q, const void *k_cache, const void *v_cac
                            int layer, int batch, int head_num, int kv_head_num, int max_q_len,
                            int max_seq_len, int head_size, int num_tokens, float scale, int dtype,
                            b200_stream_t stream);
+/* The same over a paged cache (see b200_decode_mha_paged): a 128-key tile of the tcgen05 kernel is two pages, fetched as four TMA boxes
+ * of 64 rows; a page past the context is never requested.  16-bit dtypes, head size 128 (B200_ERR_UNSUPPORTED otherwise). */
+int b200_context_attention_paged(const void *q, const void *k_pool, const void *v_pool, void *out, const int *block_table,
+                                 const int *input_len, const int *context_len, int layer, int batch, int head_num,
+                                 int kv_head_num, int max_q_len, int num_pages, int max_pages_per_seq, int head_size,
+                                 float scale, int dtype, b200_stream_t stream);
 
 /* ========================================== MLP / embedding ========================================= */
 
@@ -319,6 +335,12 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
  * the attention kernel depends on positions; see b200_decode_mha_ragged. */
 int b200_decoder_step_ragged(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, int batch,
                              const int *steps, int max_step, int layer_begin, int layer_end, b200_stream_t stream);
+/* b200_decoder_step over a paged cache: pools [L, num_pages, Hkv, B200_KV_PAGE_SIZE, d], block_table DEVICE int[batch, max_pages_per_seq],
+ * steps DEVICE int[batch].  batch <= max_batch: the pool has no batch dimension, so sequences join and leave the batch between steps
+ * without moving a byte of cache (continuous batching, b200_batcher_* below). */
+int b200_decoder_step_paged(b200_decoder_t *dec, void *hidden, void *k_pool, void *v_pool, const int *block_table,
+                            const int *steps, int batch, int max_step, int num_pages, int max_pages_per_seq,
+                            int layer_begin, int layer_end, b200_stream_t stream);
 
 /* Diagnostic (roofline measurement): exactly the weight-streaming launches of b200_decoder_step -- the QKV / O / gate_up / down linears
  * of every layer (reference src/layers/self_attention.cpp:79-86,131-138, src/layers/ffn.cpp:105-139), as the step
@@ -341,6 +363,12 @@ size_t b200_decoder_prefill_scratch_bytes(const b200_decoder_t *dec, int batch, 
 int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len,
                          const int *history_len, const int *context_len, int batch, int max_q_len, int num_tokens,
                          void *scratch, size_t scratch_bytes, int layer_begin, int layer_end, b200_stream_t stream);
+/* b200_decoder_prefill with the K / V rows written into, and read back from, the page pool (16-bit dtypes, head size 128; batch <=
+ * max_batch).  Scratch as b200_decoder_prefill_scratch_bytes. */
+int b200_decoder_prefill_paged(b200_decoder_t *dec, void *hidden, void *k_pool, void *v_pool, const int *block_table,
+                               const int *input_len, const int *history_len, const int *context_len, int batch,
+                               int max_q_len, int num_tokens, int num_pages, int max_pages_per_seq, void *scratch,
+                               size_t scratch_bytes, int layer_begin, int layer_end, b200_stream_t stream);
 
 /* Tensor-parallel halves of one layer.  Each leaves this rank's PARTIAL sum of the row-sharded linear
  * in partial[B,h] (`dtype`); the caller all-reduces it (NCCL) and passes the reduced tensor as
@@ -420,6 +448,70 @@ int b200_generate(b200_decoder_t *dec, const b200_generate_params_t *p, const in
 int b200_generate_ragged(b200_decoder_t *dec, const b200_generate_params_t *p, const int *prompt_ids, const int *prompt_lens,
                          int batch, int prompt_len, void *k_cache, void *v_cache, void *workspace, size_t workspace_bytes,
                          int *out_ids, int *n_generated, b200_stream_t stream);
+
+/* ===================================== continuous batching over a paged KV cache ===================================== */
+
+/* SURVEY.md 8f rank 4 (absent from the reference: one static [L,B,Hkv,S,d] cache, src/models/llama/llama.cpp:47-48; one prompt at a time,
+ * :327-398).  A SCHEDULER (host only: FCFS queue, allocator of B200_KV_PAGE_SIZE-position pages, per-iteration plan, preemption by
+ * recomputation) and an ITERATION that runs the plan on the engine: admitted requests are prefilled in one packed pass straight into
+ * their pages (b200_decoder_prefill_paged), running ones take one ragged decode step through the block table (b200_decoder_step_paged);
+ * both sample one token per sequence.  A row of the batch is nothing but a block-table row: sequences join and leave without moving
+ * cache bytes.  Greedy ids of a request equal those of the same prompt generated alone (up to ties inside the 16-bit tolerance: the
+ * batch size selects the GEMV kernel).  The sampling seed of an iteration is the longest position in its batch (sampling.cu:44-52 seeds
+ * with (step, row): shared by the batch as in the reference). */
+typedef struct b200_batcher b200_batcher_t;
+typedef struct {
+    int max_batch;          /* sequences decoding together; <= the engine's max_batch                                   */
+    int num_pages;          /* pages in the pool: k_pool / v_pool are [L, num_pages, Hkv, B200_KV_PAGE_SIZE, d]          */
+    int max_pages_per_seq;  /* block-table row length; the longest sequence is max_pages_per_seq * B200_KV_PAGE_SIZE     */
+    int max_prefill_tokens; /* prompt tokens of one prefill pass (bounds the workspace); also the longest single request */
+} b200_batcher_config_t;
+typedef struct {
+    int n_prefill, prefill_tokens, prefill_max_len; /* admitted this iteration: sequences, packed tokens, longest        */
+    int n_decode, decode_max_step;                  /* running sequences taking a decode step; their largest step        */
+    int n_preempted;                                /* running sequences pushed back to the queue (pages freed)          */
+    int free_pages, n_waiting;                      /* after planning                                                    */
+} b200_batch_plan_t;
+enum { B200_REQ_WAITING = 0, B200_REQ_RUNNING = 1, B200_REQ_FINISHED = 2 };
+enum {
+    B200_PLAN_PREFILL_IDS = 0,         /* int[prefill_tokens]: the admitted sequences' tokens, packed back to back           */
+    B200_PLAN_PREFILL_LENS = 1,        /* int[n_prefill]                                                                     */
+    B200_PLAN_PREFILL_REQUESTS = 2,    /* int[n_prefill]: request ids                                                        */
+    B200_PLAN_PREFILL_BLOCK_TABLE = 3, /* int[n_prefill, max_pages_per_seq], -1 where no page is held                        */
+    B200_PLAN_PREFILL_LAST_ROWS = 4,   /* int[n_prefill]: packed row of every sequence's last token                          */
+    B200_PLAN_DECODE_TOKENS = 5,       /* int[n_decode]: the token each running sequence feeds                               */
+    B200_PLAN_DECODE_STEPS = 6,        /* int[n_decode]: its 1-based position count including that token                     */
+    B200_PLAN_DECODE_REQUESTS = 7,
+    B200_PLAN_DECODE_BLOCK_TABLE = 8
+};
+
+/* ---- scheduler: host only, no CUDA call (tests/test_batcher.py drives it on a CPU-only box) */
+b200_batcher_t *b200_batcher_create(const b200_batcher_config_t *cfg); /* NULL on a bad configuration */
+void b200_batcher_destroy(b200_batcher_t *b);
+/* Queue a request; returns its id (>= 0) or a negative error.  prompt_len + max_new_tokens - 1 positions must fit a block-table row,
+ * max_prefill_tokens (a preempted request is recomputed in one prefill) and the pool. */
+int b200_batcher_submit(b200_batcher_t *b, const int *prompt_ids, int prompt_len, int max_new_tokens);
+/* Plan the next iteration: (1) every running sequence gets the page its next position needs -- none free: the most recently admitted
+ * running sequence is preempted (pages freed, re-queued at the FRONT with prompt + generated tokens); (2) unless something was
+ * preempted, waiting requests are admitted first come first served while there is a batch slot, their pages plus one spare, the
+ * prefill token budget and its padded-query budget (n * longest <= 2 * max_prefill_tokens). */
+int b200_batcher_plan(b200_batcher_t *b, b200_batch_plan_t *plan);
+const int *b200_batcher_plan_array(const b200_batcher_t *b, int which); /* host arrays of the current plan, valid until commit */
+/* Feed the iteration's sampled ids (plan order).  A sequence finishes on end_id or after max_new_tokens: its pages return to the pool.
+ * Returns the number of requests that finished in this iteration (or a negative error). */
+int b200_batcher_commit(b200_batcher_t *b, const int *prefill_sampled, const int *decode_sampled, int end_id);
+/* Generated ids so far (end_id included if it was sampled), state = B200_REQ_*. */
+int b200_batcher_result(const b200_batcher_t *b, int request, int *out_ids, int capacity, int *n_generated, int *state);
+int b200_batcher_pending(const b200_batcher_t *b);     /* waiting + running */
+int b200_batcher_free_pages(const b200_batcher_t *b);
+int b200_batcher_preemptions(const b200_batcher_t *b, int request);
+
+/* ---- one iteration on the GPU: plan -> prefill pass of the admitted -> decode step of the running -> commit.  Pools caller-owned,
+ * [L, num_pages, Hkv, B200_KV_PAGE_SIZE, d] of the engine's (16-bit) dtype; workspace caller-owned device memory, 256-byte aligned.
+ * Synchronises the stream (the scheduler needs the sampled ids).  *n_finished (optional): requests finished by this iteration. */
+size_t b200_batcher_workspace_bytes(const b200_batcher_t *b, const b200_decoder_t *dec, const b200_generate_params_t *p);
+int b200_batcher_step(b200_batcher_t *b, b200_decoder_t *dec, const b200_generate_params_t *p, void *k_pool, void *v_pool,
+                      void *workspace, size_t workspace_bytes, int *n_finished, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,22 @@ class GenerateParams(C.Structure):
                 ("end_id", C.c_int), ("max_new_tokens", C.c_int), ("check_every", C.c_int)]
 
 
+class BatcherConfig(C.Structure):
+    """b200_batcher_config_t (include/b200llm.h)."""
+    _fields_ = [("max_batch", C.c_int), ("num_pages", C.c_int), ("max_pages_per_seq", C.c_int), ("max_prefill_tokens", C.c_int)]
+
+
+class BatchPlan(C.Structure):
+    """b200_batch_plan_t (include/b200llm.h)."""
+    _fields_ = [("n_prefill", C.c_int), ("prefill_tokens", C.c_int), ("prefill_max_len", C.c_int), ("n_decode", C.c_int),
+                ("decode_max_step", C.c_int), ("n_preempted", C.c_int), ("free_pages", C.c_int), ("n_waiting", C.c_int)]
+
+
+KV_PAGE_SIZE = 64
+REQ_WAITING, REQ_RUNNING, REQ_FINISHED = 0, 1, 2
+(PLAN_PREFILL_IDS, PLAN_PREFILL_LENS, PLAN_PREFILL_REQUESTS, PLAN_PREFILL_BLOCK_TABLE, PLAN_PREFILL_LAST_ROWS, PLAN_DECODE_TOKENS,
+ PLAN_DECODE_STEPS, PLAN_DECODE_REQUESTS, PLAN_DECODE_BLOCK_TABLE) = range(9)
+
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 # name -> argtypes (restype int unless listed in _RESTYPES); must list every symbol of include/b200llm.h
 SIGNATURES = {
@@ -106,10 +122,27 @@ SIGNATURES = {
     "b200_decoder_tp_error": [_P],
     "b200_decoder_step_tp": [_P, _P, _P, _P, _I, _I, _P],
     "b200_lm_head_topk_sample": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200_decode_mha_paged": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_context_attention_paged": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_decoder_step_paged": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_decoder_prefill_paged": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _I, _I, _P],
+    "b200_batcher_create": [C.POINTER(BatcherConfig)],
+    "b200_batcher_destroy": [_P],
+    "b200_batcher_submit": [_P, _P, _I, _I],
+    "b200_batcher_plan": [_P, C.POINTER(BatchPlan)],
+    "b200_batcher_plan_array": [_P, _I],
+    "b200_batcher_commit": [_P, _P, _P, _I],
+    "b200_batcher_result": [_P, _I, _P, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "b200_batcher_pending": [_P],
+    "b200_batcher_free_pages": [_P],
+    "b200_batcher_preemptions": [_P, _I],
+    "b200_batcher_workspace_bytes": [_P, _P, C.POINTER(GenerateParams)],
+    "b200_batcher_step": [_P, _P, C.POINTER(GenerateParams), _P, _P, _P, _SZ, C.POINTER(C.c_int), _P],
 }
 _RESTYPES = {"b200_last_error_string": C.c_char_p, "b200_workspace_default_bytes": _SZ, "b200_decoder_create": _P,
              "b200_decoder_destroy": None, "b200_decoder_scratch_bytes": _SZ, "b200_decoder_prefill_scratch_bytes": _SZ,
-             "b200_decoder_tp_buffer_bytes": _SZ, "b200_generate_workspace_bytes": _SZ}
+             "b200_decoder_tp_buffer_bytes": _SZ, "b200_generate_workspace_bytes": _SZ, "b200_batcher_create": _P,
+             "b200_batcher_destroy": None, "b200_batcher_plan_array": C.POINTER(C.c_int), "b200_batcher_workspace_bytes": _SZ}
 
 _lib = None
 
@@ -273,6 +306,29 @@ def decode_mha(qkv, bias, k_cache, v_cache, head_num, kv_head_num, step, layer, 
     return out
 
 
+def decode_mha_paged(qkv, bias, k_pool, v_pool, block_table, steps, head_num, kv_head_num, layer, apply_rope=False, rot_dim=0, base=10000.0):
+    """k_pool / v_pool [L, num_pages, Hkv, 64, d]; block_table int32 [B, max_pages_per_seq] and steps int32 [B] on the device."""
+    torch = _torch()
+    ensure_workspace()
+    B, _, d = qkv.shape
+    out = torch.empty((B, head_num * d), dtype=qkv.dtype, device=qkv.device)
+    check(lib().b200_decode_mha_paged(ptr(qkv), ptr(bias), ptr(k_pool), ptr(v_pool), ptr(out), ptr(block_table), ptr(steps), B, head_num,
+                                      kv_head_num, d, k_pool.shape[1], block_table.shape[1], int(steps.max().item()), layer, int(apply_rope),
+                                      rot_dim, base, dtype_code(qkv), stream()))
+    return out
+
+
+def context_attention_paged(q, k_pool, v_pool, block_table, input_len, context_len, layer, num_tokens, scale):
+    """q [B, H, max_q_len, d]; pools [L, num_pages, Hkv, 64, d]; returns [num_tokens, H * d] (un-padded)."""
+    torch = _torch()
+    ensure_workspace()
+    B, H, mq, d = q.shape
+    out = torch.empty((num_tokens, H * d), dtype=q.dtype, device=q.device)
+    check(lib().b200_context_attention_paged(ptr(q), ptr(k_pool), ptr(v_pool), ptr(out), ptr(block_table), ptr(input_len), ptr(context_len), layer,
+                                             B, H, k_pool.shape[2], mq, k_pool.shape[1], block_table.shape[1], d, scale, dtype_code(q), stream()))
+    return out
+
+
 def silu_and_mul(x):
     torch = _torch()
     t, _, inter = x.shape
@@ -432,6 +488,25 @@ class Decoder:
         check(lib().b200_decoder_step_ragged(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), hidden.shape[0], ptr(steps), max_step,
                                              layer_begin, layer_end, stream()))
 
+    def step_paged(self, hidden, k_pool, v_pool, block_table, steps, max_step, layer_begin=0, layer_end=None):
+        """One decode step over a paged cache: pools [L, num_pages, Hkv, 64, d], block_table int32 [batch, max_pages_per_seq], steps int32 [batch]."""
+        layer_end = self.cfg.num_layers if layer_end is None else layer_end
+        check(lib().b200_decoder_step_paged(self.handle, ptr(hidden), ptr(k_pool), ptr(v_pool), ptr(block_table), ptr(steps), hidden.shape[0],
+                                            max_step, k_pool.shape[1], block_table.shape[1], layer_begin, layer_end, stream()))
+
+    def prefill_paged(self, hidden, k_pool, v_pool, block_table, input_len, history_len, context_len, max_q_len, layer_begin=0, layer_end=None):
+        torch = _torch()
+        ensure_workspace()
+        layer_end = self.cfg.num_layers if layer_end is None else layer_end
+        B, T = input_len.shape[0], hidden.shape[0]
+        nbytes = lib().b200_decoder_prefill_scratch_bytes(self.handle, B, max_q_len, T)
+        if getattr(self, "_prefill_scratch", None) is None or self._prefill_scratch.numel() < nbytes + 256:
+            self._prefill_scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=hidden.device)
+        base = (self._prefill_scratch.data_ptr() + 255) // 256 * 256
+        check(lib().b200_decoder_prefill_paged(self.handle, ptr(hidden), ptr(k_pool), ptr(v_pool), ptr(block_table), ptr(input_len),
+                                               ptr(history_len), ptr(context_len), B, max_q_len, T, k_pool.shape[1], block_table.shape[1],
+                                               C.c_void_p(base), nbytes, layer_begin, layer_end, stream()))
+
     def generate(self, prompt_ids, embedding, final_gamma, lm_head, k_cache, v_cache, max_new_tokens, top_k=1, end_id=2, check_every=0,
                  prompt_lens=None):
         """The generation loop (b200_generate / b200_generate_ragged): prompt_ids = int array [batch, prompt_len] on the HOST, prompt_lens
@@ -536,3 +611,93 @@ class Decoder:
                 self.handle = None
         except Exception:
             pass
+
+
+class Batcher:
+    """Continuous batching over a paged KV cache (b200_batcher_*): the scheduler half (submit / plan / commit) is host only."""
+
+    def __init__(self, max_batch, num_pages, max_pages_per_seq, max_prefill_tokens):
+        self.cfg = BatcherConfig(max_batch, num_pages, max_pages_per_seq, max_prefill_tokens)
+        self.handle = lib().b200_batcher_create(C.byref(self.cfg))
+        if not self.handle:
+            raise B200Error(lib().b200_last_error_string().decode())
+        self._ws = None
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().b200_batcher_destroy(self.handle)
+            self.handle = None
+
+    def submit(self, prompt_ids, max_new_tokens):
+        import numpy as np
+
+        ids = np.ascontiguousarray(np.asarray(prompt_ids, dtype=np.int32))
+        rid = lib().b200_batcher_submit(self.handle, ids.ctypes.data_as(C.c_void_p), int(ids.size), int(max_new_tokens))
+        if rid < 0:
+            raise B200Error(f"b200 status {rid}: {lib().b200_last_error_string().decode()}")
+        return rid
+
+    def plan(self):
+        import numpy as np
+
+        p = BatchPlan()
+        check(lib().b200_batcher_plan(self.handle, C.byref(p)))
+        mp = self.cfg.max_pages_per_seq
+
+        def arr(which, n):
+            if n == 0:
+                return np.zeros(0, np.int32)
+            return np.ctypeslib.as_array(lib().b200_batcher_plan_array(self.handle, which), shape=(n,)).copy()
+
+        views = dict(prefill_ids=arr(PLAN_PREFILL_IDS, p.prefill_tokens), prefill_lens=arr(PLAN_PREFILL_LENS, p.n_prefill),
+                     prefill_requests=arr(PLAN_PREFILL_REQUESTS, p.n_prefill),
+                     prefill_block_table=arr(PLAN_PREFILL_BLOCK_TABLE, p.n_prefill * mp).reshape(p.n_prefill, mp),
+                     prefill_last_rows=arr(PLAN_PREFILL_LAST_ROWS, p.n_prefill), decode_tokens=arr(PLAN_DECODE_TOKENS, p.n_decode),
+                     decode_steps=arr(PLAN_DECODE_STEPS, p.n_decode), decode_requests=arr(PLAN_DECODE_REQUESTS, p.n_decode),
+                     decode_block_table=arr(PLAN_DECODE_BLOCK_TABLE, p.n_decode * mp).reshape(p.n_decode, mp))
+        return p, views
+
+    def commit(self, prefill_sampled, decode_sampled, end_id):
+        import numpy as np
+
+        a = np.ascontiguousarray(np.asarray(prefill_sampled, dtype=np.int32))
+        b = np.ascontiguousarray(np.asarray(decode_sampled, dtype=np.int32))
+        n = lib().b200_batcher_commit(self.handle, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), int(end_id))
+        if n < 0:
+            raise B200Error(f"b200 status {n}: {lib().b200_last_error_string().decode()}")
+        return n
+
+    def result(self, request, capacity=4096):
+        import numpy as np
+
+        out = np.zeros(capacity, np.int32)
+        n, st = C.c_int(0), C.c_int(0)
+        check(lib().b200_batcher_result(self.handle, request, out.ctypes.data_as(C.c_void_p), capacity, C.byref(n), C.byref(st)))
+        return out[:n.value].copy(), st.value
+
+    def pending(self):
+        return lib().b200_batcher_pending(self.handle)
+
+    def free_pages(self):
+        return lib().b200_batcher_free_pages(self.handle)
+
+    def preemptions(self, request):
+        return lib().b200_batcher_preemptions(self.handle, request)
+
+    def step(self, dec, embedding, final_gamma, lm_head, k_pool, v_pool, top_k=1, end_id=2):
+        """One iteration on the GPU (b200_batcher_step); returns the number of requests it finished."""
+        torch = _torch()
+        ensure_workspace()
+        gp = GenerateParams(C.c_void_p(embedding.data_ptr()), C.c_void_p(final_gamma.data_ptr()), C.c_void_p(lm_head.data_ptr()),
+                            int(lm_head.shape[0]), int(top_k), int(end_id), 1, 0)
+        if self._ws is None:
+            nbytes = lib().b200_batcher_workspace_bytes(self.handle, dec.handle, C.byref(gp))
+            if nbytes == 0:
+                raise B200Error(lib().b200_last_error_string().decode())
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=k_pool.device)
+            self._ws_bytes = nbytes
+        base = (self._ws.data_ptr() + 255) // 256 * 256
+        fin = C.c_int(0)
+        check(lib().b200_batcher_step(self.handle, dec.handle, C.byref(gp), ptr(k_pool), ptr(v_pool), C.c_void_p(base), self._ws_bytes,
+                                      C.byref(fin), stream()))
+        return fin.value

@@ -113,7 +113,9 @@ __device__ __forceinline__ float final_max(float m, int step, int head_size) { r
 
 // GC = q heads served by one CTA (the whole GQA group, or half of it when the group has 8 heads: 8 x (q + output) slices do not
 // fit the register budget of a 288-thread CTA -- the two halves read the same K/V rows, the second read hits L2).
-template <typename T, int GC>
+// kPaged: the cache is a page pool addressed through a block table (attention_decode.cuh); a tile of TP positions never straddles a page
+// (TP divides kAttnPageSize, tiles start at multiples of TP), so a stage is still two contiguous bulk copies.
+template <typename T, int GC, bool kPaged>
 __global__ void __launch_bounds__(kAttnThreads)
 decode_attn_kernel(const DecodeAttnArgs a) {
     constexpr int D = kAttnD;
@@ -134,6 +136,7 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     float *wts = vnew + D;                                                            // [RG][G] merge weights, then [G] max, [G] sum
     const uint32_t full0 = a_smem_u32(wts + RG * G + 2 * G + 2), empty0 = full0 + 8 * kAttnStages;
     __shared__ bool is_last;
+    static_assert(kAttnPageSize % TP == 0, "a tile must not straddle pages");
 
     const int split = blockIdx.x, b = blockIdx.z;
     const int H = a.head_num, Hkv = a.kv_head_num;
@@ -152,20 +155,31 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     const bool has_new = split == nsplit_b - 1;
     const T *qkv = reinterpret_cast<const T *>(a.qkv) + (size_t)b * qkv_heads * D;
     const T *bias = reinterpret_cast<const T *>(a.bias);
-    T *kc = reinterpret_cast<T *>(a.k_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
-    T *vc = reinterpret_cast<T *>(a.v_cache) + ((size_t)b * Hkv + kvh) * a.max_seq_len * D;
+    // contiguous: the rows of (b, kv head); paged: the pool's layer base (rows are found through the block table)
+    T *kc = reinterpret_cast<T *>(a.k_cache) + (kPaged ? (size_t)0 : ((size_t)b * Hkv + kvh) * a.max_seq_len * D);
+    T *vc = reinterpret_cast<T *>(a.v_cache) + (kPaged ? (size_t)0 : ((size_t)b * Hkv + kvh) * a.max_seq_len * D);
+    const int *bt = kPaged ? a.block_table + (size_t)b * a.max_pages : nullptr;
+    // element offset of position `pos` of this (b, kv head) from kc / vc
+    auto row_off = [&](int pos) -> size_t {
+        if constexpr (kPaged) return (((size_t)__ldg(bt + pos / kAttnPageSize) * Hkv + kvh) * kAttnPageSize + pos % kAttnPageSize) * D;
+        else return (size_t)pos * D;
+    };
     const bool producer = warp == kAttnWarps && (tid & 31) == 0;
 
     // ---- producer: one stage = the K rows and the V rows of TP positions (two contiguous byte ranges)
     int p_t = 0, p_s = 0;
+    size_t p_off = 0;  // paged: offset of the NEXT tile, looked up one tile ahead so that the table read hides behind the ring wait
+    if (kPaged && producer && ntiles > 0) p_off = row_off(p0);
     auto issue_next = [&]() {
         const int base = p0 + p_t * TP;
         const uint32_t bytes = (uint32_t)min(TP, p1 - base) * (uint32_t)(D * sizeof(T));
         const uint32_t bar = full0 + 8 * p_s, dst = a_smem_u32(ring + (size_t)p_s * kStageBytes);
+        const size_t off = kPaged ? p_off : (size_t)base * D;
         a_mbar_expect_tx(bar, 2 * bytes);
-        a_bulk_g2s(dst, kc + (size_t)base * D, bytes, bar);
-        a_bulk_g2s(dst + kAttnTileBytes, vc + (size_t)base * D, bytes, bar);
+        a_bulk_g2s(dst, kc + off, bytes, bar);
+        a_bulk_g2s(dst + kAttnTileBytes, vc + off, bytes, bar);
         ++p_t;
+        if (kPaged && p_t < ntiles) p_off = row_off(base + TP);
         if (++p_s == kAttnStages) p_s = 0;
     };
     if (producer) {
@@ -211,9 +225,10 @@ decode_attn_kernel(const DecodeAttnArgs a) {
     }
     __syncthreads();  // q / knew / vnew complete; also publishes the producer's mbarrier initialisation
     if (has_new && g0 == 0) {  // cache append (decoder_self_attention.cu:126,172)
+        const size_t off = row_off(step - 1);
         for (int j = tid; j < D; j += kAttnThreads) {
-            kc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(knew[j]);
-            vc[(size_t)(step - 1) * D + j] = Elem<T>::from_f(vnew[j]);
+            kc[off + j] = Elem<T>::from_f(knew[j]);
+            vc[off + j] = Elem<T>::from_f(vnew[j]);
         }
     }
     pdl_launch_dependents();
@@ -537,7 +552,7 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
         dim3 grid(a.nsplit, a.kv_head_num * (G / GC), a.batch);
         auto go = [&](auto kern, int slot) {
             // the three instantiations share one function-pointer type: the opt-in to large dynamic shared memory is per kernel and device
-            static thread_local bool attr_set[3][64] = {{false}};
+            static thread_local bool attr_set[6][64] = {{false}};
             int dev = 0;
             cudaGetDevice(&dev);
             dev &= 63;
@@ -547,13 +562,22 @@ static int launch_decode_attn_t(DecodeAttnArgs a, cudaStream_t st) {
             }
             launch_pdl(kern, grid, dim3(kAttnThreads), smem, st, true, a);
         };
-        switch (GC) {
-            case 1: go(decode_attn_kernel<T, 1>, 0); break;
-            case 2: go(decode_attn_kernel<T, 2>, 1); break;
-            default: go(decode_attn_kernel<T, 4>, 2); break;
+        if (a.block_table) {
+            switch (GC) {
+                case 1: go(decode_attn_kernel<T, 1, true>, 3); break;
+                case 2: go(decode_attn_kernel<T, 2, true>, 4); break;
+                default: go(decode_attn_kernel<T, 4, true>, 5); break;
+            }
+        } else {
+            switch (GC) {
+                case 1: go(decode_attn_kernel<T, 1, false>, 0); break;
+                case 2: go(decode_attn_kernel<T, 2, false>, 1); break;
+                default: go(decode_attn_kernel<T, 4, false>, 2); break;
+            }
         }
         return cuda_status("decode_attn launch");
     }
+    if (a.block_table) return B200_ERR_UNSUPPORTED;  // the paged cache is served by the head-size-128 kernel only
     const size_t smem = sizeof(float) * ((size_t)3 * a.head_size + a.step);
     if (smem > 200 * 1024) {
         set_error("decode_mha: step %d too long for the generic head-size path", a.step);
@@ -588,8 +612,9 @@ int b200_rope_decode(void *qkv, int batch, int head_num, int kv_head_num, int he
 }
 
 static int decode_mha_impl(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const int *steps,
-                           int batch, int head_num, int kv_head_num, int head_size, int max_seq_len, int step, int layer,
-                           int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
+                           const int *block_table, int max_pages, int num_pages, int batch, int head_num, int kv_head_num, int head_size,
+                           int max_seq_len, int step, int layer, int apply_rope, int rotary_dim, float rotary_base, int dtype,
+                           b200_stream_t stream) {
     B200_REQUIRE(qkv && k_cache && v_cache && out, "decode_mha: null pointer");
     B200_REQUIRE(batch >= 0 && head_num > 0 && kv_head_num > 0 && head_size > 0, "decode_mha: bad shape");
     B200_REQUIRE(head_num % kv_head_num == 0, "decode_mha: head_num %d not a multiple of kv_head_num %d", head_num, kv_head_num);
@@ -600,13 +625,16 @@ static int decode_mha_impl(const void *qkv, const void *qkv_bias, void *k_cache,
     Workspace ws;
     if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
     const size_t eb = dtype == B200_F32 ? 4 : 2;
-    const size_t layer_off = (size_t)layer * batch * kv_head_num * max_seq_len * head_size * eb;
+    // contiguous cache [L, B, Hkv, S, d]; paged pool [L, num_pages, Hkv, kAttnPageSize, d]
+    const size_t layer_off = block_table ? (size_t)layer * num_pages * kv_head_num * kAttnPageSize * head_size * eb
+                                         : (size_t)layer * batch * kv_head_num * max_seq_len * head_size * eb;
     DecodeAttnArgs a = {};
     a.qkv = qkv, a.bias = qkv_bias;
     a.k_cache = (char *)k_cache + layer_off, a.v_cache = (char *)v_cache + layer_off;
     a.out = out;
     a.batch = batch, a.head_num = head_num, a.kv_head_num = kv_head_num, a.head_size = head_size;
     a.max_seq_len = max_seq_len, a.step = step, a.steps = steps;
+    a.block_table = block_table, a.max_pages = max_pages;
     a.apply_rope = apply_rope, a.rot_dim = rotary_dim, a.rot_base = rotary_base;
     a.nsplit = decode_attn_plan(batch, kv_head_num, step, &a.chunk);
     a.partials = reinterpret_cast<float *>(ws.scratch);
@@ -614,24 +642,34 @@ static int decode_mha_impl(const void *qkv, const void *qkv_bias, void *k_cache,
     B200_REQUIRE((size_t)batch * kv_head_num * 2 <= ws.n_tickets, "decode_mha: batch*kv_head_num exceeds the ticket pool");
     B200_REQUIRE(decode_attn_partials_floats(batch, head_num, kv_head_num, head_size, a.nsplit) * 4 <= ws.scratch_bytes,
                  "decode_mha: library workspace too small for %d splits", a.nsplit);
-    return launch_decode_attn(a, dtype, as_stream(stream));
+    const int rc = launch_decode_attn(a, dtype, as_stream(stream));
+    if (rc == B200_ERR_UNSUPPORTED && block_table) set_error("decode_mha_paged: head size %d / group %d not served by the paged kernel (head size 128, group 1/2/4/8)", head_size, head_num / kv_head_num);
+    return rc;
 }
-
 
 int b200_decode_mha(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const uint8_t *finished,
                     int batch, int head_num, int kv_head_num, int head_size, int max_seq_len, int step, int layer,
                     int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
     (void)finished;  // unused by the reference kernel as well
-    return decode_mha_impl(qkv, qkv_bias, k_cache, v_cache, out, nullptr, batch, head_num, kv_head_num, head_size, max_seq_len, step, layer,
-                           apply_rope, rotary_dim, rotary_base, dtype, stream);
+    return decode_mha_impl(qkv, qkv_bias, k_cache, v_cache, out, nullptr, nullptr, 0, 0, batch, head_num, kv_head_num, head_size, max_seq_len, step,
+                           layer, apply_rope, rotary_dim, rotary_base, dtype, stream);
 }
 
 int b200_decode_mha_ragged(const void *qkv, const void *qkv_bias, void *k_cache, void *v_cache, void *out, const int *steps, int batch,
                            int head_num, int kv_head_num, int head_size, int max_seq_len, int max_step, int layer, int apply_rope,
                            int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
     B200_REQUIRE(steps, "decode_mha_ragged: null steps");
-    return decode_mha_impl(qkv, qkv_bias, k_cache, v_cache, out, steps, batch, head_num, kv_head_num, head_size, max_seq_len, max_step, layer,
-                           apply_rope, rotary_dim, rotary_base, dtype, stream);
+    return decode_mha_impl(qkv, qkv_bias, k_cache, v_cache, out, steps, nullptr, 0, 0, batch, head_num, kv_head_num, head_size, max_seq_len,
+                           max_step, layer, apply_rope, rotary_dim, rotary_base, dtype, stream);
+}
+
+int b200_decode_mha_paged(const void *qkv, const void *qkv_bias, void *k_pool, void *v_pool, void *out, const int *block_table,
+                          const int *steps, int batch, int head_num, int kv_head_num, int head_size, int num_pages, int max_pages_per_seq,
+                          int max_step, int layer, int apply_rope, int rotary_dim, float rotary_base, int dtype, b200_stream_t stream) {
+    B200_REQUIRE(block_table && steps, "decode_mha_paged: null block table / steps");
+    B200_REQUIRE(num_pages >= 1 && max_pages_per_seq >= 1, "decode_mha_paged: bad pool (num_pages %d, max_pages_per_seq %d)", num_pages, max_pages_per_seq);
+    return decode_mha_impl(qkv, qkv_bias, k_pool, v_pool, out, steps, block_table, max_pages_per_seq, num_pages, batch, head_num, kv_head_num,
+                           head_size, max_pages_per_seq * kAttnPageSize, max_step, layer, apply_rope, rotary_dim, rotary_base, dtype, stream);
 }
 
 }  // extern "C"

@@ -18,10 +18,16 @@ struct DecodeAttnArgs {
     int apply_rope, rot_dim;
     float rot_base;
     int nsplit, chunk;
+    // paged cache (optional): k_cache / v_cache are then the LAYER base of a page pool [num_pages, Hkv, kAttnPageSize, d] and position p of
+    // batch row b lives in page block_table[b * max_pages + p / kAttnPageSize], row p % kAttnPageSize; max_seq_len = max_pages * kAttnPageSize
+    const int *block_table;
+    int max_pages;
     int prefetch;  // 1: cached K/V rows may be requested before griddepcontrol.wait (fused engine only: the kernel in front
                    // of this one does not write the cache)
 };
 
+// positions per page of the paged cache: one page of one kv head = one 16 KiB ring stage of the decode kernel (16-bit), two for fp32
+constexpr int kAttnPageSize = 64;
 // floats per (split, q head) record of the partials: o[128], max, sum, 2 pad (records stay 16-byte aligned)
 constexpr int kAttnPartStride = 132;
 inline int attn_part_stride(int head_size) { return head_size + 4; }

@@ -53,6 +53,10 @@ struct Params {
     int head_num, kv_head_num, max_q_len, max_seq_len;
     float scale;
     int is_bf16;
+    // paged cache (optional): K / V are page pools [num_pages, Hkv, 64, d] (tensor maps with boxes of 64 rows); the keys [64 i, 64 i + 64)
+    // of batch row b live in page block_table[b * max_pages + i].  A 128-key tile is then two pages = four boxes.
+    const int *block_table;
+    int max_pages;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,6 +199,25 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // one K or V tile of 128 keys: two boxes (the two 64-column halves) of 128 rows from the contiguous cache, or -- paged -- per half
+    // one box of 64 rows from each of the tile's two pages (a page past the context is not requested: its rows are masked / zeroed)
+    auto load_kv_tile = [&](const CUtensorMap &tm, unsigned char *dst_tile, uint32_t bar, int j, int kv_row0, int kvh, int klen) {
+        const uint32_t d0 = s_u32(dst_tile);
+        if (p.block_table) {
+            const int *bt = p.block_table + (size_t)b * p.max_pages;
+            const int npg = (j * kKeys + 64 < klen) ? 2 : 1;
+            bar_expect_tx(bar, (uint32_t)npg * (kTileBytes / 2));
+            for (int g = 0; g < npg; ++g) {
+                const int row = (__ldg(bt + 2 * j + g) * p.kv_head_num + kvh) * 64;
+                tma_load_2d(d0 + g * 64 * 128, &tm, 0, row, bar);
+                tma_load_2d(d0 + kHalfBytes + g * 64 * 128, &tm, 64, row, bar);
+            }
+        } else {
+            bar_expect_tx(bar, kTileBytes);
+            tma_load_2d(d0, &tm, 0, kv_row0 + j * kKeys, bar);
+            tma_load_2d(d0 + kHalfBytes, &tm, 64, kv_row0 + j * kKeys, bar);
+        }
+    };
     // ---- the producer does not wait for the TMEM allocation: Q and the first two K tiles are requested before the CTA-wide barrier
     //      (its own thread initialised the mbarriers), so their latency overlaps the rest of the prologue
     int ntiles_early = 0;
@@ -210,12 +233,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             bar_expect_tx(q_full, kTileBytes);
             tma_load_2d(s_u32(sQ), &tmQ, 0, q_row0, q_full);
             tma_load_2d(s_u32(sQ) + kHalfBytes, &tmQ, 64, q_row0, q_full);
-            for (int j = 0; j < min(ntiles_early, kKvStages); ++j) {
-                bar_expect_tx(k_full0 + 8 * j, kTileBytes);
-                const uint32_t dk = s_u32(sK + j * kTileBytes);
-                tma_load_2d(dk, &tmK, 0, kv_row0 + j * kKeys, k_full0 + 8 * j);
-                tma_load_2d(dk + kHalfBytes, &tmK, 64, kv_row0 + j * kKeys, k_full0 + 8 * j);
-            }
+            for (int j = 0; j < min(ntiles_early, kKvStages); ++j) load_kv_tile(tmK, sK + j * kTileBytes, k_full0 + 8 * j, j, kv_row0, kvh, klen);
         }
     }
     tc_fence_before();
@@ -242,17 +260,11 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 if (j >= kKvStages && j < ntiles) {
                     const int s = j % kKvStages;
                     bar_wait(k_empty0 + 8 * s, ((j / kKvStages) & 1) ^ 1);
-                    bar_expect_tx(k_full0 + 8 * s, kTileBytes);
-                    const uint32_t dk = s_u32(sK + s * kTileBytes);
-                    tma_load_2d(dk, &tmK, 0, kv_row0 + j * kKeys, k_full0 + 8 * s);
-                    tma_load_2d(dk + kHalfBytes, &tmK, 64, kv_row0 + j * kKeys, k_full0 + 8 * s);
+                    load_kv_tile(tmK, sK + s * kTileBytes, k_full0 + 8 * s, j, kv_row0, kvh, klen);
                 }
                 const int jv = j - 1, s = jv % kKvStages;
                 bar_wait(v_empty0 + 8 * s, ((jv / kKvStages) & 1) ^ 1);
-                bar_expect_tx(v_full0 + 8 * s, kTileBytes);
-                const uint32_t dv = s_u32(sV + s * kTileBytes);
-                tma_load_2d(dv, &tmV, 0, kv_row0 + jv * kKeys, v_full0 + 8 * s);
-                tma_load_2d(dv + kHalfBytes, &tmV, 64, kv_row0 + jv * kKeys, v_full0 + 8 * s);
+                load_kv_tile(tmV, sV + s * kTileBytes, v_full0 + 8 * s, jv, kv_row0, kvh, klen);
             }
         }
     } else if (warp == kSoftmaxWarps + 1) {
@@ -450,12 +462,12 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 // rows x 128 matrix of a 16-bit type, boxes of 128 rows x 64 columns, 128-byte swizzle
-static bool make_map(CUtensorMap *map, const void *ptr, size_t rows, bool bf16) {
+static bool make_map(CUtensorMap *map, const void *ptr, size_t rows, bool bf16, int box_rows = 128) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)kD * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -465,17 +477,21 @@ static bool make_map(CUtensorMap *map, const void *ptr, size_t rows, bool bf16) 
 }  // namespace catc
 
 // q [B, H, max_q_len, 128]; k/v: LAYER base of the cache [B, Hkv, S, 128]; out [T, H, 128]; seq_off [B] (device).
+// block_table != NULL: k/v are the layer base of a page pool [num_pages, Hkv, 64, 128] and block_table [B, max_pages] (device) maps
+// 64-key blocks to pages (max_seq_len is then ignored).
 // Returns B200_ERR_UNSUPPORTED (no error text) when the shape / type cannot use the tensor-core kernel.
 int launch_context_attention_tc(const void *q, const void *k_layer, const void *v_layer, void *out, const int *seq_off, const int *input_len,
                                 const int *context_len, int batch, int head_num, int kv_head_num, int max_q_len, int max_seq_len, int head_size,
-                                float scale, int dtype, cudaStream_t st) {
+                                float scale, int dtype, cudaStream_t st, const int *block_table, int max_pages, int num_pages) {
     using namespace catc;
     if ((dtype != B200_BF16 && dtype != B200_F16) || head_size != kD) return B200_ERR_UNSUPPORTED;
     if (!aligned16(q) || !aligned16(k_layer) || !aligned16(v_layer) || !aligned16(out)) return B200_ERR_UNSUPPORTED;
     const bool bf16 = dtype == B200_BF16;
     CUtensorMap tmQ, tmK, tmV;
-    if (!make_map(&tmQ, q, (size_t)batch * head_num * max_q_len, bf16) || !make_map(&tmK, k_layer, (size_t)batch * kv_head_num * max_seq_len, bf16) ||
-        !make_map(&tmV, v_layer, (size_t)batch * kv_head_num * max_seq_len, bf16)) {
+    const size_t kv_rows = block_table ? (size_t)num_pages * kv_head_num * 64 : (size_t)batch * kv_head_num * max_seq_len;
+    const int kv_box = block_table ? 64 : 128;
+    if (!make_map(&tmQ, q, (size_t)batch * head_num * max_q_len, bf16) || !make_map(&tmK, k_layer, kv_rows, bf16, kv_box) ||
+        !make_map(&tmV, v_layer, kv_rows, bf16, kv_box)) {
         set_error("context_attention: cuTensorMapEncodeTiled failed");
         return B200_ERR_CUDA;
     }
@@ -483,6 +499,7 @@ int launch_context_attention_tc(const void *q, const void *k_layer, const void *
     p.out = out, p.seq_off = seq_off, p.input_len = input_len, p.context_len = context_len;
     p.head_num = head_num, p.kv_head_num = kv_head_num, p.max_q_len = max_q_len, p.max_seq_len = max_seq_len;
     p.scale = scale, p.is_bf16 = bf16 ? 1 : 0;
+    p.block_table = block_table, p.max_pages = max_pages;
     const size_t smem = (size_t)(2 + 2 * kKvStages) * kTileBytes + 1024 + 18 * 8 + 16 + 2 * kRows * 4 * sizeof(float);
     dim3 grid((max_q_len + kRows - 1) / kRows, head_num, batch);
     auto go = [&](auto kern) {

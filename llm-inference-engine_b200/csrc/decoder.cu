@@ -34,7 +34,10 @@ struct b200_decoder {
     float2 *rope_cs = nullptr;  // (cos, sin) per (position, rotary pair), filled once by set_scratch
     int max_splits = 0;
     int cur = 0;  // which res[] holds the residual stream
-    const int *steps_dev = nullptr;  // per-row steps of a ragged batch (device int[batch]); set only inside b200_decoder_step_ragged
+    const int *steps_dev = nullptr;  // per-row steps of a ragged batch (device int[batch]); set only inside b200_decoder_step_ragged / _paged
+    // paged cache (set only inside b200_decoder_step_paged): the caches are page pools [L, num_pages, Hkv, 64, d] addressed through a block table
+    const int *block_table = nullptr;
+    int max_pages = 0, num_pages = 0;
     // fused tensor-parallel exchange (b200_decoder_tp_attach): every rank's exchange buffer as mapped in this process
     char *tp_base[b200::kTpMaxWorld] = {};
     bool tp_attached = false;
@@ -44,7 +47,7 @@ namespace b200 {
 
 int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const void *bias, const int *padding_offset,
                                   const int *history_len, int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size,
-                                  int max_seq_len, int rot_dim, float base, int dtype, cudaStream_t st);
+                                  int max_seq_len, int rot_dim, float base, int dtype, cudaStream_t st, const int *block_table, int max_pages);
 
 int launch_dequant_vec(const void *w, const void *scales, const void *zeros, void *dst, int N, int K, int w_format, int group, int dtype,
                        cudaStream_t st);  // linear.cu
@@ -329,12 +332,14 @@ static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache,
     const b200_decoder_config_t &c = dec->cfg;
     const b200_layer_weights_t &w = dec->layers[layer];
     DecodeAttnArgs a = {};
-    const size_t layer_off = (size_t)layer * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
+    const size_t layer_off = dec->block_table ? (size_t)layer * dec->num_pages * c.kv_head_num * kAttnPageSize * c.head_size * esize(c.dtype)
+                                              : (size_t)layer * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
     a.qkv = dec->qkv, a.bias = w.qkv_bias;
     a.k_cache = (char *)k_cache + layer_off, a.v_cache = (char *)v_cache + layer_off;
     a.out = dec->attn;
     a.batch = batch, a.head_num = c.head_num, a.kv_head_num = c.kv_head_num, a.head_size = c.head_size;
-    a.max_seq_len = c.max_seq_len, a.step = step, a.steps = dec->steps_dev;
+    a.max_seq_len = dec->block_table ? dec->max_pages * kAttnPageSize : c.max_seq_len, a.step = step, a.steps = dec->steps_dev;
+    a.block_table = dec->block_table, a.max_pages = dec->max_pages;
     a.apply_rope = c.rotary_dim > 0, a.rot_dim = c.rotary_dim, a.rot_base = c.rotary_base;
     a.nsplit = decode_attn_plan(batch, c.kv_head_num, step, &a.chunk);
     a.partials = dec->partials, a.tickets = dec->tickets;
@@ -532,6 +537,22 @@ int b200_decoder_step_ragged(b200_decoder_t *dec, void *hidden, void *k_cache, v
     return rc;
 }
 
+// The same step over a PAGED cache: k_pool / v_pool [L, num_pages, Hkv, 64, d]; row b's position p lives in page
+// block_table[b * max_pages_per_seq + p / 64].  Rows are ragged by construction (steps[b]); batch <= max_batch: the pool has no batch
+// dimension, so sequences join and leave the batch between steps without moving a byte of cache.
+int b200_decoder_step_paged(b200_decoder_t *dec, void *hidden, void *k_pool, void *v_pool, const int *block_table, const int *steps, int batch,
+                            int max_step, int num_pages, int max_pages_per_seq, int layer_begin, int layer_end, b200_stream_t stream) {
+    B200_REQUIRE(dec && block_table && steps, "decoder_step_paged: null argument");
+    B200_REQUIRE(num_pages >= 1 && max_pages_per_seq >= 1, "decoder_step_paged: bad pool (num_pages %d, max_pages_per_seq %d)", num_pages, max_pages_per_seq);
+    B200_REQUIRE(max_step <= max_pages_per_seq * kAttnPageSize, "decoder_step_paged: max_step %d exceeds the block table's reach (%d pages of %d)",
+                 max_step, max_pages_per_seq, kAttnPageSize);
+    B200_REQUIRE(dec->cfg.head_size == 128, "decoder_step_paged: the paged attention kernel serves head size 128 (got %d)", dec->cfg.head_size);
+    dec->steps_dev = steps, dec->block_table = block_table, dec->max_pages = max_pages_per_seq, dec->num_pages = num_pages;
+    const int rc = b200_decoder_step(dec, hidden, k_pool, v_pool, batch, max_step, layer_begin, layer_end, stream);
+    dec->steps_dev = nullptr, dec->block_table = nullptr, dec->max_pages = dec->num_pages = 0;
+    return rc;
+}
+
 // Diagnostic for roofline measurements: exactly the weight-streaming launches of b200_decoder_step (four GEMVs per layer) without the
 // attention kernels and the final fold (a tensor-parallel engine runs them on its shard, without the exchange).  The activations are
 // whatever the scratch buffers hold: call it after at least one real step;
@@ -602,16 +623,22 @@ size_t b200_decoder_prefill_scratch_bytes(const b200_decoder_t *dec, int batch, 
     return prefill_carve(dec->cfg, batch, max_q_len, num_tokens, off);
 }
 
-int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len, const int *history_len,
-                         const int *context_len, int batch, int max_q_len, int num_tokens, void *scratch, size_t scratch_bytes,
-                         int layer_begin, int layer_end, b200_stream_t stream) {
+// paging (block_table != NULL): k_cache / v_cache are page pools [L, num_pages, Hkv, 64, d]
+static int prefill_impl(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len, const int *history_len,
+                        const int *context_len, int batch, int max_q_len, int num_tokens, void *scratch, size_t scratch_bytes,
+                        int layer_begin, int layer_end, b200_stream_t stream, const int *block_table, int max_pages, int num_pages) {
     B200_REQUIRE(dec, "decoder_prefill: null handle");
     const b200_decoder_config_t &c = dec->cfg;
     B200_REQUIRE(c.tp_world <= 1, "decoder_prefill: tensor-parallel prefill is not implemented");
     B200_REQUIRE(hidden && k_cache && v_cache && input_len && history_len && context_len && scratch, "decoder_prefill: null pointer");
     B200_REQUIRE(batch >= 1 && batch <= c.max_batch && max_q_len >= 1 && num_tokens >= 1 && num_tokens <= batch * max_q_len,
                  "decoder_prefill: bad shape (batch %d, max_q_len %d, num_tokens %d)", batch, max_q_len, num_tokens);
-    B200_REQUIRE(batch == c.max_batch, "decoder_prefill: batch %d must equal the cache's batch dimension (max_batch %d)", batch, c.max_batch);
+    if (block_table) {
+        B200_REQUIRE(c.head_size == 128 && c.dtype != B200_F32, "decoder_prefill_paged: head size 128 and a 16-bit dtype (the tensor-core context attention)");
+        B200_REQUIRE(max_q_len <= max_pages * kAttnPageSize, "decoder_prefill_paged: max_q_len %d exceeds the block table's reach", max_q_len);
+    } else {
+        B200_REQUIRE(batch == c.max_batch, "decoder_prefill: batch %d must equal the cache's batch dimension (max_batch %d)", batch, c.max_batch);
+    }
     B200_REQUIRE(max_q_len <= c.max_seq_len, "decoder_prefill: max_q_len %d exceeds the cache length %d", max_q_len, c.max_seq_len);
     B200_REQUIRE(layer_begin >= 0 && layer_end <= c.num_layers && layer_begin < layer_end, "decoder_prefill: bad layer range");
     B200_REQUIRE(((uintptr_t)scratch & 255) == 0, "decoder_prefill: scratch must be 256-byte aligned");
@@ -647,10 +674,12 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
         if (rc != B200_OK) return rc;
         if ((rc = linear(xn, w.qkv, qkv, h, qkv_n)) != B200_OK) return rc;
         // split + RoPE + KV append: one fused pass (k / v go straight into the cache); un-vectorisable shapes take the two launchers
-        const size_t layer_off = (size_t)l * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
+        const size_t layer_off = block_table ? (size_t)l * num_pages * c.kv_head_num * kAttnPageSize * c.head_size * esize(c.dtype)
+                                             : (size_t)l * c.max_batch * c.kv_head_num * c.max_seq_len * c.head_size * esize(c.dtype);
         rc = launch_prefill_qkv_rope_cache(qp, (char *)k_cache + layer_off, (char *)v_cache + layer_off, qkv, w.qkv_bias, padding_offset, history_len,
-                                           max_q_len, T, c.head_num, c.kv_head_num, c.head_size, c.max_seq_len, c.rotary_dim, c.rotary_base, c.dtype, st);
-        if (rc == B200_ERR_UNSUPPORTED) {
+                                           max_q_len, T, c.head_num, c.kv_head_num, c.head_size, c.max_seq_len, c.rotary_dim, c.rotary_base, c.dtype, st,
+                                           block_table, max_pages);
+        if (rc == B200_ERR_UNSUPPORTED && !block_table) {
             // un-vectorisable head sizes take the reference's two launchers, whose prefill kernel has no bias term
             B200_REQUIRE(!w.qkv_bias, "decoder_prefill: qkv bias needs a head size the fused prefill kernel supports (multiple of %d)",
                          c.dtype == B200_F32 ? 8 : 16);
@@ -661,8 +690,10 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
                                       c.head_size, c.dtype, stream);
         }
         if (rc != B200_OK) return rc;
-        rc = b200_context_attention(qp, k_cache, v_cache, attn, padding_offset, input_len, context_len, l, batch, c.head_num, c.kv_head_num,
-                                    max_q_len, c.max_seq_len, c.head_size, T, scale, c.dtype, stream);
+        rc = block_table ? b200_context_attention_paged(qp, k_cache, v_cache, attn, block_table, input_len, context_len, l, batch, c.head_num,
+                                                        c.kv_head_num, max_q_len, num_pages, max_pages, c.head_size, scale, c.dtype, stream)
+                         : b200_context_attention(qp, k_cache, v_cache, attn, padding_offset, input_len, context_len, l, batch, c.head_num,
+                                                  c.kv_head_num, max_q_len, c.max_seq_len, c.head_size, T, scale, c.dtype, stream);
         if (rc != B200_OK) return rc;
         if ((rc = linear(attn, w.o, y, qh, h)) != B200_OK) return rc;
         // residual += attention output; (+ o bias); xn = RMSNorm
@@ -692,6 +723,25 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
     // hidden <- residual + last FFN output
     if (cudaMemcpyAsync(hidden, res, (size_t)T * h * esize(c.dtype), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return cuda_status("decoder_prefill copy");
     return b200_add_residual(pending, hidden, T, h, c.dtype, stream);
+}
+
+int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len, const int *history_len,
+                         const int *context_len, int batch, int max_q_len, int num_tokens, void *scratch, size_t scratch_bytes,
+                         int layer_begin, int layer_end, b200_stream_t stream) {
+    return prefill_impl(dec, hidden, k_cache, v_cache, input_len, history_len, context_len, batch, max_q_len, num_tokens, scratch, scratch_bytes,
+                        layer_begin, layer_end, stream, nullptr, 0, 0);
+}
+
+// The same pass with the K / V rows written into, and read back from, a PAGE POOL [L, num_pages, Hkv, 64, d] through block_table
+// [batch, max_pages_per_seq] (device): the prompt's keys [64 i, 64 i + 64) of row b go to page block_table[b * max_pages_per_seq + i].
+// batch <= max_batch (the pool has no batch dimension).  16-bit dtypes, head size 128.
+int b200_decoder_prefill_paged(b200_decoder_t *dec, void *hidden, void *k_pool, void *v_pool, const int *block_table, const int *input_len,
+                               const int *history_len, const int *context_len, int batch, int max_q_len, int num_tokens, int num_pages,
+                               int max_pages_per_seq, void *scratch, size_t scratch_bytes, int layer_begin, int layer_end, b200_stream_t stream) {
+    B200_REQUIRE(block_table, "decoder_prefill_paged: null block table");
+    B200_REQUIRE(num_pages >= 1 && max_pages_per_seq >= 1, "decoder_prefill_paged: bad pool (num_pages %d, max_pages_per_seq %d)", num_pages, max_pages_per_seq);
+    return prefill_impl(dec, hidden, k_pool, v_pool, input_len, history_len, context_len, batch, max_q_len, num_tokens, scratch, scratch_bytes,
+                        layer_begin, layer_end, stream, block_table, max_pages_per_seq, num_pages);
 }
 
 int b200_lm_head_topk_sample(b200_decoder_t *dec, const void *hidden, const void *final_gamma, const void *lm_head, int vocab,

@@ -13,7 +13,7 @@ namespace b200 {
 
 int launch_context_attention_tc(const void *q, const void *k_layer, const void *v_layer, void *out, const int *seq_off, const int *input_len,
                                 const int *context_len, int batch, int head_num, int kv_head_num, int max_q_len, int max_seq_len, int head_size,
-                                float scale, int dtype, cudaStream_t st);
+                                float scale, int dtype, cudaStream_t st, const int *block_table, int max_pages, int num_pages);
 
 __device__ __forceinline__ float rope_denominator_p(float base, int zid, int rot_dim) {
     const float e = (float)zid / (float)rot_dim;
@@ -98,7 +98,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict__ qkv, const T *__restrict__ bias,
                               const int *__restrict__ padding_offset, const int *__restrict__ history_len, int seq_len, int head_num,
-                              int kv_head_num, int head_size, int max_seq_len, int rot_dim, float base) {
+                              int kv_head_num, int head_size, int max_seq_len, int rot_dim, float base, const int *__restrict__ block_table,
+                              int max_pages) {
     constexpr int V = Elem<T>::kVec;
     extern __shared__ float2 cs[];  // [head_size / 2] (cos, sin); identity past rot_dim / 2
     const int t = blockIdx.x;
@@ -127,12 +128,15 @@ prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict_
         T *d;
         if (head < head_num) {
             d = q + (((size_t)b * head_num + head) * seq_len + s) * head_size;
-        } else if (head < head_num + kv_head_num) {
-            d = k_cache + (((size_t)b * kv_head_num + (head - head_num)) * max_seq_len + pos_i) * head_size;
         } else {
-            d = v_cache + (((size_t)b * kv_head_num + (head - head_num - kv_head_num)) * max_seq_len + pos_i) * head_size;
+            if (pos_i >= max_seq_len) continue;  // a prompt longer than the cache: never write past the layer's slab / the block table's reach
+            const bool is_k = head < head_num + kv_head_num;
+            const int kvh = is_k ? head - head_num : head - head_num - kv_head_num;
+            // contiguous [B, Hkv, S, d], or a page pool [num_pages, Hkv, 64, d] addressed through the block table (max_seq_len = max_pages * 64)
+            const size_t row = block_table ? ((size_t)block_table[(size_t)b * max_pages + pos_i / 64] * kv_head_num + kvh) * 64 + pos_i % 64
+                                           : ((size_t)b * kv_head_num + kvh) * max_seq_len + pos_i;
+            d = (is_k ? k_cache : v_cache) + row * head_size;
         }
-        if (head >= head_num && pos_i >= max_seq_len) continue;  // a prompt longer than the cache: never write past the layer's slab
         if (head < head_num + kv_head_num) {
 #pragma unroll
             for (int e = 0; e < V; ++e) {
@@ -163,14 +167,14 @@ prefill_qkv_rope_cache_kernel(T *q, T *k_cache, T *v_cache, const T *__restrict_
 // q [B,H,max_q,d]; k_cache / v_cache: LAYER base [B,Hkv,S,d].  B200_ERR_UNSUPPORTED when the shape cannot be vectorised.
 int launch_prefill_qkv_rope_cache(void *q, void *k_layer, void *v_layer, const void *qkv, const void *bias, const int *padding_offset,
                                   const int *history_len, int seq_len, int num_tokens, int head_num, int kv_head_num, int head_size,
-                                  int max_seq_len, int rot_dim, float base, int dtype, cudaStream_t st) {
+                                  int max_seq_len, int rot_dim, float base, int dtype, cudaStream_t st, const int *block_table, int max_pages) {
     const int vec = dtype == B200_F32 ? 4 : 8;
     if (head_size % (2 * vec) != 0 || !aligned16(q) || !aligned16(k_layer) || !aligned16(v_layer) || !aligned16(qkv) || (bias && !aligned16(bias)))
         return B200_ERR_UNSUPPORTED;
     const size_t smem = sizeof(float2) * (size_t)(head_size / 2);
     B200_DISPATCH_DTYPE(dtype, launch_pdl(prefill_qkv_rope_cache_kernel<T>, dim3(num_tokens), dim3(256), smem, st, true, (T *)q, (T *)k_layer,
                                           (T *)v_layer, (const T *)qkv, (const T *)bias, padding_offset, history_len, seq_len, head_num, kv_head_num,
-                                          head_size, max_seq_len, rot_dim, base));
+                                          head_size, block_table ? max_pages * 64 : max_seq_len, rot_dim, base, block_table, max_pages));
     return cuda_status("prefill_qkv_rope_cache launch");
 }
 
@@ -468,12 +472,10 @@ int b200_transpose_remove_padding(const void *src, const int *padding_offset, vo
     return cuda_status("transpose_remove_padding launch");
 }
 
-int b200_context_attention(const void *q, const void *k_cache, const void *v_cache, void *out, const int *padding_offset,
-                           const int *input_len, const int *context_len, int layer, int batch, int head_num, int kv_head_num,
-                           int max_q_len, int max_seq_len, int head_size, int num_tokens, float scale, int dtype,
-                           b200_stream_t stream) {
-    (void)padding_offset;
-    (void)num_tokens;
+static int context_attention_impl(const void *q, const void *k_cache, const void *v_cache, void *out, const int *input_len,
+                                  const int *context_len, int layer, int batch, int head_num, int kv_head_num, int max_q_len, int max_seq_len,
+                                  int head_size, float scale, int dtype, b200_stream_t stream, const int *block_table, int max_pages,
+                                  int num_pages) {
     B200_REQUIRE(q && k_cache && v_cache && out && input_len && context_len, "context_attention: null pointer");
     B200_REQUIRE(batch >= 0 && head_num > 0 && kv_head_num > 0 && head_num % kv_head_num == 0 && max_q_len >= 0 && max_seq_len > 0 &&
                      head_size > 0 && head_size <= 256 && layer >= 0,
@@ -489,12 +491,19 @@ int b200_context_attention(const void *q, const void *k_cache, const void *v_cac
     const size_t smem = sizeof(float) * ((size_t)kCaRows * head_size + (size_t)kCaKeys * (head_size + 1) + (size_t)kCaKeys * head_size +
                                          (size_t)kCaRows * kCaKeys);
     const size_t eb = dtype == B200_F32 ? 4 : 2;
-    const size_t loff = (size_t)layer * batch * kv_head_num * max_seq_len * head_size * eb;
+    // contiguous cache [L, B, Hkv, S, d]; paged pool [L, num_pages, Hkv, 64, d]
+    const size_t loff = block_table ? (size_t)layer * num_pages * kv_head_num * 64 * head_size * eb
+                                    : (size_t)layer * batch * kv_head_num * max_seq_len * head_size * eb;
     // head size 128, 16-bit: tcgen05 / TMEM flash attention (context_attn_tc.cu); everything else: the SIMT tiles below
     {
         const int rc = launch_context_attention_tc(q, (const char *)k_cache + loff, (const char *)v_cache + loff, out, seq_off, input_len,
-                                                   context_len, batch, head_num, kv_head_num, max_q_len, max_seq_len, head_size, scale, dtype, st);
+                                                   context_len, batch, head_num, kv_head_num, max_q_len, max_seq_len, head_size, scale, dtype, st,
+                                                   block_table, max_pages, num_pages);
         if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+    if (block_table) {
+        set_error("context_attention_paged: served by the tensor-core kernel only (head size 128, 16-bit); got head size %d, dtype %d", head_size, dtype);
+        return B200_ERR_UNSUPPORTED;
     }
     dim3 grid((max_q_len + kCaRows - 1) / kCaRows, head_num, batch);
     B200_DISPATCH_DTYPE(dtype, {
@@ -504,6 +513,25 @@ int b200_context_attention(const void *q, const void *k_cache, const void *v_cac
                    (const int *)seq_off, input_len, context_len, head_num, kv_head_num, max_q_len, max_seq_len, head_size, scale);
     });
     return cuda_status("context_attention launch");
+}
+
+int b200_context_attention(const void *q, const void *k_cache, const void *v_cache, void *out, const int *padding_offset,
+                           const int *input_len, const int *context_len, int layer, int batch, int head_num, int kv_head_num,
+                           int max_q_len, int max_seq_len, int head_size, int num_tokens, float scale, int dtype,
+                           b200_stream_t stream) {
+    (void)padding_offset;
+    (void)num_tokens;
+    return context_attention_impl(q, k_cache, v_cache, out, input_len, context_len, layer, batch, head_num, kv_head_num, max_q_len, max_seq_len,
+                                  head_size, scale, dtype, stream, nullptr, 0, 0);
+}
+
+int b200_context_attention_paged(const void *q, const void *k_pool, const void *v_pool, void *out, const int *block_table, const int *input_len,
+                                 const int *context_len, int layer, int batch, int head_num, int kv_head_num, int max_q_len, int num_pages,
+                                 int max_pages_per_seq, int head_size, float scale, int dtype, b200_stream_t stream) {
+    B200_REQUIRE(block_table, "context_attention_paged: null block table");
+    B200_REQUIRE(num_pages >= 1 && max_pages_per_seq >= 1, "context_attention_paged: bad pool (num_pages %d, max_pages_per_seq %d)", num_pages, max_pages_per_seq);
+    return context_attention_impl(q, k_pool, v_pool, out, input_len, context_len, layer, batch, head_num, kv_head_num, max_q_len,
+                                  max_pages_per_seq * 64, head_size, scale, dtype, stream, block_table, max_pages_per_seq, num_pages);
 }
 
 }  // extern "C"
