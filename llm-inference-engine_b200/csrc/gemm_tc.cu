@@ -36,6 +36,9 @@ struct GemmTcParams {
     int rowsA, rowsB, K;
     int tilesA, tiles, kb_total;
     int streamk;   // 0: whole tiles dealt round-robin; 1: the tiles x k-blocks space cut into gridDim.x equal contiguous ranges
+    int dp_tiles;  // tiles [0, dp_tiles) are dealt round-robin as WHOLE tiles, tiles [dp_tiles, tiles) are cut stream-K style: 0 for the
+                   // HBM-bound decode shapes (all stream-K); a multiple of the grid for prefill shapes whose tile count is not (the
+                   // last, partial wave is spread over every SM instead of leaving most of them idle); = tiles: no stream-K at all
     int maxslots;  // stream-K: partial slots reserved per tile
     int bn;        // UMMA N: rows of B per tile, multiple of 16, <= 256
     int stages;
@@ -60,7 +63,7 @@ struct SegIter {
     int item, G;
     __device__ SegIter(const GemmTcParams &pp) : p(pp) {
         G = gridDim.x;
-        total = (long long)p.tiles * p.kb_total;
+        total = (long long)(p.tiles - p.dp_tiles) * p.kb_total;  // the stream-K part
         item = blockIdx.x;
         g = start(blockIdx.x);
         gend = start(blockIdx.x + 1);
@@ -68,18 +71,18 @@ struct SegIter {
     __device__ long long start(int c) const { return (long long)c * total / G; }
     __device__ int owner(long long gg) const { return (int)(((gg + 1) * G + total - 1) / total) - 1; }  // max c: start(c) <= gg
     __device__ bool next(Seg &s) {
-        if (!p.streamk) {
-            if (item >= p.tiles) return false;
+        if (item < p.dp_tiles) {  // whole tiles first
             s.tile = item, s.kb0 = 0, s.kb1 = p.kb_total, s.slot = 0, s.nslots = 1;
             item += G;
             return true;
         }
         if (g >= gend) return false;
-        s.tile = (int)(g / p.kb_total);
-        s.kb0 = (int)(g - (long long)s.tile * p.kb_total);
+        const int t = (int)(g / p.kb_total);  // index inside the stream-K part
+        s.tile = p.dp_tiles + t;
+        s.kb0 = (int)(g - (long long)t * p.kb_total);
         const long long len = min((long long)(p.kb_total - s.kb0), gend - g);
         s.kb1 = s.kb0 + (int)len;
-        const int first = owner((long long)s.tile * p.kb_total), last = owner((long long)(s.tile + 1) * p.kb_total - 1);
+        const int first = owner((long long)t * p.kb_total), last = owner((long long)(t + 1) * p.kb_total - 1);
         s.slot = (int)blockIdx.x - first;
         s.nslots = last - first + 1;
         g += len;
@@ -293,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn);
             const int i = ta * kBM + q * 32 + lane;  // row of A this thread owns
             const int j0 = tb * p.bn;
-            if (p.swiglu_inter) {
+            if (p.swiglu_inter && sg.nslots == 1) {
                 // gate in accumulator columns [0, 128), up in [128, 256): both rounded to T first (the reference's linear writes a T
                 // tensor that launchSiluAndMul reads back, src/kernels/silu_and_mul.cu:6-41), same expression as silu_and_mul_kernel
                 for (int c = 0; c < 128; c += 16) {
@@ -333,10 +336,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(tempty0 + 8 * acc);
-            } else {
+            } else if (p.swap) {
                 // shared tile: publish this CTA's fp32 partial [bn][128] (coalesced over lanes); the last arriver reduces
                 const size_t tile_floats = (size_t)p.bn * kBM;
-                float *part = p.partial + ((size_t)sg.tile * p.maxslots + sg.slot) * tile_floats;
+                const int st = sg.tile - p.dp_tiles;  // partial slots and tickets are indexed inside the stream-K part
+                float *part = p.partial + ((size_t)st * p.maxslots + sg.slot) * tile_floats;
                 for (int c = 0; c < p.bn; c += 16) {
                     uint32_t r[16];
                     tc_ld16(taddr + c, r);
@@ -349,14 +353,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) bar_arrive(tempty0 + 8 * acc);  // the accumulator is free: the MMA warp may start the next segment
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[sg.tile], (unsigned)(sg.nslots - 1)) == (unsigned)(sg.nslots - 1);
+                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[st], (unsigned)(sg.nslots - 1)) == (unsigned)(sg.nslots - 1);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const bool last = *flag_slot != 0;
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot may be rewritten by the next segment
                 if (last) {
                     __threadfence();
                     // 128 threads x float4: element f = (column c, 4 consecutive A rows); slots added in order (deterministic)
-                    const float4 *pt = reinterpret_cast<const float4 *>(p.partial + (size_t)sg.tile * p.maxslots * tile_floats);
+                    const float4 *pt = reinterpret_cast<const float4 *>(p.partial + (size_t)st * p.maxslots * tile_floats);
                     const int nf = p.bn * (kBM / 4), slot_f4 = (int)(tile_floats / 4);
                     constexpr int U = 4;
                     for (int f0 = ep_tid; f0 < nf; f0 += 128 * U) {
@@ -380,24 +384,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int c = f / (kBM / 4), ii = ta * kBM + (f % (kBM / 4)) * 4;
                             if (j0 + c >= p.rowsB) continue;
                             const float v[4] = {sum[u].x, sum[u].y, sum[u].z, sum[u].w};
-                            if (p.swap) {
-                                T *dst = C + (size_t)(j0 + c) * p.ldc + ii;
-                                if (ii + 3 < p.rowsA && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
-                                    uint2 pk;
-                                    const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
-                                    pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
-                                    pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
-                                    *reinterpret_cast<uint2 *>(dst) = pk;
-                                } else {
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        if (ii + e < p.rowsA) dst[e] = Elem<T>::from_f(v[e]);
-                                }
+                            T *dst = C + (size_t)(j0 + c) * p.ldc + ii;
+                            if (ii + 3 < p.rowsA && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
+                                uint2 pk;
+                                const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
+                                pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+                                pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
+                                *reinterpret_cast<uint2 *>(dst) = pk;
                             } else {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
-                                    if (ii + e < p.rowsA) C[(size_t)(ii + e) * p.ldc + j0 + c] = Elem<T>::from_f(v[e]);
+                                    if (ii + e < p.rowsA) dst[e] = Elem<T>::from_f(v[e]);
                             }
+                        }
+                    }
+                }
+            } else {
+                // shared tile of a prefill-shaped GEMM (the stream-K tail): fp32 partial, ROW-major [128][bn] -- a thread owns a row of the
+                // accumulator and writes 64 contiguous bytes per tcgen05.ld; the last arriver adds the slots in order and stores rows
+                // of C with coalesced 8-byte stores (SwiGLU: the activation is applied to the reduced gate / up halves)
+                const size_t tile_floats = (size_t)p.bn * kBM;
+                const int st = sg.tile - p.dp_tiles;
+                float *part = p.partial + ((size_t)st * p.maxslots + sg.slot) * tile_floats + (size_t)(q * 32 + lane) * p.bn;
+                for (int c = 0; c < p.bn; c += 16) {
+                    uint32_t r[16];
+                    tc_ld16(taddr + c, r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4)
+                        __stcg(reinterpret_cast<float4 *>(part + c + e),
+                               make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(tempty0 + 8 * acc);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[st], (unsigned)(sg.nslots - 1)) == (unsigned)(sg.nslots - 1);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = *flag_slot != 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (last) {
+                    __threadfence();
+                    const float *pt = p.partial + (size_t)st * p.maxslots * tile_floats;
+                    const int ncol = p.swiglu_inter ? 128 : p.bn;        // output columns of the tile
+                    const int col0 = p.swiglu_inter ? tb * 128 : j0;
+                    const int c4n = ncol / 4;                             // float4 groups per output row (bn is a multiple of 16)
+                    for (int f = ep_tid; f < kBM * c4n; f += 128) {
+                        const int row = f / c4n, c = (f % c4n) * 4;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), u4 = a;
+                        for (int k2 = 0; k2 < sg.nslots; ++k2) {
+                            const float *src = pt + (size_t)k2 * tile_floats + (size_t)row * p.bn + c;
+                            const float4 v = __ldcg(reinterpret_cast<const float4 *>(src));
+                            a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+                            if (p.swiglu_inter) {
+                                const float4 w = __ldcg(reinterpret_cast<const float4 *>(src + 128));
+                                u4.x += w.x, u4.y += w.y, u4.z += w.z, u4.w += w.w;
+                            }
+                        }
+                        float v[4] = {a.x, a.y, a.z, a.w};
+                        if (p.swiglu_inter) {
+                            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float gf = round_to<T>(v[e]), uf = round_to<T>(uu[e]);
+                                v[e] = (gf / (1.0f + expf(-gf))) * uf;
+                            }
+                        }
+                        const int ii = ta * kBM + row;
+                        if (ii >= p.rowsA) continue;
+                        T *dst = C + (size_t)ii * p.ldc + col0 + c;
+                        if (col0 + c + 3 < p.rowsB && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
+                            uint2 pk;
+                            const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
+                            pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+                            pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
+                            *reinterpret_cast<uint2 *>(dst) = pk;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col0 + c + e < p.rowsB) dst[e] = Elem<T>::from_f(v[e]);
                         }
                     }
                 }
@@ -489,7 +555,7 @@ static int launch_gemm_tc_impl(const void *x, const void *w, void *y, int M, int
     int grid = p.tiles < sms ? p.tiles : sms;
     // Few tiles relative to the SM count (HBM-bound decode shapes): stream-K -- the tiles x k-blocks space is cut into one equal
     // contiguous range per SM, so every SM streams the same number of weight bytes.
-    p.streamk = 0;
+    p.streamk = 0, p.dp_tiles = p.tiles;
     if (swap && p.tiles < 4 * sms && total >= 2 * sms) {
         const int g2 = (int)(total < sms ? total : sms);
         const long long per = total / g2;  // >= 2 k-blocks per CTA
@@ -498,9 +564,26 @@ static int launch_gemm_tc_impl(const void *x, const void *w, void *y, int M, int
         if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
         const size_t need = (size_t)p.tiles * maxslots * p.bn * kBM * sizeof(float);
         if (need <= ws.scratch_bytes && (size_t)p.tiles <= ws.n_tickets) {
-            p.streamk = 1, p.maxslots = maxslots, grid = g2;
+            p.streamk = 1, p.dp_tiles = 0, p.maxslots = maxslots, grid = g2;
             p.partial = reinterpret_cast<float *>(ws.scratch);
             p.tickets = ws.tickets;
+        }
+    } else if (!swap && p.tiles > sms && p.tiles % sms != 0) {
+        // Prefill shapes (tensor-pipe bound): whole waves of whole tiles, then the last, partial wave cut stream-K style over ALL SMs --
+        // 256 tiles on 148 SMs cost 1.73 tile times instead of 2 (7B O / down projection at 2048 tokens; QKV: 5.19 instead of 6)
+        const int tail = p.tiles % sms;
+        const long long tail_total = (long long)tail * p.kb_total;
+        const long long per = tail_total / sms;
+        if (per >= 2) {
+            const int maxslots = (int)((p.kb_total + per - 1) / per) + 1;
+            Workspace ws;
+            if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
+            const size_t need = (size_t)tail * maxslots * p.bn * kBM * sizeof(float);
+            if (need <= ws.scratch_bytes && (size_t)tail <= ws.n_tickets) {
+                p.streamk = 1, p.dp_tiles = p.tiles - tail, p.maxslots = maxslots, grid = sms;
+                p.partial = reinterpret_cast<float *>(ws.scratch);
+                p.tickets = ws.tickets;
+            }
         }
     }
     p.acc_bufs = 2 * p.bn <= 512 ? 2 : 1;

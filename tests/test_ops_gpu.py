@@ -122,10 +122,13 @@ def test_linear_dense(M, K, N, layout, dtype):
 
 @pytest.mark.parametrize("dtype", ["bf16", "f16"])
 @pytest.mark.parametrize("M,K,N", [(5, 64, 128), (8, 4096, 4096), (16, 11008, 512), (33, 1024, 1000), (128, 512, 384), (129, 256, 256),
-                                   (300, 4096, 1024), (1024, 1024, 776), (2048, 4096, 512)])
+                                   (300, 4096, 1024), (1024, 1024, 776), (2048, 4096, 512), (2048, 4096, 4096), (2048, 1024, 12288),
+                                   (1100, 704, 4900)])
 def test_linear_tensor_core_gemm(M, K, N, dtype):
     """M > 4, dense 16-bit, [N,K] weights: the tcgen05 / TMEM GEMM (gemm_tc.cu) -- swap-AB + split-K up to 128 rows, 128x256 tiles
-    above -- against an fp32 matmul of the same (rounded) inputs.  Integer-valued inputs must come out exact."""
+    above -- against an fp32 matmul of the same (rounded) inputs.  Integer-valued inputs must come out exact.  The last three shapes have
+    more tiles than SMs and not a multiple of them (256, 768 and 180 tiles on 148 SMs): whole waves of whole tiles, then a stream-K tail
+    whose tiles are shared by several CTAs (fp32 partials, fixed-order reduction; ragged M / N edges inside shared tiles)."""
     import torch
 
     mod = b200()
@@ -318,7 +321,15 @@ def test_linear_swiglu_fused_epilogue_is_linear_then_silu_and_mul_bit_for_bit(M,
     fused = to_np(mod.linear_swiglu(xd, wd))
     gu = mod.linear(xd, wd)
     two = to_np(mod.silu_and_mul(gu.view(M, 2, inter)))
-    assert np.array_equal(fused, two), f"fused epilogue differs from the two launchers: max {np.abs(fused - two).max():.3e}"
+    tiles, sms = -(-M // 128) * -(-inter // 128), mod.lib().b200_sm_count()
+    if tiles <= sms or tiles % sms == 0:
+        assert np.array_equal(fused, two), f"fused epilogue differs from the two launchers: max {np.abs(fused - two).max():.3e}"
+    else:
+        # more tiles than SMs: the last partial wave is cut stream-K style, and the fused and the plain GEMM share DIFFERENT tiles between
+        # CTAs (fp32 partial sums added in a different grouping): equal to the last bit of T almost everywhere, never further than the
+        # dtype's tolerance
+        assert_close(fused, two, dtype, "fused gate_up + swiglu vs the two launchers (stream-K tail)")
+        assert (fused != two).mean() < 0.02
     if M * K * inter <= 316 * 512 * 768 * 8:
         ref = oracle.silu_and_mul(rounded(oracle.linear(x, w, "nk"), dtype).reshape(M, 2, inter))
         assert_close(fused, ref, dtype, "fused gate_up + swiglu")
