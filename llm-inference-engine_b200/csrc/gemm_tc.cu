@@ -71,22 +71,26 @@ struct SegIter {
     __device__ long long start(int c) const { return (long long)c * total / G; }
     __device__ int owner(long long gg) const { return (int)(((gg + 1) * G + total - 1) / total) - 1; }  // max c: start(c) <= gg
     __device__ bool next(Seg &s) {
-        if (item < p.dp_tiles) {  // whole tiles first
+        // the stream-K share FIRST: every CTA works on its (equal) range at the same time, so the CTAs that share a tile arrive together,
+        // and the last arriver's reduction overlaps the MMAs of the whole tiles that follow (two accumulators: the MMA warp runs ahead)
+        if (g < gend) {
+            const int t = (int)(g / p.kb_total);  // index inside the stream-K part
+            s.tile = p.dp_tiles + t;
+            s.kb0 = (int)(g - (long long)t * p.kb_total);
+            const long long len = min((long long)(p.kb_total - s.kb0), gend - g);
+            s.kb1 = s.kb0 + (int)len;
+            const int first = owner((long long)t * p.kb_total), last = owner((long long)(t + 1) * p.kb_total - 1);
+            s.slot = (int)blockIdx.x - first;
+            s.nslots = last - first + 1;
+            g += len;
+            return true;
+        }
+        if (item < p.dp_tiles) {  // then whole tiles, dealt round-robin
             s.tile = item, s.kb0 = 0, s.kb1 = p.kb_total, s.slot = 0, s.nslots = 1;
             item += G;
             return true;
         }
-        if (g >= gend) return false;
-        const int t = (int)(g / p.kb_total);  // index inside the stream-K part
-        s.tile = p.dp_tiles + t;
-        s.kb0 = (int)(g - (long long)t * p.kb_total);
-        const long long len = min((long long)(p.kb_total - s.kb0), gend - g);
-        s.kb1 = s.kb0 + (int)len;
-        const int first = owner((long long)t * p.kb_total), last = owner((long long)(t + 1) * p.kb_total - 1);
-        s.slot = (int)blockIdx.x - first;
-        s.nslots = last - first + 1;
-        g += len;
-        return true;
+        return false;
     }
 };
 
@@ -430,40 +434,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int ncol = p.swiglu_inter ? 128 : p.bn;        // output columns of the tile
                     const int col0 = p.swiglu_inter ? tb * 128 : j0;
                     const int c4n = ncol / 4;                             // float4 groups per output row (bn is a multiple of 16)
-                    for (int f = ep_tid; f < kBM * c4n; f += 128) {
-                        const int row = f / c4n, c = (f % c4n) * 4;
-                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), u4 = a;
+                    // U float4 groups per thread and pass, every slot's loads of a pass requested before the first add: the reduction is a
+                    // chain of L2 round trips (a rolled loop ran 64 dependent iterations per tile: 60+ us)
+                    constexpr int U = 8;
+                    for (int f0 = ep_tid; f0 < kBM * c4n; f0 += 128 * U) {
+                        float4 a[U], u4[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) a[u] = u4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int k2 = 0; k2 < sg.nslots; ++k2) {
-                            const float *src = pt + (size_t)k2 * tile_floats + (size_t)row * p.bn + c;
-                            const float4 v = __ldcg(reinterpret_cast<const float4 *>(src));
-                            a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+                            float4 v[U], w[U];
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int f = f0 + u * 128;
+                                v[u] = w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (f < kBM * c4n) {
+                                    const float *src = pt + (size_t)k2 * tile_floats + (size_t)(f / c4n) * p.bn + (f % c4n) * 4;
+                                    v[u] = __ldcg(reinterpret_cast<const float4 *>(src));
+                                    if (p.swiglu_inter) w[u] = __ldcg(reinterpret_cast<const float4 *>(src + 128));
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                a[u].x += v[u].x, a[u].y += v[u].y, a[u].z += v[u].z, a[u].w += v[u].w;
+                                u4[u].x += w[u].x, u4[u].y += w[u].y, u4[u].z += w[u].z, u4[u].w += w[u].w;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int f = f0 + u * 128;
+                            if (f >= kBM * c4n) continue;
+                            const int row = f / c4n, c = (f % c4n) * 4;
+                            float v[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
                             if (p.swiglu_inter) {
-                                const float4 w = __ldcg(reinterpret_cast<const float4 *>(src + 128));
-                                u4.x += w.x, u4.y += w.y, u4.z += w.z, u4.w += w.w;
-                            }
-                        }
-                        float v[4] = {a.x, a.y, a.z, a.w};
-                        if (p.swiglu_inter) {
-                            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+                                const float uu[4] = {u4[u].x, u4[u].y, u4[u].z, u4[u].w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float gf = round_to<T>(v[e]), uf = round_to<T>(uu[e]);
-                                v[e] = (gf / (1.0f + expf(-gf))) * uf;
+                                for (int e = 0; e < 4; ++e) {
+                                    const float gf = round_to<T>(v[e]), uf = round_to<T>(uu[e]);
+                                    v[e] = (gf / (1.0f + expf(-gf))) * uf;
+                                }
                             }
-                        }
-                        const int ii = ta * kBM + row;
-                        if (ii >= p.rowsA) continue;
-                        T *dst = C + (size_t)ii * p.ldc + col0 + c;
-                        if (col0 + c + 3 < p.rowsB && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
-                            uint2 pk;
-                            const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
-                            pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
-                            pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
-                            *reinterpret_cast<uint2 *>(dst) = pk;
-                        } else {
+                            const int ii = ta * kBM + row;
+                            if (ii >= p.rowsA) continue;
+                            T *dst = C + (size_t)ii * p.ldc + col0 + c;
+                            if (col0 + c + 3 < p.rowsB && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
+                                uint2 pk;
+                                const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
+                                pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+                                pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
+                                *reinterpret_cast<uint2 *>(dst) = pk;
+                            } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (col0 + c + e < p.rowsB) dst[e] = Elem<T>::from_f(v[e]);
+                                for (int e = 0; e < 4; ++e)
+                                    if (col0 + c + e < p.rowsB) dst[e] = Elem<T>::from_f(v[e]);
+                            }
                         }
                     }
                 }
