@@ -36,20 +36,19 @@ struct GemmTcParams {
     int rowsA, rowsB, K;
     int tilesA, tiles, kb_total;
     int streamk;   // 0: whole tiles dealt round-robin; 1: the tiles x k-blocks space cut into gridDim.x equal contiguous ranges
-    int dp_tiles;  // tiles [0, dp_tiles) are dealt round-robin as WHOLE tiles, tiles [dp_tiles, tiles) are cut stream-K style: 0 for the
-                   // HBM-bound decode shapes (all stream-K); a multiple of the grid for prefill shapes whose tile count is not (the
-                   // last, partial wave is spread over every SM instead of leaving most of them idle); = tiles: no stream-K at all
     int maxslots;  // stream-K: partial slots reserved per tile
     int bn;        // UMMA N: rows of B per tile, multiple of 16, <= 256
     int stages;
     int swap;      // 0: C[i*ldc + j]   1: C[j*ldc + i]
     int is_bf16;
     int acc_bufs;  // TMEM accumulators (2 when 2*bn <= 512)
+    int acc_stride;  // TMEM columns between the accumulators: bn, or 256 for the 192..240-column tiles (power-of-two placement)
     unsigned int tmem_cols;
     // SwiGLU epilogue (gate_up linear of the prefill path, launchLinearGemm + launchSiluAndMul in one kernel): B = W [2I, K] with the gate
-    // rows first; tile tb multiplies gate rows [128 tb, +128) AND up rows [I + 128 tb, +128) as one N = 256 tile (two TMA boxes into one
+    // rows first; tile tb multiplies gate rows [hw tb, +hw) AND up rows [I + hw tb, +hw) as one N = 2 hw tile (two TMA boxes into one
     // B stage), the epilogue reads both halves of the accumulator and writes silu(gate) * up: C [rowsA, I], rowsB = I.  0: plain GEMM.
     int swiglu_inter;
+    int swiglu_hw;  // gate (and up) columns per tile: bn = 2 * swiglu_hw (128, 112 or 96: whichever wastes least of the last wave)
 };
 
 // One contiguous piece of work of a CTA: k-blocks [kb0, kb1) of one output tile.  nslots > 1: the tile is shared with
@@ -63,7 +62,7 @@ struct SegIter {
     int item, G;
     __device__ SegIter(const GemmTcParams &pp) : p(pp) {
         G = gridDim.x;
-        total = (long long)(p.tiles - p.dp_tiles) * p.kb_total;  // the stream-K part
+        total = (long long)p.tiles * p.kb_total;
         item = blockIdx.x;
         g = start(blockIdx.x);
         gend = start(blockIdx.x + 1);
@@ -71,26 +70,22 @@ struct SegIter {
     __device__ long long start(int c) const { return (long long)c * total / G; }
     __device__ int owner(long long gg) const { return (int)(((gg + 1) * G + total - 1) / total) - 1; }  // max c: start(c) <= gg
     __device__ bool next(Seg &s) {
-        // the stream-K share FIRST: every CTA works on its (equal) range at the same time, so the CTAs that share a tile arrive together,
-        // and the last arriver's reduction overlaps the MMAs of the whole tiles that follow (two accumulators: the MMA warp runs ahead)
-        if (g < gend) {
-            const int t = (int)(g / p.kb_total);  // index inside the stream-K part
-            s.tile = p.dp_tiles + t;
-            s.kb0 = (int)(g - (long long)t * p.kb_total);
-            const long long len = min((long long)(p.kb_total - s.kb0), gend - g);
-            s.kb1 = s.kb0 + (int)len;
-            const int first = owner((long long)t * p.kb_total), last = owner((long long)(t + 1) * p.kb_total - 1);
-            s.slot = (int)blockIdx.x - first;
-            s.nslots = last - first + 1;
-            g += len;
-            return true;
-        }
-        if (item < p.dp_tiles) {  // then whole tiles, dealt round-robin
+        if (!p.streamk) {
+            if (item >= p.tiles) return false;
             s.tile = item, s.kb0 = 0, s.kb1 = p.kb_total, s.slot = 0, s.nslots = 1;
             item += G;
             return true;
         }
-        return false;
+        if (g >= gend) return false;
+        s.tile = (int)(g / p.kb_total);
+        s.kb0 = (int)(g - (long long)s.tile * p.kb_total);
+        const long long len = min((long long)(p.kb_total - s.kb0), gend - g);
+        s.kb1 = s.kb0 + (int)len;
+        const int first = owner((long long)s.tile * p.kb_total), last = owner((long long)(s.tile + 1) * p.kb_total - 1);
+        s.slot = (int)blockIdx.x - first;
+        s.nslots = last - first + 1;
+        g += len;
+        return true;
     }
 };
 
@@ -246,9 +241,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = s_u32(smem + (size_t)s * stage_bytes);
                     bar_expect_tx(full0 + 8 * s, (uint32_t)stage_bytes);
                     tma_load_2d(sa, &tmA, kb * kBK, ta * kBM, full0 + 8 * s);
-                    if (p.swiglu_inter) {  // box = 128 rows: the gate rows, then the up rows of the same columns
-                        tma_load_2d(sa + kATileBytes, &tmB, kb * kBK, tb * 128, full0 + 8 * s);
-                        tma_load_2d(sa + kATileBytes + 128 * kBK * 2, &tmB, kb * kBK, p.swiglu_inter + tb * 128, full0 + 8 * s);
+                    if (p.swiglu_inter) {  // box = hw rows: the gate rows, then the up rows of the same columns
+                        tma_load_2d(sa + kATileBytes, &tmB, kb * kBK, tb * p.swiglu_hw, full0 + 8 * s);
+                        tma_load_2d(sa + kATileBytes + p.swiglu_hw * kBK * 2, &tmB, kb * kBK, p.swiglu_inter + tb * p.swiglu_hw, full0 + 8 * s);
                     } else {
                         tma_load_2d(sa + kATileBytes, &tmB, kb * kBK, tb * p.bn, full0 + 8 * s);
                     }
@@ -265,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int acc = t % p.acc_bufs;
             bar_wait(tempty0 + 8 * acc, ((t / p.acc_bufs) & 1) ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
             for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++it) {
                 const int s = it % p.stages;
                 bar_wait(full0 + 8 * s, (it / p.stages) & 1);
@@ -297,25 +292,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int acc = t % p.acc_bufs;
             bar_wait(tfull0 + 8 * acc, (t / p.acc_bufs) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
             const int i = ta * kBM + q * 32 + lane;  // row of A this thread owns
             const int j0 = tb * p.bn;
-            if (p.swiglu_inter && sg.nslots == 1) {
-                // gate in accumulator columns [0, 128), up in [128, 256): both rounded to T first (the reference's linear writes a T
+            if (p.swiglu_inter) {
+                // gate in accumulator columns [0, hw), up in [hw, 2 hw): both rounded to T first (the reference's linear writes a T
                 // tensor that launchSiluAndMul reads back, src/kernels/silu_and_mul.cu:6-41), same expression as silu_and_mul_kernel
-                for (int c = 0; c < 128; c += 16) {
+                const int hw = p.swiglu_hw;
+                for (int c = 0; c < hw; c += 16) {
                     uint32_t g[16], u[16];
                     tc_ld16(taddr + c, g);
-                    tc_ld16(taddr + 128 + c, u);
+                    tc_ld16(taddr + hw + c, u);
                     tc_wait_ld();
-                    const int valid = min(16, p.rowsB - (tb * 128 + c));
+                    const int valid = min(16, p.rowsB - (tb * hw + c));
                     if (i < p.rowsA && valid > 0) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             const float gf = round_to<T>(__uint_as_float(g[e])), uf = round_to<T>(__uint_as_float(u[e]));
                             g[e] = __float_as_uint((gf / (1.0f + expf(-gf))) * uf);
                         }
-                        store_row16<T>(C + (size_t)i * p.ldc + tb * 128 + c, g, valid);
+                        store_row16<T>(C + (size_t)i * p.ldc + tb * hw + c, g, valid);
                     }
                 }
                 tc_fence_before();
@@ -340,11 +336,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(tempty0 + 8 * acc);
-            } else if (p.swap) {
+            } else {
                 // shared tile: publish this CTA's fp32 partial [bn][128] (coalesced over lanes); the last arriver reduces
                 const size_t tile_floats = (size_t)p.bn * kBM;
-                const int st = sg.tile - p.dp_tiles;  // partial slots and tickets are indexed inside the stream-K part
-                float *part = p.partial + ((size_t)st * p.maxslots + sg.slot) * tile_floats;
+                float *part = p.partial + ((size_t)sg.tile * p.maxslots + sg.slot) * tile_floats;
                 for (int c = 0; c < p.bn; c += 16) {
                     uint32_t r[16];
                     tc_ld16(taddr + c, r);
@@ -357,14 +352,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) bar_arrive(tempty0 + 8 * acc);  // the accumulator is free: the MMA warp may start the next segment
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[st], (unsigned)(sg.nslots - 1)) == (unsigned)(sg.nslots - 1);
+                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[sg.tile], (unsigned)(sg.nslots - 1)) == (unsigned)(sg.nslots - 1);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const bool last = *flag_slot != 0;
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_slot may be rewritten by the next segment
                 if (last) {
                     __threadfence();
                     // 128 threads x float4: element f = (column c, 4 consecutive A rows); slots added in order (deterministic)
-                    const float4 *pt = reinterpret_cast<const float4 *>(p.partial + (size_t)st * p.maxslots * tile_floats);
+                    const float4 *pt = reinterpret_cast<const float4 *>(p.partial + (size_t)sg.tile * p.maxslots * tile_floats);
                     const int nf = p.bn * (kBM / 4), slot_f4 = (int)(tile_floats / 4);
                     constexpr int U = 4;
                     for (int f0 = ep_tid; f0 < nf; f0 += 128 * U) {
@@ -388,104 +383,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int c = f / (kBM / 4), ii = ta * kBM + (f % (kBM / 4)) * 4;
                             if (j0 + c >= p.rowsB) continue;
                             const float v[4] = {sum[u].x, sum[u].y, sum[u].z, sum[u].w};
-                            T *dst = C + (size_t)(j0 + c) * p.ldc + ii;
-                            if (ii + 3 < p.rowsA && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
-                                uint2 pk;
-                                const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
-                                pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
-                                pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
-                                *reinterpret_cast<uint2 *>(dst) = pk;
+                            if (p.swap) {
+                                T *dst = C + (size_t)(j0 + c) * p.ldc + ii;
+                                if (ii + 3 < p.rowsA && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
+                                    uint2 pk;
+                                    const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
+                                    pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
+                                    pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
+                                    *reinterpret_cast<uint2 *>(dst) = pk;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (ii + e < p.rowsA) dst[e] = Elem<T>::from_f(v[e]);
+                                }
                             } else {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
-                                    if (ii + e < p.rowsA) dst[e] = Elem<T>::from_f(v[e]);
-                            }
-                        }
-                    }
-                }
-            } else {
-                // shared tile of a prefill-shaped GEMM (the stream-K tail): fp32 partial, ROW-major [128][bn] -- a thread owns a row of the
-                // accumulator and writes 64 contiguous bytes per tcgen05.ld; the last arriver adds the slots in order and stores rows
-                // of C with coalesced 8-byte stores (SwiGLU: the activation is applied to the reduced gate / up halves)
-                const size_t tile_floats = (size_t)p.bn * kBM;
-                const int st = sg.tile - p.dp_tiles;
-                float *part = p.partial + ((size_t)st * p.maxslots + sg.slot) * tile_floats + (size_t)(q * 32 + lane) * p.bn;
-                for (int c = 0; c < p.bn; c += 16) {
-                    uint32_t r[16];
-                    tc_ld16(taddr + c, r);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4)
-                        __stcg(reinterpret_cast<float4 *>(part + c + e),
-                               make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) bar_arrive(tempty0 + 8 * acc);
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (ep_tid == 0) *flag_slot = atomicInc(&p.tickets[st], (unsigned)(sg.nslots - 1)) == (unsigned)(sg.nslots - 1);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const bool last = *flag_slot != 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (last) {
-                    __threadfence();
-                    const float *pt = p.partial + (size_t)st * p.maxslots * tile_floats;
-                    const int ncol = p.swiglu_inter ? 128 : p.bn;        // output columns of the tile
-                    const int col0 = p.swiglu_inter ? tb * 128 : j0;
-                    const int c4n = ncol / 4;                             // float4 groups per output row (bn is a multiple of 16)
-                    // U float4 groups per thread and pass, every slot's loads of a pass requested before the first add: the reduction is a
-                    // chain of L2 round trips (a rolled loop ran 64 dependent iterations per tile: 60+ us)
-                    constexpr int U = 8;
-                    for (int f0 = ep_tid; f0 < kBM * c4n; f0 += 128 * U) {
-                        float4 a[U], u4[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u) a[u] = u4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int k2 = 0; k2 < sg.nslots; ++k2) {
-                            float4 v[U], w[U];
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const int f = f0 + u * 128;
-                                v[u] = w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (f < kBM * c4n) {
-                                    const float *src = pt + (size_t)k2 * tile_floats + (size_t)(f / c4n) * p.bn + (f % c4n) * 4;
-                                    v[u] = __ldcg(reinterpret_cast<const float4 *>(src));
-                                    if (p.swiglu_inter) w[u] = __ldcg(reinterpret_cast<const float4 *>(src + 128));
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                a[u].x += v[u].x, a[u].y += v[u].y, a[u].z += v[u].z, a[u].w += v[u].w;
-                                u4[u].x += w[u].x, u4[u].y += w[u].y, u4[u].z += w[u].z, u4[u].w += w[u].w;
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const int f = f0 + u * 128;
-                            if (f >= kBM * c4n) continue;
-                            const int row = f / c4n, c = (f % c4n) * 4;
-                            float v[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
-                            if (p.swiglu_inter) {
-                                const float uu[4] = {u4[u].x, u4[u].y, u4[u].z, u4[u].w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float gf = round_to<T>(v[e]), uf = round_to<T>(uu[e]);
-                                    v[e] = (gf / (1.0f + expf(-gf))) * uf;
-                                }
-                            }
-                            const int ii = ta * kBM + row;
-                            if (ii >= p.rowsA) continue;
-                            T *dst = C + (size_t)ii * p.ldc + col0 + c;
-                            if (col0 + c + 3 < p.rowsB && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && sizeof(T) == 2) {
-                                uint2 pk;
-                                const T a0 = Elem<T>::from_f(v[0]), a1 = Elem<T>::from_f(v[1]), a2 = Elem<T>::from_f(v[2]), a3 = Elem<T>::from_f(v[3]);
-                                pk.x = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a0)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a1)) << 16);
-                                pk.y = (uint32_t)(*reinterpret_cast<const unsigned short *>(&a2)) | ((uint32_t)(*reinterpret_cast<const unsigned short *>(&a3)) << 16);
-                                *reinterpret_cast<uint2 *>(dst) = pk;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (col0 + c + e < p.rowsB) dst[e] = Elem<T>::from_f(v[e]);
+                                    if (ii + e < p.rowsA) C[(size_t)(ii + e) * p.ldc + j0 + c] = Elem<T>::from_f(v[e]);
                             }
                         }
                     }
@@ -565,20 +479,36 @@ static int launch_gemm_tc_impl(const void *x, const void *w, void *y, int M, int
         rows_b_map = N;
     }
     const int sms = sm_count();
+    const int tiles_a = ((swap ? N : M) + kBM - 1) / kBM;
+    // Tile width of the prefill shapes: the widest tile is the most efficient one, but the number of waves is an integer -- 768 tiles of
+    // 256 columns on 148 SMs (7B QKV projection at 2048 tokens) take 6 waves for 5.19 waves of work.  Choose the width whose
+    // waves x width is smallest (ties: the wider one): 224 for that shape (880 tiles, 5.95 waves: -12.5 %), 240 for N = 4096.
+    auto waves_cost = [&](int cols, int width) { return (long long)((tiles_a * ((cols + width - 1) / width) + sms - 1) / sms) * width; };
     if (swiglu_inter) {
-        p.bn = 256, p.rowsB = swiglu_inter, p.ldc = swiglu_inter;  // N = I output columns; the MMA tile is 128 gate + 128 up rows
+        int hw = 128;
+        for (int cand : {112, 96})
+            if (waves_cost(swiglu_inter, cand) < waves_cost(swiglu_inter, hw)) hw = cand;
+        p.swiglu_hw = hw;
+        p.bn = 2 * hw, p.rowsB = swiglu_inter, p.ldc = swiglu_inter;  // N = I output columns; the MMA tile is hw gate + hw up rows
         rows_b_map = 2 * swiglu_inter;
-    } else if (!swap && p.bn == 256 && ((M + kBM - 1) / kBM) * ((N + 255) / 256) * 2 <= sms) {
-        p.bn = 128;  // under half a wave: more, smaller tiles
+    } else if (!swap && p.bn == 256) {
+        if (tiles_a * ((N + 255) / 256) * 2 <= sms) {
+            p.bn = 128;  // under half a wave: more, smaller tiles
+        } else {
+            int bn = 256;
+            for (int cand : {240, 224, 208, 192})
+                if (waves_cost(N, cand) < waves_cost(N, bn)) bn = cand;
+            p.bn = bn;
+        }
     }
     p.tilesA = (p.rowsA + kBM - 1) / kBM;
-    const int tilesB = swiglu_inter ? (swiglu_inter + 127) / 128 : (p.rowsB + p.bn - 1) / p.bn;
+    const int tilesB = swiglu_inter ? (swiglu_inter + p.swiglu_hw - 1) / p.swiglu_hw : (p.rowsB + p.bn - 1) / p.bn;
     p.tiles = p.tilesA * tilesB;
     const long long total = (long long)p.tiles * p.kb_total;
     int grid = p.tiles < sms ? p.tiles : sms;
     // Few tiles relative to the SM count (HBM-bound decode shapes): stream-K -- the tiles x k-blocks space is cut into one equal
     // contiguous range per SM, so every SM streams the same number of weight bytes.
-    p.streamk = 0, p.dp_tiles = p.tiles;
+    p.streamk = 0;
     if (swap && p.tiles < 4 * sms && total >= 2 * sms) {
         const int g2 = (int)(total < sms ? total : sms);
         const long long per = total / g2;  // >= 2 k-blocks per CTA
@@ -587,30 +517,14 @@ static int launch_gemm_tc_impl(const void *x, const void *w, void *y, int M, int
         if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
         const size_t need = (size_t)p.tiles * maxslots * p.bn * kBM * sizeof(float);
         if (need <= ws.scratch_bytes && (size_t)p.tiles <= ws.n_tickets) {
-            p.streamk = 1, p.dp_tiles = 0, p.maxslots = maxslots, grid = g2;
+            p.streamk = 1, p.maxslots = maxslots, grid = g2;
             p.partial = reinterpret_cast<float *>(ws.scratch);
             p.tickets = ws.tickets;
         }
-    } else if (!swap && p.tiles > sms && p.tiles % sms != 0) {
-        // Prefill shapes (tensor-pipe bound): whole waves of whole tiles, then the last, partial wave cut stream-K style over ALL SMs --
-        // 256 tiles on 148 SMs cost 1.73 tile times instead of 2 (7B O / down projection at 2048 tokens; QKV: 5.19 instead of 6)
-        const int tail = p.tiles % sms;
-        const long long tail_total = (long long)tail * p.kb_total;
-        const long long per = tail_total / sms;
-        if (per >= 2) {
-            const int maxslots = (int)((p.kb_total + per - 1) / per) + 1;
-            Workspace ws;
-            if (!get_workspace(&ws)) return B200_ERR_WORKSPACE;
-            const size_t need = (size_t)tail * maxslots * p.bn * kBM * sizeof(float);
-            if (need <= ws.scratch_bytes && (size_t)tail <= ws.n_tickets) {
-                p.streamk = 1, p.dp_tiles = p.tiles - tail, p.maxslots = maxslots, grid = sms;
-                p.partial = reinterpret_cast<float *>(ws.scratch);
-                p.tickets = ws.tickets;
-            }
-        }
     }
     p.acc_bufs = 2 * p.bn <= 512 ? 2 : 1;
-    p.tmem_cols = pow2_cols(p.acc_bufs * p.bn);
+    p.acc_stride = p.bn > 128 ? 256 : p.bn;
+    p.tmem_cols = pow2_cols(p.acc_bufs == 2 ? p.acc_stride + p.bn : p.bn);
     const int stage_bytes = kATileBytes + p.bn * kBK * 2;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -619,7 +533,7 @@ static int launch_gemm_tc_impl(const void *x, const void *w, void *y, int M, int
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + (2 * kMaxStages + 4) * 8 + 16;
 
     CUtensorMap tmA, tmB;
-    if (!make_map(&tmA, a_ptr, p.rowsA, K, kBM, bf16) || !make_map(&tmB, b_ptr, rows_b_map, K, swiglu_inter ? 128 : p.bn, bf16)) {
+    if (!make_map(&tmA, a_ptr, p.rowsA, K, kBM, bf16) || !make_map(&tmB, b_ptr, rows_b_map, K, swiglu_inter ? p.swiglu_hw : p.bn, bf16)) {
         set_error("gemm_tc: cuTensorMapEncodeTiled failed (rows %d/%d, K %d)", p.rowsA, p.rowsB, K);
         return B200_ERR_CUDA;
     }
