@@ -482,12 +482,13 @@ static int launch_gemm_tc_impl(const void *x, const void *w, void *y, int M, int
     const int tiles_a = ((swap ? N : M) + kBM - 1) / kBM;
     // Tile width of the prefill shapes: the widest tile is the most efficient one, but the number of waves is an integer -- 768 tiles of
     // 256 columns on 148 SMs (7B QKV projection at 2048 tokens) take 6 waves for 5.19 waves of work.  Choose the width whose
-    // waves x width is smallest (ties: the wider one): 224 for that shape (880 tiles, 5.95 waves: -12.5 %), 240 for N = 4096.
+    // waves x width is smallest (ties: the wider one): 224 for that shape (880 tiles, 5.95 waves), 240 for N = 4096.  Measured gain 2-3 %
+    // per GEMM, not the 6-12 % of the wave count: a narrower MMA re-reads the 128-row A tile more often per flop.
     auto waves_cost = [&](int cols, int width) { return (long long)((tiles_a * ((cols + width - 1) / width) + sms - 1) / sms) * width; };
     if (swiglu_inter) {
-        int hw = 128;
-        for (int cand : {112, 96})
-            if (waves_cost(swiglu_inter, cand) < waves_cost(swiglu_inter, hw)) hw = cand;
+        // measured (7B, 2048 tokens): 2 x 112 columns (11 waves instead of 10 of 2 x 128) is 6 % SLOWER -- the narrower MMA re-reads the
+        // A tile more often per flop than the better wave count saves; the half width stays a parameter, the choice is 128
+        const int hw = 128;
         p.swiglu_hw = hw;
         p.bn = 2 * hw, p.rowsB = swiglu_inter, p.ldc = swiglu_inter;  // N = I output columns; the MMA tile is hw gate + hw up rows
         rows_b_map = 2 * swiglu_inter;
