@@ -324,6 +324,7 @@ int b200_batcher_step(b200_batcher_t *b, b200_decoder_t *dec, const b200_generat
     B200_REQUIRE(workspace_bytes >= k.total, "batcher_step: need %zu bytes of workspace, got %zu", k.total, workspace_bytes);
     b200_decoder_config_t c;
     b200_decoder_get_config(dec, &c);
+    NvtxRange range("b200 batcher iteration");
     b200_batch_plan_t plan;
     if ((rc = b200_batcher_plan(b, &plan)) != B200_OK) return rc;
     for (int id : b->p_ids)
@@ -351,6 +352,7 @@ int b200_batcher_step(b200_batcher_t *b, b200_decoder_t *dec, const b200_generat
 
     // ---- admitted requests: one packed prefill pass, first token from the last prompt position of each
     if (plan.n_prefill > 0) {
+        NvtxRange phase("admitted: prefill");
         const int n = plan.n_prefill, T = plan.prefill_tokens;
         std::vector<int> hl((size_t)3 * n);
         for (int i = 0; i < n; ++i) hl[i] = b->p_lens[i], hl[n + i] = 0, hl[2 * n + i] = b->p_lens[i];
@@ -378,6 +380,7 @@ int b200_batcher_step(b200_batcher_t *b, b200_decoder_t *dec, const b200_generat
     }
     // ---- running sequences: one decode step, every row at its own position, through the block table
     if (plan.n_decode > 0) {
+        NvtxRange phase("running: decode step");
         const int n = plan.n_decode;
         if (!up(toks, b->d_tok.data(), (size_t)n * sizeof(int)) || !up(steps, b->d_steps.data(), (size_t)n * sizeof(int)) ||
             !up(bt_d, b->d_bt.data(), b->d_bt.size() * sizeof(int)) || !up(seq_len, b->d_steps.data(), (size_t)n * sizeof(int)) ||

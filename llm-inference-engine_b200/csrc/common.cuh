@@ -27,6 +27,20 @@ int sm_count();
         }                                       \
     } while (0)
 
+// NVTX ranges around the host-side phases (prefill pass, decode step, layers, generation loop, batcher iteration): visible in any
+// NVTX-aware tool (the reference has no tracing beyond printf); the header-only NVTX v3 costs one predicted branch when no
+// tool is attached.  -DB200_NO_NVTX compiles them out.
+#ifndef B200_NO_NVTX
+struct NvtxRange {
+    explicit NvtxRange(const char *name);
+    ~NvtxRange();
+};
+#else
+struct NvtxRange {
+    explicit NvtxRange(const char *) {}
+};
+#endif
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -486,6 +486,7 @@ int b200_decoder_step_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void 
     B200_REQUIRE(hidden && k_cache && v_cache, "decoder_step_tp: null pointer");
     const b200_decoder_config_t &c = dec->cfg;
     B200_REQUIRE(2 * c.num_layers + 1 < 4096, "decoder_step_tp: too many layers for the flag encoding");
+    NvtxRange range("b200 decode step (tensor parallel)");
     cudaStream_t st = as_stream(stream);
     launch_pdl(tp_begin_step_kernel, dim3(1), dim3(32), 0, st, true, reinterpret_cast<unsigned int *>(dec->tp_base[c.tp_rank] + kTpEpochOff));
     if ((rc = cuda_status("tp_begin_step launch")) != B200_OK) return rc;
@@ -514,8 +515,10 @@ int b200_decoder_step(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_
     B200_REQUIRE(dec->cfg.tp_world <= 1, "decoder_step: tensor-parallel engines drive attn_block / ffn_block themselves");
     B200_REQUIRE(hidden && k_cache && v_cache, "decoder_step: null pointer");
     B200_REQUIRE(layer_begin >= 0 && layer_end <= dec->cfg.num_layers && layer_begin < layer_end, "decoder_step: bad layer range");
+    NvtxRange range(dec->block_table ? "b200 decode step (paged)" : dec->steps_dev ? "b200 decode step (ragged)" : "b200 decode step");
     const void *pending = nullptr;
     for (int l = layer_begin; l < layer_end; ++l) {
+        NvtxRange layer_range("layer");
         rc = b200_decoder_attn_block(dec, l, hidden, pending, k_cache, v_cache, dec->y_attn, batch, step, stream);
         if (rc != B200_OK) return rc;
         rc = b200_decoder_ffn_block(dec, l, hidden, dec->y_attn, dec->y_ffn, batch, stream);
@@ -665,8 +668,10 @@ static int prefill_impl(b200_decoder_t *dec, void *hidden, void *k_cache, void *
         }
         return b200_linear(x, w.w, w.scales, w.zeros, out, T, K, N, c.dtype, c.w_format, B200_LAYOUT_NK, c.group, stream);
     };
+    NvtxRange range(block_table ? "b200 prefill (paged)" : "b200 prefill");
     const void *pending = nullptr;  // output of the previous layer's FFN, folded into the residual stream by the next norm
     for (int l = layer_begin; l < layer_end; ++l) {
+        NvtxRange layer_range("layer");
         B200_REQUIRE(dec->layer_set[l], "decoder_prefill: layer %d not set", l);
         const b200_layer_weights_t &w = dec->layers[l];
         // residual <- hidden (+ pending); xn = RMSNorm(residual)
@@ -751,6 +756,7 @@ int b200_lm_head_topk_sample(b200_decoder_t *dec, const void *hidden, const void
     if (rc != B200_OK) return rc;
     B200_REQUIRE(hidden && final_gamma && lm_head && logits, "lm_head_topk_sample: null pointer");
     B200_REQUIRE(vocab > 0, "lm_head_topk_sample: bad vocab");
+    NvtxRange range("b200 lm head + top-k + sampling");
     const b200_decoder_config_t &c = dec->cfg;
     cudaStream_t st = as_stream(stream);
     // final RMSNorm (reference llama.cpp:247-253) fused into the LM-head GEMV; logits in fp32

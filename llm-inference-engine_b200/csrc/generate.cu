@@ -139,6 +139,7 @@ int b200_generate_ragged(b200_decoder_t *dec, const b200_generate_params_t *p, c
         return cuda_status("generate H2D");
     if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_status("generate H2D sync");  // pageable host vectors: done with them here
 
+    NvtxRange range("b200 generate");
     // ---- first token: embedding -> context decoder -> last prompt token of every sequence (a row gather) -> sampling tail
     if ((rc = b200_input_embedding(ids, p->embedding, hidden_prompt, T, c.hidden, c.dtype, stream)) != B200_OK) return rc;
     rc = b200_decoder_prefill(dec, hidden_prompt, k_cache, v_cache, lens, lens + batch, lens + 2 * batch, batch, max_len, T, w + k.prefill,

@@ -3,7 +3,17 @@
 
 #include <mutex>
 
+#ifndef B200_NO_NVTX
+#include <nvtx3/nvToolsExt.h>
+#endif
+
 namespace b200 {
+
+#ifndef B200_NO_NVTX
+NvtxRange::NvtxRange(const char *name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+#endif
+
 
 static thread_local char g_err[512] = "";
 
