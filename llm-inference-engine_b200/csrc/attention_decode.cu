@@ -116,7 +116,7 @@ __device__ __forceinline__ float final_max(float m, int step, int head_size) { r
 // kPaged: the cache is a page pool addressed through a block table (attention_decode.cuh); a tile of TP positions never straddles a page
 // (TP divides kAttnPageSize, tiles start at multiples of TP), so a stage is still two contiguous bulk copies.
 template <typename T, int GC, bool kPaged>
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, GC == 4 ? 1 : 2)  // 4 heads per CTA: 135+ registers, one CTA per SM (as before the merge moved in)
 decode_attn_kernel(const DecodeAttnArgs a) {
     constexpr int D = kAttnD;
     constexpr int G = GC;
@@ -389,6 +389,94 @@ decode_attn_kernel(const DecodeAttnArgs a) {
         }
         return;
     }
+    if (a.ll_merge) {
+        // ---- flagged words [b, kv head][split][q head][o[D], max, sum, pad, pad] x {value, flag}: an aligned 8-byte store is never torn,
+        //      so a word whose flag reads 1 carries its value.  The region is zero between launches: the merger clears what it consumed
+        //      (the next launch that touches these words is several kernels away in the stream).
+        uint2 *words = reinterpret_cast<uint2 *>(a.partials);
+        const size_t rec0 = (((size_t)b * Hkv + kvh) * a.nsplit * Gtot + g0) * (size_t)PS;  // record of split 0, head g0
+        const size_t sstride = (size_t)Gtot * PS;                                            // words between consecutive splits
+        const int merger = a.nsplit - 1;  // launched after every split it waits for (blockIdx.x is the fastest grid dimension)
+        if (split != merger) {
+            uint2 *mine = words + rec0 + (size_t)split * sstride;
+            for (int i = tid; i < G * D; i += kAttnThreads) {
+                const int g = i / D, d = i % D;
+                float o = 0.0f;
+#pragma unroll
+                for (int r = 0; r < RG; ++r) o = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o);
+                __stcg(mine + (size_t)g * PS + d, make_uint2(__float_as_uint(o), 1u));
+            }
+            if (tid < 2 * G) {
+                const int g = tid >> 1, which = tid & 1;  // 0: max, 1: sum
+                __stcg(mine + (size_t)g * PS + D + which, make_uint2(__float_as_uint(wts[RG * G + which * G + g]), 1u));
+            }
+            return;
+        }
+        // ---- the merger: its own partial never leaves shared memory; the others are polled (all loads of a pass in flight, then only the
+        //      words that had not landed), merged in split order with the arithmetic of the ticket path below -- bit-identical results
+        constexpr int kMaxOther = kAttnMaxSplits - 1;
+        const long long t_end = clock64() + 2000000000ll;  // ~1 s: a split that never publishes must not hang the GPU
+        // the n words p[j * stride], j < n, as floats: every load of a pass in flight, then only the words that had not landed yet
+        auto poll = [&](const uint2 *p, int n, size_t stride, float (&out)[kMaxOther]) {
+            unsigned pending = (1u << n) - 1u;
+            while (pending) {
+                uint2 v[kMaxOther];
+#pragma unroll
+                for (int j = 0; j < kMaxOther; ++j)
+                    if (pending >> j & 1u) asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[j].x), "=r"(v[j].y) : "l"(p + (size_t)j * stride));
+#pragma unroll
+                for (int j = 0; j < kMaxOther; ++j)
+                    if ((pending >> j & 1u) && v[j].y == 1u) out[j] = __uint_as_float(v[j].x), pending &= ~(1u << j);
+                if (pending && clock64() > t_end) {
+#pragma unroll
+                    for (int j = 0; j < kMaxOther; ++j)
+                        if (pending >> j & 1u) out[j] = __int_as_float(0x7fc00000);  // NaN: obvious, not plausible
+                    break;
+                }
+            }
+        };
+        const int nother = a.nsplit - 1;  // splits 0 .. nsplit-2, in this order
+        const uint2 *others = words + rec0;
+        for (int i = tid; i < G * D; i += kAttnThreads) {
+            const int g = i / D, d = i % D;
+            float o_own = 0.0f;
+#pragma unroll
+            for (int r = 0; r < RG; ++r) o_own = fmaf(merge[((size_t)r * G + g) * (D + 2) + d], wts[r * G + g], o_own);
+            const float m_own = wts[RG * G + g], s_own = wts[RG * G + G + g];
+            float cw[kMaxOther], val[kMaxOther];  // three passes over one buffer: max -> merge weights, then the sums, then the outputs
+            poll(others + (size_t)g * PS + D, nother, sstride, cw);
+            float mm = m_own;
+#pragma unroll
+            for (int j = 0; j < kMaxOther; ++j)
+                if (j < nother) mm = fmaxf(mm, cw[j]);
+            mm = final_max(mm, step, D);
+#pragma unroll
+            for (int j = 0; j < kMaxOther; ++j)
+                if (j < nother) cw[j] = expf(cw[j] - mm);
+            float ssum = 0.0f, o = 0.0f;
+            poll(others + (size_t)g * PS + D + 1, nother, sstride, val);
+#pragma unroll
+            for (int j = 0; j < kMaxOther; ++j)
+                if (j < nother) ssum = fmaf(val[j], cw[j], ssum);
+            poll(others + (size_t)g * PS + d, nother, sstride, val);
+#pragma unroll
+            for (int j = 0; j < kMaxOther; ++j)
+                if (j < nother) o = fmaf(val[j], cw[j], o);
+            {
+                const float c = expf(m_own - mm);  // the merger is the last split
+                ssum = fmaf(s_own, c, ssum);
+                o = fmaf(o_own, c, o);
+            }
+            out[(size_t)g * D + d] = Elem<T>::from_f(o / (ssum + 1e-6f));
+            for (int j = 0; j < nother; ++j) __stcg(const_cast<uint2 *>(others) + (size_t)j * sstride + (size_t)g * PS + d, make_uint2(0u, 0u));
+        }
+        __syncthreads();  // every thread has read the (max, sum) words of its head
+        for (int i = tid; i < 2 * G * nother; i += kAttnThreads) {
+            const int j = i / (2 * G), g = (i % (2 * G)) >> 1, which = i & 1;
+            __stcg(const_cast<uint2 *>(others) + (size_t)j * sstride + (size_t)g * PS + D + which, make_uint2(0u, 0u));
+        }
+        return;
+    }
     // ---- partials: [b, kv head][split][q head of the group][o[D], max, sum, pad, pad]
     float *part = a.partials + ((((size_t)b * Hkv + kvh) * a.nsplit + split) * Gtot + g0) * (size_t)PS;
     for (int i = tid; i < G * D; i += kAttnThreads) {
@@ -519,19 +607,19 @@ __global__ void decode_attn_generic_kernel(const DecodeAttnArgs a) {
 }
 
 size_t decode_attn_partials_floats(int batch, int head_num, int kv_head_num, int head_size, int max_splits) {
-    return (size_t)batch * kv_head_num * max_splits * (head_num / kv_head_num) * attn_part_stride(head_size);
+    return (size_t)batch * kv_head_num * max_splits * (head_num / kv_head_num) * attn_part_stride(head_size);  // ll_merge: twice as many
 }
 
 int decode_attn_plan(int batch, int kv_head_num, int step, int *chunk) {
     // The cached positions [0, step-1) are cut into chunks of whole 64-position tiles, about ONE CTA per SM (measured on the 7B
     // step, ctx 1024: 4 splits x 32 heads = 128 CTAs 2.535 / 2.616 ms, 8 splits = 256 CTAs 2.550 / 2.625 ms on two boxes -- a CTA with
-    // a 3-stage ring streams its share of the cache as fast as two, and the merge reads half as many partials) and at most 16 splits
+    // a 3-stage ring streams its share of the cache as fast as two, and the merge reads half as many partials) and at most kAttnMaxSplits = 8 splits
     // (the merge requests the partials in one batch); the last split also serves the token being appended, which never comes from
     // the cache.
     const int cached = step - 1;
     int want = sm_count() / (batch * kv_head_num);
     if (want < 1) want = 1;
-    if (want > 16) want = 16;
+    if (want > kAttnMaxSplits) want = kAttnMaxSplits;
     int c = (cached + want - 1) / want;
     c = (c + 63) & ~63;
     if (c < 64) c = 64;

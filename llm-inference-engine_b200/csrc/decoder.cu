@@ -72,9 +72,10 @@ static Carve carve(const b200_decoder_config_t &c, int *max_splits) {
     k.y = align_up(B * c.hidden * e);
     k.gu = align_up(B * (size_t)2 * c.inter_size * e);
     k.act = align_up(B * (size_t)c.inter_size * e);
-    // worst case number of KV splits (decode_attn_plan: chunks of >= 64 positions, at most 16 splits)
-    *max_splits = (c.max_seq_len + 63) / 64 < 16 ? (c.max_seq_len + 63) / 64 : 16;
-    k.partials = align_up(decode_attn_partials_floats(c.max_batch, c.head_num, c.kv_head_num, c.head_size, *max_splits) * sizeof(float));
+    // worst case number of KV splits (decode_attn_plan: chunks of >= 64 positions, at most kAttnMaxSplits splits)
+    *max_splits = (c.max_seq_len + 63) / 64 < kAttnMaxSplits ? (c.max_seq_len + 63) / 64 : kAttnMaxSplits;
+    // split-KV partials as flagged 8-byte words (attention_decode.cuh: ll_merge): twice the floats, zero between launches
+    k.partials = align_up(2 * decode_attn_partials_floats(c.max_batch, c.head_num, c.kv_head_num, c.head_size, *max_splits) * sizeof(float));
     k.tickets = align_up((size_t)c.max_batch * c.kv_head_num * 2 * sizeof(unsigned int));  // x 2: half-group CTAs (GQA group of 8)
     k.rope = c.rotary_dim > 0 ? align_up((size_t)c.max_seq_len * (c.rotary_dim / 2) * sizeof(float2)) : 0;
     k.total = 3 * k.res + k.xn + k.qkv + k.attn + 2 * k.y + k.gu + k.act + k.partials + k.tickets + k.rope;
@@ -315,7 +316,8 @@ int b200_decoder_set_scratch(b200_decoder_t *dec, void *ptr, size_t bytes) {
     dec->act = p, p += k.act;
     dec->partials = (float *)p, p += k.partials;
     dec->tickets = (unsigned int *)p, p += k.tickets;
-    if (cudaMemset(dec->tickets, 0, k.tickets) != cudaSuccess) return cuda_status("decoder_set_scratch memset");
+    if (cudaMemset(dec->tickets, 0, k.tickets) != cudaSuccess || cudaMemset(dec->partials, 0, k.partials) != cudaSuccess)
+        return cuda_status("decoder_set_scratch memset");
     dec->rope_cs = nullptr;
     if (k.rope) {
         dec->rope_cs = (float2 *)p;
@@ -343,6 +345,7 @@ static int launch_layer_attention(b200_decoder_t *dec, int layer, void *k_cache,
     a.apply_rope = c.rotary_dim > 0, a.rot_dim = c.rotary_dim, a.rot_base = c.rotary_base;
     a.nsplit = decode_attn_plan(batch, c.kv_head_num, step, &a.chunk);
     a.partials = dec->partials, a.tickets = dec->tickets;
+    a.ll_merge = 1;  // the engine's own zero-initialised region: flagged words, no fence / ticket (the stand-alone launcher keeps them)
     a.rope_cs = dec->rope_cs;
     a.prefetch = 1;  // the kernel in front of this one is the QKV linear: it does not touch the cache
     return launch_decode_attn(a, c.dtype, st);
