@@ -195,8 +195,19 @@ decode_attn_kernel(const DecodeAttnArgs a) {
 
     pdl_wait();
 
-    // ---- q (this CTA's G heads of the group), and the new k / v row: RoPE at step-1, then bias (reference order)
-    for (int i = tid; i < (G + 1) * (D / 2); i += kAttnThreads) {
+    // ---- q (this CTA's G heads of the group), and the new k / v row: RoPE at step-1, then bias (reference order).  One pass over
+    //      (G + 1) * D/2 rotary pairs and the D values of v, so that every global load of the prologue is in flight at once (a second
+    //      loop for v cost the CTA that serves the new token a second round trip)
+    constexpr int kPairs = (G + 1) * (D / 2);
+    for (int i = tid; i < kPairs + D; i += kAttnThreads) {
+        if (i >= kPairs) {  // the new v row
+            if (!has_new) continue;
+            const int j = i - kPairs, head = H + Hkv + kvh;
+            float v = Elem<T>::to_f(qkv[(size_t)head * D + j]);
+            if (bias) v = round_t<T>(v + Elem<T>::to_f(bias[(size_t)head * D + j]));
+            vnew[j] = v;
+            continue;
+        }
         const int g = i / (D / 2), j = i % (D / 2);  // g == G: the k head
         if (g == G && !has_new) continue;
         const int head = g < G ? kvh * Gtot + g0 + g : H + kvh;
@@ -214,14 +225,6 @@ decode_attn_kernel(const DecodeAttnArgs a) {
         float *dst = g < G ? qs + g * D : knew;
         dst[j] = x0;
         dst[j + D / 2] = x1;
-    }
-    if (has_new) {
-        for (int j = tid; j < D; j += kAttnThreads) {
-            const int head = H + Hkv + kvh;
-            float v = Elem<T>::to_f(qkv[(size_t)head * D + j]);
-            if (bias) v = round_t<T>(v + Elem<T>::to_f(bias[(size_t)head * D + j]));
-            vnew[j] = v;
-        }
     }
     __syncthreads();  // q / knew / vnew complete; also publishes the producer's mbarrier initialisation
     if (has_new && g0 == 0) {  // cache append (decoder_self_attention.cu:126,172)
