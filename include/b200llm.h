@@ -472,7 +472,7 @@ typedef struct {
     int n_preempted;                                /* running sequences pushed back to the queue (pages freed)          */
     int free_pages, n_waiting;                      /* after planning                                                    */
 } b200_batch_plan_t;
-enum { B200_REQ_WAITING = 0, B200_REQ_RUNNING = 1, B200_REQ_FINISHED = 2 };
+enum { B200_REQ_WAITING = 0, B200_REQ_RUNNING = 1, B200_REQ_FINISHED = 2, B200_REQ_REJECTED = 3 /* a prompt id outside the vocabulary */ };
 enum {
     B200_PLAN_PREFILL_IDS = 0,         /* int[prefill_tokens]: the admitted sequences' tokens, packed back to back           */
     B200_PLAN_PREFILL_LENS = 1,        /* int[n_prefill]                                                                     */
@@ -500,6 +500,9 @@ const int *b200_batcher_plan_array(const b200_batcher_t *b, int which); /* host 
 /* Feed the iteration's sampled ids (plan order).  A sequence finishes on end_id or after max_new_tokens: its pages return to the pool.
  * Returns the number of requests that finished in this iteration (or a negative error). */
 int b200_batcher_commit(b200_batcher_t *b, const int *prefill_sampled, const int *decode_sampled, int end_id);
+/* Drop the current plan without results (a launch failed): admitted requests give their pages back and return to the front of the queue
+ * in order; b200_batcher_plan can be called again.  b200_batcher_step does this itself when one of its launches fails. */
+int b200_batcher_abort(b200_batcher_t *b);
 /* Generated ids so far (end_id included if it was sampled), state = B200_REQ_*. */
 int b200_batcher_result(const b200_batcher_t *b, int request, int *out_ids, int capacity, int *n_generated, int *state);
 int b200_batcher_pending(const b200_batcher_t *b);     /* waiting + running */

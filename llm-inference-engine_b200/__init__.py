@@ -59,7 +59,7 @@ class BatchPlan(C.Structure):
 
 
 KV_PAGE_SIZE = 64
-REQ_WAITING, REQ_RUNNING, REQ_FINISHED = 0, 1, 2
+REQ_WAITING, REQ_RUNNING, REQ_FINISHED, REQ_REJECTED = 0, 1, 2, 3
 (PLAN_PREFILL_IDS, PLAN_PREFILL_LENS, PLAN_PREFILL_REQUESTS, PLAN_PREFILL_BLOCK_TABLE, PLAN_PREFILL_LAST_ROWS, PLAN_DECODE_TOKENS,
  PLAN_DECODE_STEPS, PLAN_DECODE_REQUESTS, PLAN_DECODE_BLOCK_TABLE) = range(9)
 
@@ -132,6 +132,7 @@ SIGNATURES = {
     "b200_batcher_plan": [_P, C.POINTER(BatchPlan)],
     "b200_batcher_plan_array": [_P, _I],
     "b200_batcher_commit": [_P, _P, _P, _I],
+    "b200_batcher_abort": [_P],
     "b200_batcher_result": [_P, _I, _P, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "b200_batcher_pending": [_P],
     "b200_batcher_free_pages": [_P],
@@ -666,6 +667,9 @@ class Batcher:
         if n < 0:
             raise B200Error(f"b200 status {n}: {lib().b200_last_error_string().decode()}")
         return n
+
+    def abort(self):
+        check(lib().b200_batcher_abort(self.handle))
 
     def result(self, request, capacity=4096):
         import numpy as np

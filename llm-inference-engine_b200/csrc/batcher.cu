@@ -29,6 +29,7 @@ struct Seq {
     int state = B200_REQ_WAITING;
     int admitted_at = -1;     // iteration of the (last) admission: the preemption victim is the youngest
     int preemptions = 0;
+    bool vocab_checked = false;
 };
 
 }  // namespace b200
@@ -201,6 +202,22 @@ const int *b200_batcher_plan_array(const b200_batcher_t *b, int which) {
     }
 }
 
+// Drop the current plan without results (a launch failed): the admitted requests give their pages back and return to the FRONT of the
+// queue in their original order; running sequences keep the pages they were granted (they will need them at the next attempt);
+// preempted ones stay re-queued.  The scheduler is then in a state from which b200_batcher_plan can be called again.
+int b200_batcher_abort(b200_batcher_t *b) {
+    B200_REQUIRE(b, "batcher_abort: null handle");
+    if (!b->planned) return B200_OK;
+    for (int i = b->plan.n_prefill - 1; i >= 0; --i) {
+        Seq &s = b->seqs[b->p_req[i]];
+        release_pages(b, s);
+        s.state = B200_REQ_WAITING;
+        b->waiting.push_front(s.id);
+    }
+    b->planned = false;
+    return B200_OK;
+}
+
 int b200_batcher_commit(b200_batcher_t *b, const int *prefill_sampled, const int *decode_sampled, int end_id) {
     B200_REQUIRE(b, "batcher_commit: null handle");
     B200_REQUIRE(b->planned, "batcher_commit: nothing planned");
@@ -325,14 +342,24 @@ int b200_batcher_step(b200_batcher_t *b, b200_decoder_t *dec, const b200_generat
     b200_decoder_config_t c;
     b200_decoder_get_config(dec, &c);
     NvtxRange range("b200 batcher iteration");
+    // a queued prompt with an id outside the vocabulary would read outside the embedding table: reject the REQUEST (state
+    // B200_REQ_REJECTED, out of the queue), not the iteration
+    for (auto it = b->waiting.begin(); it != b->waiting.end();) {
+        Seq &s = b->seqs[*it];
+        bool ok = true;
+        if (!s.vocab_checked) {
+            for (int t = 0; t < s.prompt_len && ok; ++t) ok = s.tokens[t] >= 0 && s.tokens[t] < p->vocab;
+            s.vocab_checked = true;
+        }
+        if (!ok) {
+            s.state = B200_REQ_REJECTED;
+            it = b->waiting.erase(it);
+        } else {
+            ++it;
+        }
+    }
     b200_batch_plan_t plan;
     if ((rc = b200_batcher_plan(b, &plan)) != B200_OK) return rc;
-    for (int id : b->p_ids)
-        if (id < 0 || id >= p->vocab) {
-            b->planned = false;
-            set_error("batcher_step: token id %d outside the vocabulary", id);
-            return B200_ERR_INVALID_ARG;
-        }
     char *w = (char *)workspace;
     const int B = b->cfg.max_batch, MP = b->cfg.max_pages_per_seq;
     int *ids = (int *)(w + k.ids), *ints = (int *)(w + k.ints);
@@ -345,7 +372,7 @@ int b200_batcher_step(b200_batcher_t *b, b200_decoder_t *dec, const b200_generat
     cudaStream_t st = as_stream(stream);
     std::vector<int> sampled_p(plan.n_prefill), sampled_d(plan.n_decode);
     auto fail = [&](int code) {
-        b->planned = false;  // the plan is void: the caller may retry after fixing the cause (page bookkeeping is NOT rolled back)
+        b200_batcher_abort(b);  // the admitted requests return to the front of the queue with their pages freed: the caller may retry
         return code;
     };
     auto up = [&](void *dst, const void *src, size_t bytes) { return bytes == 0 || cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess; };

@@ -151,6 +151,26 @@ def test_scheduler_a_request_as_large_as_the_pool_runs_alone():
     assert list(bat.result(r0)[0]) == alone(p0, 29) and list(bat.result(r1)[0]) == alone(p1, 5)
 
 
+def test_scheduler_abort_returns_the_admitted_requests_to_the_front_of_the_queue():
+    """A failed launch must not leak pages or lose requests: after b200_batcher_abort the same plan comes out again."""
+    mod = b200()
+    bat = mod.Batcher(max_batch=3, num_pages=20, max_pages_per_seq=4, max_prefill_tokens=256)
+    reqs = {}
+    for n in (70, 10, 100):
+        p = list(range(10, 10 + n))
+        reqs[bat.submit(p, 5)] = (p, 5)
+    plan1, v1 = bat.plan()
+    assert plan1.n_prefill == 3 and bat.free_pages() < 20
+    bat.abort()
+    assert bat.free_pages() == 20 and bat.pending() == 3
+    plan2, v2 = bat.plan()
+    assert list(v2["prefill_requests"]) == list(v1["prefill_requests"]) and np.array_equal(v2["prefill_ids"], v1["prefill_ids"])
+    bat.abort()
+    drive(bat, reqs, mod)
+    for rid, (p, m) in reqs.items():
+        assert list(bat.result(rid)[0]) == alone(p, m)
+
+
 def test_batcher_argument_errors():
     import ctypes as C
 
@@ -369,6 +389,36 @@ def test_batcher_with_everybody_admitted_at_once_is_generate_ragged_bit_for_bit(
         got, state = bat.result(rid)
         assert state == mod.REQ_FINISHED and np.array_equal(got, ids[b]), f"request {rid}: {got} vs {ids[b]}"
     assert bat.free_pages() == 12
+
+
+@pytest.mark.gpu
+def test_batcher_rejects_a_prompt_outside_the_vocabulary_and_serves_the_rest():
+    import torch
+
+    from test_decoder_engine import build_decoder
+    from test_generate import V
+    from util import to_dev
+
+    mod = b200()
+    dtype = "bf16"
+    cfg, model, (emb, gamma, lm) = _paged_model(dtype)
+    L, Hkv, d, S = cfg["layers"], cfg["kv_head_num"], cfg["head_size"], cfg["max_seq"]
+    dec = build_decoder(model, cfg, dtype, 2)
+    bat = mod.Batcher(max_batch=2, num_pages=6, max_pages_per_seq=S // PAGE, max_prefill_tokens=128)
+    good = bat.submit([5, 6, 7, 8], 4)
+    bad = bat.submit([5, V + 3, 7], 4)  # would read past the embedding table
+    good2 = bat.submit([9, 10], 3)
+    kp = torch.full((L, 6, Hkv, PAGE, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    vp = torch.full_like(kp, float("nan"))
+    it = 0
+    while bat.pending():
+        bat.step(dec, to_dev(emb, dtype), to_dev(gamma, dtype), to_dev(lm, dtype), kp, vp, top_k=1, end_id=-1)
+        it += 1
+        assert it < 50
+    assert bat.result(bad)[1] == mod.REQ_REJECTED and len(bat.result(bad)[0]) == 0
+    assert bat.result(good)[1] == mod.REQ_FINISHED and len(bat.result(good)[0]) == 4
+    assert bat.result(good2)[1] == mod.REQ_FINISHED and len(bat.result(good2)[0]) == 3
+    assert bat.free_pages() == 6
 
 
 @pytest.mark.gpu
