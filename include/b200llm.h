@@ -369,6 +369,16 @@ int b200_decoder_prefill_paged(b200_decoder_t *dec, void *hidden, void *k_pool, 
                                const int *input_len, const int *history_len, const int *context_len, int batch,
                                int max_q_len, int num_tokens, int num_pages, int max_pages_per_seq, void *scratch,
                                size_t scratch_bytes, int layer_begin, int layer_end, b200_stream_t stream);
+/* Tensor-parallel prefill (the reference is single-GPU; north_star's sharding: column-sharded QKV / gate_up, row-sharded O / down,
+ * head-sharded cache, one all-reduce per attention and per MLP block): b200_decoder_prefill on this rank's shard, with `reduce` called
+ * after the O projection and after the down projection of every layer to all-reduce (sum, in place, on `stream`) the partial
+ * [num_tokens, hidden] tensor of `dtype`.  The library does not link NCCL: the host supplies the collective (ncclAllReduce, or
+ * torch.distributed.all_reduce from Python).  The callback returns 0 on success. */
+typedef int (*b200_allreduce_fn)(void *buf, size_t count, int dtype, void *user, b200_stream_t stream);
+int b200_decoder_prefill_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len,
+                            const int *history_len, const int *context_len, int batch, int max_q_len, int num_tokens,
+                            void *scratch, size_t scratch_bytes, int layer_begin, int layer_end,
+                            b200_allreduce_fn reduce, void *user, b200_stream_t stream);
 
 /* Tensor-parallel halves of one layer.  Each leaves this rank's PARTIAL sum of the row-sharded linear
  * in partial[B,h] (`dtype`); the caller all-reduces it (NCCL) and passes the reduced tensor as

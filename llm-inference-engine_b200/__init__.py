@@ -126,6 +126,7 @@ SIGNATURES = {
     "b200_context_attention_paged": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_decoder_step_paged": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_decoder_prefill_paged": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _I, _I, _P],
+    "b200_decoder_prefill_tp": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _SZ, _I, _I, _P, _P, _P],
     "b200_batcher_create": [C.POINTER(BatcherConfig)],
     "b200_batcher_destroy": [_P],
     "b200_batcher_submit": [_P, _P, _I, _I],
@@ -507,6 +508,39 @@ class Decoder:
         check(lib().b200_decoder_prefill_paged(self.handle, ptr(hidden), ptr(k_pool), ptr(v_pool), ptr(block_table), ptr(input_len),
                                                ptr(history_len), ptr(context_len), B, max_q_len, T, k_pool.shape[1], block_table.shape[1],
                                                C.c_void_p(base), nbytes, layer_begin, layer_end, stream()))
+
+    def prefill_tp(self, hidden, k_cache, v_cache, input_len, history_len, context_len, max_q_len, dist_module, layer_begin=0, layer_end=None):
+        """Tensor-parallel prefill on this rank's shard (b200_decoder_prefill_tp): torch.distributed.all_reduce is the collective, called
+        by the library after the O projection and after the down projection of every layer on the partial [T, hidden] tensor."""
+        torch = _torch()
+        ensure_workspace()
+        layer_end = self.cfg.num_layers if layer_end is None else layer_end
+        B, T = input_len.shape[0], hidden.shape[0]
+        nbytes = lib().b200_decoder_prefill_scratch_bytes(self.handle, B, max_q_len, T)
+        if getattr(self, "_prefill_scratch", None) is None or self._prefill_scratch.numel() < nbytes + 256:
+            self._prefill_scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=hidden.device)
+        scratch = self._prefill_scratch
+        base = (scratch.data_ptr() + 255) // 256 * 256
+        esize = hidden.element_size()
+        failure = []
+
+        @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p)
+        def reduce(buf, count, dtype, user, stream_):
+            try:  # the partial lives inside the scratch tensor: all-reduce a view of it (no copy)
+                off = buf - scratch.data_ptr()
+                view = scratch[off:off + count * esize].view(hidden.dtype)
+                dist_module.all_reduce(view)
+                return 0
+            except Exception as e:  # never let an exception cross the C boundary
+                failure.append(e)
+                return 1
+
+        rc = lib().b200_decoder_prefill_tp(self.handle, ptr(hidden), ptr(k_cache), ptr(v_cache), ptr(input_len), ptr(history_len),
+                                           ptr(context_len), B, max_q_len, T, C.c_void_p(base), nbytes, layer_begin, layer_end, C.cast(reduce, C.c_void_p), None,
+                                           stream())
+        if failure:
+            raise failure[0]
+        check(rc)
 
     def generate(self, prompt_ids, embedding, final_gamma, lm_head, k_cache, v_cache, max_new_tokens, top_k=1, end_id=2, check_every=0,
                  prompt_lens=None):

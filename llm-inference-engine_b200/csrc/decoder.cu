@@ -632,10 +632,11 @@ size_t b200_decoder_prefill_scratch_bytes(const b200_decoder_t *dec, int batch, 
 // paging (block_table != NULL): k_cache / v_cache are page pools [L, num_pages, Hkv, 64, d]
 static int prefill_impl(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len, const int *history_len,
                         const int *context_len, int batch, int max_q_len, int num_tokens, void *scratch, size_t scratch_bytes,
-                        int layer_begin, int layer_end, b200_stream_t stream, const int *block_table, int max_pages, int num_pages) {
+                        int layer_begin, int layer_end, b200_stream_t stream, const int *block_table, int max_pages, int num_pages,
+                        b200_allreduce_fn reduce = nullptr, void *reduce_user = nullptr) {
     B200_REQUIRE(dec, "decoder_prefill: null handle");
     const b200_decoder_config_t &c = dec->cfg;
-    B200_REQUIRE(c.tp_world <= 1, "decoder_prefill: tensor-parallel prefill is not implemented");
+    B200_REQUIRE(c.tp_world <= 1 || reduce, "decoder_prefill: a tensor-parallel engine prefills through b200_decoder_prefill_tp (all-reduce callback)");
     B200_REQUIRE(hidden && k_cache && v_cache && input_len && history_len && context_len && scratch, "decoder_prefill: null pointer");
     B200_REQUIRE(batch >= 1 && batch <= c.max_batch && max_q_len >= 1 && num_tokens >= 1 && num_tokens <= batch * max_q_len,
                  "decoder_prefill: bad shape (batch %d, max_q_len %d, num_tokens %d)", batch, max_q_len, num_tokens);
@@ -704,6 +705,11 @@ static int prefill_impl(b200_decoder_t *dec, void *hidden, void *k_cache, void *
                                                   c.kv_head_num, max_q_len, c.max_seq_len, c.head_size, T, scale, c.dtype, stream);
         if (rc != B200_OK) return rc;
         if ((rc = linear(attn, w.o, y, qh, h)) != B200_OK) return rc;
+        // tensor parallel: y is this rank's partial sum of the row-sharded O projection -> the caller's all-reduce (one per block)
+        if (reduce && reduce(y, (size_t)T * h, c.dtype, reduce_user, stream) != 0) {
+            set_error("decoder_prefill_tp: the all-reduce callback failed (layer %d, attention block)", l);
+            return B200_ERR_CUDA;
+        }
         // residual += attention output; (+ o bias); xn = RMSNorm
         rc = launch_norm_any(c.dtype, y, xn, res, res, w.o_bias, w.ffn_norm_gamma, c.rmsnorm_eps, T, h, st);
         if (rc != B200_OK) return rc;
@@ -726,6 +732,10 @@ static int prefill_impl(b200_decoder_t *dec, void *hidden, void *k_cache, void *
         }
         if (rc != B200_OK) return rc;
         if ((rc = linear(act, w.down, y, c.inter_size, h)) != B200_OK) return rc;
+        if (reduce && reduce(y, (size_t)T * h, c.dtype, reduce_user, stream) != 0) {
+            set_error("decoder_prefill_tp: the all-reduce callback failed (layer %d, FFN block)", l);
+            return B200_ERR_CUDA;
+        }
         pending = y;
     }
     // hidden <- residual + last FFN output
@@ -738,6 +748,17 @@ int b200_decoder_prefill(b200_decoder_t *dec, void *hidden, void *k_cache, void 
                          int layer_begin, int layer_end, b200_stream_t stream) {
     return prefill_impl(dec, hidden, k_cache, v_cache, input_len, history_len, context_len, batch, max_q_len, num_tokens, scratch, scratch_bytes,
                         layer_begin, layer_end, stream, nullptr, 0, 0);
+}
+
+// Tensor-parallel prefill: the same pass on this rank's shard (column-sharded QKV / gate_up, row-sharded O / down, head-sharded cache);
+// `reduce` all-reduces (sum) the partial [num_tokens, hidden] tensor in place on `stream` after the O projection and after the down
+// projection of every layer -- north_star's one all-reduce per attention and per MLP block; the library itself never links NCCL.
+int b200_decoder_prefill_tp(b200_decoder_t *dec, void *hidden, void *k_cache, void *v_cache, const int *input_len, const int *history_len,
+                            const int *context_len, int batch, int max_q_len, int num_tokens, void *scratch, size_t scratch_bytes,
+                            int layer_begin, int layer_end, b200_allreduce_fn reduce, void *user, b200_stream_t stream) {
+    B200_REQUIRE(reduce, "decoder_prefill_tp: null all-reduce callback");
+    return prefill_impl(dec, hidden, k_cache, v_cache, input_len, history_len, context_len, batch, max_q_len, num_tokens, scratch, scratch_bytes,
+                        layer_begin, layer_end, stream, nullptr, 0, 0, reduce, user);
 }
 
 // The same pass with the K / V rows written into, and read back from, a PAGE POOL [L, num_pages, Hkv, 64, d] through block_table

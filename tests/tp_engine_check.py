@@ -80,6 +80,47 @@ def main():
         except AssertionError as e:
             ok = False
             print(f"[rank {rank}] {mode} {dtype} batch {batch} FAILED: {e}", flush=True)
+    # ---- tensor-parallel PREFILL (b200_decoder_prefill_tp: this rank's shard + one all-reduce per attention and per MLP block, the
+    #      collective supplied by the host) against the UN-SHARDED oracle composition; ragged batch with history; bf16 (tcgen05 path) and fp32
+    from test_decoder_engine import oracle_prefill
+
+    for dtype in ("bf16", "f32"):
+        try:
+            model = make_model(cfg, seed=19, bias=True)
+            lcfg = tp.local_cfg(dict(head_num=cfg["head_num"], kv_head_num=cfg["kv_head_num"], head_size=cfg["head_size"], inter=cfg["inter"]), world)
+            input_len, hist = np.array([150, 37], np.int32), np.array([0, 9], np.int32)
+            B, T = len(input_len), int(input_len.sum())
+            dc = mod.DecoderConfig(cfg["hidden"], lcfg["head_num"], lcfg["kv_head_num"], cfg["head_size"], lcfg["inter"], cfg["layers"], cfg["max_seq"],
+                                   B, {"f32": 0, "f16": 1, "bf16": 2}[dtype], 0, 128, cfg["eps"], cfg["head_size"], cfg["base"], world, rank)
+            dec = mod.Decoder(dc, dev)
+            for l, w in enumerate(model["layers"]):
+                s = tp.shard_layer(w, cfg, rank, world)
+                dec.set_layer(l, dict(g1=to_dev(s["g1"], dtype), qkv=to_dev(s["wqkv"], dtype), qkv_bias=to_dev(s["bqkv"], dtype), o=to_dev(s["wo"], dtype),
+                                      o_bias=to_dev(s["bo"], dtype), g2=to_dev(s["g2"], dtype), gate_up=to_dev(s["wgu"], dtype), down=to_dev(s["wd"], dtype)))
+            r = np.random.default_rng(23)
+            x = rounded(r.standard_normal((T, cfg["hidden"])), dtype)
+            kc = rounded(0.5 * r.standard_normal((cfg["layers"], B, cfg["kv_head_num"], cfg["max_seq"], cfg["head_size"])), dtype)
+            vc = rounded(0.5 * r.standard_normal(kc.shape), dtype)
+            xd = to_dev(x, dtype)
+            kcd = to_dev(tp.shard_kv_cache(kc, cfg["kv_head_num"], rank, world), dtype)
+            vcd = to_dev(tp.shard_kv_cache(vc, cfg["kv_head_num"], rank, world), dtype)
+            ctx = input_len + hist
+            dec.prefill_tp(xd, kcd, vcd, to_dev(input_len), to_dev(hist), to_dev(ctx), int(input_len.max()), dist)
+            torch.cuda.synchronize()
+            oracle.set_threads(oracle.max_threads())
+            ref, rkc, rvc = oracle_prefill(model, cfg, dtype, x, kc.copy(), vc.copy(), input_len, hist)
+            got = to_np(xd).astype(np.float64)
+            fro = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+            assert fro <= (1e-5 if dtype == "f32" else 1e-2), f"prefill output: {fro:.3e}"
+            mine, want = to_np(kcd).astype(np.float64), tp.shard_kv_cache(rkc, cfg["kv_head_num"], rank, world)
+            for b in range(B):
+                lo, hi = int(hist[b]), int(ctx[b])
+                kerr = np.linalg.norm(mine[:, b, :, lo:hi] - want[:, b, :, lo:hi]) / np.linalg.norm(want[:, b, :, lo:hi])
+                assert kerr <= (1e-5 if dtype == "f32" else 1e-2), f"K rows of this rank's heads, sequence {b}: {kerr:.3e}"
+            print(f"[rank {rank}] TP-{world} prefill {dtype} (ragged, history): OK  rel err {fro:.2e}", flush=True)
+        except (AssertionError, mod.B200Error) as e:
+            ok = False
+            print(f"[rank {rank}] TP prefill {dtype} FAILED: {e}", flush=True)
     # ---- vocab-sharded LM head + top-k + sampling: bit-identical to the un-sharded tail on the same hidden state
     try:
         V, hsz, B, K = 32000, cfg["hidden"], 3, 5
