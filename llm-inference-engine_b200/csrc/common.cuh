@@ -237,6 +237,13 @@ template <> __device__ __forceinline__ uint4 pack16<__half>(const float *f) {
     return r;
 }
 
+// round_to<T> over the Elem<T>::kVec lanes of one 16-byte vector, two lanes per conversion: a scalar cvt.rn.bf16.f32 is an F2F on the XU
+// pipe (one warp instruction per 8 cycles per scheduler -- the pipe of rsqrt / ex2), the packed cvt.rn.bf16x2.f32 an F2FP on the ALU pipe.
+// Same rounding (nearest even), bit-identical results.
+template <typename T> __device__ __forceinline__ void round_vec(float *f) {
+    if constexpr (sizeof(T) == 2) unpack16<T>(pack16<T>(f), f);
+}
+
 // ------------------------------------------------------------------ tensor-parallel exchange (device)
 __device__ __forceinline__ unsigned int tp_flag(const unsigned int *epoch, int seq) {
     unsigned int e;
@@ -328,8 +335,9 @@ __device__ __forceinline__ void tp_reduce_vec(const TpExchange &t, unsigned int 
                 for (int k = 0; k < V; ++k) f[k] += g[k];
             }
     }
+    round_vec<T>(f);  // rounded to T as an all-reduced tensor of T would be
 #pragma unroll
-    for (int j = 0; j < V; ++j) f[j] = poisoned ? __int_as_float(0x7fc00000) : Elem<T>::to_f(Elem<T>::from_f(f[j]));
+    for (int j = 0; j < V; ++j) f[j] = poisoned ? __int_as_float(0x7fc00000) : f[j];
 }
 
 // ------------------------------------------------------------------ reductions

@@ -258,14 +258,16 @@ __device__ __forceinline__ void gemv_prenorm_vec(const GemvArgs &a, unsigned int
         float r[V];
         unpack16<T>(ld_v4(rin + (size_t)m * K + (size_t)i * V), r);
 #pragma unroll
-        for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
+        for (int j = 0; j < V; ++j) f[j] += r[j];
+        round_vec<T>(f);
     }
     if (write_res && rout && blockIdx.x == 0) st_v4(rout + (size_t)m * K + (size_t)i * V, pack16<T>(f));
     if (bias) {
         float b[V];
         unpack16<T>(ld_v4(bias + (size_t)i * V), b);
 #pragma unroll
-        for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + b[j]);
+        for (int j = 0; j < V; ++j) f[j] += b[j];
+        round_vec<T>(f);
     }
 }
 

@@ -43,14 +43,16 @@ norm_kernel(const T *in, T *out, const T *residual_in, T *residual_out, const T 
                 float r[V];
                 unpack16<T>(ld_v4(rin + (size_t)i * V), r);
 #pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + r[j]);
+                for (int j = 0; j < V; ++j) f[j] += r[j];
+        round_vec<T>(f);
             }
             if (rout) st_v4(rout + (size_t)i * V, pack16<T>(f));
             if (bias) {
                 float b[V];
                 unpack16<T>(ld_v4(bias + (size_t)i * V), b);
 #pragma unroll
-                for (int j = 0; j < V; ++j) f[j] = round_to<T>(f[j] + b[j]);
+                for (int j = 0; j < V; ++j) f[j] += b[j];
+        round_vec<T>(f);
             }
         } else {
             f[0] = Elem<T>::to_f(x[i]);
