@@ -151,6 +151,55 @@ def test_scheduler_a_request_as_large_as_the_pool_runs_alone():
     assert list(bat.result(r0)[0]) == alone(p0, 29) and list(bat.result(r1)[0]) == alone(p1, 5)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_scheduler_randomised_stress(seed):
+    """Random pools (often too small), batch sizes, budgets and request mixes, requests submitted WHILE the loop runs: the invariants of
+    drive() must hold at every iteration, nothing may starve, and every request ends with its own tokens."""
+    mod = b200()
+    rng = np.random.default_rng(1000 + seed)
+    max_pages = int(rng.integers(2, 6))
+    cfg = dict(max_batch=int(rng.integers(1, 7)), num_pages=int(rng.integers(max_pages, 4 * max_pages + 1)), max_pages_per_seq=max_pages,
+               max_prefill_tokens=max_pages * PAGE)
+    bat = mod.Batcher(**cfg)
+    requests, pending_submissions = {}, []
+    for _ in range(int(rng.integers(5, 25))):
+        reach = int(rng.integers(1, max_pages * PAGE + 1))        # prompt + max_new - 1
+        plen = int(rng.integers(1, reach + 1))
+        pending_submissions.append((rng.integers(8, 1000, size=plen).tolist(), reach - plen + 1))
+    # a third of the requests are queued up front, the rest trickle in between iterations
+    tokens_of, it = {}, 0
+    def submit_some(n):
+        for _ in range(min(n, len(pending_submissions))):
+            p, m = pending_submissions.pop()
+            rid = bat.submit(p, m)
+            requests[rid] = (p, m)
+            tokens_of[rid] = list(p)
+    submit_some(max(1, len(pending_submissions) // 3))
+    while bat.pending() > 0 or pending_submissions:
+        it += 1
+        assert it < 20000, "scheduler does not make progress"
+        if pending_submissions and (bat.pending() == 0 or rng.random() < 0.3):
+            submit_some(int(rng.integers(1, 4)))
+        plan, v = bat.plan()
+        assert plan.n_prefill + plan.n_decode > 0 or plan.n_preempted > 0
+        held = []
+        for bt, need in list(zip(v["prefill_block_table"], [int(n) for n in v["prefill_lens"]])) + \
+                list(zip(v["decode_block_table"], [int(s_) for s_ in v["decode_steps"]])):
+            pages = [int(p) for p in bt if p >= 0]
+            assert len(pages) >= (need + PAGE - 1) // PAGE
+            held += pages
+        assert len(held) == len(set(held)) and len(held) + plan.free_pages == cfg["num_pages"]
+        sp = [fake_next(tokens_of[int(r)]) for r in v["prefill_requests"]]
+        sd = [fake_next(tokens_of[int(r)]) for r in v["decode_requests"]]
+        for r, t in list(zip(v["prefill_requests"], sp)) + list(zip(v["decode_requests"], sd)):
+            tokens_of[int(r)].append(t)
+        bat.commit(sp, sd, END)
+    assert bat.free_pages() == cfg["num_pages"]
+    for rid, (p, m) in requests.items():
+        got, state = bat.result(rid)
+        assert state == mod.REQ_FINISHED and list(got) == alone(p, m), f"request {rid} (preempted {bat.preemptions(rid)} times) under {cfg}"
+
+
 def test_scheduler_abort_returns_the_admitted_requests_to_the_front_of_the_queue():
     """A failed launch must not leak pages or lose requests: after b200_batcher_abort the same plan comes out again."""
     mod = b200()
