@@ -148,6 +148,19 @@ def test_llama_model_example_runs(dtype):
 
 
 @pytest.mark.gpu
+def test_serve_example_runs():
+    """Continuous batching over the paged cache driven from C++ through the C ABI alone (shim/examples/serve_example.cpp): the batcher
+    with everybody admitted at once reproduces b200_generate_ragged id for id; a stream of 9 requests through 3 slots and 5 pages finishes
+    with the token counts asked for and every page back in the pool."""
+    exe = os.path.join(OWN_DIR, "serve_example")
+    if not os.path.exists(exe):
+        pytest.skip("shim/_own_programs not built (run __graft_entry__.build())")
+    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=180)
+    out = p.stdout.decode(errors="replace")
+    assert p.returncode == 0 and "serve_example passed" in out, out[-3000:]
+
+
+@pytest.mark.gpu
 def test_chat_factory_two_rounds(tmp_path):
     """The model factory of the reference's chat entry (src/utils/model_utils.h:14-94 -> shim/src/utils/model_utils.h): config JSON ->
     LlamaModel -> two conversation rounds through MakeInput / Response / MakeHistory, non-interactively."""
