@@ -155,6 +155,25 @@ __device__ __forceinline__ uint32_t idesc_f16(bool bf16, int m, int n, bool b_mn
     return d;
 }
 
+// 2^x for x <= ~8 on the FMA / ALU pipes (no MUFU): n = round(x) by the 1.5 * 2^23 trick, 2^(x - n) by a degree-4 polynomial on [-0.5, 0.5]
+// (max relative error 3.7e-6, far inside the 2^-9 rounding of the 16-bit probabilities), 2^n added into the exponent field.  One in four
+// exponentials of the softmax goes this way: the loop's ex2 burst is bound by the XU pipe (16 results per clock per SM) while the FMA pipe
+// idles -- the split FlashAttention-4 uses.  x = -inf (masked key) gives ~1e-38: below every sum it is added to.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(0.009560510516f, f, 0.05591703951f);
+    p = fmaf(p, f, 0.2402498126f);
+    p = fmaf(p, f, 0.6931219697f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef B200_CTX_POLY_EVERY
+#define B200_CTX_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = B200_CTX_POLY_EVERY;  // every n-th exponential on the polynomial (0: all on MUFU)
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleStep = 8.0f;  // log2 domain: the accumulator is rescaled when the running max has grown by more than 2^8
 
@@ -385,7 +404,8 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 float pf[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    pf[u] = ex2f(fmaf(__uint_as_float(r[8 * q + u]), sl2, -m_use));
+                    const float x = fmaf(__uint_as_float(r[8 * q + u]), sl2, -m_use);
+                    pf[u] = (kPolyEvery > 0 && u % kPolyEvery == kPolyEvery - 1) ? ex2_poly(x) : ex2f(x);
                     psum += pf[u];
                 }
                 packed[q] = pack16<T>(pf);
