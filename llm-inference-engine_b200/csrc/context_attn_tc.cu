@@ -173,6 +173,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 #define B200_CTX_POLY_EVERY 0
 #endif
 constexpr int kPolyEvery = B200_CTX_POLY_EVERY;  // every n-th exponential on the polynomial (0: all on MUFU)
+constexpr bool poly_lane(int u) { return kPolyEvery > 0 && u % (kPolyEvery > 0 ? kPolyEvery : 1) == kPolyEvery - 1; }
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleStep = 8.0f;  // log2 domain: the accumulator is rescaled when the running max has grown by more than 2^8
@@ -405,7 +406,7 @@ context_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const float x = fmaf(__uint_as_float(r[8 * q + u]), sl2, -m_use);
-                    pf[u] = (kPolyEvery > 0 && u % kPolyEvery == kPolyEvery - 1) ? ex2_poly(x) : ex2f(x);
+                    pf[u] = poly_lane(u) ? ex2_poly(x) : ex2f(x);
                     psum += pf[u];
                 }
                 packed[q] = pack16<T>(pf);
