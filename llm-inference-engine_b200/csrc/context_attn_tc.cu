@@ -173,7 +173,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 #define B200_CTX_POLY_EVERY 0
 #endif
 constexpr int kPolyEvery = B200_CTX_POLY_EVERY;  // every n-th exponential on the polynomial (0: all on MUFU)
-constexpr bool poly_lane(int u) { return kPolyEvery > 0 && u % (kPolyEvery > 0 ? kPolyEvery : 1) == kPolyEvery - 1; }
+__host__ __device__ constexpr bool poly_lane(int u) { return kPolyEvery > 0 && u % (kPolyEvery > 0 ? kPolyEvery : 1) == kPolyEvery - 1; }
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleStep = 8.0f;  // log2 domain: the accumulator is rescaled when the running max has grown by more than 2^8
