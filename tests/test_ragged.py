@@ -158,3 +158,36 @@ def test_generate_ragged_argument_errors_without_gpu_compute():
     rc = mod.lib().b200_generate_ragged(None, C.byref(gp), ids, lens, 1, 4, None, None, None, 0, None, None, None)
     assert rc != 0 and b"null" in mod.lib().b200_last_error_string()
     assert mod.lib().b200_decoder_step_ragged(None, None, None, None, 1, None, 1, 0, 1, None) != 0
+
+
+def test_ragged_and_paged_argument_checks_run_before_any_cuda_call():
+    """Reachable on a CPU-only box: the host-side validation of the ragged generation loop and of the paged step (a decoder handle is a
+    host object; the device pointers below are never dereferenced because the checks come first)."""
+    import ctypes as C
+
+    mod = b200()
+    dc = mod.DecoderConfig(256, 2, 2, 128, 384, 2, 64, 2, mod.BF16, mod.W_DENSE, 128, 1e-6, 128, 10000.0, 1, 0)
+    h = mod.lib().b200_decoder_create(C.byref(dc))
+    assert h
+    try:
+        fake = 0x1000  # "device pointer", 256-byte aligned
+        gp = mod.GenerateParams(fake, fake, fake, 100, 1, 2, 4, 0)
+        out = (C.c_int * 8)()
+        err = lambda: mod.lib().b200_last_error_string().decode()
+        ids, lens = (C.c_int * 8)(1, 2, 3, 4, 5, 6, 7, 8), (C.c_int * 2)(3, 9)
+        assert mod.lib().b200_generate_ragged(h, C.byref(gp), ids, lens, 2, 4, fake, fake, fake, 1 << 30, out, None, None) != 0
+        assert "prompt length 9 of sequence 1" in err()
+        ids, lens = (C.c_int * 8)(1, 2, 3, 4, 5, 6, 700, 8), (C.c_int * 2)(3, 4)
+        assert mod.lib().b200_generate_ragged(h, C.byref(gp), ids, lens, 2, 4, fake, fake, fake, 1 << 30, out, None, None) != 0
+        assert "prompt id 700 at (1, 2)" in err()
+        ids = (C.c_int * 8)(1, 2, 3, -5, 5, 6, 7, 8)  # padding of row 0 (length 3) is never looked at
+        assert mod.lib().b200_generate_ragged(h, C.byref(gp), ids, lens, 2, 4, fake, fake, fake, 16, out, None, None) != 0
+        assert "bytes of workspace" in err()
+        assert mod.lib().b200_decoder_step_paged(h, fake, fake, fake, fake, fake, 2, 500, 4, 2, 0, 2, None) != 0
+        assert "block table's reach" in err()
+        assert mod.lib().b200_decoder_prefill_paged(h, fake, fake, fake, None, fake, fake, fake, 2, 4, 8, 4, 2, fake, 1 << 20, 0, 2, None) != 0
+        assert "null block table" in err()
+        assert mod.lib().b200_decoder_prefill_tp(h, fake, fake, fake, fake, fake, fake, 2, 4, 8, fake, 1 << 20, 0, 2, None, None, None) != 0
+        assert "null all-reduce callback" in err()
+    finally:
+        mod.lib().b200_decoder_destroy(h)
