@@ -181,3 +181,39 @@ class VocabShardedHead:
         torch.gather(self.cand_ids, 1, self.idx.long(), out=self.topk_ids)
         mod.check(mod.lib().b200_sampling(p(self.topk_ids), p(self.topk_vals), p(seq_len), p(finished), p(output_id), B, k, step, end_id, self.vocab,
                                           mod.F32, mod.stream()))
+
+
+def generate_tp(mod, dec, dist, prompt_ids, embedding, final_gamma, head, k_cache, v_cache, max_new_tokens, end_id=2):
+    """The generation loop on a tensor-parallel engine (what b200_generate does on one GPU, src/models/llama/llama.cpp:165-398 intended):
+    embedding -> Decoder.prefill_tp (one NCCL all-reduce per attention and per MLP block) -> last prompt row -> vocab-sharded LM head
+    (VocabShardedHead) -> then per token: embedding of the sampled id -> Decoder.step_tp (fused NVLink exchange; call dec.tp_attach
+    first) -> head.  prompt_ids: host int [B, T] (equal lengths); k_cache / v_cache: this rank's head shard [L, B, Hkv / P, S, d];
+    `head`: a VocabShardedHead built for batch B.  Every rank returns the same ids [B, max_new_tokens] (numpy); everything from a
+    sequence's first end_id on reads end_id, as b200_generate reports it."""
+    import numpy as np
+    import torch
+
+    dev = embedding.device
+    prompt = np.ascontiguousarray(np.asarray(prompt_ids, dtype=np.int32))
+    B, T = prompt.shape
+    x = mod.input_embedding(torch.from_numpy(prompt.reshape(-1)).to(dev), embedding)
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    dec.prefill_tp(x, k_cache, v_cache, il, torch.zeros_like(il), il, T, dist)
+    hidden = x.view(B, T, -1)[:, -1].contiguous()
+    seq_len, finished = il.clone(), torch.zeros(B, dtype=torch.uint8, device=dev)
+    out_id = torch.zeros(B, dtype=torch.int32, device=dev)
+    step, out = T, []
+    for i in range(max_new_tokens):
+        head.run(dist, hidden, final_gamma, seq_len, finished, out_id, step, end_id)
+        out.append(out_id.clone())
+        if i + 1 == max_new_tokens:
+            break
+        step += 1
+        hidden = mod.input_embedding(out_id, embedding)
+        dec.step_tp(hidden, k_cache, v_cache, step)
+    ids = torch.stack(out, dim=1).cpu().numpy()
+    for b in range(B):
+        hit = np.where(ids[b] == end_id)[0]
+        if len(hit):
+            ids[b, hit[0]:] = end_id
+    return ids

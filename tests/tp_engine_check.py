@@ -121,6 +121,44 @@ def main():
         except (AssertionError, mod.B200Error) as e:
             ok = False
             print(f"[rank {rank}] TP prefill {dtype} FAILED: {e}", flush=True)
+    # ---- the whole loop under tensor parallelism (tp.generate_tp: prefill_tp -> vocab-sharded head -> step_tp ...) against b200_generate
+    #      of the UN-SHARDED model on this GPU: fp32, greedy -- the same ids
+    try:
+        dtype, B, T, N, V = "f32", 2, 9, 6, 1000
+        model = make_model(cfg, seed=29, bias=True)
+        r = np.random.default_rng(31)
+        emb = rounded(r.standard_normal((V, cfg["hidden"])), dtype)
+        gam = rounded(1 + 0.1 * r.standard_normal(cfg["hidden"]), dtype)
+        lm = rounded(r.standard_normal((V, cfg["hidden"])) / 32, dtype)
+        prompt = r.integers(3, V, size=(B, T)).astype(np.int32)
+        embd, gd, lmd = to_dev(emb, dtype), to_dev(gam, dtype), to_dev(lm, dtype)
+        lcfg = tp.local_cfg(dict(head_num=cfg["head_num"], kv_head_num=cfg["kv_head_num"], head_size=cfg["head_size"], inter=cfg["inter"]), world)
+
+        def build(lc, w_of, tpw, tpr):
+            dc = mod.DecoderConfig(cfg["hidden"], lc["head_num"], lc["kv_head_num"], cfg["head_size"], lc["inter"], cfg["layers"], cfg["max_seq"], B, 0, 0,
+                                   128, cfg["eps"], cfg["head_size"], cfg["base"], tpw, tpr)
+            d_ = mod.Decoder(dc, dev)
+            for l, w in enumerate(model["layers"]):
+                s = w_of(w)
+                d_.set_layer(l, dict(g1=to_dev(s["g1"], dtype), qkv=to_dev(s["wqkv"], dtype), qkv_bias=to_dev(s["bqkv"], dtype), o=to_dev(s["wo"], dtype),
+                                     o_bias=to_dev(s["bo"], dtype), g2=to_dev(s["g2"], dtype), gate_up=to_dev(s["wgu"], dtype), down=to_dev(s["wd"], dtype)))
+            return d_
+
+        full = build(dict(head_num=cfg["head_num"], kv_head_num=cfg["kv_head_num"], inter=cfg["inter"]), lambda w: w, 1, 0)
+        kc = torch.zeros((cfg["layers"], B, cfg["kv_head_num"], cfg["max_seq"], cfg["head_size"]), dtype=torch.float32, device=dev)
+        want, _ = full.generate(prompt, embd, gd, lmd, kc, torch.zeros_like(kc), N, top_k=1, end_id=-1)
+        dec = build(lcfg, lambda w: tp.shard_layer(w, cfg, rank, world), world, rank)
+        dec.tp_attach(dist)
+        head = tp.VocabShardedHead(mod, dec, tp.shard_lm_head_rows(lmd, rank, world), V, rank, world, B, 1, dev)
+        kcs = torch.zeros((cfg["layers"], B, lcfg["kv_head_num"], cfg["max_seq"], cfg["head_size"]), dtype=torch.float32, device=dev)
+        got = tp.generate_tp(mod, dec, dist, prompt, embd, gd, head, kcs, torch.zeros_like(kcs), N, end_id=-1)
+        torch.cuda.synchronize()
+        assert dec.tp_error() == 0, "a peer never signalled (exchange timed out)"
+        assert np.array_equal(got, want), f"tensor-parallel ids {got.tolist()} vs un-sharded {want.tolist()}"
+        print(f"[rank {rank}] TP-{world} generation loop (prefill_tp + vocab-sharded head + step_tp), {B} x {N} greedy tokens = b200_generate un-sharded: OK", flush=True)
+    except (AssertionError, mod.B200Error) as e:
+        ok = False
+        print(f"[rank {rank}] TP generation loop FAILED: {e}", flush=True)
     # ---- vocab-sharded LM head + top-k + sampling: bit-identical to the un-sharded tail on the same hidden state
     try:
         V, hsz, B, K = 32000, cfg["hidden"], 3, 5
